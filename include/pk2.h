@@ -1,0 +1,178 @@
+/* pk2.h -- C ABI of libpk2.so, the B200 (sm_100a) hot path of pykaldi2.
+ *
+ * The reference (jzlianglu/pykaldi2) has no FFI: its hot path is Python calling
+ * PyTorch/cuDNN, PyKaldi->Kaldi and Horovod.  Each entry point below names the
+ * reference call site it replaces (path:line into the reference tree).  All
+ * signatures are plain C: device pointers (unless suffixed _h = host pointer),
+ * sizes, and a CUDA stream passed as void* (cudaStream_t; NULL = default stream).
+ * Every function returns 0 on success, non-zero on error; pk2_last_error() gives
+ * the message (thread-local).  Calls are asynchronous on the given stream unless
+ * stated.  Tensors are owned by the caller (torch caching allocator on the Python side).
+ *
+ * Python binding: pykaldi2_b200/_lib.py (ctypes).  See INTEGRATION.md.
+ */
+#ifndef PK2_H_
+#define PK2_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int pk2_version(void);
+const char* pk2_last_error(void);
+/* number of kernel launches this library has issued in this process (bench "gpu_launches") */
+int64_t pk2_launch_count(void);
+
+/* ---------------------------------------------------------------- fbank ----
+ * Replaces DataGeneratorTrain._logfbank_extractor (data/sr_dataset.py:279-296)
+ * + stft/_enframe (simulation/freq_analysis.py:41-150) on the CPU.
+ * plan: Hamming(400), 256-pt twiddles and the compacted [257,80] mel matrix
+ * (mel_h = host float32 [257*80], row-major, already multiplied by nothing:
+ * the 32768^2 scale and the +1 floor are applied by the kernel). */
+int pk2_fbank_plan_create(const float* mel_h, void** plan);
+int pk2_fbank_plan_destroy(void* plan);
+/* wav: concatenated float32 waveforms; wav_off[n_utts+1] sample offsets (device,
+ * int64); frame_off[n_utts+1] cumulative frame counts (device, int32), frames of
+ * utterance u = max(0, ceil((n_u-1-400)/160)+1); out [total_frames, 80]. */
+int pk2_fbank(void* plan, const float* wav, const int64_t* wav_off, const int32_t* frame_off,
+              int n_utts, int total_frames, float* out, void* stream);
+/* per-utterance column means over time: reader.preprocess.cmn (reader/preprocess.py:34-41)
+ * called with axis=0 at data/sr_dataset.py:365-366.  mean [n_utts, dim]. */
+int pk2_colmean(const float* feats, const int32_t* frame_off, int n_utts, int dim,
+                float* mean, void* stream);
+/* out[r,:] = row_src[r] < 0 ? 0 : (feats[row_src[r],:] - mean[row_utt[r],:] - mvn_mean) * mvn_istd
+ * Fuses CMN, GlobalMeanVarianceNormalization.apply_on_ndarray (reader/preprocess.py:211-229),
+ * _utt2seg chunking (data/sr_dataset.py:40-52), SeqDataloader zero padding
+ * (data/dataloader.py:96-103) and chain roll+subsample (bin/train_chain.py:251-255)
+ * into one gather.  mean / mvn_mean / mvn_istd may be NULL. */
+int pk2_gather_norm(const float* feats, const int32_t* row_src, const int32_t* row_utt,
+                    const float* mean, const float* mvn_mean, const float* mvn_istd,
+                    int n_rows, int dim, float* out, void* stream);
+
+/* ------------------------------------------------------- CE softmax+NLL ----
+ * Replaces nn.CrossEntropyLoss(ignore_index=-100) fwd+bwd (bin/train_ce.py:134,189;
+ * reduction='sum' at bin/train_se.py:214,235).  loss_rows[r] = lse - logit[label]
+ * (0 for ignored rows); grad = scale * (softmax - onehot) (0 for ignored rows);
+ * grad may be NULL, and may alias logits. */
+int pk2_ce_softmax(const float* logits, const int64_t* labels, int64_t n_rows, int n_cols,
+                   float scale, float* loss_rows, float* grad, void* stream);
+
+/* ----------------------------------------------------- LF-MMI denominator --
+ * Replaces kaldi_chain.DenominatorGraph(den_fst, num_pdfs) (bin/train_chain.py:167,202)
+ * and the denominator half of kaldi_chain.compute_chain_objf_and_deriv
+ * (ops/ops.py:265).  Host arrays are Kaldi's forward-transition CSR:
+ * fwd_off[S+1], and per arc (prob, pdf, dst state); init[S] initial probs. */
+int pk2_den_graph_create(int num_states, int num_pdfs, const int32_t* fwd_off_h,
+                         const float* fwd_prob_h, const int32_t* fwd_pdf_h,
+                         const int32_t* fwd_state_h, const float* init_h, void** graph);
+int pk2_den_graph_destroy(void* graph);
+/* bytes of alpha workspace pk2_denfb needs for n_seq sequences of at most max_frames */
+size_t pk2_denfb_workspace_bytes(void* graph, int n_seq, int max_frames);
+/* loglikes/grad: row t of sequence b at base + (b*row_stride_b + t)*num_pdfs floats.
+ * num_frames[b] (device int32) <= max_frames.  Writes grad[b,t,:] = deriv_scale *
+ * gamma_den(t,:) for t < num_frames[b] and 0 for num_frames[b] <= t < max_frames,
+ * logz[b] (double) = log Z_den.  cluster = CTAs per sequence (1, 2 or 4; 0 = auto). */
+int pk2_denfb(void* graph, const float* loglikes, const int32_t* num_frames, int n_seq,
+              int max_frames, int64_t row_stride_b, float leaky, float deriv_scale,
+              void* workspace, float* grad, double* logz, int cluster, void* stream);
+
+/* ------------------------------------------------------- LF-MMI numerator --
+ * Replaces the numerator half of compute_chain_objf_and_deriv (ops/ops.py:265):
+ * log-domain forward-backward over per-sequence supervision FSTs (epsilon-free,
+ * states sorted by time).  Concatenated CSR over all sequences:
+ *  seq_state_off[n_seq+1], seq_arc_off[n_seq+1];
+ *  per state (global index): out_off[S_tot+1], in_off[S_tot+1], final_cost[S_tot];
+ *  state_time[S_tot]; level_off: for sequence b, states of time t are
+ *  [level_off[lvl_base[b]+t], level_off[lvl_base[b]+t+1]) (global state index);
+ *  out arcs (sorted by src): out_dst, out_pdf, out_w (cost); in arcs (sorted by dst):
+ *  in_src, in_pdf, in_w.
+ * grad[b,t,p] += deriv_scale * gamma_num(t,p)  (atomic add; call after pk2_denfb);
+ * logz[b] (double) = log Z_num.  ws_alpha/ws_beta: double [S_tot] each. */
+typedef struct {
+    int n_seq;
+    const int32_t* seq_state_off;
+    const int32_t* lvl_base;
+    const int32_t* level_off;
+    const int32_t* num_frames;
+    const int32_t* out_off; const int32_t* out_dst; const int32_t* out_pdf; const float* out_w;
+    const int32_t* in_off;  const int32_t* in_src;  const int32_t* in_pdf;  const float* in_w;
+    const float* final_cost;
+    const int32_t* state_time;
+} pk2_sup_batch;
+int pk2_numfb(const pk2_sup_batch* sup, const float* loglikes, int num_pdfs, int64_t row_stride_b,
+              float deriv_scale, double* ws_alpha, double* ws_beta, float* grad, double* logz,
+              void* stream);
+
+/* ------------------------------------------------------------ lattice MMI --
+ * Replaces lattice_forward_backward_mmi + Posterior.to_pdf_matrix (ops/ops.py:57-62)
+ * for a batch of topologically sorted lattices with states ordered by time.
+ * Arc like = -lm_scale*graph_cost + ac_scale*loglikes[time(src), tid2pdf[tid]] (tid>0).
+ * Same concatenated layout as pk2_sup_batch; eps_* list same-level epsilon arcs
+ * (tid 0) of each level in topological order of src.
+ * grad (pre-zeroed by this call) [b,t,:] = -(num - den) merged posteriors with
+ * drop_frames / cancel semantics; keep[b*max_frames + t] = 0 for dropped frames
+ * (index tensor computed on host, bit-exact); tot[b] = lattice total log-like. */
+typedef struct {
+    int n_seq;
+    const int32_t* seq_state_off;
+    const int32_t* lvl_base;
+    const int32_t* level_off;
+    const int32_t* num_frames;
+    const int32_t* out_off; const int32_t* out_dst; const int32_t* out_tid; const float* out_gc;
+    const int32_t* in_off;  const int32_t* in_src;  const int32_t* in_tid;  const float* in_gc;
+    const int32_t* eps_off; const int32_t* eps_src; const int32_t* eps_dst; const float* eps_gc;
+    const float* final_cost;
+    const int32_t* state_time;
+    const int32_t* tid2pdf;
+    const int32_t* num_ali;     /* [sum T] alignment tids, offset by frame_base[b] */
+    const int32_t* frame_base;  /* [n_seq+1] */
+    const uint8_t* keep;        /* [sum T] 1 = frame kept, 0 = dropped */
+} pk2_lat_batch;
+int pk2_latfb_mmi(const pk2_lat_batch* lat, const float* loglikes, int num_pdfs, int max_frames,
+                  int64_t row_stride_b, float lm_scale, float ac_scale,
+                  double* ws_alpha, double* ws_beta, float* grad, double* tot, void* stream);
+
+/* ------------------------------------------------------------------ BLSTM --
+ * Replaces nn.LSTM(batch_first, bidirectional) + nn.Linear forward/backward
+ * (models/lstm.py:46-61 -> cuDNN RNN / cuBLAS).  See pykaldi2_b200/csrc/blstm.cu. */
+/* C[M,N] (+)= A[M,K] * B[N,K]^T (+ bias[N]), bf16 operands row-major (K contiguous),
+ * fp32 accumulate on tcgen05 tensor cores; C fp32 or bf16 (c_bf16).
+ * flags: bit0 accumulate into C, bit1 C is bf16.  */
+int pk2_gemm_bf16_nt(const void* A, const void* B, void* C, const float* bias,
+                     int M, int N, int K, int lda, int ldb, int ldc, int flags, void* stream);
+/* fp32 -> bf16 cast (row-major, same shape) */
+int pk2_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* transpose-cast: src fp32 [R,C] -> dst bf16 [C,R] */
+int pk2_transpose_bf16(const float* src, void* dst, int R, int C, void* stream);
+
+typedef struct {
+    int B, T, H;            /* batch, time steps, hidden size (per direction) */
+    const float* gx;        /* [B,T,2,4H] input projections incl. both biases (fp32) */
+    const void* whh;        /* bf16 [2,4H,H] recurrent weights (PyTorch gate order i,f,g,o) */
+    void* y;                /* bf16 [B,T,2H] layer output (fwd | bwd halves) */
+    float* gates;           /* fp32 [2,T,B,4H] post-activation gates (saved for backward) */
+    float* cstate;          /* fp32 [2,T,B,H] cell states (saved for backward) */
+    void* hbuf;             /* bf16 [2,2,B,H] ping-pong h exchange buffer */
+    unsigned int* sync;     /* [2*64] zero-initialised step counters */
+} pk2_lstm_fwd_args;
+int pk2_lstm_layer_fwd(const pk2_lstm_fwd_args* a, void* stream);
+
+typedef struct {
+    int B, T, H;
+    const void* dy;         /* bf16 or fp32? fp32 [B,T,2H] grad wrt layer output */
+    const void* whh_t;      /* bf16 [2,H,4H] transposed recurrent weights */
+    const float* gates;     /* from forward */
+    const float* cstate;    /* from forward */
+    void* dgates;           /* bf16 [B,T,2,4H] grad wrt pre-activations (output) */
+    void* dgbuf;            /* bf16 [2,2,B,4H] ping-pong exchange */
+    unsigned int* sync;     /* [2*64] zero-initialised */
+} pk2_lstm_bwd_args;
+int pk2_lstm_layer_bwd(const pk2_lstm_bwd_args* a, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PK2_H_ */

@@ -1,0 +1,530 @@
+// LF-MMI denominator forward-backward on the GPU (sm_100a).
+//
+// Replaces kaldi_chain.DenominatorGraph (reference bin/train_chain.py:167,202) and the
+// denominator half of kaldi_chain.compute_chain_objf_and_deriv (ops/ops.py:265), i.e.
+// Kaldi's chain-denominator.cc / chain-kernels.cu (one launch per frame, one thread per
+// block when called with one sequence, as the reference does).  Recursion: SURVEY.md
+// Appendix C (scaled-probability leaky-HMM, fp32, per-frame 1/sum(alpha) scaling).
+//
+// Design: one thread-block CLUSTER (K = 1, 2 or 4 CTAs) per sequence, persistent over all
+// frames, no per-frame launches and no grid-wide sync.  alpha'(t) / beta(t) (S floats) and
+// exp(loglikes[t]) (N floats) live in shared memory, replicated in every CTA of the
+// cluster; each CTA owns a contiguous range of rows, computes them, and broadcasts the
+// results into its peers' shared memory (DSMEM) followed by one cluster barrier per frame.
+// The arc table is stored in SELL-32 (sliced ELLPACK, rows sorted by degree) so that a
+// warp streams 32 rows in lock step with fully coalesced 8-byte arc records
+// {prob, idxA | idxB<<16}; three tables exist: rows = destination states (alpha pass),
+// rows = source states (beta pass), rows = pdfs (occupancy pass, so gamma needs no atomics).
+// The arc tables (~0.5 MB each) are shared by all sequences and stay L2-resident; per
+// frame HBM traffic is the loglike row (cp.async prefetched), the alpha row (written in the
+// forward, re-read in the backward) and the gradient row.
+#include "common.cuh"
+#include <cooperative_groups.h>
+#include <algorithm>
+#include <vector>
+#include <mutex>
+#include <string.h>
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int kThreads = 1024;
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxK = 4;
+
+struct SellDev {
+    const uint2* arcs;        // SELL arc records
+    const int* slice_off;     // [n_slices + 1] offsets into arcs (multiple of 32)
+    const int* slice_row;     // [n_slices * 32] row id or -1
+    int part_slice[kMaxK + 1];  // slices of part c: [part_slice[c], part_slice[c+1])
+    int part_row[kMaxK + 1];    // rows of part c
+};
+
+struct SellHost {
+    uint2* arcs = nullptr;
+    int* slice_off = nullptr;
+    int* slice_row = nullptr;
+    int part_slice[kMaxK + 1];
+    int part_row[kMaxK + 1];
+    void free_dev() { cudaFree(arcs); cudaFree(slice_off); cudaFree(slice_row); }
+    SellDev dev() const {
+        SellDev d;
+        d.arcs = arcs; d.slice_off = slice_off; d.slice_row = slice_row;
+        for (int i = 0; i <= kMaxK; ++i) { d.part_slice[i] = part_slice[i]; d.part_row[i] = part_row[i]; }
+        return d;
+    }
+};
+
+struct Arc3 { float w; int a, b; };
+inline unsigned f2u(float f) { unsigned u; memcpy(&u, &f, sizeof(u)); return u; }   // generic arc of a row: weight, gather index A, gather index B
+
+inline int part_bound(int R, int c, int K) {
+    if (c >= K) return R;
+    return (int)(((int64_t)R * c / K) & ~31LL);
+}
+
+// Build a SELL-32 table from per-row arc lists, partitioned into K contiguous row ranges.
+int build_sell(const std::vector<std::vector<Arc3>>& rows, int K, SellHost* out) {
+    const int R = (int)rows.size();
+    std::vector<uint2> arcs;
+    std::vector<int> slice_off(1, 0), slice_row;
+    for (int i = 0; i <= kMaxK; ++i) { out->part_slice[i] = 0; out->part_row[i] = R; }
+    for (int c = 0; c < K; ++c) {
+        const int r0 = part_bound(R, c, K), r1 = part_bound(R, c + 1, K);
+        out->part_row[c] = r0;
+        out->part_slice[c] = (int)slice_off.size() - 1;
+        std::vector<int> order(r1 - r0);
+        for (int i = 0; i < r1 - r0; ++i) order[i] = r0 + i;
+        std::stable_sort(order.begin(), order.end(),
+                         [&](int x, int y) { return rows[x].size() > rows[y].size(); });
+        for (size_t s = 0; s < order.size(); s += 32) {
+            size_t len = rows[order[s]].size();      // longest row of the slice (sorted desc)
+            const size_t base = arcs.size();
+            arcs.resize(base + len * 32, make_uint2(0u, 0u));
+            for (int l = 0; l < 32; ++l) {
+                if (s + l < order.size()) {
+                    const int r = order[s + l];
+                    slice_row.push_back(r);
+                    for (size_t k = 0; k < rows[r].size(); ++k) {
+                        const Arc3& a = rows[r][k];
+                        uint2 rec;
+                        rec.x = f2u(a.w);
+                        rec.y = (unsigned)a.a | ((unsigned)a.b << 16);
+                        arcs[base + k * 32 + l] = rec;
+                    }
+                } else {
+                    slice_row.push_back(-1);
+                }
+            }
+            slice_off.push_back((int)arcs.size());
+        }
+    }
+    for (int c = K; c <= kMaxK; ++c) { out->part_slice[c] = (int)slice_off.size() - 1; out->part_row[c] = R; }
+    if (arcs.empty()) arcs.push_back(make_uint2(0u, 0u));
+    if (slice_row.empty()) slice_row.push_back(-1);
+    PK2_CHECK(cudaMalloc(&out->arcs, sizeof(uint2) * arcs.size()));
+    PK2_CHECK(cudaMalloc(&out->slice_off, sizeof(int) * slice_off.size()));
+    PK2_CHECK(cudaMalloc(&out->slice_row, sizeof(int) * slice_row.size()));
+    PK2_CHECK(cudaMemcpy(out->arcs, arcs.data(), sizeof(uint2) * arcs.size(), cudaMemcpyHostToDevice));
+    PK2_CHECK(cudaMemcpy(out->slice_off, slice_off.data(), sizeof(int) * slice_off.size(), cudaMemcpyHostToDevice));
+    PK2_CHECK(cudaMemcpy(out->slice_row, slice_row.data(), sizeof(int) * slice_row.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+struct DenGraph {
+    int S = 0, N = 0;
+    int64_t A = 0;
+    std::vector<std::vector<Arc3>> rows_fwd, rows_bwd, rows_pdf;
+    float* init = nullptr;          // device [S]
+    float init_sum = 0.f;
+    bool built[kMaxK + 1] = {false, false, false, false, false};
+    SellHost t_fwd[kMaxK + 1], t_bwd[kMaxK + 1], t_pdf[kMaxK + 1];
+    std::mutex mu;
+};
+
+// ---------------------------------------------------------------- device helpers ----
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// asynchronous copy of n floats gmem -> smem (16 B chunks when aligned, else plain loads)
+__device__ __forceinline__ void row_prefetch(float* dst, const float* src, int n) {
+    const bool vec = ((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    if (vec) {
+        for (int i = threadIdx.x * 4; i < n; i += kThreads * 4) cp_async16(dst + i, src + i);
+    } else {
+        for (int i = threadIdx.x; i < n; i += kThreads) dst[i] = __ldg(src + i);
+    }
+    cp_async_commit();
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    // deterministic: warp shuffle tree, then warp 0 adds the 32 partials in order
+    v = pk2::warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = (threadIdx.x < kWarps) ? red[threadIdx.x] : 0.f;
+    if (warp == 0) {
+        t = pk2::warp_sum(t);
+        if (lane == 0) red[kWarps] = t;
+    }
+    __syncthreads();
+    return red[kWarps];
+}
+
+template <int K>
+__device__ __forceinline__ void cluster_barrier() {
+    if constexpr (K == 1) __syncthreads();
+    else cg::this_cluster().sync();
+}
+
+// acc over the arcs of every row of this CTA's part; body(row, acc) per row.
+template <class Body>
+__device__ __forceinline__ void sell_pass(const SellDev& tb, int part, const float* __restrict__ ga,
+                                          const float* __restrict__ gb, Body&& body) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s0 = tb.part_slice[part], s1 = tb.part_slice[part + 1];
+    for (int sl = s0 + warp; sl < s1; sl += kWarps) {
+        const int row = __ldg(&tb.slice_row[sl * 32 + lane]);
+        const int off = __ldg(&tb.slice_off[sl]);
+        const int len = (__ldg(&tb.slice_off[sl + 1]) - off) >> 5;
+        const uint2* p = tb.arcs + off + lane;
+        float acc0 = 0.f, acc1 = 0.f;
+        int k = 0;
+        for (; k + 4 <= len; k += 4) {
+            const uint2 r0 = __ldg(p + (k + 0) * 32);
+            const uint2 r1 = __ldg(p + (k + 1) * 32);
+            const uint2 r2 = __ldg(p + (k + 2) * 32);
+            const uint2 r3 = __ldg(p + (k + 3) * 32);
+            acc0 = fmaf(ga[r0.y & 0xffffu], __uint_as_float(r0.x) * gb[r0.y >> 16], acc0);
+            acc1 = fmaf(ga[r1.y & 0xffffu], __uint_as_float(r1.x) * gb[r1.y >> 16], acc1);
+            acc0 = fmaf(ga[r2.y & 0xffffu], __uint_as_float(r2.x) * gb[r2.y >> 16], acc0);
+            acc1 = fmaf(ga[r3.y & 0xffffu], __uint_as_float(r3.x) * gb[r3.y >> 16], acc1);
+        }
+        for (; k < len; ++k) {
+            const uint2 r0 = __ldg(p + k * 32);
+            acc0 = fmaf(ga[r0.y & 0xffffu], __uint_as_float(r0.x) * gb[r0.y >> 16], acc0);
+        }
+        body(row, acc0 + acc1);
+    }
+}
+
+struct DenArgs {
+    SellDev fwd, bwd, pdf;
+    const float* init;
+    int S, N;
+    const float* ll;
+    const int32_t* num_frames;
+    int64_t row_stride_b;
+    int max_frames;
+    float leaky, deriv_scale;
+    float* alpha_ws;     // [n_seq][max_frames][S]  alpha'(t), t < T
+    float* asum_ws;      // [n_seq][max_frames + 2] A(t), t <= T ; slot max_frames+1 = totp
+    float* grad;
+    double* logz;
+};
+
+// -------------------------------------------------------------------- forward ----
+template <int K>
+__global__ void __launch_bounds__(kThreads, 1) den_forward_kernel(DenArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int S = a.S, N = a.N;
+    const int Sp = (S + 3) & ~3, Np = (N + 3) & ~3;
+    float* buf0 = smem;
+    float* buf1 = buf0 + Sp;
+    float* ev = buf1 + Sp;          // exp(loglikes[t])
+    float* lraw = ev + Np;          // prefetched raw loglikes[t+1]
+    float* part = lraw + Np;        // [2][kMaxK]
+    float* red = part + 2 * kMaxK;  // [kWarps + 1]
+
+    const int b = blockIdx.x / K;
+    const int c = (K == 1) ? 0 : (int)cg::this_cluster().block_rank();
+    const int T = a.num_frames[b];
+    const float* ll = a.ll + (int64_t)b * a.row_stride_b * N;
+    float* aws = a.alpha_ws + (int64_t)b * a.max_frames * S;
+    float* asum = a.asum_ws + (int64_t)b * (a.max_frames + 2);
+    const int r0 = a.fwd.part_row[c], r1 = a.fwd.part_row[c + 1];
+
+    float* cur = buf0;
+    float* nxt = buf1;
+
+    // alpha(0) = init, A(0) = sum(init), alpha'(0) = alpha(0) + leaky*A(0)*init
+    float s = 0.f;
+    for (int j = threadIdx.x; j < S; j += kThreads) { const float v = __ldg(&a.init[j]); cur[j] = v; s += v; }
+    float A = block_sum(s, red);
+    for (int j = threadIdx.x; j < S; j += kThreads) cur[j] = cur[j] + a.leaky * A * cur[j];
+    if (T > 0) row_prefetch(lraw, ll, N);
+    double logsum = 0.0;
+    cluster_barrier<K>();           // peers' shared memory is live from here on
+
+    for (int t = 0; t < T; ++t) {
+        // finish frame-t inputs: store alpha'(t) slice, e(t) = exp(clamp(ll[t]))
+        for (int j = r0 + threadIdx.x; j < r1; j += kThreads) aws[(int64_t)t * S + j] = cur[j];
+        if (threadIdx.x == 0 && c == 0) asum[t] = A;
+        cp_async_wait_all();
+        __syncthreads();
+        for (int p = threadIdx.x; p < N; p += kThreads)
+            ev[p] = __expf(fminf(fmaxf(lraw[p], -30.f), 30.f));
+        __syncthreads();
+        if (t + 1 < T) row_prefetch(lraw, ll + (int64_t)(t + 1) * N, N);
+
+        const float invA = 1.0f / A;
+        float local = 0.f;
+        sell_pass(a.fwd, c, cur, ev, [&](int row, float acc) {
+            if (row >= 0) {
+                const float v = acc * invA;
+                local += v;
+                nxt[row] = v;
+                if constexpr (K > 1) {
+                    cg::cluster_group cl = cg::this_cluster();
+#pragma unroll
+                    for (int q = 1; q < K; ++q) {
+                        float* peer = cl.map_shared_rank(nxt, (c + q) % K);
+                        peer[row] = v;
+                    }
+                }
+            }
+        });
+        const float ps = block_sum(local, red);
+        const int par = t & 1;
+        if (threadIdx.x == 0) {
+            part[par * kMaxK + c] = ps;
+            if constexpr (K > 1) {
+                cg::cluster_group cl = cg::this_cluster();
+                for (int q = 1; q < K; ++q) {
+                    float* peer = cl.map_shared_rank(part, (c + q) % K);
+                    peer[par * kMaxK + c] = ps;
+                }
+            }
+            logsum += log((double)A);
+        }
+        cluster_barrier<K>();
+        float An = 0.f;
+#pragma unroll
+        for (int q = 0; q < K; ++q) An += part[par * kMaxK + q];
+        const float lk = a.leaky * An;
+        for (int j = threadIdx.x; j < S; j += kThreads) nxt[j] = fmaf(lk, __ldg(&a.init[j]), nxt[j]);
+        A = An;
+        float* tmp = cur; cur = nxt; nxt = tmp;
+        __syncthreads();
+    }
+    // total probability: sum_j alpha'(T, j)
+    float s2 = 0.f;
+    for (int j = threadIdx.x; j < S; j += kThreads) s2 += cur[j];
+    const float totp = block_sum(s2, red);
+    if (threadIdx.x == 0 && c == 0) {
+        asum[T] = A;
+        asum[a.max_frames + 1] = totp;
+        a.logz[b] = log((double)totp) + logsum;
+    }
+    cluster_barrier<K>();           // no CTA exits while peers may still write into it
+}
+
+// ------------------------------------------------------------------- backward ----
+template <int K>
+__global__ void __launch_bounds__(kThreads, 1) den_backward_kernel(DenArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int S = a.S, N = a.N;
+    const int Sp = (S + 3) & ~3, Np = (N + 3) & ~3;
+    float* buf0 = smem;
+    float* buf1 = buf0 + Sp;
+    float* al = buf1 + Sp;          // alpha'(t)
+    float* ev = al + Sp;            // exp(loglikes[t])
+    float* lraw = ev + Np;          // prefetched raw loglikes
+    float* gbuf = lraw + Np;        // gamma staging for this CTA's pdf range
+    const int gcap = ((N + K - 1) / K + 64 + 3) & ~3;
+    float* part = gbuf + gcap;      // [2][kMaxK]
+    float* red = part + 2 * kMaxK;
+
+    const int b = blockIdx.x / K;
+    const int c = (K == 1) ? 0 : (int)cg::this_cluster().block_rank();
+    const int T = a.num_frames[b];
+    const float* ll = a.ll + (int64_t)b * a.row_stride_b * N;
+    float* grad = a.grad + (int64_t)b * a.row_stride_b * N;
+    const float* aws = a.alpha_ws + (int64_t)b * a.max_frames * S;
+    const float* asum = a.asum_ws + (int64_t)b * (a.max_frames + 2);
+    const int p0 = a.pdf.part_row[c], p1 = a.pdf.part_row[c + 1];
+
+    float* cur = buf0;
+    float* nxt = buf1;
+
+    // zero-fill the padded frames of this CTA's pdf range
+    for (int t = T; t < a.max_frames; ++t)
+        for (int p = p0 + threadIdx.x; p < p1; p += kThreads) grad[(int64_t)t * N + p] = 0.f;
+    if (T <= 0) return;   // uniform across the cluster (same sequence)
+
+    // beta'(T) = 1/totp ; beta(T) = beta'(T) + leaky * sum_k beta'(T,k) init[k]
+    float s = 0.f;
+    for (int j = threadIdx.x; j < S; j += kThreads) s += __ldg(&a.init[j]);
+    const float isum = block_sum(s, red);
+    const float totp = asum[a.max_frames + 1];
+    const float bT = (1.0f / totp) * (1.0f + a.leaky * isum);
+    for (int j = threadIdx.x; j < S; j += kThreads) cur[j] = bT;
+    row_prefetch(lraw, ll + (int64_t)(T - 1) * N, N);
+    row_prefetch(al, aws + (int64_t)(T - 1) * S, S);
+    cluster_barrier<K>();
+
+    for (int t = T - 1; t >= 0; --t) {
+        cp_async_wait_all();
+        __syncthreads();
+        for (int p = threadIdx.x; p < N; p += kThreads)
+            ev[p] = __expf(fminf(fmaxf(lraw[p], -30.f), 30.f));
+        const float invA = 1.0f / asum[t];
+        __syncthreads();
+        if (t > 0) row_prefetch(lraw, ll + (int64_t)(t - 1) * N, N);
+
+        // beta'(t, i) for this CTA's source states
+        float local = 0.f;
+        sell_pass(a.bwd, c, cur, ev, [&](int row, float acc) {
+            if (row >= 0) {
+                const float v = acc * invA;
+                local = fmaf(v, __ldg(&a.init[row]), local);
+                nxt[row] = v;
+                if constexpr (K > 1) {
+                    cg::cluster_group cl = cg::this_cluster();
+#pragma unroll
+                    for (int q = 1; q < K; ++q) {
+                        float* peer = cl.map_shared_rank(nxt, (c + q) % K);
+                        peer[row] = v;
+                    }
+                }
+            }
+        });
+        // pdf occupancies gamma(t, p) for this CTA's pdf range
+        const float gs = a.deriv_scale * invA;
+        sell_pass(a.pdf, c, al, cur, [&](int row, float acc) {
+            if (row >= 0) gbuf[row - p0] = acc * ev[row] * gs;
+        });
+        const float ps = block_sum(local, red);      // contains __syncthreads: gbuf / al reads complete
+        for (int p = p0 + threadIdx.x; p < p1; p += kThreads) grad[(int64_t)t * N + p] = gbuf[p - p0];
+        if (t > 0) row_prefetch(al, aws + (int64_t)(t - 1) * S, S);
+        const int par = t & 1;
+        if (threadIdx.x == 0) {
+            part[par * kMaxK + c] = ps;
+            if constexpr (K > 1) {
+                cg::cluster_group cl = cg::this_cluster();
+                for (int q = 1; q < K; ++q) {
+                    float* peer = cl.map_shared_rank(part, (c + q) % K);
+                    peer[par * kMaxK + c] = ps;
+                }
+            }
+        }
+        cluster_barrier<K>();
+        float dot = 0.f;
+#pragma unroll
+        for (int q = 0; q < K; ++q) dot += part[par * kMaxK + q];
+        const float lk = a.leaky * dot;
+        for (int j = threadIdx.x; j < S; j += kThreads) nxt[j] += lk;
+        float* tmp = cur; cur = nxt; nxt = tmp;
+        __syncthreads();
+    }
+    cluster_barrier<K>();
+}
+
+size_t fwd_smem_bytes(int S, int N) {
+    const size_t Sp = (S + 3) & ~3, Np = (N + 3) & ~3;
+    return sizeof(float) * (2 * Sp + 2 * Np + 2 * kMaxK + kWarps + 1 + 3);
+}
+size_t bwd_smem_bytes(int S, int N, int K) {
+    const size_t Sp = (S + 3) & ~3, Np = (N + 3) & ~3;
+    const size_t gcap = ((N + K - 1) / K + 64 + 3) & ~3;
+    return sizeof(float) * (3 * Sp + 2 * Np + gcap + 2 * kMaxK + kWarps + 1 + 3);
+}
+
+template <int K>
+int launch_den(const DenArgs& args, int n_seq, cudaStream_t st) {
+    const size_t sf = fwd_smem_bytes(args.S, args.N), sb = bwd_smem_bytes(args.S, args.N, K);
+    PK2_REQUIRE(sb <= 227 * 1024, "pk2_denfb: graph too large for shared memory (S=%d N=%d needs %zu B)",
+                args.S, args.N, sb);
+    PK2_CHECK(cudaFuncSetAttribute(den_forward_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf));
+    PK2_CHECK(cudaFuncSetAttribute(den_backward_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_seq * K);
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = K; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.dynamicSmemBytes = sf;
+    PK2_CHECK(cudaLaunchKernelEx(&cfg, den_forward_kernel<K>, args));
+    PK2_LAUNCHED();
+    cfg.dynamicSmemBytes = sb;
+    PK2_CHECK(cudaLaunchKernelEx(&cfg, den_backward_kernel<K>, args));
+    PK2_LAUNCHED();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int pk2_den_graph_create(int S, int N, const int32_t* fwd_off, const float* fwd_prob,
+                                    const int32_t* fwd_pdf, const int32_t* fwd_state,
+                                    const float* init_h, void** graph) {
+    PK2_REQUIRE(fwd_off && fwd_prob && fwd_pdf && fwd_state && init_h && graph, "pk2_den_graph_create: null argument");
+    PK2_REQUIRE(S > 0 && S <= 65535 && N > 0 && N <= 65535,
+                "pk2_den_graph_create: num_states=%d / num_pdfs=%d outside the 16-bit packed index range", S, N);
+    DenGraph* g = new DenGraph();
+    g->S = S; g->N = N; g->A = fwd_off[S];
+    g->rows_fwd.resize(S); g->rows_bwd.resize(S); g->rows_pdf.resize(N);
+    for (int i = 0; i < S; ++i) {
+        for (int k = fwd_off[i]; k < fwd_off[i + 1]; ++k) {
+            const int j = fwd_state[k], p = fwd_pdf[k];
+            const float w = fwd_prob[k];
+            if (j < 0 || j >= S || p < 0 || p >= N) {
+                delete g;
+                pk2::set_error("pk2_den_graph_create: arc %d out of range (dst %d pdf %d)", k, j, p);
+                return 2;
+            }
+            g->rows_fwd[j].push_back({w, i, p});   // alpha pass: gather alpha'[src], e[pdf]
+            g->rows_bwd[i].push_back({w, j, p});   // beta pass:  gather beta[dst],  e[pdf]
+            g->rows_pdf[p].push_back({w, i, j});   // gamma pass: gather alpha'[src], beta[dst]
+        }
+    }
+    double isum = 0.0;
+    for (int i = 0; i < S; ++i) isum += init_h[i];
+    g->init_sum = (float)isum;
+    PK2_CHECK(cudaMalloc(&g->init, sizeof(float) * S));
+    PK2_CHECK(cudaMemcpy(g->init, init_h, sizeof(float) * S, cudaMemcpyHostToDevice));
+    *graph = g;
+    return 0;
+}
+
+extern "C" int pk2_den_graph_destroy(void* graph) {
+    if (!graph) return 0;
+    DenGraph* g = static_cast<DenGraph*>(graph);
+    for (int k = 1; k <= kMaxK; ++k)
+        if (g->built[k]) { g->t_fwd[k].free_dev(); g->t_bwd[k].free_dev(); g->t_pdf[k].free_dev(); }
+    cudaFree(g->init);
+    delete g;
+    return 0;
+}
+
+extern "C" size_t pk2_denfb_workspace_bytes(void* graph, int n_seq, int max_frames) {
+    if (!graph || n_seq <= 0 || max_frames <= 0) return 0;
+    DenGraph* g = static_cast<DenGraph*>(graph);
+    size_t alpha = (size_t)n_seq * (size_t)max_frames * (size_t)g->S * sizeof(float);
+    size_t asum = (size_t)n_seq * (size_t)(max_frames + 2) * sizeof(float);
+    return ((alpha + 255) & ~(size_t)255) + ((asum + 255) & ~(size_t)255);
+}
+
+extern "C" int pk2_denfb(void* graph, const float* loglikes, const int32_t* num_frames, int n_seq,
+                         int max_frames, int64_t row_stride_b, float leaky, float deriv_scale,
+                         void* workspace, float* grad, double* logz, int cluster, void* stream) {
+    PK2_REQUIRE(graph && loglikes && num_frames && workspace && grad && logz, "pk2_denfb: null argument");
+    PK2_REQUIRE(n_seq > 0 && max_frames > 0, "pk2_denfb: empty batch");
+    PK2_REQUIRE(row_stride_b >= max_frames, "pk2_denfb: row_stride_b < max_frames");
+    DenGraph* g = static_cast<DenGraph*>(graph);
+    int K = cluster;
+    if (K == 0) K = (n_seq * 4 <= 148) ? 4 : ((n_seq * 2 <= 148) ? 2 : 1);
+    PK2_REQUIRE(K == 1 || K == 2 || K == 4, "pk2_denfb: cluster must be 0, 1, 2 or 4 (got %d)", cluster);
+    {
+        std::lock_guard<std::mutex> lk(g->mu);
+        if (!g->built[K]) {
+            if (build_sell(g->rows_fwd, K, &g->t_fwd[K])) return 1;
+            if (build_sell(g->rows_bwd, K, &g->t_bwd[K])) return 1;
+            if (build_sell(g->rows_pdf, K, &g->t_pdf[K])) return 1;
+            g->built[K] = true;
+        }
+    }
+    DenArgs a;
+    a.fwd = g->t_fwd[K].dev(); a.bwd = g->t_bwd[K].dev(); a.pdf = g->t_pdf[K].dev();
+    a.init = g->init; a.S = g->S; a.N = g->N;
+    a.ll = loglikes; a.num_frames = num_frames; a.row_stride_b = row_stride_b; a.max_frames = max_frames;
+    a.leaky = leaky; a.deriv_scale = deriv_scale;
+    size_t alpha = (size_t)n_seq * (size_t)max_frames * (size_t)g->S * sizeof(float);
+    alpha = (alpha + 255) & ~(size_t)255;
+    a.alpha_ws = static_cast<float*>(workspace);
+    a.asum_ws = reinterpret_cast<float*>(static_cast<char*>(workspace) + alpha);
+    a.grad = grad; a.logz = logz;
+    cudaStream_t st = pk2::as_stream(stream);
+    if (K == 1) return launch_den<1>(a, n_seq, st);
+    if (K == 2) return launch_den<2>(a, n_seq, st);
+    return launch_den<4>(a, n_seq, st);
+}

@@ -1,0 +1,81 @@
+// LF-MMI numerator forward-backward on the GPU (sm_100a).
+//
+// Replaces the numerator half of kaldi_chain.compute_chain_objf_and_deriv (reference
+// ops/ops.py:265; Kaldi chain-numerator.cc runs it on the CPU in the log domain).
+// Supervision FSTs are epsilon-free with time-stamped states sorted by time, so the
+// recursion is level-synchronous: one warp per sequence walks the time levels, one lane
+// per state of the level, log-add in double as Kaldi does.  The work is tiny next to the
+// denominator (<= ~10 states per level); it runs concurrently with it.
+#include "common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(32)
+numfb_kernel(pk2_sup_batch sup, const float* __restrict__ loglikes, int N, int64_t row_stride_b,
+             float deriv_scale, double* alpha, double* beta,
+             float* __restrict__ grad, double* __restrict__ logz) {
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x;
+    const int T = sup.num_frames[b];
+    const int32_t* lvl = sup.level_off + sup.lvl_base[b];   // lvl[t]..lvl[t+1] = states of time t
+    const float* ll = loglikes + (int64_t)b * row_stride_b * N;
+    float* g = grad + (int64_t)b * row_stride_b * N;
+    const int s_begin = sup.seq_state_off[b];
+
+    // level 0: the start state is the first state of the sequence
+    for (int s = lvl[0] + lane; s < lvl[1]; s += 32) alpha[s] = (s == s_begin) ? 0.0 : -INFINITY;
+    __syncwarp();
+    for (int t = 1; t <= T; ++t) {
+        const float* row = ll + (int64_t)(t - 1) * N;
+        for (int s = lvl[t] + lane; s < lvl[t + 1]; s += 32) {
+            double acc = -INFINITY;
+            for (int k = sup.in_off[s]; k < sup.in_off[s + 1]; ++k) {
+                const double sc = alpha[sup.in_src[k]] + (double)row[sup.in_pdf[k]] - (double)sup.in_w[k];
+                acc = pk2::log_add(acc, sc);
+            }
+            alpha[s] = acc;
+        }
+        __syncwarp();
+    }
+    // total over final states (time T)
+    double z = -INFINITY;
+    for (int s = lvl[T] + lane; s < lvl[T + 1]; s += 32) {
+        const float fc = sup.final_cost[s];
+        const double bt = (fc < INFINITY) ? -(double)fc : -INFINITY;
+        beta[s] = bt;
+        z = pk2::log_add(z, alpha[s] + bt);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) z = pk2::log_add(z, __shfl_xor_sync(0xffffffffu, z, o));
+    if (lane == 0) logz[b] = z;
+    __syncwarp();
+    for (int t = T - 1; t >= 0; --t) {
+        const float* row = ll + (int64_t)t * N;
+        for (int s = lvl[t] + lane; s < lvl[t + 1]; s += 32) {
+            double acc = -INFINITY;
+            const double a = alpha[s];
+            for (int k = sup.out_off[s]; k < sup.out_off[s + 1]; ++k) {
+                const int p = sup.out_pdf[k];
+                const double sc = (double)row[p] - (double)sup.out_w[k] + beta[sup.out_dst[k]];
+                acc = pk2::log_add(acc, sc);
+                const double post = exp(a + sc - z);
+                if (post > 0.0) atomicAdd(&g[(int64_t)t * N + p], deriv_scale * (float)post);
+            }
+            beta[s] = acc;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+extern "C" int pk2_numfb(const pk2_sup_batch* sup, const float* loglikes, int num_pdfs,
+                         int64_t row_stride_b, float deriv_scale, double* ws_alpha, double* ws_beta,
+                         float* grad, double* logz, void* stream) {
+    PK2_REQUIRE(sup && loglikes && ws_alpha && ws_beta && grad && logz, "pk2_numfb: null argument");
+    PK2_REQUIRE(sup->n_seq > 0, "pk2_numfb: empty batch");
+    numfb_kernel<<<sup->n_seq, 32, 0, pk2::as_stream(stream)>>>(*sup, loglikes, num_pdfs, row_stride_b,
+                                                              deriv_scale, ws_alpha, ws_beta, grad, logz);
+    PK2_POST_LAUNCH();
+    return 0;
+}

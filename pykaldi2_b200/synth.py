@@ -113,6 +113,7 @@ def make_supervision_fst(T, num_pdfs, rng, slack=2, min_dur=2, max_dur=8):
         "final": np.full(S, np.inf, np.float32),
     }
     fst["final"][final_id] = 0.0
+    fst["state_times"] = np.asarray([t for (t, k) in sid] + [T], np.int32)
     return _trim(fst)
 
 
@@ -138,6 +139,8 @@ def _trim(fst):
         "ilabel": fst["ilabel"][ak], "weight": fst["weight"][ak],
         "final": fst["final"][keep],
     }
+    if "state_times" in fst:
+        out["state_times"] = fst["state_times"][keep]
     return out
 
 

@@ -1,0 +1,248 @@
+"""GPU parity tests (run on the B200 box): CUDA kernels behind the C ABI vs the CPU oracle.
+
+Tolerances (BASELINE.json north_star): losses / log-likelihoods within 1e-3 relative,
+posteriors within 1e-3 relative (+ small absolute floor for ~0 entries); index tensors bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda", 0)
+
+
+# ------------------------------------------------------------------------- fbank ----
+def test_fbank_matches_reference_golden(dev):
+    from pykaldi2_b200.data import fbank
+    gold = np.load(os.path.join(G, "fbank_golden.npz"))
+    ex = fbank.FbankExtractor()
+    wavs = [gold["wav%d" % i] for i in range(5)]
+    feats, foff, foff_d = ex(wavs)
+    feats_h = feats.cpu().numpy()
+    for i in range(5):
+        ref = gold["fbank%d" % i]
+        ours = feats_h[foff[i]:foff[i + 1]]
+        assert ours.shape == ref.shape
+        np.testing.assert_allclose(ours, ref, rtol=1e-3, atol=2e-3)
+    mean = fbank.utterance_means(feats, foff_d, 5)
+    src, utt, Tout, lens = fbank.padded_rows(foff)
+    x = fbank.gather_norm(feats, src, utt, mean).view(5, Tout, 80).cpu().numpy()
+    for i in range(5):
+        T = gold["cmn%d" % i].shape[0]
+        np.testing.assert_allclose(x[i, :T], gold["cmn%d" % i], rtol=1e-3, atol=2e-3)
+        assert (x[i, T:] == 0).all()
+    # chunks of utterance 4 with CMN, vs the reference's _utt2seg output
+    csrc, cutt, cu, cs = fbank.chunk_rows(foff)
+    ch = fbank.gather_norm(feats, csrc, cutt, mean).view(-1, 80, 80).cpu().numpy()
+    sel = ch[cu == 4]
+    assert sel.shape == gold["seg4"].shape
+    np.testing.assert_allclose(sel, gold["seg4"], rtol=1e-3, atol=2e-3)
+    # global MVN
+    mm = torch.from_numpy(gold["mvn_mean"].reshape(-1)).to(dev)
+    mi = torch.from_numpy((1.0 / gold["mvn_std"]).reshape(-1).astype(np.float32)).to(dev)
+    T4 = gold["mvn4"].shape[0]
+    s4 = np.arange(foff[4], foff[5]).astype(np.int32)
+    y = fbank.gather_norm(feats, s4, np.full(T4, 4, np.int32), mean, (mm, mi)).cpu().numpy()
+    np.testing.assert_allclose(y, gold["mvn4"], rtol=2e-3, atol=5e-3)
+
+
+def test_fbank_vs_oracle_random_lengths(dev):
+    from oracle import fbank_ref
+    from pykaldi2_b200.data import fbank, mel
+    rng = np.random.default_rng(7)
+    wavs = [(0.05 * rng.standard_normal(n)).astype(np.float32) for n in (401, 402, 561, 8000, 31999, 48000)]
+    feats, foff, _ = fbank.FbankExtractor()(wavs)
+    f = feats.cpu().numpy()
+    W = mel.mel80_window()
+    for i, w in enumerate(wavs):
+        ref = fbank_ref.logfbank(w, W)
+        assert foff[i + 1] - foff[i] == ref.shape[0] == fbank.num_frames(len(w))
+        np.testing.assert_allclose(f[foff[i]:foff[i + 1]], ref, rtol=1e-3, atol=2e-3)
+
+
+def test_chain_subsample_rows_bit_exact():
+    from oracle import fbank_ref
+    from pykaldi2_b200.data import fbank
+    foff = np.array([0, 10, 17, 40])
+    for shift in (0, 1, 2):
+        src, utt, Tout, lens = fbank.padded_rows(foff, factor=3, shift=shift)
+        Tmax = 23
+        idx = fbank_ref.chain_subsample_index(Tmax, shift, 3)
+        assert Tout == len(idx)
+        src = src.reshape(3, Tout)
+        for b in range(3):
+            exp = [foff[b] + p if p < lens[b] else -1 for p in idx]
+            assert src[b].tolist() == exp
+
+
+# -------------------------------------------------------------------- CE softmax ----
+def test_ce_softmax_matches_torch(dev):
+    from pykaldi2_b200 import _lib
+    torch.manual_seed(0)
+    R, N = 300, 5768
+    logits = torch.randn(R, N, device=dev) * 3
+    labels = torch.randint(0, N, (R,), device=dev)
+    labels[::7] = -100
+    loss = torch.empty(R, device=dev)
+    grad = torch.empty_like(logits)
+    _lib.check(_lib.lib().pk2_ce_softmax(_lib.ptr(logits), _lib.ptr(labels), R, N, 0.5, _lib.ptr(loss),
+                                         _lib.ptr(grad), _lib.stream()), "ce")
+    lg = logits.double().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(lg, labels, ignore_index=-100, reduction="sum")
+    (0.5 * ref).backward()
+    np.testing.assert_allclose(loss.sum().item(), ref.item(), rtol=1e-5)
+    np.testing.assert_allclose(grad.cpu().numpy(), lg.grad.float().cpu().numpy(), rtol=1e-4, atol=1e-7)
+
+
+# ------------------------------------------------------------------ LF-MMI chain ----
+def _chain_case(S, N, Ts, seed, mean_extra=5):
+    from pykaldi2_b200 import synth
+    rng = np.random.default_rng(seed)
+    fst = synth.make_den_fst(S, N, mean_extra, seed=seed)
+    sups = [synth.make_supervision_fst(T, N, rng) for T in Ts]
+    Tmax = max(Ts)
+    pred = rng.normal(0, 2.0, (len(Ts), Tmax, N)).astype(np.float32)
+    return fst, sups, pred
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4])
+@pytest.mark.parametrize("S,N,Ts", [(64, 50, [20, 13, 1]), (1000, 333, [37, 50])])
+def test_chain_objf_and_deriv_vs_oracle(dev, S, N, Ts, cluster):
+    from oracle import chain_ref
+    from pykaldi2_b200 import graphs
+    from pykaldi2_b200.ops import ops
+    fst, sup_fsts, pred = _chain_case(S, N, Ts, seed=S + cluster)
+    den = graphs.DenominatorGraph(fst, N)
+    oden = chain_ref.den_graph_from_fst(fst, N)
+    # index tensors bit-exact
+    for k in ("fwd_off", "fwd_pdf", "fwd_state", "bwd_off", "bwd_pdf", "bwd_state"):
+        assert (getattr(den, k) == oden[k]).all(), k
+    assert (den.fwd_prob == oden["fwd_prob"]).all() and (den.initial_probs == oden["initial_probs"]).all()
+    sups = [graphs.Supervision(f, T, N) for f, T in zip(sup_fsts, Ts)]
+    sb = graphs.SupervisionBatch(sups, device=dev)
+    opts = graphs.ChainTrainingOptions(leaky_hmm_coefficient=1e-4, xent_regularize=0.1)
+    p = torch.from_numpy(pred).to(dev)
+    objf, grad = ops.chain_objf_and_deriv(p, den, sb, opts, cluster=cluster)
+    objf = objf.cpu().numpy()
+    grad = grad.cpu().numpy()
+    for b, T in enumerate(Ts):
+        o, g, gx = chain_ref.chain_objf_and_deriv(pred[b, :T], oden, sup_fsts[b], leaky=1e-4, xent_regularize=0.1)
+        np.testing.assert_allclose(objf[b], o, rtol=1e-3)
+        np.testing.assert_allclose(grad[b, :T], -g, rtol=1e-3, atol=2e-6)
+        assert (grad[b, T:] == 0).all()
+
+
+def test_chain_function_per_utt_and_batch(dev):
+    from oracle import chain_ref
+    from pykaldi2_b200 import graphs
+    from pykaldi2_b200.ops import ops
+    S, N, Ts = 128, 90, [25, 31]
+    fst, sup_fsts, pred = _chain_case(S, N, Ts, seed=5)
+    den = graphs.DenominatorGraph(fst, N)
+    oden = chain_ref.den_graph_from_fst(fst, N)
+    opts = graphs.ChainTrainingOptions(leaky_hmm_coefficient=1e-4, xent_regularize=0.0)
+    sups = [graphs.Supervision(f, T, N) for f, T in zip(sup_fsts, Ts)]
+    p = torch.from_numpy(pred).to(dev).requires_grad_(True)
+    loss = 0.0
+    for j, T in enumerate(Ts):                      # the reference's calling pattern
+        loss = loss + ops.ChainObjtiveFunction.apply(p[j, :T, :], den, sups[j], opts)
+    assert loss.device.type == "cpu" and loss.dim() == 0
+    loss.backward()
+    g1 = p.grad.clone()
+    p.grad = None
+    loss_b = ops.ChainObjtiveFunction.apply_batch(p, den, sups, opts)
+    loss_b.backward()
+    np.testing.assert_allclose(loss.item(), loss_b.item(), rtol=1e-6)
+    np.testing.assert_allclose(g1.cpu().numpy(), p.grad.cpu().numpy(), rtol=1e-5, atol=1e-7)
+    tot = 0.0
+    for j, T in enumerate(Ts):
+        o, g, _ = chain_ref.chain_objf_and_deriv(pred[j, :T], oden, sup_fsts[j], leaky=1e-4)
+        tot += o
+        np.testing.assert_allclose(g1[j, :T].cpu().numpy(), -g, rtol=1e-3, atol=2e-6)
+    np.testing.assert_allclose(loss.item(), tot, rtol=1e-3)
+
+
+def test_denfb_full_size_properties(dev):
+    """BASELINE config 4 sizes (S=8192, N=5768): size-independent properties."""
+    from pykaldi2_b200 import graphs, synth
+    from pykaldi2_b200.ops import ops
+    N, S = 5768, 8192
+    rng = np.random.default_rng(1234)
+    den = graphs.DenominatorGraph(synth.make_den_fst(S, N, 7, seed=1234), N)
+    Ts = [150, 97, 33, 150]
+    sups = [graphs.Supervision(synth.make_supervision_fst(T, N, rng), T, N) for T in Ts]
+    sb = graphs.SupervisionBatch(sups, device=dev)
+    opts = graphs.ChainTrainingOptions(leaky_hmm_coefficient=1e-4, xent_regularize=0.0)
+    pred = torch.from_numpy(rng.normal(0, 2.0, (len(Ts), max(Ts), N)).astype(np.float32)).to(dev)
+    res = {}
+    for K in (1, 2, 4):
+        objf, grad = ops.chain_objf_and_deriv(pred, den, sb, opts, cluster=K)
+        res[K] = (objf.cpu().numpy(), grad.cpu().numpy())
+    o1, g1 = res[1]
+    assert np.isfinite(o1).all()
+    for b, T in enumerate(Ts):
+        rows = g1[b, :T].astype(np.float64).sum(1)      # gamma_den - gamma_num rows sum to 0
+        np.testing.assert_allclose(rows, 0.0, atol=2e-4)
+        assert (g1[b, T:] == 0).all()
+    for K in (2, 4):                                    # cluster size does not change the answer
+        np.testing.assert_allclose(res[K][0], o1, rtol=1e-5)
+        np.testing.assert_allclose(res[K][1], g1, rtol=1e-3, atol=1e-6)
+    # shifting all loglikes of a frame by c shifts objf by 0 (num and den both move by c)
+    pred2 = pred.clone()
+    pred2[:, 5, :] += 1.5
+    objf2, _ = ops.chain_objf_and_deriv(pred2, den, sb, opts, cluster=2)
+    np.testing.assert_allclose(objf2.cpu().numpy(), o1, rtol=1e-4, atol=1e-3)
+
+
+# ------------------------------------------------------------------- lattice MMI ----
+@pytest.mark.parametrize("eps", [0.0, 0.1])
+def test_lattice_mmi_vs_oracle(dev, eps):
+    from oracle import lattice_ref
+    from pykaldi2_b200 import graphs, synth
+    from pykaldi2_b200.ops import ops
+    rng = np.random.default_rng(11)
+    N, Ts = 200, [40, 23, 31]
+    lats, alis, olat = [], [], []
+    for T in Ts:
+        lat, tid2pdf, ali = synth.make_lattice(T, N, rng, kmin=8, kmax=20, ali_drop=0.2, eps_frac=eps)
+        olat.append(lat); alis.append(ali); lats.append(graphs.Lattice(lat))
+    pred = rng.normal(0, 3.0, (len(Ts), max(Ts), N)).astype(np.float32)
+    lb = graphs.LatticeBatch(lats, tid2pdf, alis, device=dev)
+    tot, grad = ops.lattice_mmi(torch.from_numpy(pred).to(dev), lb)
+    tot, grad = tot.cpu().numpy(), grad.cpu().numpy()
+    for b, T in enumerate(Ts):
+        rtot, post, drop, times = lattice_ref.lattice_fb_mmi(pred[b, :T], olat[b], tid2pdf, alis[b])
+        assert (lats[b].state_times_orig == times).all()          # index tensors bit-exact
+        assert (lb.keep_host[b] == (~drop).astype(np.uint8)).all()
+        np.testing.assert_allclose(tot[b], rtot, rtol=1e-6)
+        np.testing.assert_allclose(grad[b, :T], -post, rtol=1e-3, atol=1e-6)
+        assert (grad[b, T:] == 0).all()
+
+
+def test_mmi_function_reference_call_pattern(dev):
+    from oracle import lattice_ref
+    from pykaldi2_b200 import graphs, synth
+    from pykaldi2_b200.ops import ops
+    rng = np.random.default_rng(3)
+    N, T = 120, 35
+    lat, tid2pdf, ali = synth.make_lattice(T, N, rng, kmin=6, kmax=12)
+    trans_model = graphs.TidPdfMap(tid2pdf)
+    decoder = graphs.SyntheticLatticeProvider([graphs.Lattice(lat)])
+    log_prior = torch.from_numpy(synth.make_log_prior(N, rng)).to(dev)
+    logits = torch.randn(T, N, device=dev, requires_grad=True)
+    loglike = logits - log_prior                       # bin/train_se.py:241
+    loss = ops.MMIFunction.apply(loglike, decoder, trans_model, ali.tolist())
+    assert loss.device.type == "cpu"
+    loss.backward()
+    ll = (logits.detach() - log_prior).cpu().numpy()
+    rtot, post, drop, _ = lattice_ref.lattice_fb_mmi(ll, lat, tid2pdf, ali)
+    np.testing.assert_allclose(loss.item(), rtot, rtol=1e-5)
+    np.testing.assert_allclose(logits.grad.cpu().numpy(), -post, rtol=1e-3, atol=1e-6)
