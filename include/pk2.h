@@ -56,7 +56,7 @@ int pk2_gather_norm(const float* feats, const int32_t* row_src, const int32_t* r
  * Replaces nn.CrossEntropyLoss(ignore_index=-100) fwd+bwd (bin/train_ce.py:134,189;
  * reduction='sum' at bin/train_se.py:214,235).  loss_rows[r] = lse - logit[label]
  * (0 for ignored rows); grad = scale * (softmax - onehot) (0 for ignored rows);
- * grad may be NULL, and may alias logits. */
+ * grad may be NULL; it must not alias logits. */
 int pk2_ce_softmax(const float* logits, const int64_t* labels, int64_t n_rows, int n_cols,
                    float scale, float* loss_rows, float* grad, void* stream);
 
@@ -143,34 +143,44 @@ int pk2_latfb_mmi(const pk2_lat_batch* lat, const float* loglikes, int num_pdfs,
  * flags: bit0 accumulate into C, bit1 C is bf16.  */
 int pk2_gemm_bf16_nt(const void* A, const void* B, void* C, const float* bias,
                      int M, int N, int K, int lda, int ldb, int ldc, int flags, void* stream);
-/* fp32 -> bf16 cast (row-major, same shape) */
-int pk2_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
-/* transpose-cast: src fp32 [R,C] -> dst bf16 [C,R] */
-int pk2_transpose_bf16(const float* src, void* dst, int R, int C, void* stream);
+
+/* x[B*T, I] (bf16, row stride ldx) * W_ih_cat[8H, I]^T + bias[8H] -> gx in the recurrent kernel's
+ * layout [T][2][H/32][B][128] fp32 (128 = 4 gates x 32 units of one CTA).  W_ih_cat = [W_ih_fwd; W_ih_bwd],
+ * bias = b_ih + b_hh of both directions. */
+int pk2_lstm_input_proj(const void* x, const void* wih, const float* bias, float* gx, int B, int T,
+                        int I, int H, int ldx, void* stream);
 
 typedef struct {
-    int B, T, H;            /* batch, time steps, hidden size (per direction) */
-    const float* gx;        /* [B,T,2,4H] input projections incl. both biases (fp32) */
-    const void* whh;        /* bf16 [2,4H,H] recurrent weights (PyTorch gate order i,f,g,o) */
-    void* y;                /* bf16 [B,T,2H] layer output (fwd | bwd halves) */
-    float* gates;           /* fp32 [2,T,B,4H] post-activation gates (saved for backward) */
+    int B, T, H;            /* batch, time steps, hidden size per direction (multiple of 64, <= 512) */
+    const float* gx;        /* [T][2][H/32][B][128] fp32 input projections incl. both biases */
+    const void* whh;        /* bf16 [2*4H, H] recurrent weights, rows packed per CTA:
+                               row (dir*H/32 + cta)*128 + gate*32 + ul = W_hh[dir][gate*H + cta*32 + ul] */
+    void* y;                /* bf16 [B,T,2H] layer output (fwd | bwd halves); also the h exchange */
+    void* gates;            /* bf16 [2,T,B,4,H] post-activation gates i,f,g,o (saved for backward) */
     float* cstate;          /* fp32 [2,T,B,H] cell states (saved for backward) */
-    void* hbuf;             /* bf16 [2,2,B,H] ping-pong h exchange buffer */
-    unsigned int* sync;     /* [2*64] zero-initialised step counters */
+    unsigned int* sync;     /* [2*ceil(B/32)] step counters (zeroed by the call) */
 } pk2_lstm_fwd_args;
 int pk2_lstm_layer_fwd(const pk2_lstm_fwd_args* a, void* stream);
 
 typedef struct {
     int B, T, H;
-    const void* dy;         /* bf16 or fp32? fp32 [B,T,2H] grad wrt layer output */
-    const void* whh_t;      /* bf16 [2,H,4H] transposed recurrent weights */
-    const float* gates;     /* from forward */
+    const float* dy;        /* fp32 [B,T,2H] grad wrt layer output */
+    const void* whh_t;      /* bf16 [2*H, 4H]: row dir*H + j = W_hh[dir][:, j] (transposed recurrent weights) */
+    const void* gates;      /* from forward */
     const float* cstate;    /* from forward */
-    void* dgates;           /* bf16 [B,T,2,4H] grad wrt pre-activations (output) */
-    void* dgbuf;            /* bf16 [2,2,B,4H] ping-pong exchange */
-    unsigned int* sync;     /* [2*64] zero-initialised */
+    void* dgates;           /* bf16 [B,T,2,4H] grad wrt gate pre-activations (output; also the exchange) */
+    unsigned int* sync;     /* [2*ceil(B/32)] */
 } pk2_lstm_bwd_args;
 int pk2_lstm_layer_bwd(const pk2_lstm_bwd_args* a, void* stream);
+
+/* elementwise / layout helpers of the BLSTM path */
+int pk2_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* src fp32 or bf16 [R, C] (row stride lds) -> dst bf16 [C, ldd] (dst[c, r]); src_bf16 selects the input type */
+int pk2_transpose_bf16(const void* src, int src_bf16, void* dst, int R, int C, int lds, int ldd, void* stream);
+/* hprevT[dir][j][b*T+t] = y[b][t -/+ 1][dir*H + j] (0 at the sequence boundary): the h_{t-1} operand of dW_hh */
+int pk2_lstm_hprev_t(const void* y, void* hprev_t, int B, int T, int H, int ldd, void* stream);
+/* out[c] = sum_r src[r, c]  (bf16 src [R, C], fp32 out) */
+int pk2_colsum_bf16(const void* src, float* out, int64_t R, int C, void* stream);
 
 #ifdef __cplusplus
 }

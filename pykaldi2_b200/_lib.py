@@ -34,12 +34,12 @@ class LatBatch(C.Structure):
 
 class LstmFwdArgs(C.Structure):
     _fields_ = [("B", C.c_int), ("T", C.c_int), ("H", C.c_int)] + [(n, vp) for n in (
-        "gx", "whh", "y", "gates", "cstate", "hbuf", "sync")]
+        "gx", "whh", "y", "gates", "cstate", "sync")]
 
 
 class LstmBwdArgs(C.Structure):
     _fields_ = [("B", C.c_int), ("T", C.c_int), ("H", C.c_int)] + [(n, vp) for n in (
-        "dy", "whh_t", "gates", "cstate", "dgates", "dgbuf", "sync")]
+        "dy", "whh_t", "gates", "cstate", "dgates", "sync")]
 
 
 _SIGS = {
@@ -63,7 +63,10 @@ _SIGS = {
     "pk2_gemm_bf16_nt": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_int, vp]),
     "pk2_cast_bf16": (C.c_int, [vp, vp, C.c_int64, vp]),
-    "pk2_transpose_bf16": (C.c_int, [vp, vp, C.c_int, C.c_int, vp]),
+    "pk2_transpose_bf16": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "pk2_lstm_hprev_t": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "pk2_colsum_bf16": (C.c_int, [vp, vp, C.c_int64, C.c_int, vp]),
+    "pk2_lstm_input_proj": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "pk2_lstm_layer_fwd": (C.c_int, [C.POINTER(LstmFwdArgs), vp]),
     "pk2_lstm_layer_bwd": (C.c_int, [C.POINTER(LstmBwdArgs), vp]),
 }

@@ -1,0 +1,483 @@
+// Persistent bidirectional-LSTM recurrence on tcgen05 tensor cores (sm_100a).
+//
+// Replaces the cuDNN RNN the reference reaches through nn.LSTM(batch_first, bidirectional)
+// (models/lstm.py:46-58): for every layer, direction d and time step t
+//     gates = Gx[t] + h_{t-1} W_hh^T ;  i,f,o = sigmoid, g = tanh ;  c_t = f c_{t-1} + i g ;  h_t = o tanh(c_t)
+// Gx (= x W_ih^T + b_ih + b_hh for all t) is one large GEMM (gemm_tc.cu); this file is the
+// serial part: T dependent step-GEMMs [B,H]x[H,4H] per direction.
+//
+// One launch per layer, all T steps, both directions:
+//   grid = (H/32 CTAs, 2 directions, G batch groups of NB sequences), all CTAs co-resident.
+//   CTA (c, d, g) owns hidden units [32c, 32c+32) of direction d for batch rows [g*NB, g*NB+NB):
+//   * its 128 gate rows of W_hh (4 gates x 32 units, bf16, K-major SWIZZLE_128B) stay in shared
+//     memory for the whole sequence;
+//   * per step it computes gates^T[128, NB] = W_slice[128, H] * h_{t-1}^T on the tensor cores:
+//     tcgen05.mma M=128, N=NB, K=16 issued by one thread, accumulator in TMEM; h_{t-1} (all H
+//     columns, written by the H/32 CTAs of the direction) is fetched with TMA straight out of the
+//     layer output tensor y[B,T,2H] (3-D tensor map -> swizzled shared tile = the B operand);
+//   * the epilogue (tcgen05.ld, + Gx tile prefetched by a bulk copy, activations, cell update)
+//     keeps c_t in registers, writes h_t (bf16) into y and the gates / cell state for backward;
+//   * step t+1 of the other CTAs is released through a global arrive counter
+//     (red.release.gpu / ld.acquire.gpu) -- no grid-wide barrier, no per-step launch.
+// The backward kernel has the same structure with the roles swapped: dgates_t (all 4H columns,
+// bf16) is the streamed A operand, W_hh^T[32 units, 4H] the resident B operand.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include <mutex>
+
+using namespace tc;
+
+namespace {
+
+constexpr int kEpiThreads = 128;
+constexpr int kThreads = 192;          // warps 0-3 epilogue, warp 4 producer, warp 5 MMA issuer
+
+struct FwdDev {
+    int B, T, H;
+    const float* gx;            // [T][2][H/32][B][128]
+    __nv_bfloat16* y;           // [B][T][2H]
+    __nv_bfloat16* gates;       // [2][T][B][4][H]   post-activation
+    float* cstate;              // [2][T][B][H]
+    unsigned* counters;         // [G][2]
+};
+
+struct BwdDev {
+    int B, T, H;
+    const float* dy;            // [B][T][2H] fp32
+    const __nv_bfloat16* gates;
+    const float* cstate;
+    __nv_bfloat16* dgates;      // [B][T][2][4H]
+    unsigned* counters;
+};
+
+__device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_fast(float x) {
+    // 2*sigmoid(2x) - 1, exact enough for the 1e-3 parity budget and safe for large |x|
+    return __fdividef(2.0f, 1.0f + __expf(-2.0f * x)) - 1.0f;
+}
+
+__device__ __forceinline__ void spin_until(const unsigned* ctr, unsigned target) {
+    while (ld_acquire_gpu(ctr) < target) __nanosleep(20);
+}
+
+// --------------------------------------------------------------------------- forward ----
+template <int NB>
+__global__ void __launch_bounds__(kThreads, 1)
+lstm_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_y, FwdDev p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int H = p.H, T = p.T, B = p.B;
+    const int KB = H / 64;                                   // k-blocks of 64
+    uint8_t* Ws = smem;                                      // KB x [128 x 64] bf16
+    uint8_t* Hs = Ws + KB * 16384;                           // KB x [NB x 64] bf16
+    float* gxs = reinterpret_cast<float*>(Hs + KB * NB * 128);   // [NB][128] fp32
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(gxs) + NB * 512);
+    uint64_t* wbar = bars + 0;      // W slice landed
+    uint64_t* hbar = bars + 1;      // h_{t-1} tiles landed
+    uint64_t* gbar = bars + 2;      // Gx tile landed
+    uint64_t* mbar = bars + 3;      // step MMAs retired
+    uint64_t* gfree = bars + 4;     // Gx buffer may be overwritten
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cta = blockIdx.x, dir = blockIdx.y, grp = blockIdx.z;
+    const int nctas = gridDim.x;
+    const int u0 = cta * 32, b0 = grp * NB;
+    const int nbv = min(NB, B - b0);
+    unsigned* counter = p.counters + (grp * 2 + dir);
+
+    if (threadIdx.x == 0) {
+        mbar_init(wbar, 1); mbar_init(hbar, 1); mbar_init(gbar, 1); mbar_init(mbar, 1); mbar_init(gfree, 1);
+        fence_barrier_init();
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, NB < 32 ? 32 : NB);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ===== producer: TMA / bulk loads + inter-CTA step flags =====
+        if (lane == 0) {
+            mbar_expect_tx(wbar, (uint32_t)KB * 16384u);
+            for (int kb = 0; kb < KB; ++kb)
+                tma_load_2d(&map_w, wbar, Ws + kb * 16384, kb * 64, (dir * nctas + cta) * 128);
+            uint32_t ph_free = 0;
+            for (int s = 0; s < T; ++s) {
+                const int tt = dir ? (T - 1 - s) : s;
+                if (s > 0) { mbar_wait(gfree, ph_free); ph_free ^= 1; }
+                const float* src = p.gx + ((((int64_t)tt * 2 + dir) * nctas + cta) * B + b0) * 128;
+                mbar_expect_tx(gbar, (uint32_t)nbv * 512u);
+                bulk_load(gxs, src, (uint32_t)nbv * 512u, gbar);
+                if (s > 0) {
+                    const int tp = dir ? tt + 1 : tt - 1;
+                    spin_until(counter, (unsigned)(nctas * s));
+                    fence_proxy_async();
+                    mbar_expect_tx(hbar, (uint32_t)KB * NB * 128u);
+                    for (int kb = 0; kb < KB; ++kb)
+                        tma_load_3d(&map_y, hbar, Hs + kb * NB * 128, dir * H + kb * 64, tp, b0);
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(128, NB);
+            mbar_wait(wbar, 0);
+            uint32_t ph_h = 0;
+            for (int s = 1; s < T; ++s) {
+                mbar_wait(hbar, ph_h); ph_h ^= 1;
+                tc_fence_after();
+                for (int kb = 0; kb < KB; ++kb) {
+                    const uint64_t adesc = make_sw128_desc(smem_u32(Ws + kb * 16384));
+                    const uint64_t bdesc = make_sw128_desc(smem_u32(Hs + kb * NB * 128));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc_mma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                    (uint32_t)((kb | k) != 0));
+                }
+                tc_commit(mbar);
+            }
+        }
+    } else {
+        // ===== epilogue warps 0-3: thread r = gate row (gate = r/32, unit = r%32) = TMEM lane r =====
+        const int r = threadIdx.x;
+        const int gate = warp;
+        float cst[NB / 4];
+#pragma unroll
+        for (int k = 0; k < NB / 4; ++k) cst[k] = 0.f;
+        uint32_t ph_g = 0, ph_m = 0;
+        for (int s = 0; s < T; ++s) {
+            const int tt = dir ? (T - 1 - s) : s;
+            float acc[NB];
+            if (s > 0) {
+                mbar_wait(mbar, ph_m); ph_m ^= 1;
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < NB / 32; ++c) {
+                    uint32_t v[32];
+                    tc_ld_32x32b_x32(tmem_base + c * 32 + ((uint32_t)(warp * 32) << 16), v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[c * 32 + j] = __uint_as_float(v[j]);
+                }
+                tc_fence_before();
+            } else {
+#pragma unroll
+                for (int j = 0; j < NB; ++j) acc[j] = 0.f;
+            }
+            mbar_wait(gbar, ph_g); ph_g ^= 1;
+            __nv_bfloat16* gout = p.gates + ((((int64_t)dir * T + tt) * B + b0) * 4 + gate) * H + u0 + lane;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const float v = acc[b] + gxs[b * 128 + r];
+                const float a = (gate == 2) ? tanhf_fast(v) : sigmoidf_fast(v);
+                gxs[b * 128 + r] = a;
+                if (b < nbv) gout[(int64_t)b * 4 * H] = __float2bfloat16(a);
+            }
+            named_bar_sync(1, kEpiThreads);
+            // cell update: lane = unit, warp w handles batch rows w, w+4, ...
+            {
+                __nv_bfloat16* yo = p.y + ((int64_t)b0 * T + tt) * 2 * H + dir * H + u0 + lane;
+                float* co = p.cstate + (((int64_t)dir * T + tt) * B + b0) * H + u0 + lane;
+#pragma unroll
+                for (int k = 0; k < NB / 4; ++k) {
+                    const int b = warp + 4 * k;
+                    const float ig = gxs[b * 128 + lane], fg = gxs[b * 128 + 32 + lane];
+                    const float gg = gxs[b * 128 + 64 + lane], og = gxs[b * 128 + 96 + lane];
+                    const float c = fmaf(fg, cst[k], ig * gg);
+                    cst[k] = c;
+                    const float h = og * tanhf_fast(c);
+                    if (b < nbv) {
+                        co[(int64_t)b * H] = c;
+                        yo[(int64_t)b * T * 2 * H] = __float2bfloat16(h);
+                    }
+                }
+            }
+            __threadfence();
+            fence_proxy_async();
+            named_bar_sync(1, kEpiThreads);
+            if (threadIdx.x == 0) {
+                __threadfence();
+                red_release_gpu_add(counter, 1u);
+                mbar_arrive(gfree);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, NB < 32 ? 32 : NB);
+}
+
+// -------------------------------------------------------------------------- backward ----
+constexpr int kBwdStages = 4;
+
+template <int NB>
+__global__ void __launch_bounds__(kThreads, 1)
+lstm_bwd_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_constant__ CUtensorMap map_dg, BwdDev p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int H = p.H, T = p.T, B = p.B;
+    const int KB = 4 * H / 64;                               // k-blocks over the 4H gate columns
+    uint8_t* Wt = smem;                                      // KB x [32 x 64] bf16   (W_hh^T slice)
+    uint8_t* As = Wt + KB * 4096;                            // kBwdStages x [128 x 64] bf16 (NB rows valid)
+    float* dhs = reinterpret_cast<float*>(As + kBwdStages * 16384);   // [NB][33]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(dhs) + ((NB * 33 * 4 + 7) & ~7));
+    uint64_t* wbar = bars + 0;
+    uint64_t* mbar = bars + 1;
+    uint64_t* afull = bars + 2;                              // [kBwdStages]
+    uint64_t* aempty = afull + kBwdStages;                   // [kBwdStages]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + kBwdStages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cta = blockIdx.x, dir = blockIdx.y, grp = blockIdx.z;
+    const int nctas = gridDim.x;
+    const int u0 = cta * 32, b0 = grp * NB;
+    const int nbv = min(NB, B - b0);
+    unsigned* counter = p.counters + (grp * 2 + dir);
+
+    if (threadIdx.x == 0) {
+        mbar_init(wbar, 1); mbar_init(mbar, 1);
+        for (int i = 0; i < kBwdStages; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
+        fence_barrier_init();
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, 32);
+    // rows NB..127 of the A stages are never written by TMA: clear them once so the unused
+    // accumulator rows stay finite
+    for (int i = threadIdx.x; i < kBwdStages * 16384 / 16; i += kThreads)
+        reinterpret_cast<uint4*>(As)[i] = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_expect_tx(wbar, (uint32_t)KB * 4096u);
+            for (int kb = 0; kb < KB; ++kb)
+                tma_load_2d(&map_wt, wbar, Wt + kb * 4096, kb * 64, dir * H + u0);
+            uint32_t stage = 0, phase = 0;
+            for (int s = 1; s < T; ++s) {
+                // step s consumes dgates of the step processed before it (time tprev)
+                const int tt = dir ? s : (T - 1 - s);
+                const int tprev = dir ? tt - 1 : tt + 1;
+                spin_until(counter, (unsigned)(nctas * s));
+                fence_proxy_async();
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(&aempty[stage], phase ^ 1);
+                    mbar_expect_tx(&afull[stage], (uint32_t)NB * 128u);
+                    tma_load_3d(&map_dg, &afull[stage], As + stage * 16384, dir * 4 * H + kb * 64, tprev, b0);
+                    if (++stage == kBwdStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(128, 32);
+            mbar_wait(wbar, 0);
+            uint32_t stage = 0, phase = 0;
+            for (int s = 1; s < T; ++s) {
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(&afull[stage], phase);
+                    tc_fence_after();
+                    const uint64_t adesc = make_sw128_desc(smem_u32(As + stage * 16384));
+                    const uint64_t bdesc = make_sw128_desc(smem_u32(Wt + kb * 4096));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc_mma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                    (uint32_t)((kb | k) != 0));
+                    tc_commit(&aempty[stage]);
+                    if (++stage == kBwdStages) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(mbar);
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM lane = batch row, column = unit =====
+        float dcn[NB / 4];
+#pragma unroll
+        for (int k = 0; k < NB / 4; ++k) dcn[k] = 0.f;
+        uint32_t ph_m = 0;
+        for (int s = 0; s < T; ++s) {
+            const int tt = dir ? s : (T - 1 - s);
+            const int tfp = dir ? tt + 1 : tt - 1;          // time of c_{prev} in forward order
+            if (s > 0) {
+                mbar_wait(mbar, ph_m); ph_m ^= 1;
+                tc_fence_after();
+                if (warp * 32 < NB) {
+                    uint32_t v[32];
+                    tc_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16), v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) dhs[(warp * 32 + lane) * 33 + j] = __uint_as_float(v[j]);
+                }
+                tc_fence_before();
+            } else {
+                for (int i = threadIdx.x; i < NB * 33; i += kEpiThreads) dhs[i] = 0.f;
+            }
+            named_bar_sync(1, kEpiThreads);
+#pragma unroll
+            for (int k = 0; k < NB / 4; ++k) {
+                const int b = warp + 4 * k;
+                if (b < nbv) {
+                    const int64_t bb = b0 + b;
+                    const __nv_bfloat16* gp = p.gates + ((((int64_t)dir * T + tt) * B + bb) * 4) * H + u0 + lane;
+                    const float ig = __bfloat162float(gp[0]), fg = __bfloat162float(gp[H]);
+                    const float gg = __bfloat162float(gp[2 * H]), og = __bfloat162float(gp[3 * H]);
+                    const float c = p.cstate[(((int64_t)dir * T + tt) * B + bb) * H + u0 + lane];
+                    const float cp = (tfp >= 0 && tfp < T)
+                                         ? p.cstate[(((int64_t)dir * T + tfp) * B + bb) * H + u0 + lane] : 0.f;
+                    const float dh = dhs[b * 33 + lane] + p.dy[(bb * T + tt) * 2 * H + dir * H + u0 + lane];
+                    const float tc_ = tanhf_fast(c);
+                    const float dout = dh * tc_;
+                    const float dc = fmaf(dh * og, 1.0f - tc_ * tc_, dcn[k]);
+                    dcn[k] = dc * fg;
+                    const float dgi = dc * gg * ig * (1.0f - ig);
+                    const float dgf = dc * cp * fg * (1.0f - fg);
+                    const float dgg = dc * ig * (1.0f - gg * gg);
+                    const float dgo = dout * og * (1.0f - og);
+                    __nv_bfloat16* dp = p.dgates + ((bb * T + tt) * 2 + dir) * 4 * H + u0 + lane;
+                    dp[0] = __float2bfloat16(dgi);
+                    dp[H] = __float2bfloat16(dgf);
+                    dp[2 * H] = __float2bfloat16(dgg);
+                    dp[3 * H] = __float2bfloat16(dgo);
+                }
+            }
+            __threadfence();
+            fence_proxy_async();
+            named_bar_sync(1, kEpiThreads);
+            if (threadIdx.x == 0) {
+                __threadfence();
+                red_release_gpu_add(counter, 1u);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, 32);
+}
+
+// ------------------------------------------------------------------------------ host ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, []() {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    });
+    return fn;
+}
+
+// bf16 tensor map, rank 2 or 3, innermost box = 64 elements (128 B), SWIZZLE_128B
+int make_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+             const cuuint32_t* box) {
+    EncodeTiledFn enc = get_encode();
+    PK2_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                     strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PK2_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
+int pick_nb(int B) { return (B + 31) / 32 <= 4 ? 32 : 64; }
+
+int check_dims(const char* who, int B, int T, int H, int nb, int num_sms) {
+    PK2_REQUIRE(H % 64 == 0 && H >= 64 && H <= 512, "%s: hidden size %d unsupported (multiple of 64, <= 512)", who, H);
+    PK2_REQUIRE(B > 0 && T > 0, "%s: empty batch", who);
+    const int G = (B + nb - 1) / nb;
+    PK2_REQUIRE((H / 32) * 2 * G <= num_sms, "%s: B=%d needs %d co-resident CTAs (> %d SMs); split the batch", who, B,
+                (H / 32) * 2 * G, num_sms);
+    return 0;
+}
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return n;
+}
+
+template <int NB>
+int launch_fwd(const pk2_lstm_fwd_args* a, cudaStream_t st) {
+    const int H = a->H, T = a->T, B = a->B, KB = H / 64, G = (B + NB - 1) / NB;
+    CUtensorMap mw, my;
+    {   // packed W_hh rows: [(dir*H/32 + cta)*128 + gate*32 + ul][H]
+        cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)(2 * 4 * H)};
+        cuuint64_t str[1] = {(cuuint64_t)H * 2};
+        cuuint32_t box[2] = {64, 128};
+        if (make_map(&mw, a->whh, 2, dims, str, box)) return 2;
+    }
+    {   // y[B][T][2H] viewed as (col, t, b)
+        cuuint64_t dims[3] = {(cuuint64_t)(2 * H), (cuuint64_t)T, (cuuint64_t)B};
+        cuuint64_t str[2] = {(cuuint64_t)(2 * H) * 2, (cuuint64_t)T * 2 * H * 2};
+        cuuint32_t box[3] = {64, 1, (cuuint32_t)NB};
+        if (make_map(&my, a->y, 3, dims, str, box)) return 2;
+    }
+    const size_t smem = (size_t)KB * 16384 + (size_t)KB * NB * 128 + (size_t)NB * 512 + 64 + 1024;
+    PK2_CHECK(cudaFuncSetAttribute(lstm_fwd_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PK2_CHECK(cudaMemsetAsync(a->sync, 0, sizeof(unsigned) * 2 * G, st));
+    FwdDev d;
+    d.B = B; d.T = T; d.H = H; d.gx = a->gx;
+    d.y = static_cast<__nv_bfloat16*>(a->y);
+    d.gates = static_cast<__nv_bfloat16*>(a->gates);
+    d.cstate = a->cstate; d.counters = a->sync;
+    lstm_fwd_kernel<NB><<<dim3(H / 32, 2, G), kThreads, smem, st>>>(mw, my, d);
+    PK2_POST_LAUNCH();
+    return 0;
+}
+
+template <int NB>
+int launch_bwd(const pk2_lstm_bwd_args* a, cudaStream_t st) {
+    const int H = a->H, T = a->T, B = a->B, KB = 4 * H / 64, G = (B + NB - 1) / NB;
+    CUtensorMap mwt, mdg;
+    {   // W_hh^T: [dir*H + j][4H]
+        cuuint64_t dims[2] = {(cuuint64_t)(4 * H), (cuuint64_t)(2 * H)};
+        cuuint64_t str[1] = {(cuuint64_t)(4 * H) * 2};
+        cuuint32_t box[2] = {64, 32};
+        if (make_map(&mwt, a->whh_t, 2, dims, str, box)) return 2;
+    }
+    {   // dgates[B][T][2*4H] viewed as (col, t, b)
+        cuuint64_t dims[3] = {(cuuint64_t)(8 * H), (cuuint64_t)T, (cuuint64_t)B};
+        cuuint64_t str[2] = {(cuuint64_t)(8 * H) * 2, (cuuint64_t)T * 8 * H * 2};
+        cuuint32_t box[3] = {64, 1, (cuuint32_t)NB};
+        if (make_map(&mdg, a->dgates, 3, dims, str, box)) return 2;
+    }
+    const size_t smem = (size_t)KB * 4096 + (size_t)kBwdStages * 16384 + (size_t)((NB * 33 * 4 + 7) & ~7) + 128 + 1024;
+    PK2_CHECK(cudaFuncSetAttribute(lstm_bwd_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PK2_CHECK(cudaMemsetAsync(a->sync, 0, sizeof(unsigned) * 2 * G, st));
+    BwdDev d;
+    d.B = B; d.T = T; d.H = H; d.dy = a->dy;
+    d.gates = static_cast<const __nv_bfloat16*>(a->gates);
+    d.cstate = a->cstate;
+    d.dgates = static_cast<__nv_bfloat16*>(a->dgates);
+    d.counters = a->sync;
+    lstm_bwd_kernel<NB><<<dim3(H / 32, 2, G), kThreads, smem, st>>>(mwt, mdg, d);
+    PK2_POST_LAUNCH();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int pk2_lstm_layer_fwd(const pk2_lstm_fwd_args* a, void* stream) {
+    PK2_REQUIRE(a && a->gx && a->whh && a->y && a->gates && a->cstate && a->sync, "pk2_lstm_layer_fwd: null argument");
+    const int nb = pick_nb(a->B);
+    if (check_dims("pk2_lstm_layer_fwd", a->B, a->T, a->H, nb, num_sms())) return 2;
+    return nb == 32 ? launch_fwd<32>(a, pk2::as_stream(stream)) : launch_fwd<64>(a, pk2::as_stream(stream));
+}
+
+extern "C" int pk2_lstm_layer_bwd(const pk2_lstm_bwd_args* a, void* stream) {
+    PK2_REQUIRE(a && a->dy && a->whh_t && a->gates && a->cstate && a->dgates && a->sync, "pk2_lstm_layer_bwd: null argument");
+    const int nb = pick_nb(a->B);
+    if (check_dims("pk2_lstm_layer_bwd", a->B, a->T, a->H, nb, num_sms())) return 2;
+    return nb == 32 ? launch_bwd<32>(a, pk2::as_stream(stream)) : launch_bwd<64>(a, pk2::as_stream(stream));
+}

@@ -1,0 +1,146 @@
+// Layout / precision helpers of the BLSTM path (sm_100a): fp32->bf16 cast, transposing casts that
+// produce the K-major operands of the weight-gradient GEMMs, the shifted h_{t-1} operand of dW_hh,
+// and the bias gradient (column sums).  All are single-pass, HBM-bound, coalesced on both sides
+// (32x32 shared-memory tiles for the transposes).
+#include "common.cuh"
+
+namespace {
+
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(src)[i];
+        __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+        uint2 o;
+        o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
+        reinterpret_cast<uint2*>(dst)[i] = o;
+    }
+    for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = __float2bfloat16(src[i]);
+}
+
+// dst[c, r] = src[r, c]
+template <bool SRC_BF16>
+__global__ void transpose_bf16_kernel(const void* __restrict__ src, __nv_bfloat16* __restrict__ dst, int R, int C,
+                                      int lds, int ldd) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        float v = 0.f;
+        if (r < R && c < C) {
+            if (SRC_BF16) v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[(int64_t)r * lds + c]);
+            else v = reinterpret_cast<const float*>(src)[(int64_t)r * lds + c];
+        }
+        tile[i][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (c < C && r < R) dst[(int64_t)c * ldd + r] = __float2bfloat16(tile[threadIdx.x][i]);
+    }
+}
+
+// hprevT[(dir*H + j), b*T + t] = y[b, tprev, dir*H + j],  tprev = t-1 (dir 0) / t+1 (dir 1), 0 outside
+__global__ void hprev_t_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ out, int B, int T, int H,
+                               int ldd) {
+    __shared__ __nv_bfloat16 tile[32][34];
+    const int M = B * T;
+    const int c0 = blockIdx.x * 32;          // column of y (0 .. 2H)
+    const int r0 = blockIdx.y * 32;          // row m = b*T + t
+    const int dir = c0 / H;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int m = r0 + i, c = c0 + threadIdx.x;
+        __nv_bfloat16 v = __float2bfloat16(0.f);
+        if (m < M) {
+            const int b = m / T, t = m - b * T;
+            const int tp = dir ? t + 1 : t - 1;
+            if (tp >= 0 && tp < T) v = y[((int64_t)b * T + tp) * 2 * H + c];
+        }
+        tile[i][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, m = r0 + threadIdx.x;
+        if (m < M) out[(int64_t)c * ldd + m] = tile[threadIdx.x][i];
+    }
+}
+
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ partial, int64_t R, int C,
+                                   int rows_per_block) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+    const int64_t r1 = r0 + rows_per_block < R ? r0 + rows_per_block : R;
+    if (c >= C) return;
+    float acc = 0.f;
+    for (int64_t r = r0; r < r1; ++r) acc += __bfloat162float(src[r * C + c]);
+    partial[(int64_t)blockIdx.y * C + c] = acc;
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int nparts, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float acc = 0.f;
+    for (int p = 0; p < nparts; ++p) acc += partial[(int64_t)p * C + c];   // fixed order: deterministic
+    out[c] = acc;
+}
+
+float* g_partial = nullptr;
+size_t g_partial_bytes = 0;
+
+}  // namespace
+
+extern "C" int pk2_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
+    PK2_REQUIRE(src && dst, "pk2_cast_bf16: null argument");
+    if (n <= 0) return 0;
+    PK2_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0,
+                "pk2_cast_bf16: misaligned pointers");
+    int64_t blocks = (n / 4 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    cast_bf16_kernel<<<(int)blocks, 256, 0, pk2::as_stream(stream)>>>(src, static_cast<__nv_bfloat16*>(dst), n);
+    PK2_POST_LAUNCH();
+    return 0;
+}
+
+extern "C" int pk2_transpose_bf16(const void* src, int src_bf16, void* dst, int R, int C, int lds, int ldd, void* stream) {
+    PK2_REQUIRE(src && dst, "pk2_transpose_bf16: null argument");
+    if (R <= 0 || C <= 0) return 0;
+    dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
+    PK2_REQUIRE(grid.y <= 65535, "pk2_transpose_bf16: too many rows (%d)", R);
+    if (src_bf16) transpose_bf16_kernel<true><<<grid, block, 0, pk2::as_stream(stream)>>>(src, static_cast<__nv_bfloat16*>(dst), R, C, lds, ldd);
+    else transpose_bf16_kernel<false><<<grid, block, 0, pk2::as_stream(stream)>>>(src, static_cast<__nv_bfloat16*>(dst), R, C, lds, ldd);
+    PK2_POST_LAUNCH();
+    return 0;
+}
+
+extern "C" int pk2_lstm_hprev_t(const void* y, void* hprev_t, int B, int T, int H, int ldd, void* stream) {
+    PK2_REQUIRE(y && hprev_t, "pk2_lstm_hprev_t: null argument");
+    PK2_REQUIRE(H % 32 == 0, "pk2_lstm_hprev_t: H must be a multiple of 32");
+    const int M = B * T;
+    dim3 grid(2 * H / 32, (M + 31) / 32), block(32, 8);
+    PK2_REQUIRE(grid.y <= 65535, "pk2_lstm_hprev_t: too many rows (%d)", M);
+    hprev_t_kernel<<<grid, block, 0, pk2::as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(y),
+                                                            static_cast<__nv_bfloat16*>(hprev_t), B, T, H, ldd);
+    PK2_POST_LAUNCH();
+    return 0;
+}
+
+extern "C" int pk2_colsum_bf16(const void* src, float* out, int64_t R, int C, void* stream) {
+    PK2_REQUIRE(src && out, "pk2_colsum_bf16: null argument");
+    if (R <= 0 || C <= 0) return 0;
+    const int rows_per_block = 256;
+    const int nparts = (int)((R + rows_per_block - 1) / rows_per_block);
+    const size_t need = (size_t)nparts * C * sizeof(float);
+    if (need > g_partial_bytes) {
+        if (g_partial) cudaFree(g_partial);
+        PK2_CHECK(cudaMalloc(&g_partial, need));
+        g_partial_bytes = need;
+    }
+    dim3 grid((C + 127) / 128, nparts);
+    PK2_REQUIRE(grid.y <= 65535, "pk2_colsum_bf16: too many rows");
+    colsum_bf16_kernel<<<grid, 128, 0, pk2::as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(src), g_partial, R, C, rows_per_block);
+    PK2_POST_LAUNCH();
+    colsum_final_kernel<<<(C + 127) / 128, 128, 0, pk2::as_stream(stream)>>>(g_partial, out, nparts, C);
+    PK2_POST_LAUNCH();
+    return 0;
+}

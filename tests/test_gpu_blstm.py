@@ -1,0 +1,104 @@
+"""GPU parity tests of the BLSTM path: tcgen05 GEMM, persistent recurrence kernels, full model
+forward/backward vs the reference model (torch.nn.LSTM + nn.Linear, which is what
+reference models/lstm.py:46-61 is) in fp32 on the CPU.
+
+Tolerances: operands are bf16 (fp32 accumulate), so single GEMM outputs are compared with
+~1e-2 relative Frobenius error; the north_star parity quantity, per-frame log-posteriors,
+must agree within 1e-3 relative."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda", 0)
+
+
+def rel_err(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.mark.parametrize("M,N,K,bias,bf16_out", [
+    (128, 128, 64, False, False), (300, 200, 80, True, False), (1000, 5768, 1024, True, False),
+    (513, 80, 1000, False, False), (256, 4096, 4096, True, True), (130, 136, 72, False, True)])
+def test_gemm_bf16_nt(dev, M, N, K, bias, bf16_out):
+    from pykaldi2_b200.models import lstm as L
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device=dev).to(torch.bfloat16)
+    b = torch.randn(N, K, device=dev).to(torch.bfloat16)
+    bv = torch.randn(N, device=dev) if bias else None
+    c = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16 if bf16_out else torch.float32)
+    L._gemm(a, b, c, bv, M, N, K, K, K, N, bf16_out=bf16_out)
+    ref = a.double() @ b.double().t()
+    if bias:
+        ref = ref + bv.double()
+    assert torch.isfinite(c.float()).all()
+    assert rel_err(c.float(), ref) < (6e-3 if bf16_out else 2e-5)
+
+
+def _ref_model(F, N, H, L, seed):
+    import torch.nn as nn
+    torch.manual_seed(seed)
+    lstm = nn.LSTM(input_size=F, hidden_size=H, num_layers=L, batch_first=True, dropout=0.0, bidirectional=True)
+    lin = nn.Linear(2 * H, N)
+    return lstm, lin
+
+
+@pytest.mark.parametrize("B,T,F,N,H,L", [(3, 7, 16, 24, 64, 1), (5, 9, 80, 104, 128, 2), (64, 12, 80, 5768, 512, 3)])
+def test_lstmam_forward_backward_vs_torch(dev, B, T, F, N, H, L):
+    from pykaldi2_b200.models.lstm import LSTMAM
+    lstm, lin = _ref_model(F, N, H, L, seed=B + T)
+    model = LSTMAM(F, N, H, L, 0.0, True)
+    model.lstm.load_state_dict(lstm.state_dict())
+    model.output_layer.load_state_dict(lin.state_dict())
+    model = model.to(dev)
+    assert list(model.state_dict().keys())[:3] == ["output_layer.weight", "output_layer.bias", "lstm.weight_ih_l0"]
+    torch.manual_seed(1)
+    x = torch.randn(B, T, F)
+    labels = torch.randint(0, N, (B * T,))
+    # reference: fp32 CPU
+    out_ref, _ = lstm(x)
+    logits_ref = lin(out_ref)
+    loss_ref = torch.nn.functional.cross_entropy(logits_ref.view(-1, N), labels, reduction="sum")
+    loss_ref.backward()
+    # ours
+    logits = model(x.to(dev))
+    assert logits.shape == (B, T, N) and logits.dtype == torch.float32
+    lp = torch.log_softmax(logits.float().cpu(), -1)
+    lp_ref = torch.log_softmax(logits_ref.detach(), -1)
+    # north_star: per-frame log-posteriors within 1e-3 relative
+    assert float(((lp - lp_ref).abs() / lp_ref.abs()).max()) < 1e-3
+    assert rel_err(logits.detach().cpu(), logits_ref.detach()) < 2e-2
+    loss = torch.nn.functional.cross_entropy(logits.view(-1, N), labels.to(dev), reduction="sum")
+    np.testing.assert_allclose(loss.item(), loss_ref.item(), rtol=1e-3)
+    loss.backward()
+    ref_params = dict(lstm.named_parameters())
+    for name, p in model.lstm.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), name
+        assert rel_err(p.grad.cpu(), ref_params[name].grad) < 3e-2, name
+    assert rel_err(model.output_layer.weight.grad.cpu(), lin.weight.grad) < 3e-2
+    assert rel_err(model.output_layer.bias.grad.cpu(), lin.bias.grad) < 3e-2
+
+
+def test_lstmam_batch_groups_and_padding_semantics(dev):
+    """B not a multiple of the kernel's batch group (and > 128 so the 64-row groups are used):
+    results must not depend on the grouping; zero-padded frames are processed like the reference
+    does (nn.LSTM on the padded batch, no packing: data/dataloader.py:96-103 + models/lstm.py:58)."""
+    from pykaldi2_b200.models.lstm import LSTMAM
+    B, T, F, N, H, L = 150, 5, 80, 64, 64, 1
+    lstm, lin = _ref_model(F, N, H, L, seed=3)
+    model = LSTMAM(F, N, H, L, 0.0, True)
+    model.lstm.load_state_dict(lstm.state_dict())
+    model.output_layer.load_state_dict(lin.state_dict())
+    model = model.to(dev)
+    x = torch.randn(B, T, F)
+    x[::2, 3:] = 0.0
+    ref = lin(lstm(x)[0]).detach()
+    out = model(x.to(dev)).detach().cpu()
+    assert rel_err(out, ref) < 2e-2
+    out1 = model(x[:7].to(dev)).detach().cpu()          # same sequences in a different grouping
+    assert rel_err(out1, out[:7]) < 1e-6
