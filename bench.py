@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- iRTF of the LF-MMI training hot path on B200 (BASELINE.json metric).
+
+Workload (BASELINE.json configs[3], SURVEY.md section 8d "C4"): BLSTM 3x512 (N=5768) LF-MMI chain
+training, batch 64 utterances per GPU of LibriSpeech-shaped synthetic audio (durations
+clip(gamma(6, 2.05), 1.5, 30) s), synthetic 8192-state denominator FST (mean out-degree 8),
+synthetic time-constrained numerator FSTs, 3x frame subsampling, Adam(amsgrad), clip 5.
+A step = waveforms -> log-mel fbank -> CMN -> pad/subsample -> BLSTM fwd -> chain den+num
+forward-backward -> BLSTM bwd -> (NCCL grad all-reduce) -> clip -> optimizer step.
+
+  value  : hours of audio per wall-clock hour, inputs resident in HBM, all ranks (weak scaling)
+  e2e    : same, through the public API with HOST (pinned) waveforms + supervision index arrays
+           copied H2D and the loss read back D2H inside the timed region
+  roofline: denominator forward-backward kernels (den_forward+den_backward) vs measured HBM peak
+  cpu_baseline / --impl reference: the reference's CPU path (numpy fbank restatement, torch-CPU
+           nn.LSTM+Linear = the reference model, restated Kaldi chain FB) on a bounded sample.
+
+Launch: python bench.py --gpus 1 ;  torchrun --nproc-per-node N bench.py --gpus N
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PDF, HID, LAYERS, FEAT = 5768, 512, 3, 80
+DEN_STATES, DEN_EXTRA = 8192, 7
+BATCH = 64
+FACTOR = 3
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_workload(rank, batch, seed=1234):
+    from pykaldi2_b200 import synth
+    from pykaldi2_b200.data import fbank as fb
+    rng = np.random.default_rng(seed + 1000 * rank)
+    durs = synth.make_durations(batch, rng)
+    wavs = synth.make_waveforms(durs, rng)
+    frames = [fb.num_frames(len(w)) for w in wavs]
+    sub = [(t - 1) // FACTOR + 1 for t in frames]
+    sup_fsts = [synth.make_supervision_fst(t, N_PDF, rng) for t in sub]
+    return durs, wavs, frames, sub, sup_fsts
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=3)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 6:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ CPU arm ----
+def cpu_reference_sample(wavs, sup_fsts, den_fst, n_utts, threads=None):
+    """The reference's CPU path on n_utts utterances; returns (audio seconds, wall seconds)."""
+    import torch.nn as nn
+    from oracle import chain_ref, fbank_ref
+    from pykaldi2_b200.data import mel
+    if threads:
+        torch.set_num_threads(threads)
+    W = mel.mel80_window()
+    oden = chain_ref.den_graph_from_fst(den_fst, N_PDF)          # graph construction is one-off: untimed
+    torch.manual_seed(0)
+    lstm = nn.LSTM(FEAT, HID, LAYERS, batch_first=True, bidirectional=True)
+    lin = nn.Linear(2 * HID, N_PDF)
+    params = list(lstm.parameters()) + list(lin.parameters())
+    opt = torch.optim.Adam(params, lr=1e-4, amsgrad=True)
+    t0 = time.perf_counter()
+    feats = []
+    for w in wavs[:n_utts]:
+        f = fbank_ref.cmn(fbank_ref.logfbank(w, W)).astype(np.float32)
+        feats.append(f[::FACTOR])
+    Tm = max(f.shape[0] for f in feats)
+    x = np.zeros((n_utts, Tm, FEAT), np.float32)
+    for i, f in enumerate(feats):
+        x[i, :f.shape[0]] = f
+    pred = lin(lstm(torch.from_numpy(x))[0])
+    grad = torch.zeros_like(pred)
+    for i in range(n_utts):
+        T = feats[i].shape[0]
+        ll = pred[i, :T].detach().numpy()
+        objf, g, _ = chain_ref.chain_objf_and_deriv(ll, oden, sup_fsts[i], leaky=1e-4)
+        grad[i, :T] = torch.from_numpy(-g.astype(np.float32))
+    pred.backward(grad)
+    torch.nn.utils.clip_grad_norm_(params, 5.0)
+    opt.step()
+    dt = time.perf_counter() - t0
+    audio = sum(len(w) for w in wavs[:n_utts]) / 16000.0
+    return audio, dt
+
+
+def run_reference(args, rank):
+    """--impl reference: CPU path on the box's host cores; rank 0 only."""
+    if rank != 0:
+        return
+    from pykaldi2_b200 import synth
+    durs, wavs, frames, sub, sup_fsts = make_workload(0, BATCH)
+    den_fst = synth.make_den_fst(DEN_STATES, N_PDF, DEN_EXTRA, seed=1234)
+    order = np.argsort(durs)[:4]                 # bounded sample: the 4 shortest utterances per step
+    wv = [wavs[i] for i in order]; sf = [sup_fsts[i] for i in order]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_reference_sample(wv[:1], sf[:1], den_fst, 1)
+    tot_a = tot_t = 0.0
+    for _ in range(args.steps):
+        a, t = cpu_reference_sample(wv, sf, den_fst, len(wv))
+        tot_a += a; tot_t += t
+    irtf = tot_a / tot_t
+    line = {
+        "impl": "reference", "metric": "iRTF (hours audio/hour) BLSTM LF-MMI", "value": irtf,
+        "unit": "hours audio per hour", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BLSTM 3x512 LF-MMI chain, batch 64 var-len utts, S=8192 den FST (C4)",
+                   "sample": "4 shortest utterances of the batch per step"},
+        "cpu_baseline": {"value": irtf, "unit": "hours audio per hour", "cores": cores, "kind": "port",
+                         "sample": "4 shortest utterances of the 64-utt batch: numpy fbank+CMN, torch-CPU nn.LSTM+Linear "
+                                   "fwd/bwd + Adam (the reference model), restated Kaldi chain den/num FB (numpy, 1 thread)"},
+        "e2e": {"value": irtf, "unit": "hours audio per hour", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------ GPU arm ----
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    from pykaldi2_b200 import dist as pkdist
+    if args.impl == "reference":
+        run_reference(args, int(os.environ.get("RANK", "0")))
+        return
+    rank, world, local = pkdist.init()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+
+    from pykaldi2_b200 import _lib, graphs, pipeline, synth
+    from pykaldi2_b200.models.lstm import LSTMAM
+    from pykaldi2_b200.ops import ops
+
+    L = _lib.lib()
+    B = args.batch
+    durs, wavs, frames, sub, sup_fsts = make_workload(rank, B)
+    den_fst = synth.make_den_fst(DEN_STATES, N_PDF, DEN_EXTRA, seed=1234)
+    den = graphs.DenominatorGraph(den_fst, N_PDF)
+    n_arcs = len(den_fst["src"])
+    opts = graphs.ChainTrainingOptions(leaky_hmm_coefficient=1e-4, xent_regularize=0.0)
+    sups = [graphs.Supervision(f, t, N_PDF) for f, t in zip(sup_fsts, sub)]
+
+    torch.manual_seed(0)
+    model = LSTMAM(FEAT, N_PDF, HID, LAYERS, 0.0, True).to(dev)
+    model.train()
+    optimizer = torch.optim.Adam(model.parameters(), lr=1e-4, amsgrad=True)
+    pkdist.broadcast_parameters(model)
+    averager = pkdist.GradAverager(list(model.parameters())) if world > 1 else None
+    feat = pipeline.FeaturePipeline(use_cmn=True)
+    wav_pinned, woff, foff = feat.ex.pack(wavs)
+    wav_dev = wav_pinned.to(dev)
+    sup_dev = graphs.SupervisionBatch(sups, device=dev)
+    audio_s = float(sum(len(w) for w in wavs)) / 16000.0
+    h2d = wav_pinned.numel() * 4 + sup_dev.h2d_bytes + (len(woff) * 8 + len(foff) * 4) + 2 * 4 * B * ((max(frames) - 1) // FACTOR + 1)
+
+    def step(resident):
+        if resident:
+            w, sb = wav_dev, sup_dev
+        else:
+            w, sb = wav_pinned, graphs.SupervisionBatch(sups, device=dev)
+        return pipeline.chain_step(model, optimizer, averager, feat, den, opts, w, woff, foff, sb, epoch=0)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(resident, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            step(resident)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step(True)
+    step(False)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ops.DEN_TIMERS = []
+    n0 = L.pk2_launch_count()
+    t_res = timed(True, args.steps)
+    n1 = L.pk2_launch_count()
+    den_ms = [a.elapsed_time(b) for a, b in ops.DEN_TIMERS]
+    ops.DEN_TIMERS = None
+    t_e2e = timed(False, args.steps)
+    clocks = sampler.stop() if sampler else None
+
+    tot_audio = torch.tensor([audio_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(tot_audio)
+    tot_audio = float(tot_audio.item())
+    value = tot_audio * args.steps / t_res
+    e2e = tot_audio * args.steps / t_e2e
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        S = DEN_STATES
+        alg_bytes = sum(sub) * (8 * N_PDF + 8 * S) + 24 * n_arcs
+        den_s = float(np.mean(den_ms)) * 1e-3 if den_ms else float("nan")
+        achieved = alg_bytes / den_s / 1e9
+        line = {
+            "metric": "iRTF (hours audio/hour) BLSTM LF-MMI", "value": value, "unit": "hours audio per hour",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "BLSTM 3x512 LF-MMI chain, batch 64 var-len utts/GPU, S=8192 den FST (C4)",
+                       "global_batch": B * world, "audio_s_per_step": tot_audio, "parallelism": "dp%d" % world,
+                       "l2": "no flush: every step streams > 5 GB of activations/workspace, far larger than the 126 MB L2",
+                       "optimizer": "Adam(amsgrad) lr 1e-4, clip 5"},
+            "e2e": {"value": e2e, "unit": "hours audio per hour", "ms_per_step": 1e3 * t_e2e / args.steps,
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8 * B + 8},
+            "gpu_launches": int(n1 - n0),
+            "roofline": {"kernel": "den_forward_kernel+den_backward_kernel (pk2_denfb)", "bound": "hbm",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "ms_per_launch_pair": den_s * 1e3,
+                         "algorithmic_bytes": int(alg_bytes), "traffic": None,
+                         "note": "binding bound is shared-memory gather bandwidth, not HBM (DESIGN.md section 5)"},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            try:
+                order = np.argsort(durs)[:2]
+                a, t = cpu_reference_sample([wavs[i] for i in order], [sup_fsts[i] for i in order], den_fst, 2)
+                line["cpu_baseline"] = {"value": a / t, "unit": "hours audio per hour", "cores": torch.get_num_threads(),
+                                        "kind": "port",
+                                        "sample": "2 shortest utterances of the batch: numpy fbank+CMN, torch-CPU nn.LSTM+Linear "
+                                                  "fwd/bwd+Adam, restated Kaldi chain den/num FB (numpy)"}
+            except Exception as e:      # the CPU leg must never take the GPU line down
+                line["cpu_baseline"] = {"value": None, "error": repr(e)}
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -22,6 +22,10 @@ from ..graphs import (ChainTrainingOptions, DenominatorGraph, Lattice, LatticeBa
                       Supervision, SupervisionBatch, SyntheticLatticeProvider, TidPdfMap)
 
 
+# bench.py sets this to a list to collect (start, end) CUDA events around the denominator kernels
+DEN_TIMERS = None
+
+
 # --------------------------------------------------------------------------- chain ----
 def chain_objf_and_deriv(prediction, den_graph, sup_batch, chain_opts, cluster=0):
     """prediction: cuda float32 [B, Tmax, N] raw logits.  Returns
@@ -48,10 +52,16 @@ def chain_objf_and_deriv(prediction, den_graph, sup_batch, chain_opts, cluster=0
     ws = th.empty(wsb, dtype=th.uint8, device=dev)
     logz = th.empty(2, B, dtype=th.float64, device=dev)
     nf = sup_batch._dev["num_frames"]
+    if DEN_TIMERS is not None:
+        e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        e0.record()
     _lib.check(L.pk2_denfb(den_graph.handle, _lib.ptr(prediction), _lib.ptr(nf), B, Tmax, Tmax,
                            float(chain_opts.leaky_hmm_coefficient), float(w),
                            _lib.ptr(ws), _lib.ptr(grad), _lib.ptr(logz[0]), int(cluster), _lib.stream()),
                "pk2_denfb")
+    if DEN_TIMERS is not None:
+        e1.record()
+        DEN_TIMERS.append((e0, e1))
     ab = th.empty(2, max(sup_batch.total_states, 1), dtype=th.float64, device=dev)
     scale = -float(w) * (1.0 + float(chain_opts.xent_regularize))
     _lib.check(L.pk2_numfb(sup_batch.struct, _lib.ptr(prediction), N, Tmax, scale,

@@ -1,0 +1,102 @@
+"""One training step of the hot path, composed from the reference-facing pieces
+(feature pipeline -> LSTMAM -> ops.ops loss -> NCCL gradient averaging -> clip -> optimizer).
+
+Used by bench.py and by the trainers in bin/; it is the body of the reference's
+run_train_epoch loops (bin/train_ce.py:177-208, bin/train_se.py:222-277,
+bin/train_chain.py:244-308) with the CPU data path and the per-utterance host round trips
+replaced by the kernels of libpk2.so.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import dist as pkdist
+from .data import fbank as fb
+from .ops import ops
+
+
+class FeaturePipeline(object):
+    """waveforms (pinned host or device) -> normalised, padded / chunked / subsampled batch."""
+
+    def __init__(self, use_cmn=True, mvn=None):
+        self.ex = fb.FbankExtractor()
+        self.use_cmn = use_cmn
+        self.mvn = mvn
+
+    def features(self, wav, woff, foff):
+        wav_dev = wav if wav.is_cuda else wav.cuda(non_blocking=True)
+        feats, foff_d = self.ex.extract(wav_dev, woff, foff)
+        mean = fb.utterance_means(feats, foff_d, len(foff) - 1) if self.use_cmn else None
+        return feats, mean
+
+    def sequence_batch(self, wav, woff, foff, factor=1, shift=0, n_frames=None):
+        """-> (x [B, Tout, 80], input lengths per utterance)"""
+        feats, mean = self.features(wav, woff, foff)
+        src, utt, Tout, lens = fb.padded_rows(foff, n_frames, factor, shift)
+        x = fb.gather_norm(feats, src, utt, mean, self.mvn).view(len(foff) - 1, Tout, fb.FEAT_DIM)
+        return x, lens
+
+    def chunk_batch(self, wav, woff, foff, seg_len=80, seg_shift=80, n_frames=None):
+        """-> (x [n_chunks, seg_len, 80], chunk_utt, chunk_start)"""
+        feats, mean = self.features(wav, woff, foff)
+        src, utt, cu, cs = fb.chunk_rows(foff, n_frames, seg_len, seg_shift)
+        x = fb.gather_norm(feats, src, utt, mean, self.mvn).view(-1, seg_len, fb.FEAT_DIM)
+        return x, cu, cs
+
+
+def ce_loss(logits, labels, reduction="mean"):
+    """nn.CrossEntropyLoss(ignore_index=-100) on the fused kernel (bin/train_ce.py:134,189)."""
+    return _CE.apply(logits, labels, reduction)
+
+
+class _CE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, reduction):
+        from . import _lib
+        _lib.require_cuda(logits, "logits")
+        N = logits.shape[-1]
+        lg = logits.detach().contiguous().view(-1, N)
+        lab = labels.contiguous().view(-1).to(torch.int64)
+        R = lg.shape[0]
+        n_valid = (lab >= 0).sum().clamp(min=1).to(torch.float32)
+        rows = torch.empty(R, dtype=torch.float32, device=lg.device)
+        grad = torch.empty_like(lg)
+        _lib.check(_lib.lib().pk2_ce_softmax(_lib.ptr(lg), _lib.ptr(lab), R, N, 1.0, _lib.ptr(rows), _lib.ptr(grad),
+                                             _lib.stream()), "pk2_ce_softmax")
+        tot = rows.sum()
+        if reduction == "mean":
+            ctx.scale = 1.0 / n_valid
+            tot = tot / n_valid
+        else:
+            ctx.scale = None
+        ctx.save_for_backward(grad)
+        ctx.shape = logits.shape
+        return tot
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        grad, = ctx.saved_tensors
+        g = grad * (grad_out if ctx.scale is None else grad_out * ctx.scale)
+        return g.view(ctx.shape), None, None
+
+
+def finish_step(model, optimizer, averager, max_grad_norm):
+    """allreduce(mean) -> clip -> optimizer step (bin/train_ce.py:192-196 with Horovod folded in)."""
+    if averager is not None:
+        averager.average()
+    norm = nn.utils.clip_grad_norm_(model.parameters(), max_grad_norm)
+    optimizer.step()
+    optimizer.zero_grad(set_to_none=True)
+    return norm
+
+
+def chain_step(model, optimizer, averager, feat, den_graph, chain_opts, wav, woff, foff, supervisions,
+               epoch=0, max_grad_norm=5.0, factor=3):
+    """One LF-MMI step (bin/train_chain.py:244-292).  Returns (objf float, total input frames)."""
+    shift = epoch % factor                                   # frame_shift = -(epoch % 3) then roll
+    x, lens = feat.sequence_batch(wav, woff, foff, factor=factor, shift=shift)
+    prediction = model(x)
+    loss = ops.ChainObjtiveFunction.apply_batch(prediction, den_graph, supervisions, chain_opts)
+    loss.backward()
+    finish_step(model, optimizer, averager, max_grad_norm)
+    return float(loss.item()), int(np.sum(lens))
