@@ -1,0 +1,161 @@
+#!/usr/bin/env python
+"""Lattice-free MMI (chain) training of the BLSTM acoustic model on B200 (reference bin/train_chain.py).
+
+Same flags as the reference script (bin/train_chain.py:60-83).  The loop body is :244-308: 3x frame
+subsampling with the epoch-dependent shift, model forward, the chain objective per utterance
+(``ops.ChainObjtiveFunction``), Noam learning rate, clip, Adam(amsgrad), rank-0 checkpoints
+``chain.model.<i>.tar``.  ``-synthetic N`` supplies N seeded utterances, a synthetic denominator FST
+(``-den_states``) and synthetic time-constrained numerator FSTs: the reference builds those from Kaldi
+assets (den.fst, 0.trans_mdl, tree, alignments; :167-202,262-272), which is SURVEY.md row 8f-2.
+``-per_utt_loss 1`` keeps the reference's one-call-per-utterance loop; the default batches the B
+calls into one C-ABI call (identical numbers, tests/test_gpu_fb.py).
+"""
+import argparse
+import os
+import time
+import zlib
+
+import numpy as np
+import torch as th
+
+import _common
+from _common import pkdist
+from pykaldi2_b200 import graphs, pipeline, synth
+from pykaldi2_b200.data.dataloader import SyntheticWaveDataset, WaveDataloader
+from pykaldi2_b200.models import lstm
+from pykaldi2_b200.ops import ops
+from pykaldi2_b200.utils import utils
+
+
+class SupervisionOptions(object):
+    """kaldi_chain.SupervisionOptions stand-in (bin/train_chain.py:184-188)."""
+
+    def __init__(self):
+        self.convert_to_pdfs = True
+        self.frame_subsampling_factor = 3
+        self.left_tolerance = 5
+        self.right_tolerance = 5
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument("-config")
+    parser.add_argument("-data", help="data yaml file")
+    parser.add_argument("-dataPath", default='', type=str, help="path of data files")
+    parser.add_argument("-seed_model", default='', help="the seed nerual network model")
+    parser.add_argument("-exp_dir", help="the directory to save the outputs")
+    parser.add_argument("-transform", help="feature transformation matrix or mvn statistics")
+    parser.add_argument("-ali_dir", help="the directory to load trans_model and tree used for alignments")
+    parser.add_argument("-lang_dir", help="the lexicon directory to load L.fst")
+    parser.add_argument("-chain_dir", help="the directory to load trans_model, tree and den.fst for chain model")
+    parser.add_argument("-lr", type=float, default=1e-3, help="set the base learning rate")
+    parser.add_argument("-warmup_steps", default=4000, type=int, help="the number of warmup steps to adjust the learning rate")
+    parser.add_argument("-xent_regularize", default=0, type=float, help="cross-entropy regularization weight")
+    parser.add_argument("-momentum", default=0, type=float, help="set the momentum")
+    parser.add_argument("-weight_decay", default=1e-4, type=float, help="set the L2 regularization weight")
+    parser.add_argument("-batch_size", default=32, type=int, help="Override the batch size in the config")
+    parser.add_argument("-data_loader_threads", default=0, type=int, help="number of workers for data loading")
+    parser.add_argument("-max_grad_norm", default=5, type=float, help="max_grad_norm for gradient clipping")
+    parser.add_argument("-sweep_size", default=100, type=float, help="process n hours of data per sweep (default:100)")
+    parser.add_argument("-num_epochs", default=1, type=int, help="number of training epochs (default:1)")
+    parser.add_argument("-anneal_lr_epoch", default=2, type=int, help="start to anneal the learning rate from this epoch")
+    parser.add_argument("-anneal_lr_ratio", default=0.5, type=float, help="the ratio to anneal the learning rate ratio")
+    parser.add_argument('-print_freq', default=10, type=int, metavar='N', help='print frequency (default: 10)')
+    parser.add_argument('-save_freq', default=1000, type=int, metavar='N', help='save model frequency (default: 1000)')
+    parser.add_argument('-synthetic', default=0, type=int, help="train on this many seeded synthetic utterances")
+    parser.add_argument('-den_states', default=8192, type=int, help="states of the synthetic denominator FST")
+    parser.add_argument('-per_utt_loss', default=0, type=int, help="1 = one chain-objective call per utterance as the reference does")
+    parser.add_argument('-max_steps', default=0, type=int)
+    args = parser.parse_args()
+
+    config = _common.load_config(args.config, args.data)
+    config["sweep_size"] = args.sweep_size
+    config["data_path"] = args.dataPath
+    _common.dump_config(config)
+    rank, world, local = _common.init_distributed(True)
+    if not th.cuda.is_available():
+        raise SystemExit("train_chain.py: the B200 build has no CPU path")
+    dev = th.device("cuda", local)
+    os.makedirs(args.exp_dir, exist_ok=True)
+    mc, dc = config["model_config"], config["data_config"]
+    if args.synthetic <= 0:
+        raise SystemExit("train_chain.py: only -synthetic data is wired in this build (Kaldi assets: SURVEY.md 8f-2)")
+
+    dataset = SyntheticWaveDataset(args.synthetic, mc["label_size"])
+    loader = WaveDataloader(dataset, args.batch_size, num_workers=args.data_loader_threads, distributed=world > 1)
+    feat = pipeline.FeaturePipeline(use_cmn=dc.get("use_cmn", True))
+    print("Data loader set up successfully!")
+    print("Number of minibatches: {}".format(len(loader)))
+
+    model = lstm.LSTMAM(mc["feat_dim"], mc["label_size"], mc["hidden_size"], mc["num_layers"], mc["dropout"], True).to(dev)
+    optimizer = th.optim.Adam(model.parameters(), lr=args.lr, amsgrad=True)
+    if args.seed_model:
+        _common.load_model_state(model, args.seed_model)
+        print("=> loaded checkpoint '{}' ".format(args.seed_model))
+    if world > 1:
+        pkdist.broadcast_parameters(model)
+        pkdist.broadcast_optimizer_state(optimizer)
+    averager = pkdist.GradAverager(list(model.parameters())) if world > 1 else None
+
+    supervision_opts = SupervisionOptions()
+    chain_opts = graphs.ChainTrainingOptions(leaky_hmm_coefficient=1e-4, xent_regularize=args.xent_regularize)
+    den = graphs.DenominatorGraph(synth.make_den_fst(args.den_states, mc["label_size"], 7, seed=1234), mc["label_size"])
+
+    model.train()
+    for epoch in range(args.num_epochs):
+        run_train_epoch(model, optimizer, averager, feat, loader, epoch, supervision_opts, den, chain_opts, args, rank)
+        if rank == 0:
+            _common.save_checkpoint(args.exp_dir + '/chain.model.' + str(epoch) + '.tar', model, optimizer)
+
+
+def run_train_epoch(model, optimizer, averager, feat, loader, epoch, supervision_opts, den, chain_opts, args, rank):
+    batch_time = utils.AverageMeter('Time', ':6.3f')
+    losses = utils.AverageMeter('Loss', ':.4e')
+    grad_norm = utils.AverageMeter('grad_norm', ':.4e')
+    progress = utils.ProgressMeter(len(loader), batch_time, losses, grad_norm, prefix="Epoch: [{}]".format(epoch))
+    rtf = utils.RTFMeter()
+    factor = supervision_opts.frame_subsampling_factor
+    criterion = ops.ChainObjtiveFunction.apply
+    end = time.time()
+    for i, batch in enumerate(loader):
+        wav, woff, foff = feat.ex.pack(batch["wav"])
+        shift = epoch % factor                      # frame_shift = -(epoch % 3); x = roll(x, shift, 1)
+        x, num_frs = feat.sequence_batch(wav, woff, foff, factor=factor, shift=shift)
+        # numerator graphs: the reference derives them from the alignment (bin/train_chain.py:262-272);
+        # synthetic stand-in, seeded per utterance
+        sups = []
+        for j, ids in enumerate(batch["utt_ids"]):
+            t_sub = (int(num_frs[j]) - 1) // factor + 1
+            rng = np.random.default_rng(zlib.crc32(ids[0].encode()))
+            sups.append(graphs.Supervision(synth.make_supervision_fst(t_sub, den.num_pdfs(), rng), t_sub, den.num_pdfs()))
+        prediction = model(x)
+        if args.per_utt_loss:
+            loss = 0.0
+            for j, sup in enumerate(sups):
+                loglike_j = prediction[j, :sup.frames_per_sequence, :]
+                loss += criterion(loglike_j, den, sup, chain_opts)
+        else:
+            loss = ops.ChainObjtiveFunction.apply_batch(prediction, den, sups, chain_opts)
+        loss.backward()
+        step = len(loader) * epoch + i + 1
+        lr = utils.noam_decay(step, args.warmup_steps, args.lr)
+        for g in optimizer.param_groups:
+            g['lr'] = lr
+        norm = pipeline.finish_step(model, optimizer, averager, args.max_grad_norm)
+        grad_norm.update(float(norm))
+        tot_frs = np.array(num_frs).sum()
+        losses.update(loss.item() / tot_frs)
+        rtf.update(tot_frs)
+        batch_time.update(time.time() - end)
+        end = time.time()
+        if rank == 0 and i % args.save_freq == 0:
+            _common.save_checkpoint(args.exp_dir + '/chain.model.' + str(i) + '.tar', model, optimizer)
+        if rank == 0 and i % args.print_freq == 0:
+            progress.print(i)
+            print("iRTF {:.1f}".format(rtf.irtf), flush=True)
+        if args.max_steps and i + 1 >= args.max_steps:
+            break
+
+
+if __name__ == '__main__':
+    main()

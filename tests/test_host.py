@@ -1,0 +1,154 @@
+"""CPU-side tests: the C-ABI library loads and exports every symbol include/pk2.h declares, the
+host-side index logic (graphs, row maps, collate) is bit-exact against the oracle / the reference's
+golden vectors, and the N>1 data-parallel path works on gloo with world_size 2."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+
+
+def test_library_exports_every_declared_symbol():
+    from pykaldi2_b200 import _lib, build
+    build.build(verbose=False)
+    decl = set(re.findall(r"\b(pk2_[a-z0-9_]+)\s*\(", open(os.path.join(ROOT, "include", "pk2.h")).read()))
+    assert decl == set(_lib.EXPORTS)
+    L = _lib.lib()                       # dlopen + getattr of every symbol
+    for name in decl:
+        assert hasattr(L, name), name
+    assert L.pk2_version() >= 100
+    assert L.pk2_launch_count() == 0     # nothing launched: no GPU here
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under pykaldi2_b200/ or bin/ may import it."""
+    bad = []
+    for base in ("pykaldi2_b200", "bin"):
+        for dp, _, fs in os.walk(os.path.join(ROOT, base)):
+            for f in fs:
+                if f.endswith(".py"):
+                    src = open(os.path.join(dp, f)).read()
+                    if re.search(r"^\s*(from|import)\s+oracle\b", src, re.M):
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad
+
+
+def test_cpu_tensors_are_rejected():
+    from pykaldi2_b200.models.lstm import LSTMAM
+    m = LSTMAM(80, 16, 64, 1, 0.0, True)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.zeros(1, 4, 80))
+    assert "lstm.weight_hh_l0_reverse" in m.state_dict() and "output_layer.bias" in m.state_dict()
+
+
+def test_lattice_prep_index_tensors_bit_exact():
+    from oracle import lattice_ref
+    from pykaldi2_b200 import graphs, synth
+    rng = np.random.default_rng(11)
+    for eps in (0.0, 0.15):
+        lat, t2p, ali = synth.make_lattice(30, 100, rng, kmin=5, kmax=12, ali_drop=0.3, eps_frac=eps)
+        L = graphs.Lattice(lat)
+        assert (L.state_times_orig == lattice_ref.lattice_state_times(lat)).all()
+        ll = rng.normal(0, 2, (30, 100))
+        _, _, drop, _ = lattice_ref.lattice_fb_mmi(ll, lat, t2p, ali)
+        assert (L.keep_mask(ali) == (~drop)).all()
+        assert L.level_off[-1] == L.num_states and (np.diff(L.state_time) >= 0).all()
+        assert len(L.out_dst) + len(L.eps_src) == len(lat["src"])
+
+
+def test_supervision_prep_and_generic_time_sort():
+    from oracle import chain_ref
+    from pykaldi2_b200 import graphs, synth
+    rng = np.random.default_rng(2)
+    f = synth.make_supervision_fst(25, 40, rng)
+    s = graphs.Supervision(f, 25, 40)
+    assert (s.state_time == chain_ref.fst_state_times(f)).all()
+    g = dict(f)
+    del g["state_times"]                 # generic path: times recomputed by BFS
+    s2 = graphs.Supervision(g, 25, 40)
+    for k in ("state_time", "out_off", "out_dst", "out_pdf", "in_off", "in_src", "in_pdf", "level_off"):
+        assert (getattr(s, k) == getattr(s2, k)).all(), k
+    with pytest.raises(ValueError):
+        graphs.Supervision(f, 24, 40)
+
+
+def test_row_maps_match_reference_semantics():
+    from oracle import fbank_ref
+    from pykaldi2_b200.data import fbank
+    gold = np.load(os.path.join(G, "fbank_golden.npz"))
+    for i in range(5):
+        assert fbank.num_frames(len(gold["wav%d" % i])) == gold["fbank%d" % i].shape[0]
+    foff = np.array([0, 250, 330, 331])
+    src, utt, cu, cs = fbank.chunk_rows(foff)
+    assert cu.tolist() == [0, 0, 0, 1] and cs.tolist() == [0, 80, 160, 0]
+    assert cs.tolist()[:3] == fbank_ref.utt2seg_index(250)
+    src, utt, Tout, lens = fbank.padded_rows(foff)
+    assert Tout == 250 and src.reshape(3, 250)[2].tolist() == [330] + [-1] * 249
+
+
+def test_collate_golden():
+    from pykaldi2_b200.data import dataloader
+    g = np.load(os.path.join(G, "collate_golden.npz"))
+    items = [(g["feat%d" % j], ["utt%d" % j], g["lab%d" % j], [g["aux%d" % j]]) for j in range(3)]
+    b = dataloader.seq_collate(items)
+    assert (b["x"].numpy() == g["x"]).all() and (b["y"].numpy() == g["y"]).all()
+    assert list(b["num_frs"]) == g["num_frs"].tolist()
+    assert b["aux"][1][0][0].tolist() == g["aux1"][0].tolist()
+
+
+def test_cmn_and_mvn_pickle_compat():
+    import pickle
+    from pykaldi2_b200.reader import preprocess
+    g = np.load(os.path.join(G, "fbank_golden.npz"))
+    np.testing.assert_allclose(preprocess.cmn(g["fbank2"], axis=0), g["cmn2"], rtol=1e-5, atol=1e-5)
+    tr = preprocess.GlobalMeanVarianceNormalization()
+    tr.mean_vec, tr.std_vec = g["mvn_mean"], g["mvn_std"]
+    tr2 = pickle.loads(pickle.dumps(tr))
+    np.testing.assert_allclose(tr2.apply_on_ndarray(g["cmn4"]), g["mvn4"], rtol=1e-6)
+
+
+_DP_SCRIPT = r"""
+import os, sys, torch
+sys.path.insert(0, %r)
+from pykaldi2_b200 import dist as pkdist
+rank, world, local = pkdist.init(backend="gloo")
+torch.manual_seed(0)
+model = torch.nn.Linear(8, 4)
+pkdist.broadcast_parameters(model)
+opt = pkdist.DistributedOptimizer(torch.optim.SGD(model.parameters(), lr=0.1))
+x = torch.arange(16, dtype=torch.float32).view(2, 8) + 100 * rank
+loss = model(x).pow(2).sum()
+opt.zero_grad(); loss.backward(); opt.synchronize()
+g = model.weight.grad.clone()
+# reference: mean of the two ranks' gradients computed locally
+ref = torch.zeros_like(g)
+for r in range(world):
+    m2 = torch.nn.Linear(8, 4); m2.load_state_dict(model.state_dict())
+    xr = torch.arange(16, dtype=torch.float32).view(2, 8) + 100 * r
+    m2(xr).pow(2).sum().backward(); ref += m2.weight.grad / world
+assert torch.allclose(g, ref, rtol=1e-5, atol=1e-5), (g, ref)
+opt.step()
+w = model.weight.detach().clone()
+ws = [torch.zeros_like(w) for _ in range(world)]
+torch.distributed.all_gather(ws, w)
+assert all(torch.equal(ws[0], t) for t in ws)
+assert pkdist.shard_indices(5, world, rank) == [(rank + i * world) %% 5 for i in range(3)]
+print("rank", rank, "ok")
+"""
+
+
+def test_data_parallel_gloo_world2(tmp_path):
+    script = tmp_path / "dp.py"
+    script.write_text(_DP_SCRIPT % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29613")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)],
+                       capture_output=True, text=True, timeout=240, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2
