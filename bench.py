@@ -93,7 +93,7 @@ class ClockSampler(threading.Thread):
 def cpu_reference_sample(wavs, sup_fsts, den_fst, n_utts, threads=None):
     """The reference's CPU path on n_utts utterances; returns (audio seconds, wall seconds)."""
     import torch.nn as nn
-    from oracle import chain_ref, fbank_ref
+    from oracle import c_port, chain_ref, fbank_ref
     from pykaldi2_b200.data import mel
     if threads:
         torch.set_num_threads(threads)
@@ -118,7 +118,7 @@ def cpu_reference_sample(wavs, sup_fsts, den_fst, n_utts, threads=None):
     for i in range(n_utts):
         T = feats[i].shape[0]
         ll = pred[i, :T].detach().numpy()
-        objf, g, _ = chain_ref.chain_objf_and_deriv(ll, oden, sup_fsts[i], leaky=1e-4)
+        objf, g, _ = c_port.chain_objf_and_deriv(ll, oden, sup_fsts[i], leaky=1e-4)
         grad[i, :T] = torch.from_numpy(-g.astype(np.float32))
     pred.backward(grad)
     torch.nn.utils.clip_grad_norm_(params, 5.0)
@@ -155,7 +155,7 @@ def run_reference(args, rank):
                    "sample": "4 shortest utterances of the batch per step"},
         "cpu_baseline": {"value": irtf, "unit": "hours audio per hour", "cores": cores, "kind": "port",
                          "sample": "4 shortest utterances of the 64-utt batch: numpy fbank+CMN, torch-CPU nn.LSTM+Linear "
-                                   "fwd/bwd + Adam (the reference model), restated Kaldi chain den/num FB (numpy, 1 thread)"},
+                                   "fwd/bwd + Adam (the reference model), restated Kaldi chain den/num FB (C -O3, 1 thread per utterance)"},
         "e2e": {"value": irtf, "unit": "hours audio per hour", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -289,7 +289,7 @@ def main():
                 line["cpu_baseline"] = {"value": a / t, "unit": "hours audio per hour", "cores": torch.get_num_threads(),
                                         "kind": "port",
                                         "sample": "2 shortest utterances of the batch: numpy fbank+CMN, torch-CPU nn.LSTM+Linear "
-                                                  "fwd/bwd+Adam, restated Kaldi chain den/num FB (numpy)"}
+                                                  "fwd/bwd+Adam, restated Kaldi chain den/num FB (C -O3)"}
             except Exception as e:      # the CPU leg must never take the GPU line down
                 line["cpu_baseline"] = {"value": None, "error": repr(e)}
         print(json.dumps(line))

@@ -57,7 +57,7 @@ __device__ __forceinline__ float tanhf_fast(float x) {
 }
 
 __device__ __forceinline__ void spin_until(const unsigned* ctr, unsigned target) {
-    while (ld_acquire_gpu(ctr) < target) __nanosleep(20);
+    while (ld_acquire_gpu(ctr) < target) { }
 }
 
 // --------------------------------------------------------------------------- forward ----
@@ -114,8 +114,8 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                     spin_until(counter, (unsigned)(nctas * s));
                     fence_proxy_async();
                     mbar_expect_tx(hbar, (uint32_t)KB * NB * 128u);
-                    for (int kb = 0; kb < KB; ++kb)
-                        tma_load_3d(&map_y, hbar, Hs + kb * NB * 128, dir * H + kb * 64, tp, b0);
+                    // one 4-D box {64 cols, NB rows, 1 step, KB k-blocks} -> KB swizzled [NB x 64] tiles
+                    tma_load_4d(&map_y, hbar, Hs, 0, b0, tp, dir * KB);
                 }
             }
         }
@@ -166,19 +166,15 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                 for (int j = 0; j < NB; ++j) acc[j] = 0.f;
             }
             mbar_wait(gbar, ph_g); ph_g ^= 1;
-            __nv_bfloat16* gout = p.gates + ((((int64_t)dir * T + tt) * B + b0) * 4 + gate) * H + u0 + lane;
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
                 const float v = acc[b] + gxs[b * 128 + r];
-                const float a = (gate == 2) ? tanhf_fast(v) : sigmoidf_fast(v);
-                gxs[b * 128 + r] = a;
-                if (b < nbv) gout[(int64_t)b * 4 * H] = __float2bfloat16(a);
+                gxs[b * 128 + r] = (gate == 2) ? tanhf_fast(v) : sigmoidf_fast(v);
             }
             named_bar_sync(1, kEpiThreads);
-            // cell update: lane = unit, warp w handles batch rows w, w+4, ...
+            // cell update: lane = unit, warp w handles batch rows w, w+4, ...  (critical path: h_t -> y)
             {
                 __nv_bfloat16* yo = p.y + ((int64_t)b0 * T + tt) * 2 * H + dir * H + u0 + lane;
-                float* co = p.cstate + (((int64_t)dir * T + tt) * B + b0) * H + u0 + lane;
 #pragma unroll
                 for (int k = 0; k < NB / 4; ++k) {
                     const int b = warp + 4 * k;
@@ -187,20 +183,29 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                     const float c = fmaf(fg, cst[k], ig * gg);
                     cst[k] = c;
                     const float h = og * tanhf_fast(c);
+                    if (b < nbv) yo[(int64_t)b * T * 2 * H] = __float2bfloat16(h);
+                }
+            }
+            fence_proxy_async();
+            named_bar_sync(1, kEpiThreads);
+            if (threadIdx.x == 0) red_release_gpu_add(counter, 1u);     // publish h_t: releases step s+1 everywhere
+            // off the critical path: save gates and cell state for the backward pass
+            {
+                float* co = p.cstate + (((int64_t)dir * T + tt) * B + b0) * H + u0 + lane;
+                __nv_bfloat16* gout = p.gates + (((int64_t)dir * T + tt) * B + b0) * 4 * H + u0 + lane;
+#pragma unroll
+                for (int k = 0; k < NB / 4; ++k) {
+                    const int b = warp + 4 * k;
                     if (b < nbv) {
-                        co[(int64_t)b * H] = c;
-                        yo[(int64_t)b * T * 2 * H] = __float2bfloat16(h);
+                        co[(int64_t)b * H] = cst[k];
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+                            gout[((int64_t)b * 4 + g) * H] = __float2bfloat16(gxs[b * 128 + g * 32 + lane]);
                     }
                 }
             }
-            __threadfence();
-            fence_proxy_async();
             named_bar_sync(1, kEpiThreads);
-            if (threadIdx.x == 0) {
-                __threadfence();
-                red_release_gpu_add(counter, 1u);
-                mbar_arrive(gfree);
-            }
+            if (threadIdx.x == 0) mbar_arrive(gfree);
         }
     }
     tc_fence_before();
@@ -209,7 +214,11 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
 }
 
 // -------------------------------------------------------------------------- backward ----
-constexpr int kBwdStages = 4;
+// dgates_t of the previous step is streamed as the A operand in chunks of kChunkBytes (CH k-blocks of
+// [NB x 64] bf16) through a 2-deep ring; W_hh^T[32 units, 4H] is the resident B operand.
+constexpr int kChunkBytes = 32768;
+constexpr int kRing = 2;
+constexpr int kASlack = 16384;           // the M=128 MMA reads 16 KB from each tile base (rows >= NB ignored)
 
 template <int NB>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -218,15 +227,18 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_constan
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int H = p.H, T = p.T, B = p.B;
     const int KB = 4 * H / 64;                               // k-blocks over the 4H gate columns
+    const int CH = min(kChunkBytes / (NB * 128), KB);        // k-blocks per chunk
+    const int NCH = KB / CH;                                 // chunks per step
+    const uint32_t chunk_bytes = (uint32_t)CH * NB * 128u;
     uint8_t* Wt = smem;                                      // KB x [32 x 64] bf16   (W_hh^T slice)
-    uint8_t* As = Wt + KB * 4096;                            // kBwdStages x [128 x 64] bf16 (NB rows valid)
-    float* dhs = reinterpret_cast<float*>(As + kBwdStages * 16384);   // [NB][33]
+    uint8_t* As = Wt + KB * 4096;                            // kRing chunks + slack
+    float* dhs = reinterpret_cast<float*>(As + kRing * kChunkBytes + kASlack);   // [NB][33]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(dhs) + ((NB * 33 * 4 + 7) & ~7));
     uint64_t* wbar = bars + 0;
     uint64_t* mbar = bars + 1;
-    uint64_t* afull = bars + 2;                              // [kBwdStages]
-    uint64_t* aempty = afull + kBwdStages;                   // [kBwdStages]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + kBwdStages);
+    uint64_t* afull = bars + 2;                              // [kRing]
+    uint64_t* aempty = afull + kRing;                        // [kRing]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + kRing);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cta = blockIdx.x, dir = blockIdx.y, grp = blockIdx.z;
@@ -237,13 +249,12 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_constan
 
     if (threadIdx.x == 0) {
         mbar_init(wbar, 1); mbar_init(mbar, 1);
-        for (int i = 0; i < kBwdStages; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
+        for (int i = 0; i < kRing; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
         fence_barrier_init();
     }
     if (warp == 5) tmem_alloc(tmem_slot, 32);
-    // rows NB..127 of the A stages are never written by TMA: clear them once so the unused
-    // accumulator rows stay finite
-    for (int i = threadIdx.x; i < kBwdStages * 16384 / 16; i += kThreads)
+    // the slack behind the ring is read (never written) by the MMAs: keep it finite
+    for (int i = threadIdx.x; i < (kRing * kChunkBytes + kASlack) / 16; i += kThreads)
         reinterpret_cast<uint4*>(As)[i] = make_uint4(0u, 0u, 0u, 0u);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
@@ -263,11 +274,11 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_constan
                 const int tprev = dir ? tt - 1 : tt + 1;
                 spin_until(counter, (unsigned)(nctas * s));
                 fence_proxy_async();
-                for (int kb = 0; kb < KB; ++kb) {
+                for (int c = 0; c < NCH; ++c) {
                     mbar_wait(&aempty[stage], phase ^ 1);
-                    mbar_expect_tx(&afull[stage], (uint32_t)NB * 128u);
-                    tma_load_3d(&map_dg, &afull[stage], As + stage * 16384, dir * 4 * H + kb * 64, tprev, b0);
-                    if (++stage == kBwdStages) { stage = 0; phase ^= 1; }
+                    mbar_expect_tx(&afull[stage], chunk_bytes);
+                    tma_load_4d(&map_dg, &afull[stage], As + stage * kChunkBytes, 0, b0, tprev, dir * KB + c * CH);
+                    if (++stage == kRing) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -277,23 +288,26 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_constan
             mbar_wait(wbar, 0);
             uint32_t stage = 0, phase = 0;
             for (int s = 1; s < T; ++s) {
-                for (int kb = 0; kb < KB; ++kb) {
+                for (int c = 0; c < NCH; ++c) {
                     mbar_wait(&afull[stage], phase);
                     tc_fence_after();
-                    const uint64_t adesc = make_sw128_desc(smem_u32(As + stage * 16384));
-                    const uint64_t bdesc = make_sw128_desc(smem_u32(Wt + kb * 4096));
+                    for (int q = 0; q < CH; ++q) {
+                        const int kb = c * CH + q;
+                        const uint64_t adesc = make_sw128_desc(smem_u32(As + stage * kChunkBytes + q * NB * 128));
+                        const uint64_t bdesc = make_sw128_desc(smem_u32(Wt + kb * 4096));
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        tc_mma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                                    (uint32_t)((kb | k) != 0));
+                        for (int k = 0; k < 4; ++k)
+                            tc_mma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                        (uint32_t)((kb | k) != 0));
+                    }
                     tc_commit(&aempty[stage]);
-                    if (++stage == kBwdStages) { stage = 0; phase ^= 1; }
+                    if (++stage == kRing) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(mbar);
             }
         }
     } else {
-        // ===== epilogue: TMEM lane = batch row, column = unit =====
+        // ===== epilogue: TMEM lane = batch row, column = unit; then lane = unit, warp strides batch rows =====
         float dcn[NB / 4];
 #pragma unroll
         for (int k = 0; k < NB / 4; ++k) dcn[k] = 0.f;
@@ -301,6 +315,30 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_constan
         for (int s = 0; s < T; ++s) {
             const int tt = dir ? s : (T - 1 - s);
             const int tfp = dir ? tt + 1 : tt - 1;          // time of c_{prev} in forward order
+            // everything that does not depend on dh_rec is fetched and folded before the MMAs retire
+            float cO[NB / 4], a1[NB / 4], cI[NB / 4], cF[NB / 4], cG[NB / 4], fgv[NB / 4], dyv[NB / 4];
+#pragma unroll
+            for (int k = 0; k < NB / 4; ++k) {
+                const int b = warp + 4 * k;
+                cO[k] = a1[k] = cI[k] = cF[k] = cG[k] = fgv[k] = dyv[k] = 0.f;
+                if (b < nbv) {
+                    const int64_t bb = b0 + b;
+                    const __nv_bfloat16* gp = p.gates + ((((int64_t)dir * T + tt) * B + bb) * 4) * H + u0 + lane;
+                    const float ig = __bfloat162float(gp[0]), fg = __bfloat162float(gp[H]);
+                    const float gg = __bfloat162float(gp[2 * H]), og = __bfloat162float(gp[3 * H]);
+                    const float c = p.cstate[(((int64_t)dir * T + tt) * B + bb) * H + u0 + lane];
+                    const float cp = (tfp >= 0 && tfp < T)
+                                         ? p.cstate[(((int64_t)dir * T + tfp) * B + bb) * H + u0 + lane] : 0.f;
+                    dyv[k] = p.dy[(bb * T + tt) * 2 * H + dir * H + u0 + lane];
+                    const float tc_ = tanhf_fast(c);
+                    cO[k] = tc_ * og * (1.0f - og);
+                    a1[k] = og * (1.0f - tc_ * tc_);
+                    cI[k] = gg * ig * (1.0f - ig);
+                    cF[k] = cp * fg * (1.0f - fg);
+                    cG[k] = ig * (1.0f - gg * gg);
+                    fgv[k] = fg;
+                }
+            }
             if (s > 0) {
                 mbar_wait(mbar, ph_m); ph_m ^= 1;
                 tc_fence_after();
@@ -320,35 +358,19 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_constan
                 const int b = warp + 4 * k;
                 if (b < nbv) {
                     const int64_t bb = b0 + b;
-                    const __nv_bfloat16* gp = p.gates + ((((int64_t)dir * T + tt) * B + bb) * 4) * H + u0 + lane;
-                    const float ig = __bfloat162float(gp[0]), fg = __bfloat162float(gp[H]);
-                    const float gg = __bfloat162float(gp[2 * H]), og = __bfloat162float(gp[3 * H]);
-                    const float c = p.cstate[(((int64_t)dir * T + tt) * B + bb) * H + u0 + lane];
-                    const float cp = (tfp >= 0 && tfp < T)
-                                         ? p.cstate[(((int64_t)dir * T + tfp) * B + bb) * H + u0 + lane] : 0.f;
-                    const float dh = dhs[b * 33 + lane] + p.dy[(bb * T + tt) * 2 * H + dir * H + u0 + lane];
-                    const float tc_ = tanhf_fast(c);
-                    const float dout = dh * tc_;
-                    const float dc = fmaf(dh * og, 1.0f - tc_ * tc_, dcn[k]);
-                    dcn[k] = dc * fg;
-                    const float dgi = dc * gg * ig * (1.0f - ig);
-                    const float dgf = dc * cp * fg * (1.0f - fg);
-                    const float dgg = dc * ig * (1.0f - gg * gg);
-                    const float dgo = dout * og * (1.0f - og);
+                    const float dh = dhs[b * 33 + lane] + dyv[k];
+                    const float dc = fmaf(dh, a1[k], dcn[k]);
+                    dcn[k] = dc * fgv[k];
                     __nv_bfloat16* dp = p.dgates + ((bb * T + tt) * 2 + dir) * 4 * H + u0 + lane;
-                    dp[0] = __float2bfloat16(dgi);
-                    dp[H] = __float2bfloat16(dgf);
-                    dp[2 * H] = __float2bfloat16(dgg);
-                    dp[3 * H] = __float2bfloat16(dgo);
+                    dp[0] = __float2bfloat16(dc * cI[k]);
+                    dp[H] = __float2bfloat16(dc * cF[k]);
+                    dp[2 * H] = __float2bfloat16(dc * cG[k]);
+                    dp[3 * H] = __float2bfloat16(dh * cO[k]);
                 }
             }
-            __threadfence();
             fence_proxy_async();
             named_bar_sync(1, kEpiThreads);
-            if (threadIdx.x == 0) {
-                __threadfence();
-                red_release_gpu_add(counter, 1u);
-            }
+            if (threadIdx.x == 0) red_release_gpu_add(counter, 1u);
         }
     }
     tc_fence_before();
@@ -378,7 +400,7 @@ int make_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dim
              const cuuint32_t* box) {
     EncodeTiledFn enc = get_encode();
     PK2_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
-    cuuint32_t estr[3] = {1, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
                      strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -417,11 +439,11 @@ int launch_fwd(const pk2_lstm_fwd_args* a, cudaStream_t st) {
         cuuint32_t box[2] = {64, 128};
         if (make_map(&mw, a->whh, 2, dims, str, box)) return 2;
     }
-    {   // y[B][T][2H] viewed as (col, t, b)
-        cuuint64_t dims[3] = {(cuuint64_t)(2 * H), (cuuint64_t)T, (cuuint64_t)B};
-        cuuint64_t str[2] = {(cuuint64_t)(2 * H) * 2, (cuuint64_t)T * 2 * H * 2};
-        cuuint32_t box[3] = {64, 1, (cuuint32_t)NB};
-        if (make_map(&my, a->y, 3, dims, str, box)) return 2;
+    {   // y[B][T][2H] viewed as (64 cols, b, t, 64-col block): one box = KB swizzled [NB x 64] tiles
+        cuuint64_t dims[4] = {64, (cuuint64_t)B, (cuuint64_t)T, (cuuint64_t)(2 * H / 64)};
+        cuuint64_t str[3] = {(cuuint64_t)T * 2 * H * 2, (cuuint64_t)(2 * H) * 2, 128};
+        cuuint32_t box[4] = {64, (cuuint32_t)NB, 1, (cuuint32_t)KB};
+        if (make_map(&my, a->y, 4, dims, str, box)) return 2;
     }
     const size_t smem = (size_t)KB * 16384 + (size_t)KB * NB * 128 + (size_t)NB * 512 + 64 + 1024;
     PK2_CHECK(cudaFuncSetAttribute(lstm_fwd_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -446,13 +468,15 @@ int launch_bwd(const pk2_lstm_bwd_args* a, cudaStream_t st) {
         cuuint32_t box[2] = {64, 32};
         if (make_map(&mwt, a->whh_t, 2, dims, str, box)) return 2;
     }
-    {   // dgates[B][T][2*4H] viewed as (col, t, b)
-        cuuint64_t dims[3] = {(cuuint64_t)(8 * H), (cuuint64_t)T, (cuuint64_t)B};
-        cuuint64_t str[2] = {(cuuint64_t)(8 * H) * 2, (cuuint64_t)T * 8 * H * 2};
-        cuuint32_t box[3] = {64, 1, (cuuint32_t)NB};
-        if (make_map(&mdg, a->dgates, 3, dims, str, box)) return 2;
+    {   // dgates[B][T][2*4H] viewed as (64 cols, b, t, 64-col block): one box = CH swizzled [NB x 64] tiles
+        cuuint64_t dims[4] = {64, (cuuint64_t)B, (cuuint64_t)T, (cuuint64_t)(8 * H / 64)};
+        cuuint64_t str[3] = {(cuuint64_t)T * 8 * H * 2, (cuuint64_t)(8 * H) * 2, 128};
+        const int ch = (kChunkBytes / (NB * 128)) < KB ? (kChunkBytes / (NB * 128)) : KB;
+        cuuint32_t box[4] = {64, (cuuint32_t)NB, 1, (cuuint32_t)ch};
+        PK2_REQUIRE(KB % ch == 0, "pk2_lstm_layer_bwd: hidden size %d not supported with batch group %d", H, NB);
+        if (make_map(&mdg, a->dgates, 4, dims, str, box)) return 2;
     }
-    const size_t smem = (size_t)KB * 4096 + (size_t)kBwdStages * 16384 + (size_t)((NB * 33 * 4 + 7) & ~7) + 128 + 1024;
+    const size_t smem = (size_t)KB * 4096 + (size_t)kRing * kChunkBytes + kASlack + (size_t)((NB * 33 * 4 + 7) & ~7) + 128 + 1024;
     PK2_CHECK(cudaFuncSetAttribute(lstm_bwd_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PK2_CHECK(cudaMemsetAsync(a->sync, 0, sizeof(unsigned) * 2 * G, st));
     BwdDev d;

@@ -82,19 +82,38 @@ int build_sell(const std::vector<std::vector<Arc3>>& rows, int K, SellHost* out)
             size_t len = rows[order[s]].size();      // longest row of the slice (sorted desc)
             const size_t base = arcs.size();
             arcs.resize(base + len * 32, make_uint2(0u, 0u));
+            // Schedule the arcs of the slice: at step k every lane issues one arc of its row.  The two
+            // shared-memory gathers of a step conflict when lanes hit the same bank (index mod 32), so
+            // each lane greedily takes, among its remaining arcs, the one whose banks are least used
+            // in this step (summation order inside a row is free).
+            std::vector<std::vector<Arc3>> rem(32);
             for (int l = 0; l < 32; ++l) {
                 if (s + l < order.size()) {
-                    const int r = order[s + l];
-                    slice_row.push_back(r);
-                    for (size_t k = 0; k < rows[r].size(); ++k) {
-                        const Arc3& a = rows[r][k];
-                        uint2 rec;
-                        rec.x = f2u(a.w);
-                        rec.y = (unsigned)a.a | ((unsigned)a.b << 16);
-                        arcs[base + k * 32 + l] = rec;
-                    }
+                    slice_row.push_back(order[s + l]);
+                    rem[l] = rows[order[s + l]];
                 } else {
                     slice_row.push_back(-1);
+                }
+            }
+            for (size_t k = 0; k < len; ++k) {
+                int ca[32] = {0}, cb[32] = {0};
+                for (int l0 = 0; l0 < 32; ++l0) {
+                    const int l = (int)((l0 + k) & 31);          // rotate the lane that chooses first
+                    if (rem[l].empty()) continue;
+                    size_t best = 0;
+                    int bc = 1 << 30;
+                    for (size_t q = 0; q < rem[l].size(); ++q) {
+                        const int c = ca[rem[l][q].a & 31] + cb[rem[l][q].b & 31];
+                        if (c < bc) { bc = c; best = q; }
+                    }
+                    const Arc3 a = rem[l][best];
+                    rem[l][best] = rem[l].back();
+                    rem[l].pop_back();
+                    ca[a.a & 31]++; cb[a.b & 31]++;
+                    uint2 rec;
+                    rec.x = f2u(a.w);
+                    rec.y = (unsigned)a.a | ((unsigned)a.b << 16);
+                    arcs[base + k * 32 + l] = rec;
                 }
             }
             slice_off.push_back((int)arcs.size());
@@ -178,15 +197,26 @@ __device__ __forceinline__ void sell_pass(const SellDev& tb, int part, const flo
         const uint2* p = tb.arcs + off + lane;
         float acc0 = 0.f, acc1 = 0.f;
         int k = 0;
-        for (; k + 4 <= len; k += 4) {
-            const uint2 r0 = __ldg(p + (k + 0) * 32);
-            const uint2 r1 = __ldg(p + (k + 1) * 32);
-            const uint2 r2 = __ldg(p + (k + 2) * 32);
-            const uint2 r3 = __ldg(p + (k + 3) * 32);
-            acc0 = fmaf(ga[r0.y & 0xffffu], __uint_as_float(r0.x) * gb[r0.y >> 16], acc0);
-            acc1 = fmaf(ga[r1.y & 0xffffu], __uint_as_float(r1.x) * gb[r1.y >> 16], acc1);
-            acc0 = fmaf(ga[r2.y & 0xffffu], __uint_as_float(r2.x) * gb[r2.y >> 16], acc0);
-            acc1 = fmaf(ga[r3.y & 0xffffu], __uint_as_float(r3.x) * gb[r3.y >> 16], acc1);
+        for (; k + 8 <= len; k += 8) {
+            uint2 r[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) r[q] = __ldg(p + (k + q) * 32);
+#pragma unroll
+            for (int q = 0; q < 8; q += 2) {
+                acc0 = fmaf(ga[r[q].y & 0xffffu], __uint_as_float(r[q].x) * gb[r[q].y >> 16], acc0);
+                acc1 = fmaf(ga[r[q + 1].y & 0xffffu], __uint_as_float(r[q + 1].x) * gb[r[q + 1].y >> 16], acc1);
+            }
+        }
+        if (k + 4 <= len) {
+            uint2 r[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) r[q] = __ldg(p + (k + q) * 32);
+#pragma unroll
+            for (int q = 0; q < 4; q += 2) {
+                acc0 = fmaf(ga[r[q].y & 0xffffu], __uint_as_float(r[q].x) * gb[r[q].y >> 16], acc0);
+                acc1 = fmaf(ga[r[q + 1].y & 0xffffu], __uint_as_float(r[q + 1].x) * gb[r[q + 1].y >> 16], acc1);
+            }
+            k += 4;
         }
         for (; k < len; ++k) {
             const uint2 r0 = __ldg(p + k * 32);
