@@ -74,10 +74,13 @@ size_t pk2_denfb_workspace_bytes(void* graph, int n_seq, int max_frames);
 /* loglikes/grad: row t of sequence b at base + (b*row_stride_b + t)*num_pdfs floats.
  * num_frames[b] (device int32) <= max_frames.  Writes grad[b,t,:] = deriv_scale *
  * gamma_den(t,:) for t < num_frames[b] and 0 for num_frames[b] <= t < max_frames,
- * logz[b] (double) = log Z_den.  cluster = CTAs per sequence (1, 2 or 4; 0 = auto). */
-int pk2_denfb(void* graph, const float* loglikes, const int32_t* num_frames, int n_seq,
-              int max_frames, int64_t row_stride_b, float leaky, float deriv_scale,
-              void* workspace, float* grad, double* logz, int cluster, void* stream);
+ * logz[b] (double) = log Z_den.  cluster = CTAs per sequence (1, 2 or 4); 0 = auto: with the optional
+ * host copy num_frames_h the batch is scheduled length-aware (long sequences get 4-CTA clusters, short
+ * ones 1) as up to three concurrent launches that fill the SMs in one wave. */
+int pk2_denfb(void* graph, const float* loglikes, const int32_t* num_frames,
+              const int32_t* num_frames_h, int n_seq, int max_frames, int64_t row_stride_b,
+              float leaky, float deriv_scale, void* workspace, float* grad, double* logz,
+              int cluster, void* stream);
 
 /* ------------------------------------------------------- LF-MMI numerator --
  * Replaces the numerator half of compute_chain_objf_and_deriv (ops/ops.py:265):

@@ -55,7 +55,7 @@ _SIGS = {
     "pk2_den_graph_create": (C.c_int, [C.c_int, C.c_int, vp, vp, vp, vp, vp, C.POINTER(vp)]),
     "pk2_den_graph_destroy": (C.c_int, [vp]),
     "pk2_denfb_workspace_bytes": (C.c_size_t, [vp, C.c_int, C.c_int]),
-    "pk2_denfb": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int64, C.c_float, C.c_float,
+    "pk2_denfb": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int64, C.c_float, C.c_float,
                             vp, vp, vp, C.c_int, vp]),
     "pk2_numfb": (C.c_int, [C.POINTER(SupBatch), vp, C.c_int, C.c_int64, C.c_float, vp, vp, vp, vp, vp]),
     "pk2_latfb_mmi": (C.c_int, [C.POINTER(LatBatch), vp, C.c_int, C.c_int, C.c_int64, C.c_float,

@@ -60,8 +60,13 @@ __device__ __forceinline__ void spin_until(const unsigned* ctr, unsigned target)
     while (ld_acquire_gpu(ctr) < target) { }
 }
 
+// Batch rows are processed in groups of NB = 32 (the MMA's N).  Each CTA interleaves NG groups: while
+// the h_t of group A travels (publish -> peers' acquire -> TMA), the CTA runs the MMA + epilogue of
+// group B, so the inter-CTA hand-off latency is hidden behind useful work.
+constexpr int NB = 32;
+
 // --------------------------------------------------------------------------- forward ----
-template <int NB>
+template <int NG>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_y, FwdDev p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -69,28 +74,31 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
     const int H = p.H, T = p.T, B = p.B;
     const int KB = H / 64;                                   // k-blocks of 64
     uint8_t* Ws = smem;                                      // KB x [128 x 64] bf16
-    uint8_t* Hs = Ws + KB * 16384;                           // KB x [NB x 64] bf16
-    float* gxs = reinterpret_cast<float*>(Hs + KB * NB * 128);   // [NB][128] fp32
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(gxs) + NB * 512);
-    uint64_t* wbar = bars + 0;      // W slice landed
-    uint64_t* hbar = bars + 1;      // h_{t-1} tiles landed
-    uint64_t* gbar = bars + 2;      // Gx tile landed
-    uint64_t* mbar = bars + 3;      // step MMAs retired
-    uint64_t* gfree = bars + 4;     // Gx buffer may be overwritten
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    uint8_t* Hs0 = Ws + KB * 16384;                          // NG x KB x [NB x 64] bf16
+    const int hs_bytes = KB * NB * 128;
+    float* gxs0 = reinterpret_cast<float*>(Hs0 + NG * hs_bytes);   // NG x [NB][128] fp32
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(gxs0) + NG * NB * 512);
+    uint64_t* wbar = bars + 0;          // W slice landed
+    uint64_t* hbar = bars + 1;          // [NG] h_{t-1} tiles landed
+    uint64_t* gbar = hbar + NG;         // [NG] Gx tile landed
+    uint64_t* mbar = gbar + NG;         // [NG] step MMAs retired
+    uint64_t* gfree = mbar + NG;        // [NG] Gx buffer may be overwritten
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gfree + NG);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cta = blockIdx.x, dir = blockIdx.y, grp = blockIdx.z;
+    const int cta = blockIdx.x, dir = blockIdx.y;
     const int nctas = gridDim.x;
-    const int u0 = cta * 32, b0 = grp * NB;
-    const int nbv = min(NB, B - b0);
-    unsigned* counter = p.counters + (grp * 2 + dir);
+    const int u0 = cta * 32;
+    const int grp0 = blockIdx.z * NG;                        // first batch group of this CTA
+    int nga = 0;                                             // groups that hold at least one row
+    for (int g = 0; g < NG; ++g) nga += ((grp0 + g) * NB < B) ? 1 : 0;
 
     if (threadIdx.x == 0) {
-        mbar_init(wbar, 1); mbar_init(hbar, 1); mbar_init(gbar, 1); mbar_init(mbar, 1); mbar_init(gfree, 1);
+        mbar_init(wbar, 1);
+        for (int g = 0; g < NG; ++g) { mbar_init(&hbar[g], 1); mbar_init(&gbar[g], 1); mbar_init(&mbar[g], 1); mbar_init(&gfree[g], 1); }
         fence_barrier_init();
     }
-    if (warp == 5) tmem_alloc(tmem_slot, NB < 32 ? 32 : NB);
+    if (warp == 5) tmem_alloc(tmem_slot, NG * NB < 32 ? 32 : NG * NB);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -105,18 +113,22 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
             uint32_t ph_free = 0;
             for (int s = 0; s < T; ++s) {
                 const int tt = dir ? (T - 1 - s) : s;
-                if (s > 0) { mbar_wait(gfree, ph_free); ph_free ^= 1; }
-                const float* src = p.gx + ((((int64_t)tt * 2 + dir) * nctas + cta) * B + b0) * 128;
-                mbar_expect_tx(gbar, (uint32_t)nbv * 512u);
-                bulk_load(gxs, src, (uint32_t)nbv * 512u, gbar);
-                if (s > 0) {
-                    const int tp = dir ? tt + 1 : tt - 1;
-                    spin_until(counter, (unsigned)(nctas * s));
-                    fence_proxy_async();
-                    mbar_expect_tx(hbar, (uint32_t)KB * NB * 128u);
-                    // one 4-D box {64 cols, NB rows, 1 step, KB k-blocks} -> KB swizzled [NB x 64] tiles
-                    tma_load_4d(&map_y, hbar, Hs, 0, b0, tp, dir * KB);
+                for (int g = 0; g < nga; ++g) {
+                    const int b0 = (grp0 + g) * NB, nbv = min(NB, B - b0);
+                    if (s > 0) mbar_wait(&gfree[g], ph_free);
+                    const float* src = p.gx + ((((int64_t)tt * 2 + dir) * nctas + cta) * B + b0) * 128;
+                    mbar_expect_tx(&gbar[g], (uint32_t)nbv * 512u);
+                    bulk_load(gxs0 + g * NB * 128, src, (uint32_t)nbv * 512u, &gbar[g]);
+                    if (s > 0) {
+                        const int tp = dir ? tt + 1 : tt - 1;
+                        spin_until(p.counters + ((grp0 + g) * 2 + dir), (unsigned)(nctas * s));
+                        fence_proxy_async();
+                        mbar_expect_tx(&hbar[g], (uint32_t)hs_bytes);
+                        // one 4-D box {64 cols, NB rows, 1 step, KB k-blocks} -> KB swizzled [NB x 64] tiles
+                        tma_load_4d(&map_y, &hbar[g], Hs0 + g * hs_bytes, 0, b0, tp, dir * KB);
+                    }
                 }
+                if (s > 0) ph_free ^= 1;
             }
         }
     } else if (warp == 5) {
@@ -126,101 +138,111 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
             mbar_wait(wbar, 0);
             uint32_t ph_h = 0;
             for (int s = 1; s < T; ++s) {
-                mbar_wait(hbar, ph_h); ph_h ^= 1;
-                tc_fence_after();
-                for (int kb = 0; kb < KB; ++kb) {
-                    const uint64_t adesc = make_sw128_desc(smem_u32(Ws + kb * 16384));
-                    const uint64_t bdesc = make_sw128_desc(smem_u32(Hs + kb * NB * 128));
+                for (int g = 0; g < nga; ++g) {
+                    mbar_wait(&hbar[g], ph_h);
+                    tc_fence_after();
+                    for (int kb = 0; kb < KB; ++kb) {
+                        const uint64_t adesc = make_sw128_desc(smem_u32(Ws + kb * 16384));
+                        const uint64_t bdesc = make_sw128_desc(smem_u32(Hs0 + g * hs_bytes + kb * NB * 128));
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        tc_mma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                                    (uint32_t)((kb | k) != 0));
+                        for (int k = 0; k < 4; ++k)
+                            tc_mma_bf16(tmem_base + g * NB, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                        (uint32_t)((kb | k) != 0));
+                    }
+                    tc_commit(&mbar[g]);
                 }
-                tc_commit(mbar);
+                ph_h ^= 1;
             }
         }
     } else {
         // ===== epilogue warps 0-3: thread r = gate row (gate = r/32, unit = r%32) = TMEM lane r =====
         const int r = threadIdx.x;
         const int gate = warp;
-        float cst[NB / 4];
+        float cst[NG][NB / 4];
 #pragma unroll
-        for (int k = 0; k < NB / 4; ++k) cst[k] = 0.f;
+        for (int g = 0; g < NG; ++g)
+#pragma unroll
+            for (int k = 0; k < NB / 4; ++k) cst[g][k] = 0.f;
         uint32_t ph_g = 0, ph_m = 0;
         for (int s = 0; s < T; ++s) {
             const int tt = dir ? (T - 1 - s) : s;
-            float acc[NB];
-            if (s > 0) {
-                mbar_wait(mbar, ph_m); ph_m ^= 1;
-                tc_fence_after();
 #pragma unroll
-                for (int c = 0; c < NB / 32; ++c) {
+            for (int g = 0; g < NG; ++g) {
+                if (g >= nga) break;
+                const int b0 = (grp0 + g) * NB, nbv = min(NB, B - b0);
+                float* gxs = gxs0 + g * NB * 128;
+                float acc[NB];
+                if (s > 0) {
+                    mbar_wait(&mbar[g], ph_m);
+                    tc_fence_after();
                     uint32_t v[32];
-                    tc_ld_32x32b_x32(tmem_base + c * 32 + ((uint32_t)(warp * 32) << 16), v);
+                    tc_ld_32x32b_x32(tmem_base + g * NB + ((uint32_t)(warp * 32) << 16), v);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[c * 32 + j] = __uint_as_float(v[j]);
+                    for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
+                    tc_fence_before();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) acc[j] = 0.f;
                 }
-                tc_fence_before();
-            } else {
+                mbar_wait(&gbar[g], ph_g);
 #pragma unroll
-                for (int j = 0; j < NB; ++j) acc[j] = 0.f;
-            }
-            mbar_wait(gbar, ph_g); ph_g ^= 1;
-#pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                const float v = acc[b] + gxs[b * 128 + r];
-                gxs[b * 128 + r] = (gate == 2) ? tanhf_fast(v) : sigmoidf_fast(v);
-            }
-            named_bar_sync(1, kEpiThreads);
-            // cell update: lane = unit, warp w handles batch rows w, w+4, ...  (critical path: h_t -> y)
-            {
-                __nv_bfloat16* yo = p.y + ((int64_t)b0 * T + tt) * 2 * H + dir * H + u0 + lane;
-#pragma unroll
-                for (int k = 0; k < NB / 4; ++k) {
-                    const int b = warp + 4 * k;
-                    const float ig = gxs[b * 128 + lane], fg = gxs[b * 128 + 32 + lane];
-                    const float gg = gxs[b * 128 + 64 + lane], og = gxs[b * 128 + 96 + lane];
-                    const float c = fmaf(fg, cst[k], ig * gg);
-                    cst[k] = c;
-                    const float h = og * tanhf_fast(c);
-                    if (b < nbv) yo[(int64_t)b * T * 2 * H] = __float2bfloat16(h);
+                for (int b = 0; b < NB; ++b) {
+                    const float v = acc[b] + gxs[b * 128 + r];
+                    gxs[b * 128 + r] = (gate == 2) ? tanhf_fast(v) : sigmoidf_fast(v);
                 }
-            }
-            fence_proxy_async();
-            named_bar_sync(1, kEpiThreads);
-            if (threadIdx.x == 0) red_release_gpu_add(counter, 1u);     // publish h_t: releases step s+1 everywhere
-            // off the critical path: save gates and cell state for the backward pass
-            {
-                float* co = p.cstate + (((int64_t)dir * T + tt) * B + b0) * H + u0 + lane;
-                __nv_bfloat16* gout = p.gates + (((int64_t)dir * T + tt) * B + b0) * 4 * H + u0 + lane;
+                named_bar_sync(1, kEpiThreads);
+                // cell update: lane = unit, warp w handles batch rows w, w+4, ...  (critical path: h_t -> y)
+                {
+                    __nv_bfloat16* yo = p.y + ((int64_t)b0 * T + tt) * 2 * H + dir * H + u0 + lane;
 #pragma unroll
-                for (int k = 0; k < NB / 4; ++k) {
-                    const int b = warp + 4 * k;
-                    if (b < nbv) {
-                        co[(int64_t)b * H] = cst[k];
-#pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            gout[((int64_t)b * 4 + g) * H] = __float2bfloat16(gxs[b * 128 + g * 32 + lane]);
+                    for (int k = 0; k < NB / 4; ++k) {
+                        const int b = warp + 4 * k;
+                        const float ig = gxs[b * 128 + lane], fg = gxs[b * 128 + 32 + lane];
+                        const float gg = gxs[b * 128 + 64 + lane], og = gxs[b * 128 + 96 + lane];
+                        const float c = fmaf(fg, cst[g][k], ig * gg);
+                        cst[g][k] = c;
+                        const float h = og * tanhf_fast(c);
+                        if (b < nbv) yo[(int64_t)b * T * 2 * H] = __float2bfloat16(h);
                     }
                 }
+                fence_proxy_async();
+                named_bar_sync(1, kEpiThreads);
+                if (threadIdx.x == 0) red_release_gpu_add(p.counters + ((grp0 + g) * 2 + dir), 1u);   // publish h_t
+                // off the critical path: save gates and cell state for the backward pass
+                {
+                    float* co = p.cstate + (((int64_t)dir * T + tt) * B + b0) * H + u0 + lane;
+                    __nv_bfloat16* gout = p.gates + (((int64_t)dir * T + tt) * B + b0) * 4 * H + u0 + lane;
+#pragma unroll
+                    for (int k = 0; k < NB / 4; ++k) {
+                        const int b = warp + 4 * k;
+                        if (b < nbv) {
+                            co[(int64_t)b * H] = cst[g][k];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                gout[((int64_t)b * 4 + q) * H] = __float2bfloat16(gxs[b * 128 + q * 32 + lane]);
+                        }
+                    }
+                }
+                named_bar_sync(1, kEpiThreads);
+                if (threadIdx.x == 0) mbar_arrive(&gfree[g]);
             }
-            named_bar_sync(1, kEpiThreads);
-            if (threadIdx.x == 0) mbar_arrive(gfree);
+            ph_g ^= 1;
+            if (s > 0) ph_m ^= 1;
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_base, NB < 32 ? 32 : NB);
+    if (warp == 5) tmem_dealloc(tmem_base, NG * NB < 32 ? 32 : NG * NB);
 }
 
 // -------------------------------------------------------------------------- backward ----
-// dgates_t of the previous step is streamed as the A operand in chunks of kChunkBytes (CH k-blocks of
-// [NB x 64] bf16) through a 2-deep ring; W_hh^T[32 units, 4H] is the resident B operand.
+// dgates_t of the previous step is streamed as the A operand in chunks of CH k-blocks of [NB x 64] bf16
+// through a 2-deep ring (shared by the NG interleaved groups); W_hh^T[32 units, 4H] is the resident B operand.
 constexpr int kChunkBytes = 32768;
 constexpr int kRing = 2;
 constexpr int kASlack = 16384;           // the M=128 MMA reads 16 KB from each tile base (rows >= NB ignored)
 
-template <int NB>
+template <int NG>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_bwd_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_constant__ CUtensorMap map_dg, BwdDev p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -232,27 +254,30 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_constan
     const uint32_t chunk_bytes = (uint32_t)CH * NB * 128u;
     uint8_t* Wt = smem;                                      // KB x [32 x 64] bf16   (W_hh^T slice)
     uint8_t* As = Wt + KB * 4096;                            // kRing chunks + slack
-    float* dhs = reinterpret_cast<float*>(As + kRing * kChunkBytes + kASlack);   // [NB][33]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(dhs) + ((NB * 33 * 4 + 7) & ~7));
+    float* dhs0 = reinterpret_cast<float*>(As + kRing * kChunkBytes + kASlack);   // NG x [NB][33]
+    constexpr int kDhs = NB * 33;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(dhs0) + ((NG * kDhs * 4 + 7) & ~7));
     uint64_t* wbar = bars + 0;
-    uint64_t* mbar = bars + 1;
-    uint64_t* afull = bars + 2;                              // [kRing]
+    uint64_t* mbar = bars + 1;                               // [NG]
+    uint64_t* afull = mbar + NG;                             // [kRing]
     uint64_t* aempty = afull + kRing;                        // [kRing]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + kRing);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cta = blockIdx.x, dir = blockIdx.y, grp = blockIdx.z;
+    const int cta = blockIdx.x, dir = blockIdx.y;
     const int nctas = gridDim.x;
-    const int u0 = cta * 32, b0 = grp * NB;
-    const int nbv = min(NB, B - b0);
-    unsigned* counter = p.counters + (grp * 2 + dir);
+    const int u0 = cta * 32;
+    const int grp0 = blockIdx.z * NG;
+    int nga = 0;
+    for (int g = 0; g < NG; ++g) nga += ((grp0 + g) * NB < B) ? 1 : 0;
 
     if (threadIdx.x == 0) {
-        mbar_init(wbar, 1); mbar_init(mbar, 1);
+        mbar_init(wbar, 1);
+        for (int g = 0; g < NG; ++g) mbar_init(&mbar[g], 1);
         for (int i = 0; i < kRing; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
         fence_barrier_init();
     }
-    if (warp == 5) tmem_alloc(tmem_slot, 32);
+    if (warp == 5) tmem_alloc(tmem_slot, NG * 32 < 32 ? 32 : NG * 32);
     // the slack behind the ring is read (never written) by the MMAs: keep it finite
     for (int i = threadIdx.x; i < (kRing * kChunkBytes + kASlack) / 16; i += kThreads)
         reinterpret_cast<uint4*>(As)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -272,13 +297,15 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_constan
                 // step s consumes dgates of the step processed before it (time tprev)
                 const int tt = dir ? s : (T - 1 - s);
                 const int tprev = dir ? tt - 1 : tt + 1;
-                spin_until(counter, (unsigned)(nctas * s));
-                fence_proxy_async();
-                for (int c = 0; c < NCH; ++c) {
-                    mbar_wait(&aempty[stage], phase ^ 1);
-                    mbar_expect_tx(&afull[stage], chunk_bytes);
-                    tma_load_4d(&map_dg, &afull[stage], As + stage * kChunkBytes, 0, b0, tprev, dir * KB + c * CH);
-                    if (++stage == kRing) { stage = 0; phase ^= 1; }
+                for (int g = 0; g < nga; ++g) {
+                    spin_until(p.counters + ((grp0 + g) * 2 + dir), (unsigned)(nctas * s));
+                    fence_proxy_async();
+                    for (int c = 0; c < NCH; ++c) {
+                        mbar_wait(&aempty[stage], phase ^ 1);
+                        mbar_expect_tx(&afull[stage], chunk_bytes);
+                        tma_load_4d(&map_dg, &afull[stage], As + stage * kChunkBytes, 0, (grp0 + g) * NB, tprev, dir * KB + c * CH);
+                        if (++stage == kRing) { stage = 0; phase ^= 1; }
+                    }
                 }
             }
         }
@@ -288,94 +315,105 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_constan
             mbar_wait(wbar, 0);
             uint32_t stage = 0, phase = 0;
             for (int s = 1; s < T; ++s) {
-                for (int c = 0; c < NCH; ++c) {
-                    mbar_wait(&afull[stage], phase);
-                    tc_fence_after();
-                    for (int q = 0; q < CH; ++q) {
-                        const int kb = c * CH + q;
-                        const uint64_t adesc = make_sw128_desc(smem_u32(As + stage * kChunkBytes + q * NB * 128));
-                        const uint64_t bdesc = make_sw128_desc(smem_u32(Wt + kb * 4096));
+                for (int g = 0; g < nga; ++g) {
+                    for (int c = 0; c < NCH; ++c) {
+                        mbar_wait(&afull[stage], phase);
+                        tc_fence_after();
+                        for (int q = 0; q < CH; ++q) {
+                            const int kb = c * CH + q;
+                            const uint64_t adesc = make_sw128_desc(smem_u32(As + stage * kChunkBytes + q * NB * 128));
+                            const uint64_t bdesc = make_sw128_desc(smem_u32(Wt + kb * 4096));
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            tc_mma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                                        (uint32_t)((kb | k) != 0));
+                            for (int k = 0; k < 4; ++k)
+                                tc_mma_bf16(tmem_base + g * 32, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                            (uint32_t)((kb | k) != 0));
+                        }
+                        tc_commit(&aempty[stage]);
+                        if (++stage == kRing) { stage = 0; phase ^= 1; }
                     }
-                    tc_commit(&aempty[stage]);
-                    if (++stage == kRing) { stage = 0; phase ^= 1; }
+                    tc_commit(&mbar[g]);
                 }
-                tc_commit(mbar);
             }
         }
     } else {
         // ===== epilogue: TMEM lane = batch row, column = unit; then lane = unit, warp strides batch rows =====
-        float dcn[NB / 4];
+        float dcn[NG][NB / 4];
 #pragma unroll
-        for (int k = 0; k < NB / 4; ++k) dcn[k] = 0.f;
+        for (int g = 0; g < NG; ++g)
+#pragma unroll
+            for (int k = 0; k < NB / 4; ++k) dcn[g][k] = 0.f;
         uint32_t ph_m = 0;
         for (int s = 0; s < T; ++s) {
             const int tt = dir ? s : (T - 1 - s);
             const int tfp = dir ? tt + 1 : tt - 1;          // time of c_{prev} in forward order
-            // everything that does not depend on dh_rec is fetched and folded before the MMAs retire
-            float cO[NB / 4], a1[NB / 4], cI[NB / 4], cF[NB / 4], cG[NB / 4], fgv[NB / 4], dyv[NB / 4];
 #pragma unroll
-            for (int k = 0; k < NB / 4; ++k) {
-                const int b = warp + 4 * k;
-                cO[k] = a1[k] = cI[k] = cF[k] = cG[k] = fgv[k] = dyv[k] = 0.f;
-                if (b < nbv) {
-                    const int64_t bb = b0 + b;
-                    const __nv_bfloat16* gp = p.gates + ((((int64_t)dir * T + tt) * B + bb) * 4) * H + u0 + lane;
-                    const float ig = __bfloat162float(gp[0]), fg = __bfloat162float(gp[H]);
-                    const float gg = __bfloat162float(gp[2 * H]), og = __bfloat162float(gp[3 * H]);
-                    const float c = p.cstate[(((int64_t)dir * T + tt) * B + bb) * H + u0 + lane];
-                    const float cp = (tfp >= 0 && tfp < T)
-                                         ? p.cstate[(((int64_t)dir * T + tfp) * B + bb) * H + u0 + lane] : 0.f;
-                    dyv[k] = p.dy[(bb * T + tt) * 2 * H + dir * H + u0 + lane];
-                    const float tc_ = tanhf_fast(c);
-                    cO[k] = tc_ * og * (1.0f - og);
-                    a1[k] = og * (1.0f - tc_ * tc_);
-                    cI[k] = gg * ig * (1.0f - ig);
-                    cF[k] = cp * fg * (1.0f - fg);
-                    cG[k] = ig * (1.0f - gg * gg);
-                    fgv[k] = fg;
-                }
-            }
-            if (s > 0) {
-                mbar_wait(mbar, ph_m); ph_m ^= 1;
-                tc_fence_after();
-                if (warp * 32 < NB) {
-                    uint32_t v[32];
-                    tc_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16), v);
+            for (int g = 0; g < NG; ++g) {
+                if (g >= nga) break;
+                const int b0 = (grp0 + g) * NB, nbv = min(NB, B - b0);
+                float* dhs = dhs0 + g * kDhs;
+                // everything that does not depend on dh_rec is fetched and folded before the MMAs retire
+                float cO[NB / 4], a1[NB / 4], cI[NB / 4], cF[NB / 4], cG[NB / 4], fgv[NB / 4], dyv[NB / 4];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) dhs[(warp * 32 + lane) * 33 + j] = __uint_as_float(v[j]);
+                for (int k = 0; k < NB / 4; ++k) {
+                    const int b = warp + 4 * k;
+                    cO[k] = a1[k] = cI[k] = cF[k] = cG[k] = fgv[k] = dyv[k] = 0.f;
+                    if (b < nbv) {
+                        const int64_t bb = b0 + b;
+                        const __nv_bfloat16* gp = p.gates + ((((int64_t)dir * T + tt) * B + bb) * 4) * H + u0 + lane;
+                        const float ig = __bfloat162float(gp[0]), fg = __bfloat162float(gp[H]);
+                        const float gg = __bfloat162float(gp[2 * H]), og = __bfloat162float(gp[3 * H]);
+                        const float c = p.cstate[(((int64_t)dir * T + tt) * B + bb) * H + u0 + lane];
+                        const float cp = (tfp >= 0 && tfp < T)
+                                             ? p.cstate[(((int64_t)dir * T + tfp) * B + bb) * H + u0 + lane] : 0.f;
+                        dyv[k] = p.dy[(bb * T + tt) * 2 * H + dir * H + u0 + lane];
+                        const float tc_ = tanhf_fast(c);
+                        cO[k] = tc_ * og * (1.0f - og);
+                        a1[k] = og * (1.0f - tc_ * tc_);
+                        cI[k] = gg * ig * (1.0f - ig);
+                        cF[k] = cp * fg * (1.0f - fg);
+                        cG[k] = ig * (1.0f - gg * gg);
+                        fgv[k] = fg;
+                    }
                 }
-                tc_fence_before();
-            } else {
-                for (int i = threadIdx.x; i < NB * 33; i += kEpiThreads) dhs[i] = 0.f;
-            }
-            named_bar_sync(1, kEpiThreads);
+                if (s > 0) {
+                    mbar_wait(&mbar[g], ph_m);
+                    tc_fence_after();
+                    if (warp == 0) {                        // NB = 32 rows live in TMEM lanes 0..31
+                        uint32_t v[32];
+                        tc_ld_32x32b_x32(tmem_base + g * 32, v);
 #pragma unroll
-            for (int k = 0; k < NB / 4; ++k) {
-                const int b = warp + 4 * k;
-                if (b < nbv) {
-                    const int64_t bb = b0 + b;
-                    const float dh = dhs[b * 33 + lane] + dyv[k];
-                    const float dc = fmaf(dh, a1[k], dcn[k]);
-                    dcn[k] = dc * fgv[k];
-                    __nv_bfloat16* dp = p.dgates + ((bb * T + tt) * 2 + dir) * 4 * H + u0 + lane;
-                    dp[0] = __float2bfloat16(dc * cI[k]);
-                    dp[H] = __float2bfloat16(dc * cF[k]);
-                    dp[2 * H] = __float2bfloat16(dc * cG[k]);
-                    dp[3 * H] = __float2bfloat16(dh * cO[k]);
+                        for (int j = 0; j < 32; ++j) dhs[lane * 33 + j] = __uint_as_float(v[j]);
+                    }
+                    tc_fence_before();
+                } else {
+                    for (int i = threadIdx.x; i < kDhs; i += kEpiThreads) dhs[i] = 0.f;
                 }
+                named_bar_sync(1, kEpiThreads);
+#pragma unroll
+                for (int k = 0; k < NB / 4; ++k) {
+                    const int b = warp + 4 * k;
+                    if (b < nbv) {
+                        const int64_t bb = b0 + b;
+                        const float dh = dhs[b * 33 + lane] + dyv[k];
+                        const float dc = fmaf(dh, a1[k], dcn[g][k]);
+                        dcn[g][k] = dc * fgv[k];
+                        __nv_bfloat16* dp = p.dgates + ((bb * T + tt) * 2 + dir) * 4 * H + u0 + lane;
+                        dp[0] = __float2bfloat16(dc * cI[k]);
+                        dp[H] = __float2bfloat16(dc * cF[k]);
+                        dp[2 * H] = __float2bfloat16(dc * cG[k]);
+                        dp[3 * H] = __float2bfloat16(dh * cO[k]);
+                    }
+                }
+                fence_proxy_async();
+                named_bar_sync(1, kEpiThreads);
+                if (threadIdx.x == 0) red_release_gpu_add(p.counters + ((grp0 + g) * 2 + dir), 1u);
             }
-            fence_proxy_async();
-            named_bar_sync(1, kEpiThreads);
-            if (threadIdx.x == 0) red_release_gpu_add(counter, 1u);
+            if (s > 0) ph_m ^= 1;
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_base, 32);
+    if (warp == 5) tmem_dealloc(tmem_base, NG * 32 < 32 ? 32 : NG * 32);
 }
 
 // ------------------------------------------------------------------------------ host ----
@@ -408,12 +446,10 @@ int make_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dim
     return 0;
 }
 
-int pick_nb(int B) { return (B + 31) / 32 <= 4 ? 32 : 64; }
-
-int check_dims(const char* who, int B, int T, int H, int nb, int num_sms) {
+int check_dims(const char* who, int B, int T, int H, int ng, int num_sms) {
     PK2_REQUIRE(H % 64 == 0 && H >= 64 && H <= 512, "%s: hidden size %d unsupported (multiple of 64, <= 512)", who, H);
     PK2_REQUIRE(B > 0 && T > 0, "%s: empty batch", who);
-    const int G = (B + nb - 1) / nb;
+    const int G = (B + NB * ng - 1) / (NB * ng);
     PK2_REQUIRE((H / 32) * 2 * G <= num_sms, "%s: B=%d needs %d co-resident CTAs (> %d SMs); split the batch", who, B,
                 (H / 32) * 2 * G, num_sms);
     return 0;
@@ -429,9 +465,10 @@ int num_sms() {
     return n;
 }
 
-template <int NB>
+template <int NG>
 int launch_fwd(const pk2_lstm_fwd_args* a, cudaStream_t st) {
-    const int H = a->H, T = a->T, B = a->B, KB = H / 64, G = (B + NB - 1) / NB;
+    const int H = a->H, T = a->T, B = a->B, KB = H / 64;
+    const int groups = (B + NB - 1) / NB, G = (groups + NG - 1) / NG;
     CUtensorMap mw, my;
     {   // packed W_hh rows: [(dir*H/32 + cta)*128 + gate*32 + ul][H]
         cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)(2 * 4 * H)};
@@ -445,22 +482,23 @@ int launch_fwd(const pk2_lstm_fwd_args* a, cudaStream_t st) {
         cuuint32_t box[4] = {64, (cuuint32_t)NB, 1, (cuuint32_t)KB};
         if (make_map(&my, a->y, 4, dims, str, box)) return 2;
     }
-    const size_t smem = (size_t)KB * 16384 + (size_t)KB * NB * 128 + (size_t)NB * 512 + 64 + 1024;
-    PK2_CHECK(cudaFuncSetAttribute(lstm_fwd_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PK2_CHECK(cudaMemsetAsync(a->sync, 0, sizeof(unsigned) * 2 * G, st));
+    const size_t smem = (size_t)KB * 16384 + (size_t)NG * KB * NB * 128 + (size_t)NG * NB * 512 + 128 + 1024;
+    PK2_CHECK(cudaFuncSetAttribute(lstm_fwd_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PK2_CHECK(cudaMemsetAsync(a->sync, 0, sizeof(unsigned) * 2 * groups, st));
     FwdDev d;
     d.B = B; d.T = T; d.H = H; d.gx = a->gx;
     d.y = static_cast<__nv_bfloat16*>(a->y);
     d.gates = static_cast<__nv_bfloat16*>(a->gates);
     d.cstate = a->cstate; d.counters = a->sync;
-    lstm_fwd_kernel<NB><<<dim3(H / 32, 2, G), kThreads, smem, st>>>(mw, my, d);
+    lstm_fwd_kernel<NG><<<dim3(H / 32, 2, G), kThreads, smem, st>>>(mw, my, d);
     PK2_POST_LAUNCH();
     return 0;
 }
 
-template <int NB>
+template <int NG>
 int launch_bwd(const pk2_lstm_bwd_args* a, cudaStream_t st) {
-    const int H = a->H, T = a->T, B = a->B, KB = 4 * H / 64, G = (B + NB - 1) / NB;
+    const int H = a->H, T = a->T, B = a->B, KB = 4 * H / 64;
+    const int groups = (B + NB - 1) / NB, G = (groups + NG - 1) / NG;
     CUtensorMap mwt, mdg;
     {   // W_hh^T: [dir*H + j][4H]
         cuuint64_t dims[2] = {(cuuint64_t)(4 * H), (cuuint64_t)(2 * H)};
@@ -473,19 +511,19 @@ int launch_bwd(const pk2_lstm_bwd_args* a, cudaStream_t st) {
         cuuint64_t str[3] = {(cuuint64_t)T * 8 * H * 2, (cuuint64_t)(8 * H) * 2, 128};
         const int ch = (kChunkBytes / (NB * 128)) < KB ? (kChunkBytes / (NB * 128)) : KB;
         cuuint32_t box[4] = {64, (cuuint32_t)NB, 1, (cuuint32_t)ch};
-        PK2_REQUIRE(KB % ch == 0, "pk2_lstm_layer_bwd: hidden size %d not supported with batch group %d", H, NB);
+        PK2_REQUIRE(KB % ch == 0, "pk2_lstm_layer_bwd: hidden size %d not supported", H);
         if (make_map(&mdg, a->dgates, 4, dims, str, box)) return 2;
     }
-    const size_t smem = (size_t)KB * 4096 + (size_t)kRing * kChunkBytes + kASlack + (size_t)((NB * 33 * 4 + 7) & ~7) + 128 + 1024;
-    PK2_CHECK(cudaFuncSetAttribute(lstm_bwd_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PK2_CHECK(cudaMemsetAsync(a->sync, 0, sizeof(unsigned) * 2 * G, st));
+    const size_t smem = (size_t)KB * 4096 + (size_t)kRing * kChunkBytes + kASlack + (size_t)((NG * NB * 33 * 4 + 7) & ~7) + 128 + 1024;
+    PK2_CHECK(cudaFuncSetAttribute(lstm_bwd_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PK2_CHECK(cudaMemsetAsync(a->sync, 0, sizeof(unsigned) * 2 * groups, st));
     BwdDev d;
     d.B = B; d.T = T; d.H = H; d.dy = a->dy;
     d.gates = static_cast<const __nv_bfloat16*>(a->gates);
     d.cstate = a->cstate;
     d.dgates = static_cast<__nv_bfloat16*>(a->dgates);
     d.counters = a->sync;
-    lstm_bwd_kernel<NB><<<dim3(H / 32, 2, G), kThreads, smem, st>>>(mwt, mdg, d);
+    lstm_bwd_kernel<NG><<<dim3(H / 32, 2, G), kThreads, smem, st>>>(mwt, mdg, d);
     PK2_POST_LAUNCH();
     return 0;
 }
@@ -494,14 +532,14 @@ int launch_bwd(const pk2_lstm_bwd_args* a, cudaStream_t st) {
 
 extern "C" int pk2_lstm_layer_fwd(const pk2_lstm_fwd_args* a, void* stream) {
     PK2_REQUIRE(a && a->gx && a->whh && a->y && a->gates && a->cstate && a->sync, "pk2_lstm_layer_fwd: null argument");
-    const int nb = pick_nb(a->B);
-    if (check_dims("pk2_lstm_layer_fwd", a->B, a->T, a->H, nb, num_sms())) return 2;
-    return nb == 32 ? launch_fwd<32>(a, pk2::as_stream(stream)) : launch_fwd<64>(a, pk2::as_stream(stream));
+    const int ng = a->B > NB ? 2 : 1;            // interleave two batch groups per CTA whenever there are two
+    if (check_dims("pk2_lstm_layer_fwd", a->B, a->T, a->H, ng, num_sms())) return 2;
+    return ng == 1 ? launch_fwd<1>(a, pk2::as_stream(stream)) : launch_fwd<2>(a, pk2::as_stream(stream));
 }
 
 extern "C" int pk2_lstm_layer_bwd(const pk2_lstm_bwd_args* a, void* stream) {
     PK2_REQUIRE(a && a->dy && a->whh_t && a->gates && a->cstate && a->dgates && a->sync, "pk2_lstm_layer_bwd: null argument");
-    const int nb = pick_nb(a->B);
-    if (check_dims("pk2_lstm_layer_bwd", a->B, a->T, a->H, nb, num_sms())) return 2;
-    return nb == 32 ? launch_bwd<32>(a, pk2::as_stream(stream)) : launch_bwd<64>(a, pk2::as_stream(stream));
+    const int ng = a->B > NB ? 2 : 1;
+    if (check_dims("pk2_lstm_layer_bwd", a->B, a->T, a->H, ng, num_sms())) return 2;
+    return ng == 1 ? launch_bwd<1>(a, pk2::as_stream(stream)) : launch_bwd<2>(a, pk2::as_stream(stream));
 }

@@ -140,6 +140,8 @@ struct DenGraph {
     bool built[kMaxK + 1] = {false, false, false, false, false};
     SellHost t_fwd[kMaxK + 1], t_bwd[kMaxK + 1], t_pdf[kMaxK + 1];
     std::mutex mu;
+    cudaStream_t side[2] = {nullptr, nullptr};     // side streams for the mixed-cluster schedule
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
 };
 
 // ---------------------------------------------------------------- device helpers ----
@@ -239,6 +241,7 @@ struct DenArgs {
     float* asum_ws;      // [n_seq][max_frames + 2] A(t), t <= T ; slot max_frames+1 = totp
     float* grad;
     double* logz;
+    const int32_t* seq_map;   // sequence handled by cluster i (NULL = identity)
 };
 
 // -------------------------------------------------------------------- forward ----
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(kThreads, 1) den_forward_kernel(DenArgs a) {
     float* part = lraw + Np;        // [2][kMaxK]
     float* red = part + 2 * kMaxK;  // [kWarps + 1]
 
-    const int b = blockIdx.x / K;
+    const int b = a.seq_map ? a.seq_map[blockIdx.x / K] : (int)(blockIdx.x / K);
     const int c = (K == 1) ? 0 : (int)cg::this_cluster().block_rank();
     const int T = a.num_frames[b];
     const float* ll = a.ll + (int64_t)b * a.row_stride_b * N;
@@ -353,7 +356,7 @@ __global__ void __launch_bounds__(kThreads, 1) den_backward_kernel(DenArgs a) {
     float* part = gbuf + gcap;      // [2][kMaxK]
     float* red = part + 2 * kMaxK;
 
-    const int b = blockIdx.x / K;
+    const int b = a.seq_map ? a.seq_map[blockIdx.x / K] : (int)(blockIdx.x / K);
     const int c = (K == 1) ? 0 : (int)cg::this_cluster().block_rank();
     const int T = a.num_frames[b];
     const float* ll = a.ll + (int64_t)b * a.row_stride_b * N;
@@ -450,6 +453,7 @@ size_t bwd_smem_bytes(int S, int N, int K) {
 
 template <int K>
 int launch_den(const DenArgs& args, int n_seq, cudaStream_t st) {
+    if (n_seq <= 0) return 0;
     const size_t sf = fwd_smem_bytes(args.S, args.N), sb = bwd_smem_bytes(args.S, args.N, K);
     PK2_REQUIRE(sb <= 227 * 1024, "pk2_denfb: graph too large for shared memory (S=%d N=%d needs %zu B)",
                 args.S, args.N, sb);
@@ -470,6 +474,46 @@ int launch_den(const DenArgs& args, int n_seq, cudaStream_t st) {
     PK2_CHECK(cudaLaunchKernelEx(&cfg, den_backward_kernel<K>, args));
     PK2_LAUNCHED();
     return 0;
+}
+
+int launch_den_k(int K, const DenArgs& a, int n_seq, cudaStream_t st) {
+    if (K == 1) return launch_den<1>(a, n_seq, st);
+    if (K == 2) return launch_den<2>(a, n_seq, st);
+    return launch_den<4>(a, n_seq, st);
+}
+
+int ensure_tables(DenGraph* g, int K) {
+    std::lock_guard<std::mutex> lk(g->mu);
+    if (!g->built[K]) {
+        if (build_sell(g->rows_fwd, K, &g->t_fwd[K])) return 1;
+        if (build_sell(g->rows_bwd, K, &g->t_bwd[K])) return 1;
+        if (build_sell(g->rows_pdf, K, &g->t_pdf[K])) return 1;
+        g->built[K] = true;
+    }
+    return 0;
+}
+
+// Mixed-cluster schedule: the kernels are persistent per sequence, so a launch lasts as long as its
+// longest sequence.  Give long sequences more CTAs (K = 4), short ones fewer (K = 1) so that all
+// clusters of the batch fit the SMs in ONE wave and finish at about the same time.  Relative
+// per-frame cost of a cluster of K CTAs (measured): K=1: 1.9, K=2: 1.0, K=4: 0.62.
+void plan_clusters(const int32_t* frames, int n, int budget, std::vector<int>* ks) {
+    static const double cost[5] = {0, 1.9, 1.0, 0, 0.62};
+    ks->assign(n, 1);
+    int used = n;
+    for (;;) {
+        int worst = -1;
+        double wt = -1.0;
+        for (int i = 0; i < n; ++i) {
+            const double t = frames[i] * cost[(*ks)[i]];
+            if (t > wt) { wt = t; worst = i; }
+        }
+        if (worst < 0 || (*ks)[worst] == 4) break;
+        const int k = (*ks)[worst], extra = k;            // 1->2 costs 1 CTA, 2->4 costs 2
+        if (used + extra > budget) break;
+        (*ks)[worst] = 2 * k;
+        used += extra;
+    }
 }
 
 }  // namespace
@@ -521,40 +565,87 @@ extern "C" size_t pk2_denfb_workspace_bytes(void* graph, int n_seq, int max_fram
     DenGraph* g = static_cast<DenGraph*>(graph);
     size_t alpha = (size_t)n_seq * (size_t)max_frames * (size_t)g->S * sizeof(float);
     size_t asum = (size_t)n_seq * (size_t)(max_frames + 2) * sizeof(float);
-    return ((alpha + 255) & ~(size_t)255) + ((asum + 255) & ~(size_t)255);
+    size_t maps = (size_t)n_seq * sizeof(int32_t);
+    return ((alpha + 255) & ~(size_t)255) + ((asum + 255) & ~(size_t)255) + ((maps + 255) & ~(size_t)255);
 }
 
-extern "C" int pk2_denfb(void* graph, const float* loglikes, const int32_t* num_frames, int n_seq,
-                         int max_frames, int64_t row_stride_b, float leaky, float deriv_scale,
-                         void* workspace, float* grad, double* logz, int cluster, void* stream) {
+extern "C" int pk2_denfb(void* graph, const float* loglikes, const int32_t* num_frames,
+                         const int32_t* num_frames_h, int n_seq, int max_frames, int64_t row_stride_b,
+                         float leaky, float deriv_scale, void* workspace, float* grad, double* logz,
+                         int cluster, void* stream) {
     PK2_REQUIRE(graph && loglikes && num_frames && workspace && grad && logz, "pk2_denfb: null argument");
     PK2_REQUIRE(n_seq > 0 && max_frames > 0, "pk2_denfb: empty batch");
     PK2_REQUIRE(row_stride_b >= max_frames, "pk2_denfb: row_stride_b < max_frames");
+    PK2_REQUIRE(cluster == 0 || cluster == 1 || cluster == 2 || cluster == 4,
+                "pk2_denfb: cluster must be 0, 1, 2 or 4 (got %d)", cluster);
     DenGraph* g = static_cast<DenGraph*>(graph);
-    int K = cluster;
-    if (K == 0) K = (n_seq * 4 <= 148) ? 4 : ((n_seq * 2 <= 148) ? 2 : 1);
-    PK2_REQUIRE(K == 1 || K == 2 || K == 4, "pk2_denfb: cluster must be 0, 1, 2 or 4 (got %d)", cluster);
-    {
-        std::lock_guard<std::mutex> lk(g->mu);
-        if (!g->built[K]) {
-            if (build_sell(g->rows_fwd, K, &g->t_fwd[K])) return 1;
-            if (build_sell(g->rows_bwd, K, &g->t_bwd[K])) return 1;
-            if (build_sell(g->rows_pdf, K, &g->t_pdf[K])) return 1;
-            g->built[K] = true;
-        }
-    }
+    cudaStream_t st = pk2::as_stream(stream);
     DenArgs a;
-    a.fwd = g->t_fwd[K].dev(); a.bwd = g->t_bwd[K].dev(); a.pdf = g->t_pdf[K].dev();
     a.init = g->init; a.S = g->S; a.N = g->N;
     a.ll = loglikes; a.num_frames = num_frames; a.row_stride_b = row_stride_b; a.max_frames = max_frames;
     a.leaky = leaky; a.deriv_scale = deriv_scale;
     size_t alpha = (size_t)n_seq * (size_t)max_frames * (size_t)g->S * sizeof(float);
     alpha = (alpha + 255) & ~(size_t)255;
+    size_t asum = (size_t)n_seq * (size_t)(max_frames + 2) * sizeof(float);
+    asum = (asum + 255) & ~(size_t)255;
     a.alpha_ws = static_cast<float*>(workspace);
     a.asum_ws = reinterpret_cast<float*>(static_cast<char*>(workspace) + alpha);
-    a.grad = grad; a.logz = logz;
-    cudaStream_t st = pk2::as_stream(stream);
-    if (K == 1) return launch_den<1>(a, n_seq, st);
-    if (K == 2) return launch_den<2>(a, n_seq, st);
-    return launch_den<4>(a, n_seq, st);
+    int32_t* maps_dev = reinterpret_cast<int32_t*>(static_cast<char*>(workspace) + alpha + asum);
+    a.grad = grad; a.logz = logz; a.seq_map = nullptr;
+
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+
+    if (cluster != 0 || num_frames_h == nullptr || n_seq > sms) {
+        // uniform cluster size
+        int K = cluster;
+        if (K == 0) K = (n_seq * 4 <= sms) ? 4 : ((n_seq * 2 <= sms) ? 2 : 1);
+        if (ensure_tables(g, K)) return 1;
+        a.fwd = g->t_fwd[K].dev(); a.bwd = g->t_bwd[K].dev(); a.pdf = g->t_pdf[K].dev();
+        return launch_den_k(K, a, n_seq, st);
+    }
+
+    // length-aware mixed schedule: up to three concurrent launches (K = 4, 2, 1), longest first
+    std::vector<int> ks;
+    plan_clusters(num_frames_h, n_seq, sms, &ks);
+    std::vector<int32_t> order;
+    int count[5] = {0, 0, 0, 0, 0};
+    for (int K : {4, 2, 1}) {
+        std::vector<int> idx;
+        for (int i = 0; i < n_seq; ++i) if (ks[i] == K) idx.push_back(i);
+        std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return num_frames_h[x] > num_frames_h[y]; });
+        for (int i : idx) order.push_back(i);
+        count[K] = (int)idx.size();
+    }
+    PK2_CHECK(cudaMemcpyAsync(maps_dev, order.data(), sizeof(int32_t) * n_seq, cudaMemcpyHostToDevice, st));
+    if (!g->side[0]) {
+        for (int i = 0; i < 2; ++i) {
+            PK2_CHECK(cudaStreamCreateWithFlags(&g->side[i], cudaStreamNonBlocking));
+            PK2_CHECK(cudaEventCreateWithFlags(&g->ev_join[i], cudaEventDisableTiming));
+        }
+        PK2_CHECK(cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming));
+    }
+    PK2_CHECK(cudaEventRecord(g->ev_fork, st));
+    int off = 0, lane = 0;
+    for (int K : {4, 2, 1}) {
+        if (count[K] == 0) continue;
+        if (ensure_tables(g, K)) return 1;
+        DenArgs ak = a;
+        ak.fwd = g->t_fwd[K].dev(); ak.bwd = g->t_bwd[K].dev(); ak.pdf = g->t_pdf[K].dev();
+        ak.seq_map = maps_dev + off;
+        cudaStream_t s = st;
+        if (lane > 0) {
+            s = g->side[lane - 1];
+            PK2_CHECK(cudaStreamWaitEvent(s, g->ev_fork, 0));
+        }
+        if (launch_den_k(K, ak, count[K], s)) return 1;
+        if (lane > 0) {
+            PK2_CHECK(cudaEventRecord(g->ev_join[lane - 1], s));
+            PK2_CHECK(cudaStreamWaitEvent(st, g->ev_join[lane - 1], 0));
+        }
+        off += count[K];
+        ++lane;
+    }
+    return 0;
 }

@@ -8,8 +8,8 @@
 //
 // Persistent, warp-specialised kernel (one CTA per SM, 256 threads):
 //   warp 0   TMA producer  : cp.async.bulk.tensor (SWIZZLE_128B) A/B tiles -> 4-stage smem ring
-//   warp 1   MMA issuer    : one elected thread issues tcgen05.mma (M=128, N=128, K=16) into TMEM
-//   warp 2   TMEM allocator (2 accumulator stages x 128 fp32 columns)
+//   warp 1   MMA issuer    : one elected thread issues tcgen05.mma (M=128, N=256, K=16) into TMEM
+//   warp 2   TMEM allocator (2 accumulator stages x 256 fp32 columns = all 512 columns)
 //   warps 4-7 epilogue     : tcgen05.ld TMEM -> registers -> (+bias) -> global (fp32 or bf16)
 // smem full/empty mbarriers couple TMA and MMA; tmem full/empty mbarriers couple MMA and the
 // epilogue so the epilogue of tile i overlaps the main loop of tile i+1.
@@ -19,13 +19,13 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64;      // BK * 2 B = 128 B = one swizzle row
+constexpr int BM = 128, BN = 256, BK = 64;      // BK * 2 B = 128 B = one swizzle row
 constexpr int kStages = 4;
 constexpr int kAccStages = 2;
 constexpr int kThreads = 256;
 constexpr uint32_t kStageBytesA = BM * BK * 2, kStageBytesB = BN * BK * 2;
 constexpr uint32_t kStageBytes = kStageBytesA + kStageBytesB;
-constexpr uint32_t kTmemCols = kAccStages * BN;  // 256
+constexpr uint32_t kTmemCols = kAccStages * BN;  // 512: the whole TMEM
 
 using namespace tc;
 

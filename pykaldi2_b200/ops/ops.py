@@ -55,7 +55,9 @@ def chain_objf_and_deriv(prediction, den_graph, sup_batch, chain_opts, cluster=0
     if DEN_TIMERS is not None:
         e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
         e0.record()
-    _lib.check(L.pk2_denfb(den_graph.handle, _lib.ptr(prediction), _lib.ptr(nf), B, Tmax, Tmax,
+    nf_h = np.ascontiguousarray(sup_batch.num_frames_host, np.int32)      # host copy: length-aware schedule
+    _lib.check(L.pk2_denfb(den_graph.handle, _lib.ptr(prediction), _lib.ptr(nf), nf_h.ctypes.data_as(_lib.vp),
+                           B, Tmax, Tmax,
                            float(chain_opts.leaky_hmm_coefficient), float(w),
                            _lib.ptr(ws), _lib.ptr(grad), _lib.ptr(logz[0]), int(cluster), _lib.stream()),
                "pk2_denfb")

@@ -1,0 +1,124 @@
+#!/usr/bin/env python
+"""Per-kernel timings on the GPU box (CUDA events, warm, on the launching stream).
+
+  python tools/kernel_bench.py den      # denominator FB: uniform cluster sizes vs the mixed schedule
+  python tools/kernel_bench.py lstm     # recurrent kernels: us per step, forward and backward
+  python tools/kernel_bench.py gemm     # tcgen05 GEMM TFLOP/s on the model's shapes
+  python tools/kernel_bench.py fbank    # fbank GB/s
+Prints one JSON object per measurement (copied into profiles/ by hand).
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def timeit(fn, iters=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return json.load(open(p)) if os.path.exists(p) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+
+
+def bench_den():
+    from pykaldi2_b200 import graphs, synth
+    from pykaldi2_b200.ops import ops
+    N, S = 5768, 8192
+    dev = torch.device("cuda", 0)
+    fst = synth.make_den_fst(S, N, 7, seed=1234)
+    den = graphs.DenominatorGraph(fst, N)
+    A = len(fst["src"])
+    opts = graphs.ChainTrainingOptions(leaky_hmm_coefficient=1e-4)
+    rng = np.random.default_rng(1234)
+    durs = synth.make_durations(64, rng)
+    Ts = [int((int(d * 100) - 1) // 3 + 1) for d in durs]
+    sups = [graphs.Supervision(synth.make_supervision_fst(t, N, rng), t, N) for t in Ts]
+    sb = graphs.SupervisionBatch(sups, device=dev)
+    pred = torch.randn(64, max(Ts), N, device=dev) * 2
+    alg = sum(Ts) * (8 * N + 8 * S) + 24 * A
+    for K in (1, 2, 4, 0):
+        ms = timeit(lambda: ops.chain_objf_and_deriv(pred, den, sb, opts, cluster=K), iters=3, warm=1)
+        # uniform T batch to get the per-frame cost of a cluster size
+        print(json.dumps({"kernel": "denfb+numfb", "cluster": K if K else "mixed", "ms": ms, "frames": sum(Ts),
+                          "max_T": max(Ts), "alg_GBps": alg / ms / 1e6, "frac_hbm": alg / ms / 1e6 / peaks()["hbm_gbs"]}))
+    Tu = 200
+    supu = [graphs.Supervision(synth.make_supervision_fst(Tu, N, rng), Tu, N) for _ in range(16)]
+    sbu = graphs.SupervisionBatch(supu, device=dev)
+    predu = torch.randn(16, Tu, N, device=dev) * 2
+    for K in (1, 2, 4):
+        ms = timeit(lambda: ops.chain_objf_and_deriv(predu, den, sbu, opts, cluster=K), iters=3, warm=1)
+        print(json.dumps({"kernel": "denfb uniform T=200 B=16", "cluster": K, "ms": ms, "us_per_frame": 1e3 * ms / Tu}))
+
+
+def bench_lstm():
+    from pykaldi2_b200.models.lstm import LSTMAM
+    dev = torch.device("cuda", 0)
+    for B, T in ((64, 300), (64, 900), (256, 80), (4, 1500)):
+        model = LSTMAM(80, 5768, 512, 3, 0.0, True).to(dev)
+        x = torch.randn(B, T, 80, device=dev)
+        g = torch.randn(B, T, 5768, device=dev) * 1e-3
+
+        def fwd():
+            with torch.no_grad():
+                model(x)
+
+        def fwdbwd():
+            out = model(x)
+            out.backward(g)
+        mf = timeit(fwd, 3, 1)
+        mfb = timeit(fwdbwd, 3, 1)
+        flops = 125.5e6 * B * T
+        print(json.dumps({"kernel": "LSTMAM 3x512", "B": B, "T": T, "fwd_ms": mf, "fwd_bwd_ms": mfb,
+                          "fwd_us_per_step_layer": 1e3 * mf / (3 * T), "train_TFLOPs": flops / mfb / 1e9}))
+
+
+def bench_gemm():
+    from pykaldi2_b200.models import lstm as L
+    dev = torch.device("cuda", 0)
+    pk = peaks()
+    for M, N, K in ((57600, 4096, 1024), (57600, 5768, 1024), (57600, 1024, 5768), (4096, 1024, 57600),
+                    (5768, 1024, 57600), (2048, 512, 57600), (57600, 1024, 4096), (20480, 4096, 1024), (8192, 8192, 8192)):
+        a = torch.randn(M, K, device=dev).to(torch.bfloat16)
+        b = torch.randn(N, K, device=dev).to(torch.bfloat16)
+        c = torch.empty(M, N, device=dev)
+        ms = timeit(lambda: L._gemm(a, b, c, None, M, N, K, K, K, N), 5, 2)
+        tf = 2.0 * M * N * K / ms / 1e9
+        ms_t = timeit(lambda: torch.matmul(a, b.t()), 5, 2)
+        print(json.dumps({"kernel": "gemm_bf16_nt", "M": M, "N": N, "K": K, "ms": ms, "TFLOPs": tf,
+                          "frac_of_measured_peak": tf / pk["bf16_tflops"], "cublas_ms": ms_t}))
+
+
+def bench_fbank():
+    from pykaldi2_b200 import synth
+    from pykaldi2_b200.data import fbank
+    rng = np.random.default_rng(0)
+    wavs = synth.make_waveforms(synth.make_durations(64, rng), rng)
+    ex = fbank.FbankExtractor()
+    buf, woff, foff = ex.pack(wavs)
+    wd = buf.cuda()
+    ms = timeit(lambda: ex.extract(wd, woff, foff), 10, 3)
+    byts = 4 * buf.numel() + 320 * int(foff[-1])
+    print(json.dumps({"kernel": "fbank", "ms": ms, "audio_s": buf.numel() / 16000.0, "GBps": byts / ms / 1e6,
+                      "frac_hbm": byts / ms / 1e6 / peaks()["hbm_gbs"]}))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["den", "lstm", "gemm", "fbank"]
+    for w in which:
+        {"den": bench_den, "lstm": bench_lstm, "gemm": bench_gemm, "fbank": bench_fbank}[w]()
