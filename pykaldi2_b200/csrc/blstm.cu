@@ -532,14 +532,18 @@ int launch_bwd(const pk2_lstm_bwd_args* a, cudaStream_t st) {
 
 extern "C" int pk2_lstm_layer_fwd(const pk2_lstm_fwd_args* a, void* stream) {
     PK2_REQUIRE(a && a->gx && a->whh && a->y && a->gates && a->cstate && a->sync, "pk2_lstm_layer_fwd: null argument");
-    const int ng = a->B > NB ? 2 : 1;            // interleave two batch groups per CTA whenever there are two
+    // Measured (profiles/kernel_bench_r1_v2.jsonl): interleaving two groups per CTA does not hide the
+    // hand-off latency (period = latency + work either way) and serialises the groups; one group per
+    // CTA, groups side by side on different SMs, is faster.  NG = 2 is kept for batches that would
+    // otherwise not fit the SMs (B > 128).
+    const int ng = a->B > 4 * NB ? 2 : 1;
     if (check_dims("pk2_lstm_layer_fwd", a->B, a->T, a->H, ng, num_sms())) return 2;
     return ng == 1 ? launch_fwd<1>(a, pk2::as_stream(stream)) : launch_fwd<2>(a, pk2::as_stream(stream));
 }
 
 extern "C" int pk2_lstm_layer_bwd(const pk2_lstm_bwd_args* a, void* stream) {
     PK2_REQUIRE(a && a->dy && a->whh_t && a->gates && a->cstate && a->dgates && a->sync, "pk2_lstm_layer_bwd: null argument");
-    const int ng = a->B > NB ? 2 : 1;
+    const int ng = a->B > 4 * NB ? 2 : 1;
     if (check_dims("pk2_lstm_layer_bwd", a->B, a->T, a->H, ng, num_sms())) return 2;
     return ng == 1 ? launch_bwd<1>(a, pk2::as_stream(stream)) : launch_bwd<2>(a, pk2::as_stream(stream));
 }
