@@ -44,9 +44,12 @@ def main():
     parser.add_argument('-print_freq', default=100, type=int, metavar='N', help='print frequency (default: 100)')
     parser.add_argument('-hvd', default=False, type=_common.str2bool, help="multi-GPU data parallelism (NCCL; launch with torchrun)")
     parser.add_argument('-synthetic', default=0, type=int, help="train on this many seeded synthetic utterances")
+    parser.add_argument('-seed', default=1234, type=int, help="random seed (model init, sampling)")
     parser.add_argument('-max_steps', default=0, type=int, help="stop after this many minibatches (0 = whole epoch)")
     args = parser.parse_args()
 
+    th.manual_seed(args.seed)
+    np.random.seed(args.seed)
     config = _common.load_config(args.train_config, args.data_config)
     config["sweep_size"] = args.sweep_size
     config["data_path"] = args.dataPath

@@ -49,9 +49,12 @@ def main():
     parser.add_argument('-save_freq', default=1000, type=int, metavar='N', help='save model frequency (default: 1000)')
     parser.add_argument('-synthetic', default=0, type=int, help="train on this many seeded synthetic utterances")
     parser.add_argument('-batched_loss', default=1, type=int, help="0 = one MMIFunction call per utterance as the reference does")
+    parser.add_argument('-seed', default=1234, type=int, help="random seed (model init, sampling)")
     parser.add_argument('-max_steps', default=0, type=int)
     args = parser.parse_args()
 
+    th.manual_seed(args.seed)
+    np.random.seed(args.seed)
     config = _common.load_config(args.config, args.data)
     config["sweep_size"] = args.sweep_size
     config["data_path"] = args.dataPath

@@ -186,45 +186,65 @@ __device__ __forceinline__ void cluster_barrier() {
     else cg::this_cluster().sync();
 }
 
-// acc over the arcs of every row of this CTA's part; body(row, acc) per row.
+// Per-CTA view of one SELL table, staged once into shared memory: slice (offset, length) and the row
+// ids as uint16 (0xFFFF = padding row).  Re-reading this metadata from L2 every frame (L1 is flushed by
+// every cluster barrier) was the largest fixed per-frame cost of the first version.
+struct TabView {
+    const uint2* arcs;
+    const int2* meta;        // [nsl] {arc offset, slice length}
+    const uint16_t* rows;    // [nsl * 32]
+    int nsl;
+};
+
+__device__ __forceinline__ void stage_table(const SellDev& tb, int part, int2* meta, uint16_t* rows) {
+    const int s0 = tb.part_slice[part], n = tb.part_slice[part + 1] - s0;
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+        const int off = __ldg(&tb.slice_off[s0 + i]);
+        meta[i] = make_int2(off, (__ldg(&tb.slice_off[s0 + i + 1]) - off) >> 5);
+    }
+    for (int i = threadIdx.x; i < n * 32; i += kThreads) {
+        const int r = __ldg(&tb.slice_row[s0 * 32 + i]);
+        rows[i] = r < 0 ? (uint16_t)0xFFFFu : (uint16_t)r;
+    }
+}
+
+// Sum over the arcs of every row of this CTA's part; body(row, acc) per valid row.  A warp streams TWO
+// slices at a time (8 independent 8-byte loads in flight per lane) to cover the L2 latency of the arc
+// records; the two shared-memory gathers per arc are scheduled bank-aware at build time.
 template <class Body>
-__device__ __forceinline__ void sell_pass(const SellDev& tb, int part, const float* __restrict__ ga,
+__device__ __forceinline__ void sell_pass(const TabView& tv, const float* __restrict__ ga,
                                           const float* __restrict__ gb, Body&& body) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int s0 = tb.part_slice[part], s1 = tb.part_slice[part + 1];
-    for (int sl = s0 + warp; sl < s1; sl += kWarps) {
-        const int row = __ldg(&tb.slice_row[sl * 32 + lane]);
-        const int off = __ldg(&tb.slice_off[sl]);
-        const int len = (__ldg(&tb.slice_off[sl + 1]) - off) >> 5;
-        const uint2* p = tb.arcs + off + lane;
-        float acc0 = 0.f, acc1 = 0.f;
-        int k = 0;
-        for (; k + 8 <= len; k += 8) {
-            uint2 r[8];
+    for (int ia = warp; ia < tv.nsl; ia += 2 * kWarps) {
+        const int ib = ia + kWarps;
+        const bool hasb = ib < tv.nsl;
+        const int2 ma = tv.meta[ia];
+        const int2 mb = hasb ? tv.meta[ib] : make_int2(0, 0);
+        const uint2* pa = tv.arcs + ma.x + lane;
+        const uint2* pb = tv.arcs + mb.x + lane;
+        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+        const int lmax = max(ma.y, mb.y);
+        for (int k = 0; k < lmax; k += 4) {
+            uint2 ra[4], rb[4];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) r[q] = __ldg(p + (k + q) * 32);
-#pragma unroll
-            for (int q = 0; q < 8; q += 2) {
-                acc0 = fmaf(ga[r[q].y & 0xffffu], __uint_as_float(r[q].x) * gb[r[q].y >> 16], acc0);
-                acc1 = fmaf(ga[r[q + 1].y & 0xffffu], __uint_as_float(r[q + 1].x) * gb[r[q + 1].y >> 16], acc1);
+            for (int q = 0; q < 4; ++q) {
+                ra[q] = (k + q < ma.y) ? __ldg(pa + (k + q) * 32) : make_uint2(0u, 0u);
+                rb[q] = (k + q < mb.y) ? __ldg(pb + (k + q) * 32) : make_uint2(0u, 0u);
             }
-        }
-        if (k + 4 <= len) {
-            uint2 r[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) r[q] = __ldg(p + (k + q) * 32);
 #pragma unroll
             for (int q = 0; q < 4; q += 2) {
-                acc0 = fmaf(ga[r[q].y & 0xffffu], __uint_as_float(r[q].x) * gb[r[q].y >> 16], acc0);
-                acc1 = fmaf(ga[r[q + 1].y & 0xffffu], __uint_as_float(r[q + 1].x) * gb[r[q + 1].y >> 16], acc1);
+                a0 = fmaf(ga[ra[q].y & 0xffffu], __uint_as_float(ra[q].x) * gb[ra[q].y >> 16], a0);
+                b0 = fmaf(ga[rb[q].y & 0xffffu], __uint_as_float(rb[q].x) * gb[rb[q].y >> 16], b0);
+                a1 = fmaf(ga[ra[q + 1].y & 0xffffu], __uint_as_float(ra[q + 1].x) * gb[ra[q + 1].y >> 16], a1);
+                b1 = fmaf(ga[rb[q + 1].y & 0xffffu], __uint_as_float(rb[q + 1].x) * gb[rb[q + 1].y >> 16], b1);
             }
-            k += 4;
         }
-        for (; k < len; ++k) {
-            const uint2 r0 = __ldg(p + k * 32);
-            acc0 = fmaf(ga[r0.y & 0xffffu], __uint_as_float(r0.x) * gb[r0.y >> 16], acc0);
+        const unsigned rowa = tv.rows[ia * 32 + lane];
+        if (rowa != 0xFFFFu) body((int)rowa, a0 + a1);
+        if (hasb) {
+            const unsigned rowb = tv.rows[ib * 32 + lane];
+            if (rowb != 0xFFFFu) body((int)rowb, b0 + b1);
         }
-        body(row, acc0 + acc1);
     }
 }
 
@@ -244,89 +264,132 @@ struct DenArgs {
     const int32_t* seq_map;   // sequence handled by cluster i (NULL = identity)
 };
 
+constexpr int kInitRegs = 8;     // init[] values a thread keeps in registers (covers S <= 8192)
+
+// Cluster-wide sum of one float per warp: every warp deposits its partial in the `wsum` array of every
+// CTA of the cluster (DSMEM), one cluster barrier, then each CTA adds the K*kWarps partials in a
+// fixed order (bit-identical in all CTAs).  Returns the total; uses one __syncthreads after the barrier.
+template <int K>
+__device__ __forceinline__ float cluster_sum(float warp_partial, float* wsum /* [kMaxK*kWarps] */,
+                                             float* bcast, int c) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        wsum[c * kWarps + warp] = warp_partial;
+        if constexpr (K > 1) {
+            cg::cluster_group cl = cg::this_cluster();
+#pragma unroll
+            for (int q = 1; q < K; ++q) cl.map_shared_rank(wsum, (c + q) % K)[c * kWarps + warp] = warp_partial;
+        }
+    }
+    cluster_barrier<K>();
+    if (warp == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < K; ++q) t += wsum[q * kWarps + lane];
+        t = pk2::warp_sum(t);
+        if (lane == 0) *bcast = t;
+    }
+    __syncthreads();
+    return *bcast;
+}
+
 // -------------------------------------------------------------------- forward ----
 template <int K>
 __global__ void __launch_bounds__(kThreads, 1) den_forward_kernel(DenArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int S = a.S, N = a.N;
     const int Sp = (S + 3) & ~3, Np = (N + 3) & ~3;
+    const int c = (K == 1) ? 0 : (int)cg::this_cluster().block_rank();
+    const int nsl = a.fwd.part_slice[c + 1] - a.fwd.part_slice[c];
     float* buf0 = smem;
     float* buf1 = buf0 + Sp;
     float* ev = buf1 + Sp;          // exp(loglikes[t])
     float* lraw = ev + Np;          // prefetched raw loglikes[t+1]
-    float* part = lraw + Np;        // [2][kMaxK]
-    float* red = part + 2 * kMaxK;  // [kWarps + 1]
+    float* wsum = lraw + Np;        // [2][kMaxK*kWarps] (double-buffered by frame parity)
+    float* red = wsum + 2 * kMaxK * kWarps;   // [kWarps + 1] + bcast[2]
+    int2* meta = reinterpret_cast<int2*>(red + kWarps + 4);
+    uint16_t* rows = reinterpret_cast<uint16_t*>(meta + ((S + 31) / 32 + 2));
 
     const int b = a.seq_map ? a.seq_map[blockIdx.x / K] : (int)(blockIdx.x / K);
-    const int c = (K == 1) ? 0 : (int)cg::this_cluster().block_rank();
     const int T = a.num_frames[b];
     const float* ll = a.ll + (int64_t)b * a.row_stride_b * N;
     float* aws = a.alpha_ws + (int64_t)b * a.max_frames * S;
     float* asum = a.asum_ws + (int64_t)b * (a.max_frames + 2);
     const int r0 = a.fwd.part_row[c], r1 = a.fwd.part_row[c + 1];
 
+    stage_table(a.fwd, c, meta, rows);
+    TabView tv;
+    tv.arcs = a.fwd.arcs; tv.meta = meta; tv.rows = rows; tv.nsl = nsl;
+
     float* cur = buf0;
     float* nxt = buf1;
 
-    // alpha(0) = init, A(0) = sum(init), alpha'(0) = alpha(0) + leaky*A(0)*init
+    // alpha(0) = init, A(0) = sum(init), alpha'(0) = alpha(0) + leaky*A(0)*init ; init kept in registers
+    float rinit[kInitRegs];
     float s = 0.f;
-    for (int j = threadIdx.x; j < S; j += kThreads) { const float v = __ldg(&a.init[j]); cur[j] = v; s += v; }
+#pragma unroll
+    for (int q = 0; q < kInitRegs; ++q) {
+        const int j = threadIdx.x + q * kThreads;
+        rinit[q] = (j < S) ? __ldg(&a.init[j]) : 0.f;
+        s += rinit[q];
+    }
+    for (int j = threadIdx.x + kInitRegs * kThreads; j < S; j += kThreads) s += __ldg(&a.init[j]);
     float A = block_sum(s, red);
-    for (int j = threadIdx.x; j < S; j += kThreads) cur[j] = cur[j] + a.leaky * A * cur[j];
+#pragma unroll
+    for (int q = 0; q < kInitRegs; ++q) {
+        const int j = threadIdx.x + q * kThreads;
+        if (j < S) cur[j] = rinit[q] + a.leaky * A * rinit[q];
+    }
+    for (int j = threadIdx.x + kInitRegs * kThreads; j < S; j += kThreads) {
+        const float v = __ldg(&a.init[j]);
+        cur[j] = v + a.leaky * A * v;
+    }
     if (T > 0) row_prefetch(lraw, ll, N);
     double logsum = 0.0;
-    cluster_barrier<K>();           // peers' shared memory is live from here on
+    cp_async_wait_all();
+    __syncthreads();
+    for (int p = threadIdx.x; p < N; p += kThreads) ev[p] = __expf(fminf(fmaxf(lraw[p], -30.f), 30.f));
+    cluster_barrier<K>();           // peers' shared memory is live from here on; ev / cur complete
+    if (T > 1) row_prefetch(lraw, ll + (int64_t)N, N);
 
     for (int t = 0; t < T; ++t) {
-        // finish frame-t inputs: store alpha'(t) slice, e(t) = exp(clamp(ll[t]))
+        // cur = alpha'(t) (complete in every CTA), ev = e(t), lraw <- loglikes[t+1] in flight
         for (int j = r0 + threadIdx.x; j < r1; j += kThreads) aws[(int64_t)t * S + j] = cur[j];
         if (threadIdx.x == 0 && c == 0) asum[t] = A;
-        cp_async_wait_all();
-        __syncthreads();
-        for (int p = threadIdx.x; p < N; p += kThreads)
-            ev[p] = __expf(fminf(fmaxf(lraw[p], -30.f), 30.f));
-        __syncthreads();
-        if (t + 1 < T) row_prefetch(lraw, ll + (int64_t)(t + 1) * N, N);
 
         const float invA = 1.0f / A;
         float local = 0.f;
-        sell_pass(a.fwd, c, cur, ev, [&](int row, float acc) {
-            if (row >= 0) {
-                const float v = acc * invA;
-                local += v;
-                nxt[row] = v;
-                if constexpr (K > 1) {
-                    cg::cluster_group cl = cg::this_cluster();
-#pragma unroll
-                    for (int q = 1; q < K; ++q) {
-                        float* peer = cl.map_shared_rank(nxt, (c + q) % K);
-                        peer[row] = v;
-                    }
-                }
-            }
-        });
-        const float ps = block_sum(local, red);
-        const int par = t & 1;
-        if (threadIdx.x == 0) {
-            part[par * kMaxK + c] = ps;
+        sell_pass(tv, cur, ev, [&](int row, float acc) {
+            const float v = acc * invA;
+            local += v;
+            nxt[row] = v;
             if constexpr (K > 1) {
                 cg::cluster_group cl = cg::this_cluster();
-                for (int q = 1; q < K; ++q) {
-                    float* peer = cl.map_shared_rank(part, (c + q) % K);
-                    peer[par * kMaxK + c] = ps;
-                }
-            }
-            logsum += log((double)A);
-        }
-        cluster_barrier<K>();
-        float An = 0.f;
 #pragma unroll
-        for (int q = 0; q < K; ++q) An += part[par * kMaxK + q];
+                for (int q = 1; q < K; ++q) cl.map_shared_rank(nxt, (c + q) % K)[row] = v;
+            }
+        });
+        const int par = t & 1;
+        if (threadIdx.x == 0) logsum += log((double)A);
+        const float An = cluster_sum<K>(pk2::warp_sum(local), wsum + par * kMaxK * kWarps, red + kWarps + 1 + par, c);
+        // alpha'(t+1) in place, e(t+1) from the prefetched row
         const float lk = a.leaky * An;
-        for (int j = threadIdx.x; j < S; j += kThreads) nxt[j] = fmaf(lk, __ldg(&a.init[j]), nxt[j]);
+#pragma unroll
+        for (int q = 0; q < kInitRegs; ++q) {
+            const int j = threadIdx.x + q * kThreads;
+            if (j < S) nxt[j] = fmaf(lk, rinit[q], nxt[j]);
+        }
+        for (int j = threadIdx.x + kInitRegs * kThreads; j < S; j += kThreads)
+            nxt[j] = fmaf(lk, __ldg(&a.init[j]), nxt[j]);
+        if (t + 1 < T) {
+            cp_async_wait_all();
+            __syncthreads();                          // lraw visible to all threads; nxt update done
+            for (int p = threadIdx.x; p < N; p += kThreads) ev[p] = __expf(fminf(fmaxf(lraw[p], -30.f), 30.f));
+        }
         A = An;
         float* tmp = cur; cur = nxt; nxt = tmp;
         __syncthreads();
+        if (t + 2 < T) row_prefetch(lraw, ll + (int64_t)(t + 2) * N, N);
     }
     // total probability: sum_j alpha'(T, j)
     float s2 = 0.f;
@@ -346,6 +409,7 @@ __global__ void __launch_bounds__(kThreads, 1) den_backward_kernel(DenArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int S = a.S, N = a.N;
     const int Sp = (S + 3) & ~3, Np = (N + 3) & ~3;
+    const int c = (K == 1) ? 0 : (int)cg::this_cluster().block_rank();
     float* buf0 = smem;
     float* buf1 = buf0 + Sp;
     float* al = buf1 + Sp;          // alpha'(t)
@@ -353,11 +417,19 @@ __global__ void __launch_bounds__(kThreads, 1) den_backward_kernel(DenArgs a) {
     float* lraw = ev + Np;          // prefetched raw loglikes
     float* gbuf = lraw + Np;        // gamma staging for this CTA's pdf range
     const int gcap = ((N + K - 1) / K + 64 + 3) & ~3;
-    float* part = gbuf + gcap;      // [2][kMaxK]
-    float* red = part + 2 * kMaxK;
+    // initial probs for the leaky dot product: shared memory when it fits (K > 1), else read through L2
+    constexpr bool kSinit = (K > 1);
+    float* sinit = gbuf + gcap;
+    float* wsum = sinit + (kSinit ? Sp : 0);   // [2][kMaxK*kWarps]
+    float* red = wsum + 2 * kMaxK * kWarps;
+    int2* meta_b = reinterpret_cast<int2*>(red + kWarps + 4);
+    int2* meta_g = meta_b + ((S + 31) / 32 + 2);
+    uint16_t* rows_b = reinterpret_cast<uint16_t*>(meta_g + ((N + 31) / 32 + 2));
+    const int nsl_b = a.bwd.part_slice[c + 1] - a.bwd.part_slice[c];
+    const int nsl_g = a.pdf.part_slice[c + 1] - a.pdf.part_slice[c];
+    uint16_t* rows_g = rows_b + nsl_b * 32;
 
     const int b = a.seq_map ? a.seq_map[blockIdx.x / K] : (int)(blockIdx.x / K);
-    const int c = (K == 1) ? 0 : (int)cg::this_cluster().block_rank();
     const int T = a.num_frames[b];
     const float* ll = a.ll + (int64_t)b * a.row_stride_b * N;
     float* grad = a.grad + (int64_t)b * a.row_stride_b * N;
@@ -365,17 +437,27 @@ __global__ void __launch_bounds__(kThreads, 1) den_backward_kernel(DenArgs a) {
     const float* asum = a.asum_ws + (int64_t)b * (a.max_frames + 2);
     const int p0 = a.pdf.part_row[c], p1 = a.pdf.part_row[c + 1];
 
-    float* cur = buf0;
-    float* nxt = buf1;
-
     // zero-fill the padded frames of this CTA's pdf range
     for (int t = T; t < a.max_frames; ++t)
         for (int p = p0 + threadIdx.x; p < p1; p += kThreads) grad[(int64_t)t * N + p] = 0.f;
     if (T <= 0) return;   // uniform across the cluster (same sequence)
 
+    stage_table(a.bwd, c, meta_b, rows_b);
+    stage_table(a.pdf, c, meta_g, rows_g);
+    TabView tb, tg;
+    tb.arcs = a.bwd.arcs; tb.meta = meta_b; tb.rows = rows_b; tb.nsl = nsl_b;
+    tg.arcs = a.pdf.arcs; tg.meta = meta_g; tg.rows = rows_g; tg.nsl = nsl_g;
+
+    float* cur = buf0;
+    float* nxt = buf1;
+
     // beta'(T) = 1/totp ; beta(T) = beta'(T) + leaky * sum_k beta'(T,k) init[k]
     float s = 0.f;
-    for (int j = threadIdx.x; j < S; j += kThreads) s += __ldg(&a.init[j]);
+    for (int j = threadIdx.x; j < S; j += kThreads) {
+        const float v = __ldg(&a.init[j]);
+        if (kSinit) sinit[j] = v;
+        s += v;
+    }
     const float isum = block_sum(s, red);
     const float totp = asum[a.max_frames + 1];
     const float bT = (1.0f / totp) * (1.0f + a.leaky * isum);
@@ -395,66 +477,49 @@ __global__ void __launch_bounds__(kThreads, 1) den_backward_kernel(DenArgs a) {
 
         // beta'(t, i) for this CTA's source states
         float local = 0.f;
-        sell_pass(a.bwd, c, cur, ev, [&](int row, float acc) {
-            if (row >= 0) {
-                const float v = acc * invA;
-                local = fmaf(v, __ldg(&a.init[row]), local);
-                nxt[row] = v;
-                if constexpr (K > 1) {
-                    cg::cluster_group cl = cg::this_cluster();
+        sell_pass(tb, cur, ev, [&](int row, float acc) {
+            const float v = acc * invA;
+            local = fmaf(v, kSinit ? sinit[row] : __ldg(&a.init[row]), local);
+            nxt[row] = v;
+            if constexpr (K > 1) {
+                cg::cluster_group cl = cg::this_cluster();
 #pragma unroll
-                    for (int q = 1; q < K; ++q) {
-                        float* peer = cl.map_shared_rank(nxt, (c + q) % K);
-                        peer[row] = v;
-                    }
-                }
+                for (int q = 1; q < K; ++q) cl.map_shared_rank(nxt, (c + q) % K)[row] = v;
             }
         });
         // pdf occupancies gamma(t, p) for this CTA's pdf range
         const float gs = a.deriv_scale * invA;
-        sell_pass(a.pdf, c, al, cur, [&](int row, float acc) {
-            if (row >= 0) gbuf[row - p0] = acc * ev[row] * gs;
-        });
-        const float ps = block_sum(local, red);      // contains __syncthreads: gbuf / al reads complete
+        sell_pass(tg, al, cur, [&](int row, float acc) { gbuf[row - p0] = acc * ev[row] * gs; });
+        const int par = t & 1;
+        const float dot = cluster_sum<K>(pk2::warp_sum(local), wsum + par * kMaxK * kWarps, red + kWarps + 1 + par, c);
+        // (cluster barrier passed: gbuf / al reads of this frame are complete in this CTA)
         for (int p = p0 + threadIdx.x; p < p1; p += kThreads) grad[(int64_t)t * N + p] = gbuf[p - p0];
         if (t > 0) row_prefetch(al, aws + (int64_t)(t - 1) * S, S);
-        const int par = t & 1;
-        if (threadIdx.x == 0) {
-            part[par * kMaxK + c] = ps;
-            if constexpr (K > 1) {
-                cg::cluster_group cl = cg::this_cluster();
-                for (int q = 1; q < K; ++q) {
-                    float* peer = cl.map_shared_rank(part, (c + q) % K);
-                    peer[par * kMaxK + c] = ps;
-                }
-            }
-        }
-        cluster_barrier<K>();
-        float dot = 0.f;
-#pragma unroll
-        for (int q = 0; q < K; ++q) dot += part[par * kMaxK + q];
         const float lk = a.leaky * dot;
         for (int j = threadIdx.x; j < S; j += kThreads) nxt[j] += lk;
         float* tmp = cur; cur = nxt; nxt = tmp;
-        __syncthreads();
     }
     cluster_barrier<K>();
 }
 
-size_t fwd_smem_bytes(int S, int N) {
+size_t fwd_smem_bytes(int S, int N, int K) {
     const size_t Sp = (S + 3) & ~3, Np = (N + 3) & ~3;
-    return sizeof(float) * (2 * Sp + 2 * Np + 2 * kMaxK + kWarps + 1 + 3);
+    const size_t rows_part = (size_t)((S + K - 1) / K + 64);            // rows staged per CTA (+ slice padding)
+    return sizeof(float) * (2 * Sp + 2 * Np + 2 * kMaxK * kWarps + kWarps + 4) +
+           sizeof(int2) * ((S + 31) / 32 + 2) + sizeof(uint16_t) * (rows_part + 32) + 64;
 }
 size_t bwd_smem_bytes(int S, int N, int K) {
     const size_t Sp = (S + 3) & ~3, Np = (N + 3) & ~3;
     const size_t gcap = ((N + K - 1) / K + 64 + 3) & ~3;
-    return sizeof(float) * (3 * Sp + 2 * Np + gcap + 2 * kMaxK + kWarps + 1 + 3);
+    const size_t rows_part = (size_t)((S + K - 1) / K + 64) + (size_t)((N + K - 1) / K + 64);
+    return sizeof(float) * ((K > 1 ? 4 : 3) * Sp + 2 * Np + gcap + 2 * kMaxK * kWarps + kWarps + 4) +
+           sizeof(int2) * ((S + 31) / 32 + (N + 31) / 32 + 4) + sizeof(uint16_t) * (rows_part + 64) + 64;
 }
 
 template <int K>
 int launch_den(const DenArgs& args, int n_seq, cudaStream_t st) {
     if (n_seq <= 0) return 0;
-    const size_t sf = fwd_smem_bytes(args.S, args.N), sb = bwd_smem_bytes(args.S, args.N, K);
+    const size_t sf = fwd_smem_bytes(args.S, args.N, K), sb = bwd_smem_bytes(args.S, args.N, K);
     PK2_REQUIRE(sb <= 227 * 1024, "pk2_denfb: graph too large for shared memory (S=%d N=%d needs %zu B)",
                 args.S, args.N, sb);
     PK2_CHECK(cudaFuncSetAttribute(den_forward_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sf));
