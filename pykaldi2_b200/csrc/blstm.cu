@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include <mutex>
+#include <stdlib.h>
 
 using namespace tc;
 
@@ -233,6 +234,169 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
     tc_fence_before();
     __syncthreads();
     if (warp == 5) tmem_dealloc(tmem_base, NG * NB < 32 ? 32 : NG * NB);
+}
+
+// ------------------------------------------------------------ forward, cluster + DSMEM ----
+// Same recurrence, but the H/32 CTAs of one (direction, batch group) form ONE thread-block cluster and
+// exchange h_t through distributed shared memory instead of global memory: after the cell update each
+// CTA stages its [NB x 32] bf16 slice and sends it to every CTA of the cluster with one bulk copy
+// (cp.async.bulk.shared::cluster) whose completion bytes land on the RECEIVER's mbarrier.  The receiver's
+// MMA warp simply waits on that mbarrier: no global flag, no acquire poll, no TMA round trip through L2
+// on the critical path.  The h operand uses the SWIZZLE_NONE K-major layout
+// [K/8 chunks][NB/8 row groups][8 rows][16 B] so that each sender's slice is one contiguous 2 KB block.
+// h tiles are double buffered (a sender may run one step ahead of a receiver's MMA).
+__global__ void __launch_bounds__(kThreads, 1)
+lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int H = p.H, T = p.T, B = p.B;
+    const int KB = H / 64;
+    constexpr int kChunk = NB / 8 * 128;                     // bytes of one 16-byte K-chunk over NB rows
+    constexpr int kSlice = NB * 64;                          // bytes one CTA contributes per step
+    const int hs_bytes = H * NB * 2;
+    uint8_t* Ws = smem;                                      // KB x [128 x 64] bf16, SWIZZLE_128B
+    uint8_t* Hb = Ws + KB * 16384;                           // 2 x [H/8 chunks][NB/8][8][16 B]
+    float* gxs = reinterpret_cast<float*>(Hb + 2 * hs_bytes);    // [NB][128] fp32
+    uint8_t* stg = reinterpret_cast<uint8_t*>(gxs) + NB * 512;   // 2 x kSlice
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stg + 2 * kSlice);
+    uint64_t* wbar = bars + 0;
+    uint64_t* hfull = bars + 1;          // [2]
+    uint64_t* gbar = bars + 3;
+    uint64_t* mbar = bars + 4;
+    uint64_t* gfree = bars + 5;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int CS = gridDim.x;                                // cluster size = H/32
+    const int cta = (int)cluster_ctarank();                  // == blockIdx.x
+    const int dir = blockIdx.y, grp = blockIdx.z;
+    const int u0 = cta * 32, b0 = grp * NB;
+    const int nbv = min(NB, B - b0);
+    const uint32_t step_bytes = (uint32_t)CS * kSlice;
+
+    if (threadIdx.x == 0) {
+        mbar_init(wbar, 1); mbar_init(&hfull[0], 1); mbar_init(&hfull[1], 1);
+        mbar_init(gbar, 1); mbar_init(mbar, 1); mbar_init(gfree, 1);
+        fence_barrier_init();
+        if (T >= 2) mbar_expect_tx(&hfull[0], step_bytes);    // h_0
+        if (T >= 3) mbar_expect_tx(&hfull[1], step_bytes);    // h_1
+    }
+    for (int i = threadIdx.x; i < NB * 128; i += kThreads) gxs[i] = 0.f;   // padded batch rows stay finite
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // before the bulk copies write gxs
+    if (warp == 5) tmem_alloc(tmem_slot, 32);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                      // every CTA's barriers are initialised
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_expect_tx(wbar, (uint32_t)KB * 16384u);
+            for (int kb = 0; kb < KB; ++kb)
+                tma_load_2d(&map_w, wbar, Ws + kb * 16384, kb * 64, (dir * CS + cta) * 128);
+            uint32_t ph_free = 0;
+            for (int s = 0; s < T; ++s) {
+                const int tt = dir ? (T - 1 - s) : s;
+                if (s > 0) { mbar_wait(gfree, ph_free); ph_free ^= 1; }
+                const float* src = p.gx + ((((int64_t)tt * 2 + dir) * CS + cta) * B + b0) * 128;
+                mbar_expect_tx(gbar, (uint32_t)nbv * 512u);
+                bulk_load(gxs, src, (uint32_t)nbv * 512u, gbar);
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(128, NB);
+            mbar_wait(wbar, 0);
+            for (int s = 1; s < T; ++s) {
+                const int buf = (s - 1) & 1;
+                mbar_wait(&hfull[buf], (uint32_t)(((s - 1) >> 1) & 1));      // h_{s-1} from all CTAs
+                if (s + 1 <= T - 2) mbar_expect_tx(&hfull[buf], step_bytes);  // re-arm for h_{s+1}
+                tc_fence_after();
+                const uint32_t hb = smem_u32(Hb + buf * hs_bytes);
+                for (int kk = 0; kk < H / 16; ++kk) {
+                    const uint64_t adesc = make_sw128_desc(smem_u32(Ws + (kk >> 2) * 16384)) + (uint64_t)((kk & 3) * 2);
+                    const uint64_t bdesc = make_nosw_desc(hb + kk * 2 * kChunk, kChunk, 128);
+                    tc_mma_bf16(tmem_base, adesc, bdesc, idesc, (uint32_t)(kk != 0));
+                }
+                tc_commit(mbar);
+            }
+        }
+    } else {
+        const int r = threadIdx.x;
+        const int gate = warp;
+        float cst[NB / 4];
+#pragma unroll
+        for (int k = 0; k < NB / 4; ++k) cst[k] = 0.f;
+        uint32_t ph_g = 0, ph_m = 0;
+        for (int s = 0; s < T; ++s) {
+            const int tt = dir ? (T - 1 - s) : s;
+            float acc[NB];
+            if (s > 0) {
+                mbar_wait(mbar, ph_m); ph_m ^= 1;
+                tc_fence_after();
+                uint32_t v[32];
+                tc_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16), v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
+                tc_fence_before();
+            } else {
+#pragma unroll
+                for (int j = 0; j < NB; ++j) acc[j] = 0.f;
+            }
+            mbar_wait(gbar, ph_g); ph_g ^= 1;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const float v = acc[b] + gxs[b * 128 + r];
+                gxs[b * 128 + r] = (gate == 2) ? tanhf_fast(v) : sigmoidf_fast(v);
+            }
+            named_bar_sync(1, kEpiThreads);
+            // cell update (lane = unit, warp w handles rows w, w+4, ...); h_t goes to the staging slice
+            __nv_bfloat16 hv[NB / 4];
+            uint8_t* st = stg + (s & 1) * kSlice;
+#pragma unroll
+            for (int k = 0; k < NB / 4; ++k) {
+                const int b = warp + 4 * k;
+                const float ig = gxs[b * 128 + lane], fg = gxs[b * 128 + 32 + lane];
+                const float gg = gxs[b * 128 + 64 + lane], og = gxs[b * 128 + 96 + lane];
+                const float c = fmaf(fg, cst[k], ig * gg);
+                cst[k] = c;
+                hv[k] = __float2bfloat16(og * tanhf_fast(c));
+                *reinterpret_cast<__nv_bfloat16*>(st + (lane >> 3) * kChunk + (b >> 3) * 128 + (b & 7) * 16 + (lane & 7) * 2) = hv[k];
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            named_bar_sync(1, kEpiThreads);
+            if (s < T - 1 && warp == 0 && lane < CS) {
+                // my slice -> CTA `lane` of the cluster: Hb[s&1] + cta*kSlice there, bytes counted on its hfull[s&1]
+                const uint32_t dst = mapa_u32(smem_u32(Hb + (s & 1) * hs_bytes + cta * kSlice), (uint32_t)lane);
+                const uint32_t bar = mapa_u32(smem_u32(&hfull[s & 1]), (uint32_t)lane);
+                dsmem_bulk_copy(dst, smem_u32(st), (uint32_t)kSlice, bar);
+            }
+            // off the critical path: layer output, gates and cell state to global memory
+            {
+                __nv_bfloat16* yo = p.y + ((int64_t)b0 * T + tt) * 2 * H + dir * H + u0 + lane;
+                float* co = p.cstate + (((int64_t)dir * T + tt) * B + b0) * H + u0 + lane;
+                __nv_bfloat16* gout = p.gates + (((int64_t)dir * T + tt) * B + b0) * 4 * H + u0 + lane;
+#pragma unroll
+                for (int k = 0; k < NB / 4; ++k) {
+                    const int b = warp + 4 * k;
+                    if (b < nbv) {
+                        yo[(int64_t)b * T * 2 * H] = hv[k];
+                        co[(int64_t)b * H] = cst[k];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            gout[((int64_t)b * 4 + q) * H] = __float2bfloat16(gxs[b * 128 + q * 32 + lane]);
+                    }
+                }
+            }
+            named_bar_sync(1, kEpiThreads);
+            if (threadIdx.x == 0) mbar_arrive(gfree);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                  // peers have consumed everything this CTA sent
+    if (warp == 5) tmem_dealloc(tmem_base, 32);
 }
 
 // -------------------------------------------------------------------------- backward ----
@@ -495,6 +659,54 @@ int launch_fwd(const pk2_lstm_fwd_args* a, cudaStream_t st) {
     return 0;
 }
 
+// Cluster/DSMEM forward: returns 0 on success, -1 if this device cannot co-schedule the clusters.
+int launch_fwd_cluster(const pk2_lstm_fwd_args* a, cudaStream_t st) {
+    const int H = a->H, T = a->T, B = a->B, KB = H / 64, CS = H / 32;
+    const int G = (B + NB - 1) / NB;
+    if (CS > 16 || (CS & (CS - 1)) != 0) return -1;
+    CUtensorMap mw;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)(2 * 4 * H)};
+        cuuint64_t str[1] = {(cuuint64_t)H * 2};
+        cuuint32_t box[2] = {64, 128};
+        if (make_map(&mw, a->whh, 2, dims, str, box)) return 2;
+    }
+    const size_t smem = (size_t)KB * 16384 + 2 * (size_t)H * NB * 2 + (size_t)NB * 512 + 2 * NB * 64 + 128 + 1024;
+    static bool attr_done = false, usable = true;
+    if (!attr_done) {
+        attr_done = true;
+        if (cudaFuncSetAttribute(lstm_fwd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) != cudaSuccess ||
+            cudaFuncSetAttribute(lstm_fwd_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+            cudaGetLastError();
+            usable = false;
+        }
+    }
+    if (!usable) return -1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CS, 2, G);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, lstm_fwd_cluster_kernel, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    if (max_clusters < 1) return -1;             // clusters are independent: fewer resident ones just run in waves
+    FwdDev d;
+    d.B = B; d.T = T; d.H = H; d.gx = a->gx;
+    d.y = static_cast<__nv_bfloat16*>(a->y);
+    d.gates = static_cast<__nv_bfloat16*>(a->gates);
+    d.cstate = a->cstate; d.counters = a->sync;
+    PK2_CHECK(cudaLaunchKernelEx(&cfg, lstm_fwd_cluster_kernel, mw, d));
+    PK2_LAUNCHED();
+    return 0;
+}
+
 template <int NG>
 int launch_bwd(const pk2_lstm_bwd_args* a, cudaStream_t st) {
     const int H = a->H, T = a->T, B = a->B, KB = 4 * H / 64;
@@ -538,6 +750,11 @@ extern "C" int pk2_lstm_layer_fwd(const pk2_lstm_fwd_args* a, void* stream) {
     // otherwise not fit the SMs (B > 128).
     const int ng = a->B > 4 * NB ? 2 : 1;
     if (check_dims("pk2_lstm_layer_fwd", a->B, a->T, a->H, ng, num_sms())) return 2;
+    static const bool no_cluster = getenv("PK2_LSTM_NO_CLUSTER") != nullptr;
+    if (!no_cluster) {
+        const int rc = launch_fwd_cluster(a, pk2::as_stream(stream));
+        if (rc >= 0) return rc;                   // -1: clusters of H/32 CTAs not schedulable -> global-memory exchange
+    }
     return ng == 1 ? launch_fwd<1>(a, pk2::as_stream(stream)) : launch_fwd<2>(a, pk2::as_stream(stream));
 }
 

@@ -24,6 +24,7 @@
 #include <vector>
 #include <mutex>
 #include <string.h>
+#include <stdlib.h>
 
 namespace cg = cooperative_groups;
 
@@ -213,8 +214,9 @@ __device__ __forceinline__ void stage_table(const SellDev& tb, int part, int2* m
 // records; the two shared-memory gathers per arc are scheduled bank-aware at build time.
 template <class Body>
 __device__ __forceinline__ void sell_pass(const TabView& tv, const float* __restrict__ ga,
-                                          const float* __restrict__ gb, Body&& body) {
+                                          const float* __restrict__ gb, Body&& body, int debug = 0) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (debug == 2) return;
     for (int ia = warp; ia < tv.nsl; ia += 2 * kWarps) {
         const int ib = ia + kWarps;
         const bool hasb = ib < tv.nsl;
@@ -223,7 +225,7 @@ __device__ __forceinline__ void sell_pass(const TabView& tv, const float* __rest
         const uint2* pa = tv.arcs + ma.x + lane;
         const uint2* pb = tv.arcs + mb.x + lane;
         float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-        const int lmax = max(ma.y, mb.y);
+        const int lmax = debug == 1 ? 0 : max(ma.y, mb.y);
         for (int k = 0; k < lmax; k += 4) {
             uint2 ra[4], rb[4];
 #pragma unroll
@@ -262,6 +264,7 @@ struct DenArgs {
     float* grad;
     double* logz;
     const int32_t* seq_map;   // sequence handled by cluster i (NULL = identity)
+    int debug;                // profiling only (PK2_DEN_DEBUG): 1 = skip the arc loops, 2 = skip the passes
 };
 
 constexpr int kInitRegs = 8;     // init[] values a thread keeps in registers (covers S <= 8192)
@@ -368,7 +371,7 @@ __global__ void __launch_bounds__(kThreads, 1) den_forward_kernel(DenArgs a) {
 #pragma unroll
                 for (int q = 1; q < K; ++q) cl.map_shared_rank(nxt, (c + q) % K)[row] = v;
             }
-        });
+        }, a.debug);
         const int par = t & 1;
         if (threadIdx.x == 0) logsum += log((double)A);
         const float An = cluster_sum<K>(pk2::warp_sum(local), wsum + par * kMaxK * kWarps, red + kWarps + 1 + par, c);
@@ -486,10 +489,10 @@ __global__ void __launch_bounds__(kThreads, 1) den_backward_kernel(DenArgs a) {
 #pragma unroll
                 for (int q = 1; q < K; ++q) cl.map_shared_rank(nxt, (c + q) % K)[row] = v;
             }
-        });
+        }, a.debug);
         // pdf occupancies gamma(t, p) for this CTA's pdf range
         const float gs = a.deriv_scale * invA;
-        sell_pass(tg, al, cur, [&](int row, float acc) { gbuf[row - p0] = acc * ev[row] * gs; });
+        sell_pass(tg, al, cur, [&](int row, float acc) { gbuf[row - p0] = acc * ev[row] * gs; }, a.debug);
         const int par = t & 1;
         const float dot = cluster_sum<K>(pk2::warp_sum(local), wsum + par * kMaxK * kWarps, red + kWarps + 1 + par, c);
         // (cluster barrier passed: gbuf / al reads of this frame are complete in this CTA)
@@ -657,6 +660,7 @@ extern "C" int pk2_denfb(void* graph, const float* loglikes, const int32_t* num_
     a.asum_ws = reinterpret_cast<float*>(static_cast<char*>(workspace) + alpha);
     int32_t* maps_dev = reinterpret_cast<int32_t*>(static_cast<char*>(workspace) + alpha + asum);
     a.grad = grad; a.logz = logz; a.seq_map = nullptr;
+    { const char* e = getenv("PK2_DEN_DEBUG"); a.debug = e ? atoi(e) : 0; }
 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
