@@ -108,6 +108,13 @@ typedef struct {
 int pk2_numfb(const pk2_sup_batch* sup, const float* loglikes, int num_pdfs, int64_t row_stride_b,
               float deriv_scale, double* ws_alpha, double* ws_beta, float* grad, double* logz,
               void* stream);
+/* Split form, so that the numerator can run on a side stream while the denominator kernels run:
+ * pk2_numfb_post computes log Z_num and the per-arc posteriors arc_post[A_tot] (no write to grad);
+ * pk2_numfb_scatter adds deriv_scale * arc_post into grad afterwards (after pk2_denfb). */
+int pk2_numfb_post(const pk2_sup_batch* sup, const float* loglikes, int num_pdfs, int64_t row_stride_b,
+                   double* ws_alpha, double* ws_beta, float* arc_post, double* logz, void* stream);
+int pk2_numfb_scatter(const pk2_sup_batch* sup, int total_states, const float* arc_post, int num_pdfs,
+                      int64_t row_stride_b, float deriv_scale, float* grad, void* stream);
 
 /* ------------------------------------------------------------ lattice MMI --
  * Replaces lattice_forward_backward_mmi + Posterior.to_pdf_matrix (ops/ops.py:57-62)

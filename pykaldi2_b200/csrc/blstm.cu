@@ -351,14 +351,18 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
                 gxs[b * 128 + r] = (gate == 2) ? tanhf_fast(v) : sigmoidf_fast(v);
             }
             named_bar_sync(1, kEpiThreads);
-            // cell update (lane = unit, warp w handles rows w, w+4, ...); h_t goes to the staging slice
+            // cell update (lane = unit, warp w handles rows w, w+4, ...); h_t goes to the staging slice.
+            // The activations are copied to registers so the Gx buffer can be refilled right away.
             __nv_bfloat16 hv[NB / 4];
+            __nv_bfloat16 gv[NB / 4][4];
             uint8_t* st = stg + (s & 1) * kSlice;
 #pragma unroll
             for (int k = 0; k < NB / 4; ++k) {
                 const int b = warp + 4 * k;
                 const float ig = gxs[b * 128 + lane], fg = gxs[b * 128 + 32 + lane];
                 const float gg = gxs[b * 128 + 64 + lane], og = gxs[b * 128 + 96 + lane];
+                gv[k][0] = __float2bfloat16(ig); gv[k][1] = __float2bfloat16(fg);
+                gv[k][2] = __float2bfloat16(gg); gv[k][3] = __float2bfloat16(og);
                 const float c = fmaf(fg, cst[k], ig * gg);
                 cst[k] = c;
                 hv[k] = __float2bfloat16(og * tanhf_fast(c));
@@ -366,6 +370,7 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             named_bar_sync(1, kEpiThreads);
+            if (threadIdx.x == 0) mbar_arrive(gfree);          // Gx buffer consumed: prefetch the next step now
             if (s < T - 1 && warp == 0 && lane < CS) {
                 // my slice -> CTA `lane` of the cluster: Hb[s&1] + cta*kSlice there, bytes counted on its hfull[s&1]
                 const uint32_t dst = mapa_u32(smem_u32(Hb + (s & 1) * hs_bytes + cta * kSlice), (uint32_t)lane);
@@ -384,13 +389,10 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
                         yo[(int64_t)b * T * 2 * H] = hv[k];
                         co[(int64_t)b * H] = cst[k];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            gout[((int64_t)b * 4 + q) * H] = __float2bfloat16(gxs[b * 128 + q * 32 + lane]);
+                        for (int q = 0; q < 4; ++q) gout[((int64_t)b * 4 + q) * H] = gv[k][q];
                     }
                 }
             }
-            named_bar_sync(1, kEpiThreads);
-            if (threadIdx.x == 0) mbar_arrive(gfree);
         }
     }
     tc_fence_before();

@@ -13,7 +13,7 @@ namespace {
 __global__ void __launch_bounds__(32)
 numfb_kernel(pk2_sup_batch sup, const float* __restrict__ loglikes, int N, int64_t row_stride_b,
              float deriv_scale, double* alpha, double* beta,
-             float* __restrict__ grad, double* __restrict__ logz) {
+             float* __restrict__ grad, double* __restrict__ logz, float* __restrict__ arc_post) {
     const int b = blockIdx.x;
     const int lane = threadIdx.x;
     const int T = sup.num_frames[b];
@@ -59,7 +59,8 @@ numfb_kernel(pk2_sup_batch sup, const float* __restrict__ loglikes, int N, int64
                 const double sc = (double)row[p] - (double)sup.out_w[k] + beta[sup.out_dst[k]];
                 acc = pk2::log_add(acc, sc);
                 const double post = exp(a + sc - z);
-                if (post > 0.0) atomicAdd(&g[(int64_t)t * N + p], deriv_scale * (float)post);
+                if (arc_post) arc_post[k] = (float)post;          // split mode: scatter later
+                else if (post > 0.0) atomicAdd(&g[(int64_t)t * N + p], deriv_scale * (float)post);
             }
             beta[s] = acc;
         }
@@ -67,7 +68,46 @@ numfb_kernel(pk2_sup_batch sup, const float* __restrict__ loglikes, int N, int64
     }
 }
 
+// grad[b, time(s), pdf] += scale * arc_post[k] for every out-arc k of every state s (split mode)
+__global__ void num_scatter_kernel(pk2_sup_batch sup, int total_states, const float* __restrict__ arc_post, int N,
+                                   int64_t row_stride_b, float scale, float* __restrict__ grad) {
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < total_states; s += gridDim.x * blockDim.x) {
+        int lo = 0, hi = sup.n_seq;                 // sequence of this state
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (sup.seq_state_off[mid] <= s) lo = mid; else hi = mid;
+        }
+        float* g = grad + ((int64_t)lo * row_stride_b + sup.state_time[s]) * N;
+        for (int k = sup.out_off[s]; k < sup.out_off[s + 1]; ++k) {
+            const float v = arc_post[k];
+            if (v > 0.f) atomicAdd(&g[sup.out_pdf[k]], scale * v);
+        }
+    }
+}
+
 }  // namespace
+
+extern "C" int pk2_numfb_post(const pk2_sup_batch* sup, const float* loglikes, int num_pdfs, int64_t row_stride_b,
+                              double* ws_alpha, double* ws_beta, float* arc_post, double* logz, void* stream) {
+    PK2_REQUIRE(sup && loglikes && ws_alpha && ws_beta && arc_post && logz, "pk2_numfb_post: null argument");
+    PK2_REQUIRE(sup->n_seq > 0, "pk2_numfb_post: empty batch");
+    numfb_kernel<<<sup->n_seq, 32, 0, pk2::as_stream(stream)>>>(*sup, loglikes, num_pdfs, row_stride_b, 0.f, ws_alpha,
+                                                              ws_beta, nullptr, logz, arc_post);
+    PK2_POST_LAUNCH();
+    return 0;
+}
+
+extern "C" int pk2_numfb_scatter(const pk2_sup_batch* sup, int total_states, const float* arc_post, int num_pdfs,
+                                 int64_t row_stride_b, float deriv_scale, float* grad, void* stream) {
+    PK2_REQUIRE(sup && arc_post && grad, "pk2_numfb_scatter: null argument");
+    if (total_states <= 0) return 0;
+    int blocks = (total_states + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    num_scatter_kernel<<<blocks, 256, 0, pk2::as_stream(stream)>>>(*sup, total_states, arc_post, num_pdfs, row_stride_b,
+                                                                 deriv_scale, grad);
+    PK2_POST_LAUNCH();
+    return 0;
+}
 
 extern "C" int pk2_numfb(const pk2_sup_batch* sup, const float* loglikes, int num_pdfs,
                          int64_t row_stride_b, float deriv_scale, double* ws_alpha, double* ws_beta,
@@ -75,7 +115,7 @@ extern "C" int pk2_numfb(const pk2_sup_batch* sup, const float* loglikes, int nu
     PK2_REQUIRE(sup && loglikes && ws_alpha && ws_beta && grad && logz, "pk2_numfb: null argument");
     PK2_REQUIRE(sup->n_seq > 0, "pk2_numfb: empty batch");
     numfb_kernel<<<sup->n_seq, 32, 0, pk2::as_stream(stream)>>>(*sup, loglikes, num_pdfs, row_stride_b,
-                                                              deriv_scale, ws_alpha, ws_beta, grad, logz);
+                                                              deriv_scale, ws_alpha, ws_beta, grad, logz, nullptr);
     PK2_POST_LAUNCH();
     return 0;
 }

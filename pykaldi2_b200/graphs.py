@@ -210,6 +210,7 @@ class SupervisionBatch(object):
         sbase = np.concatenate([[0], np.cumsum(ns)])
         abase = np.concatenate([[0], np.cumsum([len(s.out_dst) for s in sups])])
         self.total_states = int(sbase[-1])
+        self.total_arcs = int(sum(len(s.out_dst) for s in sups))
         self.num_frames_host = [s.frames_per_sequence for s in sups]
         lvl_base = np.concatenate([[0], np.cumsum([len(s.level_off) for s in sups])])[:-1]
         host = {
