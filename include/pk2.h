@@ -171,6 +171,8 @@ typedef struct {
     unsigned int* sync;     /* [2*ceil(B/32)] step counters (zeroed by the call) */
 } pk2_lstm_fwd_args;
 int pk2_lstm_layer_fwd(const pk2_lstm_fwd_args* a, void* stream);
+/* profiling aid: device int64[128] receiving clock64() stamps of 8 steps of one CTA; NULL = off */
+int pk2_lstm_set_profile_buffer(void* buf);
 
 typedef struct {
     int B, T, H;
@@ -180,6 +182,8 @@ typedef struct {
     const float* cstate;    /* from forward */
     void* dgates;           /* bf16 [B,T,2,4H] grad wrt gate pre-activations (output; also the exchange) */
     unsigned int* sync;     /* [2*ceil(B/32)] */
+    const void* whh_t_perm; /* bf16 [2*H, 4H]: whh_t with the 4H index permuted to cta*128 + gate*32 + unit
+                               (cta = unit/32): operand of the cluster/DSMEM kernel; NULL = global-memory kernel */
 } pk2_lstm_bwd_args;
 int pk2_lstm_layer_bwd(const pk2_lstm_bwd_args* a, void* stream);
 

@@ -39,7 +39,7 @@ class LstmFwdArgs(C.Structure):
 
 class LstmBwdArgs(C.Structure):
     _fields_ = [("B", C.c_int), ("T", C.c_int), ("H", C.c_int)] + [(n, vp) for n in (
-        "dy", "whh_t", "gates", "cstate", "dgates", "sync")]
+        "dy", "whh_t", "gates", "cstate", "dgates", "sync", "whh_t_perm")]
 
 
 _SIGS = {
@@ -70,6 +70,7 @@ _SIGS = {
     "pk2_colsum_bf16": (C.c_int, [vp, vp, C.c_int64, C.c_int, vp]),
     "pk2_lstm_input_proj": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "pk2_lstm_layer_fwd": (C.c_int, [C.POINTER(LstmFwdArgs), vp]),
+    "pk2_lstm_set_profile_buffer": (C.c_int, [vp]),
     "pk2_lstm_layer_bwd": (C.c_int, [C.POINTER(LstmBwdArgs), vp]),
 }
 

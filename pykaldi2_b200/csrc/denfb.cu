@@ -19,6 +19,7 @@
 // frame HBM traffic is the loglike row (cp.async prefetched), the alpha row (written in the
 // forward, re-read in the backward) and the gradient row.
 #include "common.cuh"
+#include "tc_ptx.cuh"
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <vector>
@@ -212,7 +213,10 @@ __device__ __forceinline__ void stage_table(const SellDev& tb, int part, int2* m
 // Sum over the arcs of every row of this CTA's part; body(row, acc) per valid row.  A warp streams TWO
 // slices at a time (8 independent 8-byte loads in flight per lane) to cover the L2 latency of the arc
 // records; the two shared-memory gathers per arc are scheduled bank-aware at build time.
-template <class Body>
+// MODE 0: acc  = sum ga[a] * (w * gb[b])
+// MODE 1: also acc2 = sum w * gb[b]          (beta pass with the leaky term applied lazily)
+// MODE 2: also acc2 = sum ga[a] * w          (occupancy pass with the leaky term applied lazily)
+template <int MODE, class Body>
 __device__ __forceinline__ void sell_pass(const TabView& tv, const float* __restrict__ ga,
                                           const float* __restrict__ gb, Body&& body, int debug = 0) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -224,7 +228,7 @@ __device__ __forceinline__ void sell_pass(const TabView& tv, const float* __rest
         const int2 mb = hasb ? tv.meta[ib] : make_int2(0, 0);
         const uint2* pa = tv.arcs + ma.x + lane;
         const uint2* pb = tv.arcs + mb.x + lane;
-        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f, a2 = 0.f, b2 = 0.f;
         const int lmax = debug == 1 ? 0 : max(ma.y, mb.y);
         for (int k = 0; k < lmax; k += 4) {
             uint2 ra[4], rb[4];
@@ -234,18 +238,21 @@ __device__ __forceinline__ void sell_pass(const TabView& tv, const float* __rest
                 rb[q] = (k + q < mb.y) ? __ldg(pb + (k + q) * 32) : make_uint2(0u, 0u);
             }
 #pragma unroll
-            for (int q = 0; q < 4; q += 2) {
-                a0 = fmaf(ga[ra[q].y & 0xffffu], __uint_as_float(ra[q].x) * gb[ra[q].y >> 16], a0);
-                b0 = fmaf(ga[rb[q].y & 0xffffu], __uint_as_float(rb[q].x) * gb[rb[q].y >> 16], b0);
-                a1 = fmaf(ga[ra[q + 1].y & 0xffffu], __uint_as_float(ra[q + 1].x) * gb[ra[q + 1].y >> 16], a1);
-                b1 = fmaf(ga[rb[q + 1].y & 0xffffu], __uint_as_float(rb[q + 1].x) * gb[rb[q + 1].y >> 16], b1);
+            for (int q = 0; q < 4; ++q) {
+                const float wa = __uint_as_float(ra[q].x), wb = __uint_as_float(rb[q].x);
+                const float ga_a = ga[ra[q].y & 0xffffu], ga_b = ga[rb[q].y & 0xffffu];
+                const float ta = wa * gb[ra[q].y >> 16], tb = wb * gb[rb[q].y >> 16];
+                if (q & 1) { a1 = fmaf(ga_a, ta, a1); b1 = fmaf(ga_b, tb, b1); }
+                else       { a0 = fmaf(ga_a, ta, a0); b0 = fmaf(ga_b, tb, b0); }
+                if (MODE == 1) { a2 += ta; b2 += tb; }
+                if (MODE == 2) { a2 = fmaf(ga_a, wa, a2); b2 = fmaf(ga_b, wb, b2); }
             }
         }
         const unsigned rowa = tv.rows[ia * 32 + lane];
-        if (rowa != 0xFFFFu) body((int)rowa, a0 + a1);
+        if (rowa != 0xFFFFu) body((int)rowa, a0 + a1, a2);
         if (hasb) {
             const unsigned rowb = tv.rows[ib * 32 + lane];
-            if (rowb != 0xFFFFu) body((int)rowb, b0 + b1);
+            if (rowb != 0xFFFFu) body((int)rowb, b0 + b1, b2);
         }
     }
 }
@@ -269,31 +276,59 @@ struct DenArgs {
 
 constexpr int kInitRegs = 8;     // init[] values a thread keeps in registers (covers S <= 8192)
 
-// Cluster-wide sum of one float per warp: every warp deposits its partial in the `wsum` array of every
-// CTA of the cluster (DSMEM), one cluster barrier, then each CTA adds the K*kWarps partials in a
-// fixed order (bit-identical in all CTAs).  Returns the total; uses one __syncthreads after the barrier.
+// End of a pass: every CTA of the cluster needs (a) the rows the other CTAs computed and (b) the sum
+// of one scalar per CTA.  Each CTA has written its own rows [r0, r1) into its LOCAL copy of `vec`;
+// one thread then pushes that contiguous row block (and a 16-byte slot with the CTA's partial sum)
+// into every peer's shared memory with a DSMEM bulk copy whose completion bytes are counted on the
+// PEER's mbarrier.  No scattered remote stores, no cluster barrier on the per-frame path.
+// Returns the cluster-wide sum (added in a fixed order: bit-identical in all CTAs).
+struct XchgState {
+    uint64_t* bar;       // [2] one mbarrier per frame parity
+    float* parts;        // [2][kMaxK * 4] partial sums (16-byte slots)
+    float* wsum;         // [kWarps]
+    uint32_t phase;      // bit par = phase parity of bar[par]
+    uint32_t expect;     // bytes received from the peers per frame
+};
+
 template <int K>
-__device__ __forceinline__ float cluster_sum(float warp_partial, float* wsum /* [kMaxK*kWarps] */,
-                                             float* bcast, int c) {
+__device__ __forceinline__ float cluster_exchange(XchgState& x, float* vec, const float* src_rows, int r0, int r1,
+                                                  float warp_partial, int par, int c) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) {
-        wsum[c * kWarps + warp] = warp_partial;
+    if (lane == 0) x.wsum[warp] = warp_partial;
+    if constexpr (K > 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // my row writes -> async proxy
+    __syncthreads();
+    float* parts = x.parts + par * kMaxK * 4;
+    if (warp == 0) {
+        float t = pk2::warp_sum(x.wsum[lane]);
+        if (lane == 0) parts[c * 4] = t;
         if constexpr (K > 1) {
-            cg::cluster_group cl = cg::this_cluster();
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                const uint32_t rows_l = tc::smem_u32(vec + r0), src_l = tc::smem_u32(src_rows);
+                const uint32_t part_l = tc::smem_u32(parts + c * 4);
+                const uint32_t bar_l = tc::smem_u32(&x.bar[par]);
 #pragma unroll
-            for (int q = 1; q < K; ++q) cl.map_shared_rank(wsum, (c + q) % K)[c * kWarps + warp] = warp_partial;
+                for (int q = 1; q < K; ++q) {
+                    const uint32_t peer = (uint32_t)((c + q) % K);
+                    const uint32_t bar_r = tc::mapa_u32(bar_l, peer);
+                    tc::dsmem_bulk_copy(tc::mapa_u32(rows_l, peer), src_l, (uint32_t)(r1 - r0) * 4u, bar_r);
+                    tc::dsmem_bulk_copy(tc::mapa_u32(part_l, peer), part_l, 16u, bar_r);
+                }
+            }
         }
     }
-    cluster_barrier<K>();
-    if (warp == 0) {
-        float t = 0.f;
-#pragma unroll
-        for (int q = 0; q < K; ++q) t += wsum[q * kWarps + lane];
-        t = pk2::warp_sum(t);
-        if (lane == 0) *bcast = t;
+    if constexpr (K > 1) {
+        tc::mbar_wait(&x.bar[par], (x.phase >> par) & 1u);
+        x.phase ^= (1u << par);
+        __syncthreads();                       // everyone has seen this phase before it is re-armed
+        if (threadIdx.x == 0) tc::mbar_expect_tx(&x.bar[par], x.expect);   // arm for frame t+2
+    } else {
+        __syncthreads();
     }
-    __syncthreads();
-    return *bcast;
+    float tot = 0.f;
+#pragma unroll
+    for (int q = 0; q < K; ++q) tot += parts[q * 4];
+    return tot;
 }
 
 // -------------------------------------------------------------------- forward ----
@@ -308,10 +343,15 @@ __global__ void __launch_bounds__(kThreads, 1) den_forward_kernel(DenArgs a) {
     float* buf1 = buf0 + Sp;
     float* ev = buf1 + Sp;          // exp(loglikes[t])
     float* lraw = ev + Np;          // prefetched raw loglikes[t+1]
-    float* wsum = lraw + Np;        // [2][kMaxK*kWarps] (double-buffered by frame parity)
-    float* red = wsum + 2 * kMaxK * kWarps;   // [kWarps + 1] + bcast[2]
-    int2* meta = reinterpret_cast<int2*>(red + kWarps + 4);
+    float* wsum = lraw + Np;        // [kWarps] + parts [2][kMaxK*4]
+    float* red = wsum + 2 * kMaxK * kWarps;   // [kWarps + 1]
+    uint64_t* xbar = reinterpret_cast<uint64_t*>(red + kWarps + 4);          // [2] exchange mbarriers
+    int2* meta = reinterpret_cast<int2*>(xbar + 2);
     uint16_t* rows = reinterpret_cast<uint16_t*>(meta + ((S + 31) / 32 + 2));
+    const int rcap = ((S + K - 1) / K + 64 + 3) & ~3;                         // rows per CTA (padded)
+    // outgoing copy of this CTA's rows, double buffered: alpha(t+1) is updated in place (leaky term)
+    // while the bulk copy of the raw rows may still be reading its source
+    float* stage = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(rows + rcap + 32) + 15) & ~(uintptr_t)15);
 
     const int b = a.seq_map ? a.seq_map[blockIdx.x / K] : (int)(blockIdx.x / K);
     const int T = a.num_frames[b];
@@ -323,6 +363,15 @@ __global__ void __launch_bounds__(kThreads, 1) den_forward_kernel(DenArgs a) {
     stage_table(a.fwd, c, meta, rows);
     TabView tv;
     tv.arcs = a.fwd.arcs; tv.meta = meta; tv.rows = rows; tv.nsl = nsl;
+    XchgState xs;
+    xs.bar = xbar; xs.wsum = wsum; xs.parts = wsum + kWarps; xs.phase = 0;
+    xs.expect = (uint32_t)(S - (r1 - r0)) * 4u + (uint32_t)(K - 1) * 16u;
+    if (K > 1 && threadIdx.x == 0) {
+        tc::mbar_init(&xbar[0], 1); tc::mbar_init(&xbar[1], 1);
+        tc::fence_barrier_init();
+        tc::mbar_expect_tx(&xbar[0], xs.expect);
+        tc::mbar_expect_tx(&xbar[1], xs.expect);
+    }
 
     float* cur = buf0;
     float* nxt = buf1;
@@ -362,19 +411,16 @@ __global__ void __launch_bounds__(kThreads, 1) den_forward_kernel(DenArgs a) {
 
         const float invA = 1.0f / A;
         float local = 0.f;
-        sell_pass(tv, cur, ev, [&](int row, float acc) {
+        const int par = t & 1;
+        float* stg = stage + par * rcap;
+        sell_pass<0>(tv, cur, ev, [&](int row, float acc, float) {
             const float v = acc * invA;
             local += v;
             nxt[row] = v;
-            if constexpr (K > 1) {
-                cg::cluster_group cl = cg::this_cluster();
-#pragma unroll
-                for (int q = 1; q < K; ++q) cl.map_shared_rank(nxt, (c + q) % K)[row] = v;
-            }
+            if (K > 1) stg[row - r0] = v;
         }, a.debug);
-        const int par = t & 1;
         if (threadIdx.x == 0) logsum += log((double)A);
-        const float An = cluster_sum<K>(pk2::warp_sum(local), wsum + par * kMaxK * kWarps, red + kWarps + 1 + par, c);
+        const float An = cluster_exchange<K>(xs, nxt, stg, r0, r1, pk2::warp_sum(local), par, c);
         // alpha'(t+1) in place, e(t+1) from the prefetched row
         const float lk = a.leaky * An;
 #pragma unroll
@@ -423,9 +469,10 @@ __global__ void __launch_bounds__(kThreads, 1) den_backward_kernel(DenArgs a) {
     // initial probs for the leaky dot product: shared memory when it fits (K > 1), else read through L2
     constexpr bool kSinit = (K > 1);
     float* sinit = gbuf + gcap;
-    float* wsum = sinit + (kSinit ? Sp : 0);   // [2][kMaxK*kWarps]
+    float* wsum = sinit + (kSinit ? Sp : 0);   // [kWarps] + parts [2][kMaxK*4]
     float* red = wsum + 2 * kMaxK * kWarps;
-    int2* meta_b = reinterpret_cast<int2*>(red + kWarps + 4);
+    uint64_t* xbar = reinterpret_cast<uint64_t*>(red + kWarps + 4);
+    int2* meta_b = reinterpret_cast<int2*>(xbar + 2);
     int2* meta_g = meta_b + ((S + 31) / 32 + 2);
     uint16_t* rows_b = reinterpret_cast<uint16_t*>(meta_g + ((N + 31) / 32 + 2));
     const int nsl_b = a.bwd.part_slice[c + 1] - a.bwd.part_slice[c];
@@ -450,6 +497,16 @@ __global__ void __launch_bounds__(kThreads, 1) den_backward_kernel(DenArgs a) {
     TabView tb, tg;
     tb.arcs = a.bwd.arcs; tb.meta = meta_b; tb.rows = rows_b; tb.nsl = nsl_b;
     tg.arcs = a.pdf.arcs; tg.meta = meta_g; tg.rows = rows_g; tg.nsl = nsl_g;
+    const int r0 = a.bwd.part_row[c], r1 = a.bwd.part_row[c + 1];
+    XchgState xs;
+    xs.bar = xbar; xs.wsum = wsum; xs.parts = wsum + kWarps; xs.phase = 0;
+    xs.expect = (uint32_t)(S - (r1 - r0)) * 4u + (uint32_t)(K - 1) * 16u;
+    if (K > 1 && threadIdx.x == 0) {
+        tc::mbar_init(&xbar[0], 1); tc::mbar_init(&xbar[1], 1);
+        tc::fence_barrier_init();
+        tc::mbar_expect_tx(&xbar[0], xs.expect);
+        tc::mbar_expect_tx(&xbar[1], xs.expect);
+    }
 
     float* cur = buf0;
     float* nxt = buf1;
@@ -463,7 +520,10 @@ __global__ void __launch_bounds__(kThreads, 1) den_backward_kernel(DenArgs a) {
     }
     const float isum = block_sum(s, red);
     const float totp = asum[a.max_frames + 1];
-    const float bT = (1.0f / totp) * (1.0f + a.leaky * isum);
+    // cur holds beta'(t+1) WITHOUT the leaky term; beta = beta' + lk with the scalar lk = leaky * sum_k beta'_k init_k.
+    // (beta' rows are exchanged by asynchronous bulk copies, so they are never modified in place.)
+    const float bT = 1.0f / totp;
+    float lk = a.leaky * isum * bT;
     for (int j = threadIdx.x; j < S; j += kThreads) cur[j] = bT;
     row_prefetch(lraw, ll + (int64_t)(T - 1) * N, N);
     row_prefetch(al, aws + (int64_t)(T - 1) * S, S);
@@ -480,26 +540,22 @@ __global__ void __launch_bounds__(kThreads, 1) den_backward_kernel(DenArgs a) {
 
         // beta'(t, i) for this CTA's source states
         float local = 0.f;
-        sell_pass(tb, cur, ev, [&](int row, float acc) {
-            const float v = acc * invA;
+        sell_pass<1>(tb, cur, ev, [&](int row, float acc, float acc2) {
+            const float v = fmaf(lk, acc2, acc) * invA;
             local = fmaf(v, kSinit ? sinit[row] : __ldg(&a.init[row]), local);
             nxt[row] = v;
-            if constexpr (K > 1) {
-                cg::cluster_group cl = cg::this_cluster();
-#pragma unroll
-                for (int q = 1; q < K; ++q) cl.map_shared_rank(nxt, (c + q) % K)[row] = v;
-            }
         }, a.debug);
         // pdf occupancies gamma(t, p) for this CTA's pdf range
         const float gs = a.deriv_scale * invA;
-        sell_pass(tg, al, cur, [&](int row, float acc) { gbuf[row - p0] = acc * ev[row] * gs; }, a.debug);
+        sell_pass<2>(tg, al, cur, [&](int row, float acc, float acc2) {
+            gbuf[row - p0] = fmaf(lk, acc2, acc) * ev[row] * gs;
+        }, a.debug);
         const int par = t & 1;
-        const float dot = cluster_sum<K>(pk2::warp_sum(local), wsum + par * kMaxK * kWarps, red + kWarps + 1 + par, c);
-        // (cluster barrier passed: gbuf / al reads of this frame are complete in this CTA)
+        const float dot = cluster_exchange<K>(xs, nxt, nxt + r0, r0, r1, pk2::warp_sum(local), par, c);
+        // (block barrier passed inside: gbuf / al reads of this frame are complete in this CTA)
         for (int p = p0 + threadIdx.x; p < p1; p += kThreads) grad[(int64_t)t * N + p] = gbuf[p - p0];
         if (t > 0) row_prefetch(al, aws + (int64_t)(t - 1) * S, S);
-        const float lk = a.leaky * dot;
-        for (int j = threadIdx.x; j < S; j += kThreads) nxt[j] += lk;
+        lk = a.leaky * dot;
         float* tmp = cur; cur = nxt; nxt = tmp;
     }
     cluster_barrier<K>();
@@ -508,15 +564,16 @@ __global__ void __launch_bounds__(kThreads, 1) den_backward_kernel(DenArgs a) {
 size_t fwd_smem_bytes(int S, int N, int K) {
     const size_t Sp = (S + 3) & ~3, Np = (N + 3) & ~3;
     const size_t rows_part = (size_t)((S + K - 1) / K + 64);            // rows staged per CTA (+ slice padding)
-    return sizeof(float) * (2 * Sp + 2 * Np + 2 * kMaxK * kWarps + kWarps + 4) +
-           sizeof(int2) * ((S + 31) / 32 + 2) + sizeof(uint16_t) * (rows_part + 32) + 64;
+    const size_t rcap = (rows_part + 3) & ~(size_t)3;
+    return sizeof(float) * (2 * Sp + 2 * Np + 2 * kMaxK * kWarps + kWarps + 4 + (K > 1 ? 2 * rcap : 0)) +
+           sizeof(int2) * ((S + 31) / 32 + 2) + sizeof(uint16_t) * (rows_part + 32 + 32) + 64 + 32;
 }
 size_t bwd_smem_bytes(int S, int N, int K) {
     const size_t Sp = (S + 3) & ~3, Np = (N + 3) & ~3;
     const size_t gcap = ((N + K - 1) / K + 64 + 3) & ~3;
     const size_t rows_part = (size_t)((S + K - 1) / K + 64) + (size_t)((N + K - 1) / K + 64);
     return sizeof(float) * ((K > 1 ? 4 : 3) * Sp + 2 * Np + gcap + 2 * kMaxK * kWarps + kWarps + 4) +
-           sizeof(int2) * ((S + 31) / 32 + (N + 31) / 32 + 4) + sizeof(uint16_t) * (rows_part + 64) + 64;
+           sizeof(int2) * ((S + 31) / 32 + (N + 31) / 32 + 4) + sizeof(uint16_t) * (rows_part + 64) + 64 + 16;
 }
 
 template <int K>
@@ -666,6 +723,10 @@ extern "C" int pk2_denfb(void* graph, const float* loglikes, const int32_t* num_
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 
+    if (g->S % 4 != 0) {            // the DSMEM row exchange moves 16-byte multiples: single-CTA clusters only
+        PK2_REQUIRE(cluster == 0 || cluster == 1, "pk2_denfb: num_states %% 4 != 0 supports cluster = 1 only");
+        cluster = 1;
+    }
     if (cluster != 0 || num_frames_h == nullptr || n_seq > sms) {
         // uniform cluster size
         int K = cluster;

@@ -142,6 +142,22 @@ __device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster, uint32_t s
     asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(mbar_cluster) : "memory");
 }
+// arrive (release, cluster scope) on an mbarrier that lives in another CTA of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t mbar_cluster) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mbar_cluster) : "memory");
+}
+// wait with acquire at cluster scope (pairs with mbar_arrive_remote)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP_C:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra WAIT_DONE_C;\n"
+        "bra WAIT_LOOP_C;\n"
+        "WAIT_DONE_C:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 // K-major, SWIZZLE_NONE matrix descriptor: 8x16-byte core matrices; LBO = byte distance between the two
 // 16-byte K-chunks of one K=16 step, SBO = byte distance between 8-row groups (layout_type 0, version 1)
 __device__ __forceinline__ uint64_t make_nosw_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {

@@ -126,10 +126,13 @@ class _BlstmAM(Function):
             if saved["mask"][l] is not None:
                 dy = dy * saved["mask"][l].view(M, 2 * H).float()
             whh_t = _cast(th.cat([whh_f.t(), whh_b.t()], 0).contiguous())        # [2H, 4H]
+            # same matrix with the 4H index permuted to cta*128 + gate*32 + unit (cluster/DSMEM kernel)
+            whh_tp = _cast(th.stack([whh_f, whh_b], 0).view(2, 4, H // 32, 32, H).permute(0, 2, 1, 3, 4)
+                           .reshape(2, 4 * H, H).transpose(1, 2).reshape(2 * H, 4 * H).contiguous())
             dgates = th.empty(B, T, 2, 4 * H, dtype=th.bfloat16, device=dev)
             sync = th.empty(2 * ((B + 31) // 32), dtype=th.int32, device=dev)
             a = _lib.LstmBwdArgs(B, T, H, dy.data_ptr(), whh_t.data_ptr(), saved["gates"][l].data_ptr(),
-                                 saved["cstate"][l].data_ptr(), dgates.data_ptr(), sync.data_ptr())
+                                 saved["cstate"][l].data_ptr(), dgates.data_ptr(), sync.data_ptr(), whh_tp.data_ptr())
             _lib.check(lib.pk2_lstm_layer_bwd(C.byref(a), _lib.stream()), "pk2_lstm_layer_bwd")
             dg2 = dgates.view(M, 8 * H)
             dg_t, ldm = _transpose(dg2, M, 8 * H, 8 * H)                          # [8H, pad8(M)]
