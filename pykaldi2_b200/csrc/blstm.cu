@@ -52,6 +52,14 @@ struct BwdDev {
     unsigned* counters;
 };
 
+// tanh.approx.f32: one MUFU op, max relative error 2^-11 -- below the bf16 rounding the gates and h
+// receive anyway.  sigmoid(x) = 0.5 * tanh(0.5 x) + 0.5.
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoid_approx(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
 __device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanhf_fast(float x) {
     // 2*sigmoid(2x) - 1, exact enough for the 1e-3 parity budget and safe for large |x|
@@ -353,10 +361,21 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
             if (threadIdx.x == 0) PK2_PROF(3);
             mbar_wait(gbar, ph_g); ph_g ^= 1;
             if (threadIdx.x == 0) PK2_PROF(4);
+            // all loads first, then 32 independent activations, then all stores (the in-place
+            // read-modify-write loop serialised on the load->MUFU->store latency chain: 97 cycles/element)
+            {
+                float gxr[NB];
 #pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                const float v = acc[b] + gxs[b * 128 + r];
-                gxs[b * 128 + r] = (gate == 2) ? tanhf_fast(v) : sigmoidf_fast(v);
+                for (int b = 0; b < NB; ++b) gxr[b] = gxs[b * 128 + r];
+                if (gate == 2) {
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) gxr[b] = tanh_approx(acc[b] + gxr[b]);
+                } else {
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) gxr[b] = sigmoid_approx(acc[b] + gxr[b]);
+                }
+#pragma unroll
+                for (int b = 0; b < NB; ++b) gxs[b * 128 + r] = gxr[b];
             }
             named_bar_sync(1, kEpiThreads);
             if (threadIdx.x == 0) PK2_PROF(5);
@@ -365,25 +384,37 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
             __nv_bfloat16 hv[NB / 4];
             __nv_bfloat16 gv[NB / 4][4];
             uint8_t* st = stg + (s & 1) * kSlice;
+            {
+                float gi[NB / 4], gf[NB / 4], gg_[NB / 4], go[NB / 4], tc_[NB / 4];
 #pragma unroll
-            for (int k = 0; k < NB / 4; ++k) {
-                const int b = warp + 4 * k;
-                const float ig = gxs[b * 128 + lane], fg = gxs[b * 128 + 32 + lane];
-                const float gg = gxs[b * 128 + 64 + lane], og = gxs[b * 128 + 96 + lane];
-                gv[k][0] = __float2bfloat16(ig); gv[k][1] = __float2bfloat16(fg);
-                gv[k][2] = __float2bfloat16(gg); gv[k][3] = __float2bfloat16(og);
-                const float c = fmaf(fg, cst[k], ig * gg);
-                cst[k] = c;
-                hv[k] = __float2bfloat16(og * tanhf_fast(c));
-                *reinterpret_cast<__nv_bfloat16*>(st + (lane >> 3) * kChunk + (b >> 3) * 128 + (b & 7) * 16 + (lane & 7) * 2) = hv[k];
+                for (int k = 0; k < NB / 4; ++k) {
+                    const int b = warp + 4 * k;
+                    gi[k] = gxs[b * 128 + lane]; gf[k] = gxs[b * 128 + 32 + lane];
+                    gg_[k] = gxs[b * 128 + 64 + lane]; go[k] = gxs[b * 128 + 96 + lane];
+                }
+#pragma unroll
+                for (int k = 0; k < NB / 4; ++k) {
+                    cst[k] = fmaf(gf[k], cst[k], gi[k] * gg_[k]);
+                    tc_[k] = tanh_approx(cst[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < NB / 4; ++k) {
+                    const int b = warp + 4 * k;
+                    gv[k][0] = __float2bfloat16(gi[k]); gv[k][1] = __float2bfloat16(gf[k]);
+                    gv[k][2] = __float2bfloat16(gg_[k]); gv[k][3] = __float2bfloat16(go[k]);
+                    hv[k] = __float2bfloat16(go[k] * tc_[k]);
+                    *reinterpret_cast<__nv_bfloat16*>(st + (lane >> 3) * kChunk + (b >> 3) * 128 + (b & 7) * 16 + (lane & 7) * 2) = hv[k];
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             named_bar_sync(1, kEpiThreads);
             if (threadIdx.x == 0) { PK2_PROF(6); mbar_arrive(gfree); }   // Gx buffer consumed: prefetch the next step now
-            if (s < T - 1 && warp == 0 && lane < CS) {
-                // my slice -> CTA `lane` of the cluster: Hb[s&1] + cta*kSlice there, bytes counted on its hfull[s&1]
-                const uint32_t dst = mapa_u32(smem_u32(Hb + (s & 1) * hs_bytes + cta * kSlice), (uint32_t)lane);
-                const uint32_t bar = mapa_u32(smem_u32(&hfull[s & 1]), (uint32_t)lane);
+            if (s < T - 1 && (threadIdx.x & 7) == 0 && (threadIdx.x >> 3) < CS) {
+                // my slice -> CTA `rank` of the cluster (Hb[s&1] + cta*kSlice there); bytes are counted on its
+                // hfull[s&1].  The 16 copies are issued by 4 lanes of each of the 4 warps.
+                const uint32_t rank = threadIdx.x >> 3;
+                const uint32_t dst = mapa_u32(smem_u32(Hb + (s & 1) * hs_bytes + cta * kSlice), rank);
+                const uint32_t bar = mapa_u32(smem_u32(&hfull[s & 1]), rank);
                 dsmem_bulk_copy(dst, smem_u32(st), (uint32_t)kSlice, bar);
             }
             if (threadIdx.x == 0) PK2_PROF(7);
@@ -1003,8 +1034,11 @@ extern "C" int pk2_lstm_layer_bwd(const pk2_lstm_bwd_args* a, void* stream) {
     PK2_REQUIRE(a && a->dy && a->whh_t && a->gates && a->cstate && a->dgates && a->sync, "pk2_lstm_layer_bwd: null argument");
     const int ng = a->B > 4 * NB ? 2 : 1;
     if (check_dims("pk2_lstm_layer_bwd", a->B, a->T, a->H, ng, num_sms())) return 2;
-    static const bool no_cluster = getenv("PK2_LSTM_NO_CLUSTER") != nullptr;
-    if (!no_cluster) {
+    // The all-gather cluster kernel is correct but measured slower than the global-memory kernel (128
+    // A-read-bound MMAs per step and only 7 co-resident 16-CTA clusters on B200: profiles/README_r1.md);
+    // it stays selectable for experiments.
+    static const bool use_cluster = getenv("PK2_LSTM_BWD_CLUSTER") != nullptr;
+    if (use_cluster) {
         const int rc = launch_bwd_cluster(a, pk2::as_stream(stream));
         if (rc >= 0) return rc;
     }
