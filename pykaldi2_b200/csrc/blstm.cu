@@ -41,6 +41,7 @@ struct FwdDev {
     float* cstate;              // [2][T][B][H]
     unsigned* counters;         // [G][2]
     long long* prof;            // optional per-step clock64 trace of CTA (0,0,0) (profiling only)
+    int a_tmem;                 // 1: keep the W_hh slice (A operand) in tensor memory instead of shared memory
 };
 
 struct BwdDev {
@@ -273,7 +274,8 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
     uint64_t* gbar = bars + 3;
     uint64_t* mbar = bars + 4;
     uint64_t* gfree = bars + 5;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    uint64_t* abar = bars + 6;           // W slice copied into tensor memory
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int CS = gridDim.x;                                // cluster size = H/32
@@ -287,14 +289,15 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
 
     if (threadIdx.x == 0) {
         mbar_init(wbar, 1); mbar_init(&hfull[0], 1); mbar_init(&hfull[1], 1);
-        mbar_init(gbar, 1); mbar_init(mbar, 1); mbar_init(gfree, 1);
+        mbar_init(gbar, 1); mbar_init(mbar, 1); mbar_init(gfree, 1); mbar_init(abar, 4);
         fence_barrier_init();
         if (T >= 2) mbar_expect_tx(&hfull[0], step_bytes);    // h_0
         if (T >= 3) mbar_expect_tx(&hfull[1], step_bytes);    // h_1
     }
     for (int i = threadIdx.x; i < NB * 128; i += kThreads) gxs[i] = 0.f;   // padded batch rows stay finite
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // before the bulk copies write gxs
-    if (warp == 5) tmem_alloc(tmem_slot, 32);
+    const uint32_t tmem_cols = p.a_tmem ? 512u : 32u;        // D: 32 columns; A: H/2 columns at column 256
+    if (warp == 5) tmem_alloc(tmem_slot, tmem_cols);
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                                      // every CTA's barriers are initialised
@@ -319,6 +322,7 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc(128, NB);
             mbar_wait(wbar, 0);
+            if (p.a_tmem) { mbar_wait(abar, 0); tc_fence_after(); }
             for (int s = 1; s < T; ++s) {
                 const int buf = (s - 1) & 1;
                 mbar_wait(&hfull[buf], (uint32_t)(((s - 1) >> 1) & 1));      // h_{s-1} from all CTAs
@@ -329,7 +333,8 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
                 for (int kk = 0; kk < H / 16; ++kk) {
                     const uint64_t adesc = make_sw128_desc(smem_u32(Ws + (kk >> 2) * 16384)) + (uint64_t)((kk & 3) * 2);
                     const uint64_t bdesc = make_nosw_desc(hb + kk * 2 * kChunk, kChunk, 128);
-                    tc_mma_bf16(tmem_base, adesc, bdesc, idesc, (uint32_t)(kk != 0));
+                    if (p.a_tmem) tc_mma_bf16_ts(tmem_base, tmem_base + 256 + kk * 8, bdesc, idesc, (uint32_t)(kk != 0));
+                    else tc_mma_bf16(tmem_base, adesc, bdesc, idesc, (uint32_t)(kk != 0));
                 }
                 PK2_PROF(1);
                 tc_commit(mbar);
@@ -341,6 +346,24 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
         float cst[NB / 4];
 #pragma unroll
         for (int k = 0; k < NB / 4; ++k) cst[k] = 0.f;
+        if (p.a_tmem) {
+            // one-time: my gate row of the W_hh slice -> tensor memory lane r, two bf16 per 32-bit column,
+            // read back out of the 128B-swizzled shared-memory tiles the TMA wrote
+            mbar_wait(wbar, 0);
+            for (int kb = 0; kb < KB; ++kb) {
+                uint32_t w[32];
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(Ws + kb * 16384 + r * 128 + ((ch ^ (r & 7)) << 4));
+                    w[ch * 4 + 0] = q.x; w[ch * 4 + 1] = q.y; w[ch * 4 + 2] = q.z; w[ch * 4 + 3] = q.w;
+                }
+                tc_st_32x32b_x32(tmem_base + 256 + kb * 32 + ((uint32_t)(warp * 32) << 16), w);
+            }
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(abar);
+        }
         uint32_t ph_g = 0, ph_m = 0;
         for (int s = 0; s < T; ++s) {
             const int tt = dir ? (T - 1 - s) : s;
@@ -440,7 +463,7 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                  // peers have consumed everything this CTA sent
-    if (warp == 5) tmem_dealloc(tmem_base, 32);
+    if (warp == 5) tmem_dealloc(tmem_base, tmem_cols);
 #undef PK2_PROF
 }
 
@@ -796,6 +819,209 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap map_wt, BwdDev p) {
     if (warp == 5) tmem_dealloc(tmem_base, 32);
 }
 
+// ------------------------------------------- backward, cluster + DSMEM, K-split / reduce-scatter ----
+// dh_{t-1}[b, j] = sum_n dgates_t[b, n] W_hh[n, j].  Instead of all-gathering dgates (4H columns) and letting
+// every CTA contract over K = 4H for its 32 output units (128 A-read-bound MMAs per step), each CTA
+// contracts ONLY over the 128 gate columns it has just produced itself, for ALL H output units:
+//     P_c[b, j] = sum_{n in slice c} dgates_t[b, n] W_hh[n, j]        (16 MMAs M128 x N256 x K16 per step)
+// and the partial sums are reduce-scattered through distributed shared memory: CTA c sends
+// P_c[:, units of CTA j] (bf16, 2 KB) to CTA j with one bulk copy per destination; CTA j adds the 16 tiles it
+// receives.  No operand is gathered, the A tile is 8 KB and local, W_hh[slice c, :] (128 KB) is the resident
+// B operand.  Receivers release their receive buffer to the senders with remote mbarrier arrives.
+constexpr int NBR = 32;                  // batch rows per cluster
+
+__global__ void __launch_bounds__(kThreads, 1)
+lstm_bwd_rs_kernel(const __grid_constant__ CUtensorMap map_wt, BwdDev p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int H = p.H, T = p.T, B = p.B;
+    const int NH = H / 256;                                  // N = 256 halves of the H output units (H = 512: 2)
+    constexpr int kChunk = NBR / 8 * 128;                    // 512 B: one 16-byte K-chunk over the 32 live rows
+    constexpr int kATile = 16 * kChunk;                      // 8 KB: [128 k' / 8][4 row groups][8][16 B]
+    constexpr int kTile = NBR * 32 * 2;                      // 2 KB: one [32 rows x 32 units] bf16 partial tile
+    const int CS = gridDim.x;
+    uint8_t* Wb = smem;                                      // 2 k-blocks x [H rows x 64] bf16, SWIZZLE_128B
+    uint8_t* At = Wb + 2 * H * 128;                          // A tile + slack (the M=128 MMA reads rows >= 32)
+    uint8_t* stg = At + kATile + 2048;                       // [CS][32][32] bf16 outgoing partial tiles
+    uint8_t* rcv = stg + CS * kTile;                         // [CS][32][32] bf16 incoming partial tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(rcv + CS * kTile);
+    uint64_t* wbar = bars + 0;
+    uint64_t* aready = bars + 1;         // A tile of the step written
+    uint64_t* dready = bars + 2;         // MMAs of the step retired
+    uint64_t* dfree = bars + 3;          // accumulator drained
+    uint64_t* rfull = bars + 4;          // all partial tiles of the step landed
+    uint64_t* rfree = bars + 5;          // every receiver has consumed my tiles (count = cluster size)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cta = (int)cluster_ctarank();
+    const int dir = blockIdx.y, grp = blockIdx.z;
+    const int u0 = cta * 32, b0 = grp * NBR;
+    const int nbv = min(NBR, B - b0);
+    const uint32_t step_bytes = (uint32_t)CS * kTile;
+
+    if (threadIdx.x == 0) {
+        mbar_init(wbar, 1); mbar_init(aready, 1); mbar_init(dready, 1); mbar_init(dfree, 1);
+        mbar_init(rfull, 1); mbar_init(rfree, (uint32_t)CS);
+        fence_barrier_init();
+        if (T >= 2) mbar_expect_tx(rfull, step_bytes);
+    }
+    for (int i = threadIdx.x; i < (kATile + 2048) / 16; i += kThreads)
+        reinterpret_cast<uint4*>(At)[i] = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 5) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            // W_hh[slice c, :] as B operand: rows j (all H), K = my 128 permuted gate columns
+            mbar_expect_tx(wbar, (uint32_t)(2 * H * 128));
+            for (int kb = 0; kb < 2; ++kb)
+                for (int h = 0; h < NH; ++h)
+                    tma_load_2d(&map_wt, wbar, Wb + kb * H * 128 + h * 256 * 128, cta * 128 + kb * 64, dir * H + h * 256);
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(128, 256);
+            mbar_wait(wbar, 0);
+            for (int s = 0; s + 1 < T; ++s) {
+                mbar_wait(aready, (uint32_t)(s & 1));
+                if (s > 0) mbar_wait(dfree, (uint32_t)((s - 1) & 1));
+                tc_fence_after();
+                const uint32_t at = smem_u32(At);
+                for (int h = 0; h < NH; ++h) {
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const uint64_t adesc = make_nosw_desc(at + kk * 2 * kChunk, kChunk, 128);
+                        const uint64_t bdesc = make_sw128_desc(smem_u32(Wb + (kk >> 2) * H * 128 + h * 256 * 128)) + (uint64_t)((kk & 3) * 2);
+                        tc_mma_bf16(tmem_base + h * 256, adesc, bdesc, idesc, (uint32_t)(kk != 0));
+                    }
+                }
+                tc_commit(dready);
+            }
+        }
+    } else {
+        float dcn[NBR / 4];
+#pragma unroll
+        for (int k = 0; k < NBR / 4; ++k) dcn[k] = 0.f;
+        for (int s = 0; s < T; ++s) {
+            const int tt = dir ? s : (T - 1 - s);
+            const int tfp = dir ? tt + 1 : tt - 1;
+            float cO[NBR / 4], a1[NBR / 4], cI[NBR / 4], cF[NBR / 4], cG[NBR / 4], fgv[NBR / 4], dh[NBR / 4];
+#pragma unroll
+            for (int k = 0; k < NBR / 4; ++k) {
+                const int b = warp + 4 * k;
+                cO[k] = a1[k] = cI[k] = cF[k] = cG[k] = fgv[k] = dh[k] = 0.f;
+                if (b < nbv) {
+                    const int64_t bb = b0 + b;
+                    const __nv_bfloat16* gp = p.gates + ((((int64_t)dir * T + tt) * B + bb) * 4) * H + u0 + lane;
+                    const float ig = __bfloat162float(gp[0]), fg = __bfloat162float(gp[H]);
+                    const float gg = __bfloat162float(gp[2 * H]), og = __bfloat162float(gp[3 * H]);
+                    const float c = p.cstate[(((int64_t)dir * T + tt) * B + bb) * H + u0 + lane];
+                    const float cp = (tfp >= 0 && tfp < T)
+                                         ? p.cstate[(((int64_t)dir * T + tfp) * B + bb) * H + u0 + lane] : 0.f;
+                    dh[k] = p.dy[(bb * T + tt) * 2 * H + dir * H + u0 + lane];
+                    const float tc_ = tanh_approx(c);
+                    cO[k] = tc_ * og * (1.0f - og);
+                    a1[k] = og * (1.0f - tc_ * tc_);
+                    cI[k] = gg * ig * (1.0f - ig);
+                    cF[k] = cp * fg * (1.0f - fg);
+                    cG[k] = ig * (1.0f - gg * gg);
+                    fgv[k] = fg;
+                }
+            }
+            if (s > 0) {
+                // reduce: dh_rec[b, u] = sum over the 16 source CTAs of their partial tile
+                mbar_wait(rfull, (uint32_t)((s - 1) & 1));
+                if (threadIdx.x == 0 && s + 1 < T) mbar_expect_tx(rfull, step_bytes);   // re-arm for this step's tiles
+#pragma unroll
+                for (int k = 0; k < NBR / 4; ++k) {
+                    const int b = warp + 4 * k;
+                    float acc = 0.f;
+                    for (int src = 0; src < CS; ++src)
+                        acc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(rcv + src * kTile + (b * 32 + lane) * 2));
+                    dh[k] += acc;
+                }
+                named_bar_sync(1, kEpiThreads);                      // all reads of rcv done
+                if ((threadIdx.x & 7) == 0 && (threadIdx.x >> 3) < CS)
+                    mbar_arrive_remote(mapa_u32(smem_u32(rfree), threadIdx.x >> 3));
+            }
+            __nv_bfloat16 dg[NBR / 4][4];
+#pragma unroll
+            for (int k = 0; k < NBR / 4; ++k) {
+                const int b = warp + 4 * k;
+                const float dc = fmaf(dh[k], a1[k], dcn[k]);
+                dcn[k] = dc * fgv[k];
+                dg[k][0] = __float2bfloat16(dc * cI[k]);
+                dg[k][1] = __float2bfloat16(dc * cF[k]);
+                dg[k][2] = __float2bfloat16(dc * cG[k]);
+                dg[k][3] = __float2bfloat16(dh[k] * cO[k]);
+                if (s + 1 < T) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int col = q * 32 + lane;        // k' within my slice = gate*32 + unit
+                        *reinterpret_cast<__nv_bfloat16*>(At + (col >> 3) * kChunk + (b >> 3) * 128 + (b & 7) * 16 + (col & 7) * 2) = dg[k][q];
+                    }
+                }
+            }
+            if (s + 1 < T) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                named_bar_sync(1, kEpiThreads);
+                if (threadIdx.x == 0) mbar_arrive(aready);
+            }
+            // off the critical path: dgates in the natural layout for the weight-gradient GEMMs
+#pragma unroll
+            for (int k = 0; k < NBR / 4; ++k) {
+                const int b = warp + 4 * k;
+                if (b < nbv) {
+                    __nv_bfloat16* dp = p.dgates + (((int64_t)(b0 + b) * T + tt) * 2 + dir) * 4 * H + u0 + lane;
+                    dp[0] = dg[k][0]; dp[H] = dg[k][1]; dp[2 * H] = dg[k][2]; dp[3 * H] = dg[k][3];
+                }
+            }
+            if (s + 1 < T) {
+                // partial products of this step: TMEM rows 0..31 (lanes 0..31: warp 0) x H columns -> bf16 tiles
+                if (warp == 0) {
+                    mbar_wait(dready, (uint32_t)(s & 1));
+                    tc_fence_after();
+                    if (s > 0) mbar_wait_cluster(rfree, (uint32_t)((s - 1) & 1));   // receivers consumed my previous tiles
+                    for (int j = 0; j < CS; ++j) {
+                        uint32_t v[32];
+                        tc_ld_32x32b_x32(tmem_base + j * 32, v);
+                        uint4* dstp = reinterpret_cast<uint4*>(stg + j * kTile + lane * 64);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            __nv_bfloat162 p0 = __floats2bfloat162_rn(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
+                            __nv_bfloat162 p1 = __floats2bfloat162_rn(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
+                            __nv_bfloat162 p2 = __floats2bfloat162_rn(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
+                            __nv_bfloat162 p3 = __floats2bfloat162_rn(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
+                            uint4 o;
+                            o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+                            o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+                            dstp[q] = o;
+                        }
+                    }
+                    tc_fence_before();
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(dfree);
+                    if (lane < CS) {
+                        // tile for CTA `lane` -> slot `cta` of its receive buffer; bytes counted on its rfull
+                        const uint32_t dst = mapa_u32(smem_u32(rcv + cta * kTile), (uint32_t)lane);
+                        dsmem_bulk_copy(dst, smem_u32(stg + lane * kTile), (uint32_t)kTile, mapa_u32(smem_u32(rfull), (uint32_t)lane));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 5) tmem_dealloc(tmem_base, 512);
+}
+
 // ------------------------------------------------------------------------------ host ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -871,7 +1097,7 @@ int launch_fwd(const pk2_lstm_fwd_args* a, cudaStream_t st) {
     d.B = B; d.T = T; d.H = H; d.gx = a->gx;
     d.y = static_cast<__nv_bfloat16*>(a->y);
     d.gates = static_cast<__nv_bfloat16*>(a->gates);
-    d.cstate = a->cstate; d.counters = a->sync; d.prof = nullptr;
+    d.cstate = a->cstate; d.counters = a->sync; d.prof = nullptr; d.a_tmem = 0;
     lstm_fwd_kernel<NG><<<dim3(H / 32, 2, G), kThreads, smem, st>>>(mw, my, d);
     PK2_POST_LAUNCH();
     return 0;
@@ -920,6 +1146,8 @@ int launch_fwd_cluster(const pk2_lstm_fwd_args* a, cudaStream_t st) {
     d.y = static_cast<__nv_bfloat16*>(a->y);
     d.gates = static_cast<__nv_bfloat16*>(a->gates);
     d.cstate = a->cstate; d.counters = a->sync; d.prof = g_prof;
+    static const bool a_tmem = getenv("PK2_LSTM_A_TMEM") != nullptr;
+    d.a_tmem = (a_tmem && H <= 512) ? 1 : 0;
     PK2_CHECK(cudaLaunchKernelEx(&cfg, lstm_fwd_cluster_kernel, mw, d));
     PK2_LAUNCHED();
     return 0;
@@ -1008,6 +1236,55 @@ int launch_bwd_cluster(const pk2_lstm_bwd_args* a, cudaStream_t st) {
     return 0;
 }
 
+// K-split / reduce-scatter backward on clusters; needs the permuted W_hh^T (a->whh_t_perm).
+int launch_bwd_rs(const pk2_lstm_bwd_args* a, cudaStream_t st) {
+    const int H = a->H, T = a->T, B = a->B, CS = H / 32;
+    const int G = (B + NBR - 1) / NBR;
+    if (CS > 16 || (CS & (CS - 1)) != 0 || H % 256 != 0 || a->whh_t_perm == nullptr) return -1;
+    CUtensorMap mwt;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)(4 * H), (cuuint64_t)(2 * H)};
+        cuuint64_t str[1] = {(cuuint64_t)(4 * H) * 2};
+        cuuint32_t box[2] = {64, 256};
+        if (make_map(&mwt, a->whh_t_perm, 2, dims, str, box)) return 2;
+    }
+    const size_t smem = (size_t)2 * H * 128 + 8192 + 2048 + 2 * (size_t)CS * 2048 + 128 + 1024;
+    static bool attr_done = false, usable = true;
+    if (!attr_done) {
+        attr_done = true;
+        if (cudaFuncSetAttribute(lstm_bwd_rs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) != cudaSuccess ||
+            cudaFuncSetAttribute(lstm_bwd_rs_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+            cudaGetLastError();
+            usable = false;
+        }
+    }
+    if (!usable || smem > 232448) return -1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CS, 2, G);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, lstm_bwd_rs_kernel, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    if (max_clusters < 1) return -1;
+    BwdDev d;
+    d.B = B; d.T = T; d.H = H; d.dy = a->dy;
+    d.gates = static_cast<const __nv_bfloat16*>(a->gates);
+    d.cstate = a->cstate;
+    d.dgates = static_cast<__nv_bfloat16*>(a->dgates);
+    d.counters = a->sync;
+    PK2_CHECK(cudaLaunchKernelEx(&cfg, lstm_bwd_rs_kernel, mwt, d));
+    PK2_LAUNCHED();
+    return 0;
+}
+
 }  // namespace
 
 // Profiling aid: device buffer of 8*16 int64 that receives clock64() stamps of steps 64..71 of CTA (0,0,0)
@@ -1041,6 +1318,12 @@ extern "C" int pk2_lstm_layer_bwd(const pk2_lstm_bwd_args* a, void* stream) {
     if (use_cluster) {
         const int rc = launch_bwd_cluster(a, pk2::as_stream(stream));
         if (rc >= 0) return rc;
+    }
+    static const bool no_cluster = getenv("PK2_LSTM_NO_CLUSTER") != nullptr;
+    static const bool no_rs = getenv("PK2_LSTM_NO_RS") != nullptr;
+    if (!no_cluster && !no_rs) {
+        const int rc = launch_bwd_rs(a, pk2::as_stream(stream));
+        if (rc >= 0) return rc;                   // -1: not applicable (H % 256, clusters) -> global-memory kernel
     }
     return ng == 1 ? launch_bwd<1>(a, pk2::as_stream(stream)) : launch_bwd<2>(a, pk2::as_stream(stream));
 }
