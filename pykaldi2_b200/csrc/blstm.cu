@@ -51,6 +51,7 @@ struct BwdDev {
     const float* cstate;
     __nv_bfloat16* dgates;      // [B][T][2][4H]
     unsigned* counters;
+    long long* prof;            // optional clock64 trace (profiling only)
 };
 
 // tanh.approx.f32: one MUFU op, max relative error 2^-11 -- below the bf16 rounding the gates and h
@@ -907,47 +908,66 @@ lstm_bwd_rs_kernel(const __grid_constant__ CUtensorMap map_wt, BwdDev p) {
         float dcn[NBR / 4];
 #pragma unroll
         for (int k = 0; k < NBR / 4; ++k) dcn[k] = 0.f;
-        for (int s = 0; s < T; ++s) {
+        long long* prof = (p.prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) ? p.prof : nullptr;
+#define PK2_PROF(e) do { if (prof && s >= 64 && s < 72) prof[(s - 64) * 16 + (e)] = clock64(); } while (0)
+        // raw operands of one step (gates i,f,g,o; c; c_prev; dy), fetched one step ahead so that their HBM
+        // latency never sits between "partials landed" and "dgates ready"
+        float r_ig[NBR / 4], r_fg[NBR / 4], r_gg[NBR / 4], r_og[NBR / 4], r_c[NBR / 4], r_cp[NBR / 4], r_dy[NBR / 4];
+        auto fetch = [&](int s) {
             const int tt = dir ? s : (T - 1 - s);
             const int tfp = dir ? tt + 1 : tt - 1;
-            float cO[NBR / 4], a1[NBR / 4], cI[NBR / 4], cF[NBR / 4], cG[NBR / 4], fgv[NBR / 4], dh[NBR / 4];
 #pragma unroll
             for (int k = 0; k < NBR / 4; ++k) {
                 const int b = warp + 4 * k;
-                cO[k] = a1[k] = cI[k] = cF[k] = cG[k] = fgv[k] = dh[k] = 0.f;
+                r_ig[k] = r_fg[k] = r_gg[k] = r_og[k] = r_c[k] = r_cp[k] = r_dy[k] = 0.f;
                 if (b < nbv) {
                     const int64_t bb = b0 + b;
                     const __nv_bfloat16* gp = p.gates + ((((int64_t)dir * T + tt) * B + bb) * 4) * H + u0 + lane;
-                    const float ig = __bfloat162float(gp[0]), fg = __bfloat162float(gp[H]);
-                    const float gg = __bfloat162float(gp[2 * H]), og = __bfloat162float(gp[3 * H]);
-                    const float c = p.cstate[(((int64_t)dir * T + tt) * B + bb) * H + u0 + lane];
-                    const float cp = (tfp >= 0 && tfp < T)
-                                         ? p.cstate[(((int64_t)dir * T + tfp) * B + bb) * H + u0 + lane] : 0.f;
-                    dh[k] = p.dy[(bb * T + tt) * 2 * H + dir * H + u0 + lane];
-                    const float tc_ = tanh_approx(c);
-                    cO[k] = tc_ * og * (1.0f - og);
-                    a1[k] = og * (1.0f - tc_ * tc_);
-                    cI[k] = gg * ig * (1.0f - ig);
-                    cF[k] = cp * fg * (1.0f - fg);
-                    cG[k] = ig * (1.0f - gg * gg);
-                    fgv[k] = fg;
+                    r_ig[k] = __bfloat162float(gp[0]); r_fg[k] = __bfloat162float(gp[H]);
+                    r_gg[k] = __bfloat162float(gp[2 * H]); r_og[k] = __bfloat162float(gp[3 * H]);
+                    r_c[k] = p.cstate[(((int64_t)dir * T + tt) * B + bb) * H + u0 + lane];
+                    r_cp[k] = (tfp >= 0 && tfp < T) ? p.cstate[(((int64_t)dir * T + tfp) * B + bb) * H + u0 + lane] : 0.f;
+                    r_dy[k] = p.dy[(bb * T + tt) * 2 * H + dir * H + u0 + lane];
                 }
             }
-            if (s > 0) {
-                // reduce: dh_rec[b, u] = sum over the 16 source CTAs of their partial tile
-                mbar_wait(rfull, (uint32_t)((s - 1) & 1));
-                if (threadIdx.x == 0 && s + 1 < T) mbar_expect_tx(rfull, step_bytes);   // re-arm for this step's tiles
+        };
+        fetch(0);
+        for (int s = 0; s < T; ++s) {
+            const int tt = dir ? s : (T - 1 - s);
+            float cO[NBR / 4], a1[NBR / 4], cI[NBR / 4], cF[NBR / 4], cG[NBR / 4], fgv[NBR / 4], dh[NBR / 4];
 #pragma unroll
-                for (int k = 0; k < NBR / 4; ++k) {
-                    const int b = warp + 4 * k;
-                    float acc = 0.f;
-                    for (int src = 0; src < CS; ++src)
-                        acc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(rcv + src * kTile + (b * 32 + lane) * 2));
-                    dh[k] += acc;
+            for (int k = 0; k < NBR / 4; ++k) {
+                const float tc_ = tanh_approx(r_c[k]);
+                cO[k] = tc_ * r_og[k] * (1.0f - r_og[k]);
+                a1[k] = r_og[k] * (1.0f - tc_ * tc_);
+                cI[k] = r_gg[k] * r_ig[k] * (1.0f - r_ig[k]);
+                cF[k] = r_cp[k] * r_fg[k] * (1.0f - r_fg[k]);
+                cG[k] = r_ig[k] * (1.0f - r_gg[k] * r_gg[k]);
+                fgv[k] = r_fg[k];
+                dh[k] = r_dy[k];
+            }
+            if (s + 1 < T) fetch(s + 1);                 // next step's operands: in flight during this whole step
+            if (s > 0) {
+                // reduce: dh_rec[b, u] = sum over the source CTAs of their partial tile
+                mbar_wait(rfull, (uint32_t)((s - 1) & 1));
+                PK2_PROF(0);
+                if (threadIdx.x == 0 && s + 1 < T) mbar_expect_tx(rfull, step_bytes);   // re-arm for this step's tiles
+                float acc[NBR / 4];
+#pragma unroll
+                for (int k = 0; k < NBR / 4; ++k) acc[k] = 0.f;
+                for (int src = 0; src < CS; ++src) {
+#pragma unroll
+                    for (int k = 0; k < NBR / 4; ++k) {
+                        const int b = warp + 4 * k;
+                        acc[k] += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(rcv + src * kTile + (b * 32 + lane) * 2));
+                    }
                 }
+#pragma unroll
+                for (int k = 0; k < NBR / 4; ++k) dh[k] += acc[k];
                 named_bar_sync(1, kEpiThreads);                      // all reads of rcv done
                 if ((threadIdx.x & 7) == 0 && (threadIdx.x >> 3) < CS)
                     mbar_arrive_remote(mapa_u32(smem_u32(rfree), threadIdx.x >> 3));
+                PK2_PROF(1);
             }
             __nv_bfloat16 dg[NBR / 4][4];
 #pragma unroll
@@ -970,7 +990,7 @@ lstm_bwd_rs_kernel(const __grid_constant__ CUtensorMap map_wt, BwdDev p) {
             if (s + 1 < T) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 named_bar_sync(1, kEpiThreads);
-                if (threadIdx.x == 0) mbar_arrive(aready);
+                if (threadIdx.x == 0) { PK2_PROF(2); mbar_arrive(aready); }
             }
             // off the critical path: dgates in the natural layout for the weight-gradient GEMMs
 #pragma unroll
@@ -985,36 +1005,47 @@ lstm_bwd_rs_kernel(const __grid_constant__ CUtensorMap map_wt, BwdDev p) {
                 // partial products of this step: TMEM rows 0..31 (lanes 0..31: warp 0) x H columns -> bf16 tiles
                 if (warp == 0) {
                     mbar_wait(dready, (uint32_t)(s & 1));
+                    PK2_PROF(3);
                     tc_fence_after();
                     if (s > 0) mbar_wait_cluster(rfree, (uint32_t)((s - 1) & 1));   // receivers consumed my previous tiles
-                    for (int j = 0; j < CS; ++j) {
-                        uint32_t v[32];
-                        tc_ld_32x32b_x32(tmem_base + j * 32, v);
-                        uint4* dstp = reinterpret_cast<uint4*>(stg + j * kTile + lane * 64);
+                    for (int j = 0; j < CS; j += 2) {
+                        // two 32-column loads in flight per wait
+                        uint32_t v0[32], v1[32];
+                        tc_ld_32x32b_x32_nowait(tmem_base + j * 32, v0);
+                        tc_ld_32x32b_x32_nowait(tmem_base + (j + 1) * 32, v1);
+                        tc_wait_ld();
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            __nv_bfloat162 p0 = __floats2bfloat162_rn(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
-                            __nv_bfloat162 p1 = __floats2bfloat162_rn(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
-                            __nv_bfloat162 p2 = __floats2bfloat162_rn(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
-                            __nv_bfloat162 p3 = __floats2bfloat162_rn(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
-                            uint4 o;
-                            o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
-                            o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
-                            dstp[q] = o;
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            uint4* dstp = reinterpret_cast<uint4*>(stg + (j + h2) * kTile + lane * 64);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint32_t* v = h2 ? v1 : v0;
+                                __nv_bfloat162 p0 = __floats2bfloat162_rn(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
+                                __nv_bfloat162 p1 = __floats2bfloat162_rn(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
+                                __nv_bfloat162 p2 = __floats2bfloat162_rn(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
+                                __nv_bfloat162 p3 = __floats2bfloat162_rn(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
+                                uint4 o;
+                                o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+                                o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+                                dstp[q] = o;
+                            }
                         }
                     }
                     tc_fence_before();
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
+                    PK2_PROF(4);
                     if (lane == 0) mbar_arrive(dfree);
                     if (lane < CS) {
                         // tile for CTA `lane` -> slot `cta` of its receive buffer; bytes counted on its rfull
                         const uint32_t dst = mapa_u32(smem_u32(rcv + cta * kTile), (uint32_t)lane);
                         dsmem_bulk_copy(dst, smem_u32(stg + lane * kTile), (uint32_t)kTile, mapa_u32(smem_u32(rfull), (uint32_t)lane));
                     }
+                    PK2_PROF(5);
                 }
             }
         }
+#undef PK2_PROF
     }
     tc_fence_before();
     __syncthreads();
@@ -1062,6 +1093,7 @@ int check_dims(const char* who, int B, int T, int H, int ng, int num_sms) {
 }
 
 long long* g_prof = nullptr;    // set through pk2_lstm_set_profile_buffer (profiling only)
+long long* g_prof_bwd = nullptr;
 
 int num_sms() {
     static int n = 0;
@@ -1180,7 +1212,7 @@ int launch_bwd(const pk2_lstm_bwd_args* a, cudaStream_t st) {
     d.gates = static_cast<const __nv_bfloat16*>(a->gates);
     d.cstate = a->cstate;
     d.dgates = static_cast<__nv_bfloat16*>(a->dgates);
-    d.counters = a->sync;
+    d.counters = a->sync; d.prof = nullptr;
     lstm_bwd_kernel<NG><<<dim3(H / 32, 2, G), kThreads, smem, st>>>(mwt, mdg, d);
     PK2_POST_LAUNCH();
     return 0;
@@ -1230,7 +1262,7 @@ int launch_bwd_cluster(const pk2_lstm_bwd_args* a, cudaStream_t st) {
     d.gates = static_cast<const __nv_bfloat16*>(a->gates);
     d.cstate = a->cstate;
     d.dgates = static_cast<__nv_bfloat16*>(a->dgates);
-    d.counters = a->sync;
+    d.counters = a->sync; d.prof = nullptr;
     PK2_CHECK(cudaLaunchKernelEx(&cfg, lstm_bwd_cluster_kernel, mwt, d));
     PK2_LAUNCHED();
     return 0;
@@ -1279,7 +1311,7 @@ int launch_bwd_rs(const pk2_lstm_bwd_args* a, cudaStream_t st) {
     d.gates = static_cast<const __nv_bfloat16*>(a->gates);
     d.cstate = a->cstate;
     d.dgates = static_cast<__nv_bfloat16*>(a->dgates);
-    d.counters = a->sync;
+    d.counters = a->sync; d.prof = g_prof_bwd;
     PK2_CHECK(cudaLaunchKernelEx(&cfg, lstm_bwd_rs_kernel, mwt, d));
     PK2_LAUNCHED();
     return 0;
@@ -1289,7 +1321,11 @@ int launch_bwd_rs(const pk2_lstm_bwd_args* a, cudaStream_t st) {
 
 // Profiling aid: device buffer of 8*16 int64 that receives clock64() stamps of steps 64..71 of CTA (0,0,0)
 // of the cluster forward kernel (see tools/lstm_trace.py).  NULL switches it off.
-extern "C" int pk2_lstm_set_profile_buffer(void* buf) { g_prof = static_cast<long long*>(buf); return 0; }
+extern "C" int pk2_lstm_set_profile_buffer(void* buf) {
+    g_prof = static_cast<long long*>(buf);
+    g_prof_bwd = buf ? static_cast<long long*>(buf) + 128 : nullptr;      // second half: backward trace
+    return 0;
+}
 
 extern "C" int pk2_lstm_layer_fwd(const pk2_lstm_fwd_args* a, void* stream) {
     PK2_REQUIRE(a && a->gx && a->whh && a->y && a->gates && a->cstate && a->sync, "pk2_lstm_layer_fwd: null argument");

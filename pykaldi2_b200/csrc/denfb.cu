@@ -218,7 +218,8 @@ __device__ __forceinline__ void stage_table(const SellDev& tb, int part, int2* m
 // MODE 2: also acc2 = sum ga[a] * w          (occupancy pass with the leaky term applied lazily)
 template <int MODE, class Body>
 __device__ __forceinline__ void sell_pass(const TabView& tv, const float* __restrict__ ga,
-                                          const float* __restrict__ gb, Body&& body, int debug = 0) {
+                                          const float* __restrict__ gb, Body&& body, int debug = 0,
+                                          const float* __restrict__ rowvec = nullptr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (debug == 2) return;
     for (int ia = warp; ia < tv.nsl; ia += 2 * kWarps) {
@@ -229,6 +230,15 @@ __device__ __forceinline__ void sell_pass(const TabView& tv, const float* __rest
         const uint2* pa = tv.arcs + ma.x + lane;
         const uint2* pb = tv.arcs + mb.x + lane;
         float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f, a2 = 0.f, b2 = 0.f;
+        // row ids are known up front: fetch the per-row value of `rowvec` now, its L2 latency hides
+        // behind the arc loop
+        const unsigned rowa = tv.rows[ia * 32 + lane];
+        const unsigned rowb = hasb ? tv.rows[ib * 32 + lane] : 0xFFFFu;
+        float va = 0.f, vb = 0.f;
+        if (rowvec) {
+            if (rowa != 0xFFFFu) va = __ldg(&rowvec[rowa]);
+            if (rowb != 0xFFFFu) vb = __ldg(&rowvec[rowb]);
+        }
         const int lmax = debug == 1 ? 0 : max(ma.y, mb.y);
         for (int k = 0; k < lmax; k += 4) {
             uint2 ra[4], rb[4];
@@ -248,12 +258,8 @@ __device__ __forceinline__ void sell_pass(const TabView& tv, const float* __rest
                 if (MODE == 2) { a2 = fmaf(ga_a, wa, a2); b2 = fmaf(ga_b, wb, b2); }
             }
         }
-        const unsigned rowa = tv.rows[ia * 32 + lane];
-        if (rowa != 0xFFFFu) body((int)rowa, a0 + a1, a2);
-        if (hasb) {
-            const unsigned rowb = tv.rows[ib * 32 + lane];
-            if (rowb != 0xFFFFu) body((int)rowb, b0 + b1, b2);
-        }
+        if (rowa != 0xFFFFu) body((int)rowa, a0 + a1, a2, va);
+        if (rowb != 0xFFFFu) body((int)rowb, b0 + b1, b2, vb);
     }
 }
 
@@ -413,13 +419,12 @@ __global__ void __launch_bounds__(kThreads, 1) den_forward_kernel(DenArgs a) {
         float local = 0.f;
         const int par = t & 1;
         float* stg = stage + par * rcap;
-        sell_pass<0>(tv, cur, ev, [&](int row, float acc, float) {
+        sell_pass<0>(tv, cur, ev, [&](int row, float acc, float, float) {
             const float v = acc * invA;
             local += v;
             nxt[row] = v;
             if (K > 1) stg[row - r0] = v;
         }, a.debug);
-        if (threadIdx.x == 0) logsum += log((double)A);
         const float An = cluster_exchange<K>(xs, nxt, stg, r0, r1, pk2::warp_sum(local), par, c);
         // alpha'(t+1) in place, e(t+1) from the prefetched row
         const float lk = a.leaky * An;
@@ -444,10 +449,23 @@ __global__ void __launch_bounds__(kThreads, 1) den_forward_kernel(DenArgs a) {
     float s2 = 0.f;
     for (int j = threadIdx.x; j < S; j += kThreads) s2 += cur[j];
     const float totp = block_sum(s2, red);
-    if (threadIdx.x == 0 && c == 0) {
-        asum[T] = A;
-        asum[a.max_frames + 1] = totp;
-        a.logz[b] = log((double)totp) + logsum;
+    if (c == 0) {
+        // log Z = log totp + sum_t log A(t): the per-frame normalisers were stored by thread 0; sum their logs
+        // here in double, in parallel, instead of one double log per frame on the critical path
+        __threadfence_block();
+        __syncthreads();
+        double part = 0.0;
+        for (int t = threadIdx.x; t < T; t += kThreads) part += log((double)asum[t]);
+        part = pk2::warp_sum_d(part);
+        double* dred = reinterpret_cast<double*>(ev);         // ev is dead now
+        if ((threadIdx.x & 31) == 0) dred[threadIdx.x >> 5] = part;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 0; w < kWarps; ++w) logsum += dred[w];
+            asum[T] = A;
+            asum[a.max_frames + 1] = totp;
+            a.logz[b] = log((double)totp) + logsum;
+        }
     }
     cluster_barrier<K>();           // no CTA exits while peers may still write into it
 }
@@ -466,10 +484,10 @@ __global__ void __launch_bounds__(kThreads, 1) den_backward_kernel(DenArgs a) {
     float* lraw = ev + Np;          // prefetched raw loglikes
     float* gbuf = lraw + Np;        // gamma staging for this CTA's pdf range
     const int gcap = ((N + K - 1) / K + 64 + 3) & ~3;
-    // initial probs for the leaky dot product: shared memory when it fits (K > 1), else read through L2
-    constexpr bool kSinit = (K > 1);
-    float* sinit = gbuf + gcap;
-    float* wsum = sinit + (kSinit ? Sp : 0);   // [kWarps] + parts [2][kMaxK*4]
+    // second alpha buffer (K > 1, where it fits): alpha'(t-1) is prefetched a whole frame ahead
+    constexpr bool kAl2 = (K > 1);
+    float* al2 = gbuf + gcap;
+    float* wsum = al2 + (kAl2 ? Sp : 0);       // [kWarps] + parts [2][kMaxK*4]
     float* red = wsum + 2 * kMaxK * kWarps;
     uint64_t* xbar = reinterpret_cast<uint64_t*>(red + kWarps + 4);
     int2* meta_b = reinterpret_cast<int2*>(xbar + 2);
@@ -513,11 +531,7 @@ __global__ void __launch_bounds__(kThreads, 1) den_backward_kernel(DenArgs a) {
 
     // beta'(T) = 1/totp ; beta(T) = beta'(T) + leaky * sum_k beta'(T,k) init[k]
     float s = 0.f;
-    for (int j = threadIdx.x; j < S; j += kThreads) {
-        const float v = __ldg(&a.init[j]);
-        if (kSinit) sinit[j] = v;
-        s += v;
-    }
+    for (int j = threadIdx.x; j < S; j += kThreads) s += __ldg(&a.init[j]);
     const float isum = block_sum(s, red);
     const float totp = asum[a.max_frames + 1];
     // cur holds beta'(t+1) WITHOUT the leaky term; beta = beta' + lk with the scalar lk = leaky * sum_k beta'_k init_k.
@@ -528,33 +542,41 @@ __global__ void __launch_bounds__(kThreads, 1) den_backward_kernel(DenArgs a) {
     row_prefetch(lraw, ll + (int64_t)(T - 1) * N, N);
     row_prefetch(al, aws + (int64_t)(T - 1) * S, S);
     cluster_barrier<K>();
+    float* alc = al;                 // alpha'(t)
+    float* aln = kAl2 ? al2 : al;    // alpha'(t-1) being prefetched
+    float asum_t = asum[T - 1];
 
     for (int t = T - 1; t >= 0; --t) {
         cp_async_wait_all();
         __syncthreads();
         for (int p = threadIdx.x; p < N; p += kThreads)
             ev[p] = __expf(fminf(fmaxf(lraw[p], -30.f), 30.f));
-        const float invA = 1.0f / asum[t];
+        const float invA = 1.0f / asum_t;
+        if (t > 0) asum_t = asum[t - 1];                 // next frame's normaliser: load now, use next frame
         __syncthreads();
-        if (t > 0) row_prefetch(lraw, ll + (int64_t)(t - 1) * N, N);
+        if (t > 0) {
+            row_prefetch(lraw, ll + (int64_t)(t - 1) * N, N);
+            if (kAl2) row_prefetch(aln, aws + (int64_t)(t - 1) * S, S);
+        }
 
         // beta'(t, i) for this CTA's source states
         float local = 0.f;
-        sell_pass<1>(tb, cur, ev, [&](int row, float acc, float acc2) {
+        sell_pass<1>(tb, cur, ev, [&](int row, float acc, float acc2, float init_row) {
             const float v = fmaf(lk, acc2, acc) * invA;
-            local = fmaf(v, kSinit ? sinit[row] : __ldg(&a.init[row]), local);
+            local = fmaf(v, init_row, local);
             nxt[row] = v;
-        }, a.debug);
+        }, a.debug, a.init);
         // pdf occupancies gamma(t, p) for this CTA's pdf range
         const float gs = a.deriv_scale * invA;
-        sell_pass<2>(tg, al, cur, [&](int row, float acc, float acc2) {
+        sell_pass<2>(tg, alc, cur, [&](int row, float acc, float acc2, float) {
             gbuf[row - p0] = fmaf(lk, acc2, acc) * ev[row] * gs;
         }, a.debug);
         const int par = t & 1;
         const float dot = cluster_exchange<K>(xs, nxt, nxt + r0, r0, r1, pk2::warp_sum(local), par, c);
         // (block barrier passed inside: gbuf / al reads of this frame are complete in this CTA)
         for (int p = p0 + threadIdx.x; p < p1; p += kThreads) grad[(int64_t)t * N + p] = gbuf[p - p0];
-        if (t > 0) row_prefetch(al, aws + (int64_t)(t - 1) * S, S);
+        if (kAl2) { float* t2 = alc; alc = aln; aln = t2; }
+        else if (t > 0) row_prefetch(al, aws + (int64_t)(t - 1) * S, S);
         lk = a.leaky * dot;
         float* tmp = cur; cur = nxt; nxt = tmp;
     }
@@ -621,9 +643,10 @@ int ensure_tables(DenGraph* g, int K) {
 // Mixed-cluster schedule: the kernels are persistent per sequence, so a launch lasts as long as its
 // longest sequence.  Give long sequences more CTAs (K = 4), short ones fewer (K = 1) so that all
 // clusters of the batch fit the SMs in ONE wave and finish at about the same time.  Relative
-// per-frame cost of a cluster of K CTAs (measured): K=1: 1.9, K=2: 1.0, K=4: 0.62.
+// per-frame cost of a cluster of K CTAs (measured, profiles/kernel_bench_den_r1_v6.jsonl: 35.0 / 23.9 /
+// 17.2 us per frame): K=1: 1.46, K=2: 1.0, K=4: 0.72.
 void plan_clusters(const int32_t* frames, int n, int budget, std::vector<int>* ks) {
-    static const double cost[5] = {0, 1.9, 1.0, 0, 0.62};
+    static const double cost[5] = {0, 1.46, 1.0, 0, 0.72};
     ks->assign(n, 1);
     int used = n;
     for (;;) {

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Per-phase cycle trace of the cluster forward LSTM kernel (steps 64..71 of CTA (0,0,0))."""
+"""Per-phase clock64 trace of the cluster LSTM kernels (steps 64..71 of CTA (0,0,0)); profiling aid."""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -8,18 +8,26 @@ from pykaldi2_b200 import _lib
 from pykaldi2_b200.models.lstm import LSTMAM
 dev = torch.device("cuda", 0)
 L = _lib.lib()
-buf = torch.zeros(128, dtype=torch.int64, device=dev)
-L.pk2_lstm_set_profile_buffer(_lib.ptr(buf))
+buf = torch.zeros(256, dtype=torch.int64, device=dev)
 model = LSTMAM(80, 512, 512, 1, 0.0, True).to(dev)
 x = torch.randn(64, 200, 80, device=dev)
-with torch.no_grad():
-    model(x); model(x)
+g = torch.randn(64, 200, 512, device=dev) * 1e-3
+model(x).backward(g)
+L.pk2_lstm_set_profile_buffer(_lib.ptr(buf))
+model(x).backward(g)
 torch.cuda.synchronize()
 L.pk2_lstm_set_profile_buffer(None)
-t = buf.cpu().view(8, 16).numpy()
-names = ["h landed (MMA warp)", "MMAs issued", "MMAs retired (epi)", "tmem ld done", "gx landed", "phase1+bar",
-         "phase2+bar", "copies issued", "stores issued"]
-for s in range(1, 8):
-    base = t[s - 1][7]          # copies issued in the previous step
-    print("step %d:" % (64 + s), "  ".join("%s +%d" % (names[e], t[s][e] - base) for e in range(9)))
-print("period (copies issued -> copies issued):", [int(t[s][7] - t[s - 1][7]) for s in range(1, 8)])
+t = buf.cpu().view(2, 8, 16).numpy()
+fn = ["h landed (MMA warp)", "MMAs issued", "MMAs retired (epi)", "tmem ld done", "gx landed", "phase1+bar",
+      "phase2+bar", "copies issued", "stores issued"]
+print("forward (cycles after the previous step's 'copies issued'):")
+for s in range(5, 8):
+    base = t[0][s - 1][7]
+    print("  step %d:" % (64 + s), "  ".join("%s +%d" % (fn[e], t[0][s][e] - base) for e in range(9)))
+print("  period:", [int(t[0][s][7] - t[0][s - 1][7]) for s in range(1, 8)])
+bn = ["partials landed", "reduced+released", "A tile ready", "MMAs retired", "drained+staged", "copies issued"]
+print("backward, thread 0 of CTA 0 (cycles after the previous step's 'copies issued'):")
+for s in range(5, 8):
+    base = t[1][s - 1][5]
+    print("  step %d:" % (64 + s), "  ".join("%s +%d" % (bn[e], t[1][s][e] - base) for e in range(6)))
+print("  period:", [int(t[1][s][5] - t[1][s - 1][5]) for s in range(1, 8)])
