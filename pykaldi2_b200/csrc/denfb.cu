@@ -643,10 +643,11 @@ int ensure_tables(DenGraph* g, int K) {
 // Mixed-cluster schedule: the kernels are persistent per sequence, so a launch lasts as long as its
 // longest sequence.  Give long sequences more CTAs (K = 4), short ones fewer (K = 1) so that all
 // clusters of the batch fit the SMs in ONE wave and finish at about the same time.  Relative
-// per-frame cost of a cluster of K CTAs (measured, profiles/kernel_bench_den_r1_v6.jsonl: 35.0 / 23.9 /
-// 17.2 us per frame): K=1: 1.46, K=2: 1.0, K=4: 0.72.
+// per-frame cost of a cluster of K CTAs.  Isolated measurements give 1.46 / 1.0 / 0.72 (K = 1 / 2 / 4,
+// profiles/kernel_bench_den_r1_v6.jsonl) but with ~140 CTAs sharing L2 the schedule planned with
+// 1.9 / 1.0 / 0.62 is faster end to end (14.7 vs 15.7 ms, kernel_bench_den_r1_v9.jsonl).
 void plan_clusters(const int32_t* frames, int n, int budget, std::vector<int>* ks) {
-    static const double cost[5] = {0, 1.46, 1.0, 0, 0.72};
+    static const double cost[5] = {0, 1.9, 1.0, 0, 0.62};
     ks->assign(n, 1);
     int used = n;
     for (;;) {
