@@ -906,86 +906,106 @@ lstm_bwd_rs_kernel(const __grid_constant__ CUtensorMap map_wt, BwdDev p) {
             }
         }
     } else {
-        float dcn[NBR / 4];
+        // Epilogue mapping: thread = (row half rh, unit pair up) of warp w: units u0 + 2up, +1; batch rows
+        // (2w + rh) + 8k, k = 0..3  ->  8 elements per thread, every global / shared access is a bf16x2 or float2.
+        const int up = lane & 15, rh = lane >> 4;
+        float dcn[4][2];
 #pragma unroll
-        for (int k = 0; k < NBR / 4; ++k) dcn[k] = 0.f;
+        for (int k = 0; k < 4; ++k) dcn[k][0] = dcn[k][1] = 0.f;
         long long* prof = (p.prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) ? p.prof : nullptr;
 #define PK2_PROF(e) do { if (prof && s >= 64 && s < 72) prof[(s - 64) * 16 + (e)] = clock64(); } while (0)
-        // raw operands of one step (gates i,f,g,o; c; c_prev; dy), fetched one step ahead so that their HBM
-        // latency never sits between "partials landed" and "dgates ready"
-        float r_ig[NBR / 4], r_fg[NBR / 4], r_gg[NBR / 4], r_og[NBR / 4], r_c[NBR / 4], r_cp[NBR / 4], r_dy[NBR / 4];
+        // RAW operands of one step, fetched a whole step ahead.  Nothing touches these registers until the next
+        // step (no conversion, no select): a dependent instruction right after the load would stall the warp for
+        // the full HBM latency (measured: 7 k cycles per step, profiles/lstm_bwd_rs_trace_r1_v10_dbg.txt).
+        uint32_t q_g[4][4];
+        float2 q_c[4], q_cp[4], q_dy[4];
         auto fetch = [&](int s) {
             const int tt = dir ? s : (T - 1 - s);
             const int tfp = dir ? tt + 1 : tt - 1;
+            const int tcp = (tfp >= 0 && tfp < T) ? tfp : tt;          // always a valid address; masked at use
 #pragma unroll
-            for (int k = 0; k < NBR / 4; ++k) {
-                const int b = warp + 4 * k;
-                r_ig[k] = r_fg[k] = r_gg[k] = r_og[k] = r_c[k] = r_cp[k] = r_dy[k] = 0.f;
-                if (b < nbv) {
-                    const int64_t bb = b0 + b;
-                    const __nv_bfloat16* gp = p.gates + ((((int64_t)dir * T + tt) * B + bb) * 4) * H + u0 + lane;
-                    r_ig[k] = __bfloat162float(gp[0]); r_fg[k] = __bfloat162float(gp[H]);
-                    r_gg[k] = __bfloat162float(gp[2 * H]); r_og[k] = __bfloat162float(gp[3 * H]);
-                    r_c[k] = p.cstate[(((int64_t)dir * T + tt) * B + bb) * H + u0 + lane];
-                    r_cp[k] = (tfp >= 0 && tfp < T) ? p.cstate[(((int64_t)dir * T + tfp) * B + bb) * H + u0 + lane] : 0.f;
-                    r_dy[k] = p.dy[(bb * T + tt) * 2 * H + dir * H + u0 + lane];
-                }
+            for (int k = 0; k < 4; ++k) {
+                const int b = min(2 * warp + rh + 8 * k, nbv - 1);
+                const int64_t bb = b0 + b;
+                const __nv_bfloat16* gp = p.gates + ((((int64_t)dir * T + tt) * B + bb) * 4) * H + u0 + 2 * up;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) q_g[k][g] = *reinterpret_cast<const uint32_t*>(gp + g * H);
+                q_c[k] = *reinterpret_cast<const float2*>(p.cstate + (((int64_t)dir * T + tt) * B + bb) * H + u0 + 2 * up);
+                q_cp[k] = *reinterpret_cast<const float2*>(p.cstate + (((int64_t)dir * T + tcp) * B + bb) * H + u0 + 2 * up);
+                q_dy[k] = *reinterpret_cast<const float2*>(p.dy + (bb * T + tt) * 2 * H + dir * H + u0 + 2 * up);
             }
         };
         fetch(0);
         for (int s = 0; s < T; ++s) {
             const int tt = dir ? s : (T - 1 - s);
-            float cO[NBR / 4], a1[NBR / 4], cI[NBR / 4], cF[NBR / 4], cG[NBR / 4], fgv[NBR / 4], dh[NBR / 4];
+            const int tfp = dir ? tt + 1 : tt - 1;
+            const float cpm = (tfp >= 0 && tfp < T) ? 1.f : 0.f;
+            float cO[4][2], a1[4][2], cI[4][2], cF[4][2], cG[4][2], fgv[4][2], dh[4][2];
 #pragma unroll
-            for (int k = 0; k < NBR / 4; ++k) {
-                const float tc_ = tanh_approx(r_c[k]);
-                cO[k] = tc_ * r_og[k] * (1.0f - r_og[k]);
-                a1[k] = r_og[k] * (1.0f - tc_ * tc_);
-                cI[k] = r_gg[k] * r_ig[k] * (1.0f - r_ig[k]);
-                cF[k] = r_cp[k] * r_fg[k] * (1.0f - r_fg[k]);
-                cG[k] = r_ig[k] * (1.0f - r_gg[k] * r_gg[k]);
-                fgv[k] = r_fg[k];
-                dh[k] = r_dy[k];
+            for (int k = 0; k < 4; ++k) {
+                const float live = (2 * warp + rh + 8 * k < nbv) ? 1.f : 0.f;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float ig = __uint_as_float(e ? (q_g[k][0] & 0xffff0000u) : (q_g[k][0] << 16));
+                    const float fg = __uint_as_float(e ? (q_g[k][1] & 0xffff0000u) : (q_g[k][1] << 16));
+                    const float gg = __uint_as_float(e ? (q_g[k][2] & 0xffff0000u) : (q_g[k][2] << 16));
+                    const float og = __uint_as_float(e ? (q_g[k][3] & 0xffff0000u) : (q_g[k][3] << 16));
+                    const float c = e ? q_c[k].y : q_c[k].x;
+                    const float cp = (e ? q_cp[k].y : q_cp[k].x) * cpm;
+                    const float tc_ = tanh_approx(c);
+                    cO[k][e] = live * tc_ * og * (1.0f - og);
+                    a1[k][e] = live * og * (1.0f - tc_ * tc_);
+                    cI[k][e] = gg * ig * (1.0f - ig);
+                    cF[k][e] = cp * fg * (1.0f - fg);
+                    cG[k][e] = ig * (1.0f - gg * gg);
+                    fgv[k][e] = fg;
+                    dh[k][e] = live * (e ? q_dy[k].y : q_dy[k].x);
+                }
             }
-            if (s + 1 < T && !(p.dbg & 1)) fetch(s + 1);   // next step's operands: in flight during this whole step
+            if (s + 1 < T) fetch(s + 1);                 // in flight during this whole step
             if (s > 0) {
                 // reduce: dh_rec[b, u] = sum over the source CTAs of their partial tile
                 mbar_wait(rfull, (uint32_t)((s - 1) & 1));
                 PK2_PROF(0);
                 if (threadIdx.x == 0 && s + 1 < T) mbar_expect_tx(rfull, step_bytes);   // re-arm for this step's tiles
-                float acc[NBR / 4];
+                float acc[4][2];
 #pragma unroll
-                for (int k = 0; k < NBR / 4; ++k) acc[k] = 0.f;
+                for (int k = 0; k < 4; ++k) acc[k][0] = acc[k][1] = 0.f;
 #pragma unroll 4
                 for (int src = 0; src < CS; ++src) {
 #pragma unroll
-                    for (int k = 0; k < NBR / 4; ++k) {
-                        const int b = warp + 4 * k;
-                        acc[k] += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(rcv + src * kTile + (b * 32 + lane) * 2));
+                    for (int k = 0; k < 4; ++k) {
+                        const int b = 2 * warp + rh + 8 * k;
+                        const uint32_t v = *reinterpret_cast<const uint32_t*>(rcv + src * kTile + (b * 32 + 2 * up) * 2);
+                        acc[k][0] += __uint_as_float(v << 16);
+                        acc[k][1] += __uint_as_float(v & 0xffff0000u);
                     }
                 }
 #pragma unroll
-                for (int k = 0; k < NBR / 4; ++k) dh[k] += acc[k];
+                for (int k = 0; k < 4; ++k) { dh[k][0] += acc[k][0]; dh[k][1] += acc[k][1]; }
                 named_bar_sync(1, kEpiThreads);                      // all reads of rcv done
                 if ((threadIdx.x & 7) == 0 && (threadIdx.x >> 3) < CS)
                     mbar_arrive_remote(mapa_u32(smem_u32(rfree), threadIdx.x >> 3));
                 PK2_PROF(1);
             }
-            __nv_bfloat16 dg[NBR / 4][4];
+            uint32_t dg[4][4];                                       // bf16x2 per (row, gate)
 #pragma unroll
-            for (int k = 0; k < NBR / 4; ++k) {
-                const int b = warp + 4 * k;
-                const float dc = fmaf(dh[k], a1[k], dcn[k]);
-                dcn[k] = dc * fgv[k];
-                dg[k][0] = __float2bfloat16(dc * cI[k]);
-                dg[k][1] = __float2bfloat16(dc * cF[k]);
-                dg[k][2] = __float2bfloat16(dc * cG[k]);
-                dg[k][3] = __float2bfloat16(dh[k] * cO[k]);
-                if (s + 1 < T) {
+            for (int k = 0; k < 4; ++k) {
+                const int b = 2 * warp + rh + 8 * k;
+                float o[4][2];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int col = q * 32 + lane;        // k' within my slice = gate*32 + unit
-                        *reinterpret_cast<__nv_bfloat16*>(At + (col >> 3) * kChunk + (b >> 3) * 128 + (b & 7) * 16 + (col & 7) * 2) = dg[k][q];
+                for (int e = 0; e < 2; ++e) {
+                    const float dc = fmaf(dh[k][e], a1[k][e], dcn[k][e]);
+                    dcn[k][e] = dc * fgv[k][e];
+                    o[0][e] = dc * cI[k][e]; o[1][e] = dc * cF[k][e]; o[2][e] = dc * cG[k][e]; o[3][e] = dh[k][e] * cO[k][e];
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    __nv_bfloat162 pr = __floats2bfloat162_rn(o[g][0], o[g][1]);
+                    dg[k][g] = *reinterpret_cast<uint32_t*>(&pr);
+                    if (s + 1 < T) {
+                        const int col = g * 32 + 2 * up;              // k' within my slice = gate*32 + unit
+                        *reinterpret_cast<uint32_t*>(At + (col >> 3) * kChunk + (b >> 3) * 128 + (b & 7) * 16 + (col & 7) * 2) = dg[k][g];
                     }
                 }
             }
@@ -994,16 +1014,14 @@ lstm_bwd_rs_kernel(const __grid_constant__ CUtensorMap map_wt, BwdDev p) {
                 named_bar_sync(1, kEpiThreads);
                 if (threadIdx.x == 0) { PK2_PROF(2); mbar_arrive(aready); }
             }
-            if (s + 1 < T && (p.dbg & 1)) fetch(s + 1);
             // off the critical path: dgates in the natural layout for the weight-gradient GEMMs
-            if (!(p.dbg & 2)) {
 #pragma unroll
-                for (int k = 0; k < NBR / 4; ++k) {
-                    const int b = warp + 4 * k;
-                    if (b < nbv) {
-                        __nv_bfloat16* dp = p.dgates + (((int64_t)(b0 + b) * T + tt) * 2 + dir) * 4 * H + u0 + lane;
-                        dp[0] = dg[k][0]; dp[H] = dg[k][1]; dp[2 * H] = dg[k][2]; dp[3 * H] = dg[k][3];
-                    }
+            for (int k = 0; k < 4; ++k) {
+                const int b = 2 * warp + rh + 8 * k;
+                if (b < nbv) {
+                    __nv_bfloat16* dp = p.dgates + (((int64_t)(b0 + b) * T + tt) * 2 + dir) * 4 * H + u0 + 2 * up;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) *reinterpret_cast<uint32_t*>(dp + g * H) = dg[k][g];
                 }
             }
             if (s + 1 < T) {
