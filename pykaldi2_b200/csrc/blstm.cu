@@ -1382,10 +1382,9 @@ extern "C" int pk2_lstm_layer_bwd(const pk2_lstm_bwd_args* a, void* stream) {
         if (rc >= 0) return rc;
     }
     static const bool no_cluster = getenv("PK2_LSTM_NO_CLUSTER") != nullptr;
-    // The K-split / reduce-scatter kernel is correct (tests pass with PK2_LSTM_BWD_RS=1) but in its current
-    // state slower than the global-memory kernel: profiles/lstm_cluster_trace_r1_v9.txt shows 19.4k cycles per
-    // step, 9.1k of them waiting for the partial tiles.  Opt-in until that is understood.
-    static const bool use_rs = getenv("PK2_LSTM_BWD_RS") != nullptr;
+    // Default: K-split / reduce-scatter kernel on clusters (9.5 k cycles per step, profiles/lstm_bwd_rs_trace_r1_v11.txt);
+    // PK2_LSTM_NO_RS=1 or an unschedulable cluster falls back to the global-memory kernel (8.9 us per step).
+    static const bool use_rs = getenv("PK2_LSTM_NO_RS") == nullptr;
     if (!no_cluster && use_rs) {
         const int rc = launch_bwd_rs(a, pk2::as_stream(stream));
         if (rc >= 0) return rc;                   // -1: not applicable (H % 256, clusters) -> global-memory kernel
