@@ -45,11 +45,17 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def make_workload(rank, batch, seed=1234):
+def make_workload(rank, batch, seed=1234, world=1):
+    """Synthetic utterances of this rank.  The GLOBAL batch (batch * world utterances, durations seeded
+    independently of world) is sorted by length and dealt round-robin to the ranks: the length-bucketed
+    sharding that keeps the frame count -- and therefore the step time -- balanced across data-parallel
+    ranks (the reference's DistributedSampler shards at random; SURVEY.md section 7.3 "var-len DP load balance")."""
     from pykaldi2_b200 import synth
     from pykaldi2_b200.data import fbank as fb
-    rng = np.random.default_rng(seed + 1000 * rank)
-    durs = synth.make_durations(batch, rng)
+    rng = np.random.default_rng(seed)
+    all_durs = np.sort(synth.make_durations(batch * world, rng))[::-1]
+    durs = all_durs[rank::world]
+    rng = np.random.default_rng(seed + 1000 * (rank + 1))
     wavs = synth.make_waveforms(durs, rng)
     frames = [fb.num_frames(len(w)) for w in wavs]
     sub = [(t - 1) // FACTOR + 1 for t in frames]
@@ -188,7 +194,7 @@ def main():
 
     L = _lib.lib()
     B = args.batch
-    durs, wavs, frames, sub, sup_fsts = make_workload(rank, B)
+    durs, wavs, frames, sub, sup_fsts = make_workload(rank, B, world=world)
     den_fst = synth.make_den_fst(DEN_STATES, N_PDF, DEN_EXTRA, seed=1234)
     den = graphs.DenominatorGraph(den_fst, N_PDF)
     n_arcs = len(den_fst["src"])
@@ -270,6 +276,7 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "BLSTM 3x512 LF-MMI chain, batch 64 var-len utts/GPU, S=8192 den FST (C4)",
                        "global_batch": B * world, "audio_s_per_step": tot_audio, "parallelism": "dp%d" % world,
+                       "sharding": "global batch sorted by length, dealt round-robin to ranks",
                        "l2": "no flush: every step streams > 5 GB of activations/workspace, far larger than the 126 MB L2",
                        "optimizer": "Adam(amsgrad) lr 1e-4, clip 5"},
             "e2e": {"value": e2e, "unit": "hours audio per hour", "ms_per_step": 1e3 * t_e2e / args.steps,

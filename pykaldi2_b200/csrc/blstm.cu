@@ -983,6 +983,7 @@ lstm_bwd_rs_kernel(const __grid_constant__ CUtensorMap map_wt, BwdDev p) {
                 }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { dh[k][0] += acc[k][0]; dh[k][1] += acc[k][1]; }
+                PK2_PROF(6);
                 named_bar_sync(1, kEpiThreads);                      // all reads of rcv done
                 if ((threadIdx.x & 7) == 0 && (threadIdx.x >> 3) < CS)
                     mbar_arrive_remote(mapa_u32(smem_u32(rfree), threadIdx.x >> 3));
@@ -1031,22 +1032,23 @@ lstm_bwd_rs_kernel(const __grid_constant__ CUtensorMap map_wt, BwdDev p) {
                     PK2_PROF(3);
                     tc_fence_after();
                     if (s > 0) mbar_wait_cluster(rfree, (uint32_t)((s - 1) & 1));   // receivers consumed my previous tiles
-                    for (int j = 0; j < CS; j += 2) {
-                        // two 32-column loads in flight per wait
-                        uint32_t v0[32], v1[32];
-                        tc_ld_32x32b_x32_nowait(tmem_base + j * 32, v0);
-                        tc_ld_32x32b_x32_nowait(tmem_base + (j + 1) * 32, v1);
+                    for (int j = 0; j < CS; j += 4) {
+                        // four 32-column loads in flight per wait (128 accumulator columns per round)
+                        uint32_t v[4][32];
+#pragma unroll
+                        for (int h2 = 0; h2 < 4; ++h2)
+                            if (j + h2 < CS) tc_ld_32x32b_x32_nowait(tmem_base + (j + h2) * 32, v[h2]);
                         tc_wait_ld();
 #pragma unroll
-                        for (int h2 = 0; h2 < 2; ++h2) {
+                        for (int h2 = 0; h2 < 4; ++h2) {
+                            if (j + h2 >= CS) break;
                             uint4* dstp = reinterpret_cast<uint4*>(stg + (j + h2) * kTile + lane * 64);
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
-                                const uint32_t* v = h2 ? v1 : v0;
-                                __nv_bfloat162 p0 = __floats2bfloat162_rn(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
-                                __nv_bfloat162 p1 = __floats2bfloat162_rn(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
-                                __nv_bfloat162 p2 = __floats2bfloat162_rn(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
-                                __nv_bfloat162 p3 = __floats2bfloat162_rn(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
+                                __nv_bfloat162 p0 = __floats2bfloat162_rn(__uint_as_float(v[h2][q * 8 + 0]), __uint_as_float(v[h2][q * 8 + 1]));
+                                __nv_bfloat162 p1 = __floats2bfloat162_rn(__uint_as_float(v[h2][q * 8 + 2]), __uint_as_float(v[h2][q * 8 + 3]));
+                                __nv_bfloat162 p2 = __floats2bfloat162_rn(__uint_as_float(v[h2][q * 8 + 4]), __uint_as_float(v[h2][q * 8 + 5]));
+                                __nv_bfloat162 p3 = __floats2bfloat162_rn(__uint_as_float(v[h2][q * 8 + 6]), __uint_as_float(v[h2][q * 8 + 7]));
                                 uint4 o;
                                 o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
                                 o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);

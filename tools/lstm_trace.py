@@ -29,5 +29,6 @@ bn = ["partials landed", "reduced+released", "A tile ready", "MMAs retired", "dr
 print("backward, thread 0 of CTA 0 (cycles after the previous step's 'copies issued'):")
 for s in range(5, 8):
     base = t[1][s - 1][5]
-    print("  step %d:" % (64 + s), "  ".join("%s +%d" % (bn[e], t[1][s][e] - base) for e in range(6)))
+    print("  step %d:" % (64 + s), "  ".join("%s +%d" % (bn[e], t[1][s][e] - base) for e in range(6)),
+          " (sum loop done +%d)" % (t[1][s][6] - base))
 print("  period:", [int(t[1][s][5] - t[1][s - 1][5]) for s in range(1, 8)])
