@@ -151,6 +151,8 @@ int pk2_latfb_mmi(const pk2_lat_batch* lat, const float* loglikes, int num_pdfs,
 /* C[M,N] (+)= A[M,K] * B[N,K]^T (+ bias[N]), bf16 operands row-major (K contiguous),
  * fp32 accumulate on tcgen05 tensor cores; C fp32 or bf16 (c_bf16).
  * flags: bit0 accumulate into C, bit1 C is bf16.  */
+/* cap on the CTAs of later GEMM launches of the calling thread (0 = all SMs) */
+int pk2_gemm_set_max_ctas(int n);
 int pk2_gemm_bf16_nt(const void* A, const void* B, void* C, const float* bias,
                      int M, int N, int K, int lda, int ldb, int ldc, int flags, void* stream);
 

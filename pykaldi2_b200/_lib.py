@@ -64,6 +64,7 @@ _SIGS = {
                                 C.c_float, vp, vp, vp, vp, vp]),
     "pk2_gemm_bf16_nt": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_int, vp]),
+    "pk2_gemm_set_max_ctas": (C.c_int, [C.c_int]),
     "pk2_cast_bf16": (C.c_int, [vp, vp, C.c_int64, vp]),
     "pk2_transpose_bf16": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "pk2_lstm_hprev_t": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),

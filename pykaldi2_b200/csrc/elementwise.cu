@@ -3,6 +3,8 @@
 // and the bias gradient (column sums).  All are single-pass, HBM-bound, coalesced on both sides
 // (32x32 shared-memory tiles for the transposes).
 #include "common.cuh"
+#include <map>
+#include <mutex>
 
 namespace {
 
@@ -84,8 +86,10 @@ __global__ void colsum_final_kernel(const float* __restrict__ partial, float* __
     out[c] = acc;
 }
 
-float* g_partial = nullptr;
-size_t g_partial_bytes = 0;
+// scratch for the two-stage column sum, one buffer per stream (calls on different streams may overlap)
+struct Scratch { float* ptr = nullptr; size_t bytes = 0; };
+std::map<cudaStream_t, Scratch> g_scratch;
+std::mutex g_scratch_mu;
 
 }  // namespace
 
@@ -131,10 +135,16 @@ extern "C" int pk2_colsum_bf16(const void* src, float* out, int64_t R, int C, vo
     const int rows_per_block = 256;
     const int nparts = (int)((R + rows_per_block - 1) / rows_per_block);
     const size_t need = (size_t)nparts * C * sizeof(float);
-    if (need > g_partial_bytes) {
-        if (g_partial) cudaFree(g_partial);
-        PK2_CHECK(cudaMalloc(&g_partial, need));
-        g_partial_bytes = need;
+    float* g_partial = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_scratch_mu);
+        Scratch& sc = g_scratch[pk2::as_stream(stream)];
+        if (need > sc.bytes) {
+            if (sc.ptr) { PK2_CHECK(cudaStreamSynchronize(pk2::as_stream(stream))); cudaFree(sc.ptr); }
+            PK2_CHECK(cudaMalloc(&sc.ptr, need));
+            sc.bytes = need;
+        }
+        g_partial = sc.ptr;
     }
     dim3 grid((C + 127) / 128, nparts);
     PK2_REQUIRE(grid.y <= 65535, "pk2_colsum_bf16: too many rows");

@@ -231,6 +231,7 @@ int make_map(CUtensorMap* map, const void* base, int rows, int cols, int ld, int
 
 int g_num_sms = 0;
 thread_local int g_lstm_T = 0, g_lstm_B = 0, g_lstm_H = 0;
+thread_local int g_max_ctas = 0;      // 0 = all SMs; set to leave SMs to a concurrently running persistent kernel
 
 }  // namespace
 
@@ -257,12 +258,17 @@ extern "C" int pk2_gemm_bf16_nt(const void* A, const void* B, void* C, const flo
         attr = true;
     }
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    if (g_max_ctas > 0 && grid > g_max_ctas) grid = g_max_ctas;
     gemm_bf16_nt_kernel<<<grid, kThreads, smem, pk2::as_stream(stream)>>>(ma, mb, C, bias, M, N, K, ldc, (flags >> 1) & 1,
                                                                           g_lstm_T, g_lstm_B, g_lstm_H);
     PK2_POST_LAUNCH();
     return 0;
 }
+
+// Cap the number of CTAs of subsequent GEMM launches from this thread (0 = no cap): used when weight-gradient
+// GEMMs run on a side stream next to the persistent recurrence kernels, which own part of the SMs.
+extern "C" int pk2_gemm_set_max_ctas(int n) { g_max_ctas = n > 0 ? n : 0; return 0; }
 
 extern "C" int pk2_lstm_input_proj(const void* x, const void* wih, const float* bias, float* gx, int B, int T,
                                    int I, int H, int ldx, void* stream) {

@@ -99,6 +99,10 @@ class _BlstmAM(Function):
 
     @staticmethod
     def backward(ctx, dlogits):
+        """Backward pass.  The recurrence kernels of a layer own 64 of the 148 SMs for ~4 ms; the weight /
+        bias gradients of the layer ABOVE (transposes + K-long GEMMs, needed only by the optimizer) run on a
+        side stream on the remaining SMs meanwhile.  The recurrence is always launched first so that its
+        16-CTA clusters get whole GPCs; the side-stream GEMMs are capped to the SMs that are left."""
         B, T, F, L, H, N = ctx.dims
         M = B * T
         w_out, *lstm_params = ctx.saved_tensors
@@ -107,18 +111,42 @@ class _BlstmAM(Function):
         lib = _lib.lib()
         if N % 8 != 0:
             raise RuntimeError("output size must be a multiple of 8 for the bf16 backward (got %d)" % N)
+        main = th.cuda.current_stream(dev)
+        side = _side_stream(dev)
+        side_cap = max(32, _num_sms(dev) - 2 * (H // 32) * ((B + 31) // 32))
+        results = {}
+
+        def on_side(ready_event, fn):
+            side.wait_event(ready_event)
+            with th.cuda.stream(side):
+                lib.pk2_gemm_set_max_ctas(side_cap)
+                try:
+                    fn()
+                finally:
+                    lib.pk2_gemm_set_max_ctas(0)
+
+        def mark_ready():
+            ev = th.cuda.Event()
+            ev.record(main)
+            return ev
+
         dl = _cast(dlogits.contiguous().view(M, N))                      # [M, N] bf16
-        # output layer
         w_out_t, ldw = _transpose(w_out.contiguous(), N, 2 * H, 2 * H)   # [2H, pad8(N)]
         dy = th.empty(M, 2 * H, dtype=th.float32, device=dev)
         _gemm(dl, w_out_t, dy, None, M, 2 * H, N, N, ldw, 2 * H)
-        dl_t, ldm = _transpose(dl, M, N, N)                              # [N, pad8(M)]
-        top_t, _ = _transpose(ctx.top_in, M, 2 * H, 2 * H)               # [2H, pad8(M)]
-        d_w_out = th.empty(N, 2 * H, dtype=th.float32, device=dev)
-        _gemm(dl_t, top_t, d_w_out, None, N, 2 * H, M, ldm, ldm, 2 * H)
-        d_b_out = th.empty(N, dtype=th.float32, device=dev)
-        _lib.check(lib.pk2_colsum_bf16(_lib.ptr(dl), _lib.ptr(d_b_out), M, N, _lib.stream()), "pk2_colsum_bf16")
-        del dl, dl_t, top_t
+        top_in = ctx.top_in
+
+        def out_layer_grads():
+            dl.record_stream(side); top_in.record_stream(side)
+            dl_t, ldm = _transpose(dl, M, N, N)                          # [N, pad8(M)]
+            top_t, _ = _transpose(top_in, M, 2 * H, 2 * H)               # [2H, pad8(M)]
+            d_w_out = th.empty(N, 2 * H, dtype=th.float32, device=dev)
+            _gemm(dl_t, top_t, d_w_out, None, N, 2 * H, M, ldm, ldm, 2 * H)
+            d_b_out = th.empty(N, dtype=th.float32, device=dev)
+            _lib.check(lib.pk2_colsum_bf16(_lib.ptr(dl), _lib.ptr(d_b_out), M, N, _lib.stream()), "pk2_colsum_bf16")
+            results["out"] = (d_w_out, d_b_out)
+
+        pending = (mark_ready(), out_layer_grads)
         grads = [None] * (8 * L)
         for l in range(L - 1, -1, -1):
             wih_f, whh_f, _, _, wih_b, whh_b, _, _ = lstm_params[8 * l:8 * l + 8]
@@ -134,30 +162,70 @@ class _BlstmAM(Function):
             a = _lib.LstmBwdArgs(B, T, H, dy.data_ptr(), whh_t.data_ptr(), saved["gates"][l].data_ptr(),
                                  saved["cstate"][l].data_ptr(), dgates.data_ptr(), sync.data_ptr(), whh_tp.data_ptr())
             _lib.check(lib.pk2_lstm_layer_bwd(C.byref(a), _lib.stream()), "pk2_lstm_layer_bwd")
+            if pending is not None:               # gradients of the layer above: overlap with this recurrence
+                on_side(*pending)
+                pending = None
             dg2 = dgates.view(M, 8 * H)
-            dg_t, ldm = _transpose(dg2, M, 8 * H, 8 * H)                          # [8H, pad8(M)]
-            x_t, _ = _transpose(saved["xin"][l], M, I, I)                          # [I, pad8(M)]
-            d_wih = th.empty(8 * H, I, dtype=th.float32, device=dev)
-            _gemm(dg_t, x_t, d_wih, None, 8 * H, I, M, ldm, ldm, I)
-            hp_t = th.empty(2 * H, ldm, dtype=th.bfloat16, device=dev)
-            _lib.check(lib.pk2_lstm_hprev_t(_lib.ptr(saved["y"][l]), _lib.ptr(hp_t), B, T, H, ldm, _lib.stream()),
-                       "pk2_lstm_hprev_t")
-            d_whh = th.empty(2, 4 * H, H, dtype=th.float32, device=dev)
-            for d in range(2):
-                _gemm(dg_t[d * 4 * H:(d + 1) * 4 * H], hp_t[d * H:(d + 1) * H], d_whh[d], None, 4 * H, H, M, ldm, ldm, H)
-            d_b = th.empty(8 * H, dtype=th.float32, device=dev)
-            _lib.check(lib.pk2_colsum_bf16(_lib.ptr(dg2), _lib.ptr(d_b), M, 8 * H, _lib.stream()), "pk2_colsum_bf16")
+            if l > 0:
+                wih_t, ldk = _transpose(th.cat([wih_f, wih_b], 0).contiguous(), 8 * H, I, I)   # [I, 8H]
+                dy_next = th.empty(M, I, dtype=th.float32, device=dev)
+                _gemm(dg2, wih_t, dy_next, None, M, I, 8 * H, 8 * H, ldk, I)
+            xin_l, y_l = saved["xin"][l], saved["y"][l]
+
+            def layer_grads(l=l, dg2=dg2, xin_l=xin_l, y_l=y_l, I=I):
+                dg2.record_stream(side); xin_l.record_stream(side); y_l.record_stream(side)
+                dg_t, ldm = _transpose(dg2, M, 8 * H, 8 * H)                          # [8H, pad8(M)]
+                x_t, _ = _transpose(xin_l, M, I, I)                                    # [I, pad8(M)]
+                d_wih = th.empty(8 * H, I, dtype=th.float32, device=dev)
+                _gemm(dg_t, x_t, d_wih, None, 8 * H, I, M, ldm, ldm, I)
+                hp_t = th.empty(2 * H, ldm, dtype=th.bfloat16, device=dev)
+                _lib.check(lib.pk2_lstm_hprev_t(_lib.ptr(y_l), _lib.ptr(hp_t), B, T, H, ldm, _lib.stream()),
+                           "pk2_lstm_hprev_t")
+                d_whh = th.empty(2, 4 * H, H, dtype=th.float32, device=dev)
+                for d in range(2):
+                    _gemm(dg_t[d * 4 * H:(d + 1) * 4 * H], hp_t[d * H:(d + 1) * H], d_whh[d], None, 4 * H, H, M, ldm, ldm, H)
+                d_b = th.empty(8 * H, dtype=th.float32, device=dev)
+                _lib.check(lib.pk2_colsum_bf16(_lib.ptr(dg2), _lib.ptr(d_b), M, 8 * H, _lib.stream()), "pk2_colsum_bf16")
+                results[l] = (d_wih, d_whh, d_b)
+
+            if l > 0:
+                pending = (mark_ready(), layer_grads)
+                dy = dy_next
+            else:
+                layer_grads()                     # bottom layer: nothing left to overlap with; stay on the main stream
+        done = th.cuda.Event()
+        done.record(side)
+        main.wait_event(done)
+        d_w_out, d_b_out = results["out"]
+        d_w_out.record_stream(main); d_b_out.record_stream(main)
+        for l in range(L):
+            d_wih, d_whh, d_b = results[l]
+            for t in (d_wih, d_whh, d_b):
+                t.record_stream(main)
             grads[8 * l + 0] = d_wih[:4 * H]; grads[8 * l + 4] = d_wih[4 * H:]
             grads[8 * l + 1] = d_whh[0]; grads[8 * l + 5] = d_whh[1]
             grads[8 * l + 2] = d_b[:4 * H]; grads[8 * l + 3] = d_b[:4 * H]
             grads[8 * l + 6] = d_b[4 * H:]; grads[8 * l + 7] = d_b[4 * H:]
-            if l > 0:
-                wih_t, ldk = _transpose(th.cat([wih_f, wih_b], 0).contiguous(), 8 * H, I, I)   # [I, 8H]
-                dy = th.empty(M, I, dtype=th.float32, device=dev)
-                _gemm(dg2, wih_t, dy, None, M, I, 8 * H, 8 * H, ldk, I)
-            del dgates, dg_t, x_t, hp_t
         ctx.saved = None
         return (None, None, None, None, None, d_w_out, d_b_out) + tuple(grads)
+
+
+_SIDE = {}
+_SMS = {}
+
+
+def _side_stream(dev):
+    key = (dev.type, dev.index)
+    if key not in _SIDE:
+        _SIDE[key] = th.cuda.Stream(device=dev)
+    return _SIDE[key]
+
+
+def _num_sms(dev):
+    key = (dev.type, dev.index)
+    if key not in _SMS:
+        _SMS[key] = th.cuda.get_device_properties(dev).multi_processor_count
+    return _SMS[key]
 
 
 class LSTMAM(nn.Module):
