@@ -143,8 +143,9 @@ def run_reference(args, rank):
     den_fst = synth.make_den_fst(DEN_STATES, N_PDF, DEN_EXTRA, seed=1234)
     order = np.argsort(durs)[:4]                 # bounded sample: the 4 shortest utterances per step
     wv = [wavs[i] for i in order]; sf = [sup_fsts[i] for i in order]
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    # torch's default intra-op thread count (= physical cores) for the BLSTM; more threads than that
+    # (os.cpu_count() counts hyper-threads) made the small-batch CPU LSTM 20x slower on the 64-core box
+    cores = torch.get_num_threads()
     for _ in range(max(args.warmup, 0) and 1):
         cpu_reference_sample(wv[:1], sf[:1], den_fst, 1)
     tot_a = tot_t = 0.0

@@ -264,6 +264,7 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
     const int H = p.H, T = p.T, B = p.B;
     const int KB = H / 64;
     constexpr int kChunk = NB / 8 * 128;                     // bytes of one 16-byte K-chunk over NB rows
+    constexpr int kAcc = 4;                                  // independent TMEM accumulators (summed in the epilogue)
     constexpr int kSlice = NB * 64;                          // bytes one CTA contributes per step
     const int hs_bytes = H * NB * 2;
     uint8_t* Ws = smem;                                      // KB x [128 x 64] bf16, SWIZZLE_128B
@@ -298,7 +299,9 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
     }
     for (int i = threadIdx.x; i < NB * 128; i += kThreads) gxs[i] = 0.f;   // padded batch rows stay finite
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // before the bulk copies write gxs
-    const uint32_t tmem_cols = p.a_tmem ? 512u : 32u;        // D: 32 columns; A: H/2 columns at column 256
+    // D: kAcc independent accumulators of 32 columns (dependent tcgen05.mma on ONE accumulator serialise at the
+    // full pipeline latency, ~97 cycles each: 4 accumulators let them pipeline); A: H/2 columns at column 256
+    const uint32_t tmem_cols = p.a_tmem ? 512u : 128u;
     if (warp == 5) tmem_alloc(tmem_slot, tmem_cols);
     tc_fence_before();
     __syncthreads();
@@ -335,8 +338,9 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
                 for (int kk = 0; kk < H / 16; ++kk) {
                     const uint64_t adesc = make_sw128_desc(smem_u32(Ws + (kk >> 2) * 16384)) + (uint64_t)((kk & 3) * 2);
                     const uint64_t bdesc = make_nosw_desc(hb + kk * 2 * kChunk, kChunk, 128);
-                    if (p.a_tmem) tc_mma_bf16_ts(tmem_base, tmem_base + 256 + kk * 8, bdesc, idesc, (uint32_t)(kk != 0));
-                    else tc_mma_bf16(tmem_base, adesc, bdesc, idesc, (uint32_t)(kk != 0));
+                    const uint32_t dq = tmem_base + (uint32_t)(kk & (kAcc - 1)) * NB;      // accumulator kk mod kAcc
+                    if (p.a_tmem) tc_mma_bf16_ts(dq, tmem_base + 256 + kk * 8, bdesc, idesc, (uint32_t)(kk >= kAcc));
+                    else tc_mma_bf16(dq, adesc, bdesc, idesc, (uint32_t)(kk >= kAcc));
                 }
                 PK2_PROF(1);
                 tc_commit(mbar);
@@ -374,10 +378,18 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
                 mbar_wait(mbar, ph_m); ph_m ^= 1;
                 if (threadIdx.x == 0) PK2_PROF(2);
                 tc_fence_after();
-                uint32_t v[32];
-                tc_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16), v);
+                uint32_t v[kAcc][32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
+                for (int q = 0; q < kAcc; ++q)
+                    tc_ld_32x32b_x32_nowait(tmem_base + q * NB + ((uint32_t)(warp * 32) << 16), v[q]);
+                tc_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float t = __uint_as_float(v[0][j]);
+#pragma unroll
+                    for (int q = 1; q < kAcc; ++q) t += __uint_as_float(v[q][j]);
+                    acc[j] = t;
+                }
                 tc_fence_before();
             } else {
 #pragma unroll
@@ -895,9 +907,9 @@ lstm_bwd_rs_kernel(const __grid_constant__ CUtensorMap map_wt, BwdDev p) {
                 if (s > 0) mbar_wait(dfree, (uint32_t)((s - 1) & 1));
                 tc_fence_after();
                 const uint32_t at = smem_u32(At);
-                for (int h = 0; h < NH; ++h) {
-                    for (int kk = 0; kk < 8; ++kk) {
-                        const uint64_t adesc = make_nosw_desc(at + kk * 2 * kChunk, kChunk, 128);
+                for (int kk = 0; kk < 8; ++kk) {                 // alternate the N halves: consecutive MMAs hit different accumulators
+                    const uint64_t adesc = make_nosw_desc(at + kk * 2 * kChunk, kChunk, 128);
+                    for (int h = 0; h < NH; ++h) {
                         const uint64_t bdesc = make_sw128_desc(smem_u32(Wb + (kk >> 2) * H * 128 + h * 256 * 128)) + (uint64_t)((kk & 3) * 2);
                         tc_mma_bf16(tmem_base + h * 256, adesc, bdesc, idesc, (uint32_t)(kk != 0));
                     }
