@@ -154,13 +154,13 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
                 for (int g = 0; g < nga; ++g) {
                     mbar_wait(&hbar[g], ph_h);
                     tc_fence_after();
+                    const uint64_t ad0 = make_sw128_desc(smem_u32(Ws));
+                    const uint64_t bd0 = make_sw128_desc(smem_u32(Hs0 + g * hs_bytes));
                     for (int kb = 0; kb < KB; ++kb) {
-                        const uint64_t adesc = make_sw128_desc(smem_u32(Ws + kb * 16384));
-                        const uint64_t bdesc = make_sw128_desc(smem_u32(Hs0 + g * hs_bytes + kb * NB * 128));
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            tc_mma_bf16(tmem_base + g * NB, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                                        (uint32_t)((kb | k) != 0));
+                            tc_mma_bf16(tmem_base + g * NB, ad0 + (uint64_t)(kb * (16384 / 16) + k * 2),
+                                        bd0 + (uint64_t)(kb * (NB * 128 / 16) + k * 2), idesc, (uint32_t)((kb | k) != 0));
                     }
                     tc_commit(&mbar[g]);
                 }
@@ -334,13 +334,16 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
                 PK2_PROF(0);
                 if (s + 1 <= T - 2) mbar_expect_tx(&hfull[buf], step_bytes);  // re-arm for h_{s+1}
                 tc_fence_after();
-                const uint32_t hb = smem_u32(Hb + buf * hs_bytes);
+                // descriptors are affine in kk: build the bases once, add per MMA (a single thread issues
+                // these; ~20 dependent integer ops per MMA cost ~100 cycles each before -- the whole MMA phase)
+                const uint64_t bd0 = make_nosw_desc(smem_u32(Hb + buf * hs_bytes), kChunk, 128);
+                const uint64_t ad0 = make_sw128_desc(smem_u32(Ws));
+#pragma unroll 8
                 for (int kk = 0; kk < H / 16; ++kk) {
-                    const uint64_t adesc = make_sw128_desc(smem_u32(Ws + (kk >> 2) * 16384)) + (uint64_t)((kk & 3) * 2);
-                    const uint64_t bdesc = make_nosw_desc(hb + kk * 2 * kChunk, kChunk, 128);
+                    const uint64_t bdesc = bd0 + (uint64_t)(kk * (2 * kChunk / 16));
                     const uint32_t dq = tmem_base + (uint32_t)(kk & (kAcc - 1)) * NB;      // accumulator kk mod kAcc
                     if (p.a_tmem) tc_mma_bf16_ts(dq, tmem_base + 256 + kk * 8, bdesc, idesc, (uint32_t)(kk >= kAcc));
-                    else tc_mma_bf16(dq, adesc, bdesc, idesc, (uint32_t)(kk >= kAcc));
+                    else tc_mma_bf16(dq, ad0 + (uint64_t)((kk >> 2) * (16384 / 16) + (kk & 3) * 2), bdesc, idesc, (uint32_t)(kk >= kAcc));
                 }
                 PK2_PROF(1);
                 tc_commit(mbar);
@@ -565,14 +568,13 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_constan
                     for (int c = 0; c < NCH; ++c) {
                         mbar_wait(&afull[stage], phase);
                         tc_fence_after();
+                        const uint64_t ad0 = make_sw128_desc(smem_u32(As + stage * kChunkBytes));
+                        const uint64_t bd0 = make_sw128_desc(smem_u32(Wt)) + (uint64_t)(c * CH * (4096 / 16));
                         for (int q = 0; q < CH; ++q) {
-                            const int kb = c * CH + q;
-                            const uint64_t adesc = make_sw128_desc(smem_u32(As + stage * kChunkBytes + q * NB * 128));
-                            const uint64_t bdesc = make_sw128_desc(smem_u32(Wt + kb * 4096));
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                tc_mma_bf16(tmem_base + g * 32, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                                            (uint32_t)((kb | k) != 0));
+                                tc_mma_bf16(tmem_base + g * 32, ad0 + (uint64_t)(q * (NB * 128 / 16) + k * 2),
+                                            bd0 + (uint64_t)(q * (4096 / 16) + k * 2), idesc, (uint32_t)((c | q | k) != 0));
                         }
                         tc_commit(&aempty[stage]);
                         if (++stage == kRing) { stage = 0; phase ^= 1; }
@@ -731,11 +733,12 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap map_wt, BwdDev p) {
                 if (s <= T - 2) mbar_expect_tx(afull, step_bytes);            // re-arm for the dgates of step s
                 tc_fence_after();
                 const uint32_t ab = smem_u32(Ab);
-                for (int kk = 0; kk < 4 * H / 16; ++kk) {
-                    const uint64_t adesc = make_nosw_desc(ab + kk * 2 * kChunk, kChunk, 128);
-                    const uint64_t bdesc = make_sw128_desc(smem_u32(Wt + (kk >> 2) * 4096)) + (uint64_t)((kk & 3) * 2);
-                    tc_mma_bf16(tmem_base, adesc, bdesc, idesc, (uint32_t)(kk != 0));
-                }
+                const uint64_t ad0 = make_nosw_desc(ab, kChunk, 128);
+                const uint64_t bd0 = make_sw128_desc(smem_u32(Wt));
+#pragma unroll 8
+                for (int kk = 0; kk < 4 * H / 16; ++kk)
+                    tc_mma_bf16(tmem_base, ad0 + (uint64_t)(kk * (2 * kChunk / 16)),
+                                bd0 + (uint64_t)((kk >> 2) * (4096 / 16) + (kk & 3) * 2), idesc, (uint32_t)(kk != 0));
                 tc_commit(mbar);
             }
         }
@@ -876,7 +879,7 @@ lstm_bwd_rs_kernel(const __grid_constant__ CUtensorMap map_wt, BwdDev p) {
 
     if (threadIdx.x == 0) {
         mbar_init(wbar, 1); mbar_init(aready, 1); mbar_init(dready, 1); mbar_init(dfree, 1);
-        mbar_init(rfull, 1); mbar_init(rfree, (uint32_t)CS);
+        mbar_init(rfull, 1); mbar_init(rfree, (uint32_t)CS * 4u);   // rfree: one arrival per epilogue warp of every CTA
         fence_barrier_init();
         if (T >= 2) mbar_expect_tx(rfull, step_bytes);
     }
@@ -907,12 +910,14 @@ lstm_bwd_rs_kernel(const __grid_constant__ CUtensorMap map_wt, BwdDev p) {
                 if (s > 0) mbar_wait(dfree, (uint32_t)((s - 1) & 1));
                 tc_fence_after();
                 const uint32_t at = smem_u32(At);
+                const uint64_t ad0 = make_nosw_desc(at, kChunk, 128);
+                const uint64_t bd0 = make_sw128_desc(smem_u32(Wb));
+#pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {                 // alternate the N halves: consecutive MMAs hit different accumulators
-                    const uint64_t adesc = make_nosw_desc(at + kk * 2 * kChunk, kChunk, 128);
-                    for (int h = 0; h < NH; ++h) {
-                        const uint64_t bdesc = make_sw128_desc(smem_u32(Wb + (kk >> 2) * H * 128 + h * 256 * 128)) + (uint64_t)((kk & 3) * 2);
-                        tc_mma_bf16(tmem_base + h * 256, adesc, bdesc, idesc, (uint32_t)(kk != 0));
-                    }
+                    for (int h = 0; h < NH; ++h)
+                        tc_mma_bf16(tmem_base + h * 256, ad0 + (uint64_t)(kk * (2 * kChunk / 16)),
+                                    bd0 + (uint64_t)(((kk >> 2) * H * 128 + h * 256 * 128) / 16 + (kk & 3) * 2), idesc,
+                                    (uint32_t)(kk != 0));
                 }
                 tc_commit(dready);
             }
@@ -996,9 +1001,8 @@ lstm_bwd_rs_kernel(const __grid_constant__ CUtensorMap map_wt, BwdDev p) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { dh[k][0] += acc[k][0]; dh[k][1] += acc[k][1]; }
                 PK2_PROF(6);
-                named_bar_sync(1, kEpiThreads);                      // all reads of rcv done
-                if ((threadIdx.x & 7) == 0 && (threadIdx.x >> 3) < CS)
-                    mbar_arrive_remote(mapa_u32(smem_u32(rfree), threadIdx.x >> 3));
+                __syncwarp();                                        // this warp's reads of rcv are done
+                if (lane < CS) mbar_arrive_remote(mapa_u32(smem_u32(rfree), (uint32_t)lane));
                 PK2_PROF(1);
             }
             uint32_t dg[4][4];                                       // bf16x2 per (row, gate)
@@ -1045,7 +1049,8 @@ lstm_bwd_rs_kernel(const __grid_constant__ CUtensorMap map_wt, BwdDev p) {
                     tc_fence_after();
                     if (s > 0) mbar_wait_cluster(rfree, (uint32_t)((s - 1) & 1));   // receivers consumed my previous tiles
                     for (int j = 0; j < CS; j += 4) {
-                        // four 32-column loads in flight per wait (128 accumulator columns per round)
+                        // four 32-column loads in flight per wait (128 accumulator columns per round); the four
+                        // tiles are sent as soon as they are staged, while the next round drains
                         uint32_t v[4][32];
 #pragma unroll
                         for (int h2 = 0; h2 < 4; ++h2)
@@ -1067,19 +1072,19 @@ lstm_bwd_rs_kernel(const __grid_constant__ CUtensorMap map_wt, BwdDev p) {
                                 dstp[q] = o;
                             }
                         }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane < 4 && j + lane < CS) {
+                            // tile for CTA j+lane -> slot `cta` of its receive buffer; bytes counted on its rfull
+                            const uint32_t rank = (uint32_t)(j + lane);
+                            dsmem_bulk_copy(mapa_u32(smem_u32(rcv + cta * kTile), rank), smem_u32(stg + rank * kTile),
+                                            (uint32_t)kTile, mapa_u32(smem_u32(rfull), rank));
+                        }
                     }
                     tc_fence_before();
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     PK2_PROF(4);
                     if (lane == 0) mbar_arrive(dfree);
-                }
-                named_bar_sync(2, kEpiThreads);            // staging complete: any thread may send
-                if ((threadIdx.x & 7) == 0 && (threadIdx.x >> 3) < CS) {
-                    // tile for CTA `rank` -> slot `cta` of its receive buffer; bytes counted on its rfull
-                    const uint32_t rank = threadIdx.x >> 3;
-                    const uint32_t dst = mapa_u32(smem_u32(rcv + cta * kTile), rank);
-                    dsmem_bulk_copy(dst, smem_u32(stg + rank * kTile), (uint32_t)kTile, mapa_u32(smem_u32(rfull), rank));
                 }
                 PK2_PROF(5);
             }

@@ -91,12 +91,15 @@ def finish_step(model, optimizer, averager, max_grad_norm):
 
 
 def chain_step(model, optimizer, averager, feat, den_graph, chain_opts, wav, woff, foff, supervisions,
-               epoch=0, max_grad_norm=5.0, factor=3):
-    """One LF-MMI step (bin/train_chain.py:244-292).  Returns (objf float, total input frames)."""
+               epoch=0, max_grad_norm=5.0, factor=3, after_backward=None):
+    """One LF-MMI step (bin/train_chain.py:244-292).  Returns (objf float, total input frames).
+    ``after_backward``: host callback run once the backward pass is enqueued (e.g. prefetch of the next batch)."""
     shift = epoch % factor                                   # frame_shift = -(epoch % 3) then roll
     x, lens = feat.sequence_batch(wav, woff, foff, factor=factor, shift=shift)
     prediction = model(x)
     loss = ops.ChainObjtiveFunction.apply_batch(prediction, den_graph, supervisions, chain_opts)
     loss.backward()
+    if after_backward is not None:
+        after_backward()
     finish_step(model, optimizer, averager, max_grad_norm)
     return float(loss.item()), int(np.sum(lens))
