@@ -98,7 +98,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
     uint64_t* gfree = mbar + NG;        // [NG] Gx buffer may be overwritten
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gfree + NG);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // shfl: warp-uniform for ptxas
     const int cta = blockIdx.x, dir = blockIdx.y;
     const int nctas = gridDim.x;
     const int u0 = cta * 32;
@@ -115,7 +115,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // uniform register: no R2UR waterfall per tcgen05 op
 
     if (warp == 4) {
         // ===== producer: TMA / bulk loads + inter-CTA step flags =====
@@ -146,23 +146,26 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
         }
     } else if (warp == 5) {
         // ===== MMA issuer =====
-        if (lane == 0) {
+        {   // whole warp in the loop, one elected lane issues (see lstm_fwd_cluster_kernel)
             const uint32_t idesc = make_idesc(128, NB);
             mbar_wait(wbar, 0);
+            const uint64_t ad0 = make_sw128_desc(smem_u32(Ws));
             uint32_t ph_h = 0;
             for (int s = 1; s < T; ++s) {
                 for (int g = 0; g < nga; ++g) {
                     mbar_wait(&hbar[g], ph_h);
                     tc_fence_after();
-                    const uint64_t ad0 = make_sw128_desc(smem_u32(Ws));
                     const uint64_t bd0 = make_sw128_desc(smem_u32(Hs0 + g * hs_bytes));
-                    for (int kb = 0; kb < KB; ++kb) {
+                    if (elect_one()) {
+                        for (int kb = 0; kb < KB; ++kb) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            tc_mma_bf16(tmem_base + g * NB, ad0 + (uint64_t)(kb * (16384 / 16) + k * 2),
-                                        bd0 + (uint64_t)(kb * (NB * 128 / 16) + k * 2), idesc, (uint32_t)((kb | k) != 0));
+                            for (int k = 0; k < 4; ++k)
+                                tc_mma_bf16(tmem_base + g * NB, ad0 + (uint64_t)(kb * (16384 / 16) + k * 2),
+                                            bd0 + (uint64_t)(kb * (NB * 128 / 16) + k * 2), idesc, (uint32_t)((kb | k) != 0));
+                        }
+                        tc_commit(&mbar[g]);
                     }
-                    tc_commit(&mbar[g]);
+                    __syncwarp();
                 }
                 ph_h ^= 1;
             }
@@ -280,7 +283,7 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
     uint64_t* abar = bars + 6;           // W slice copied into tensor memory
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // shfl: warp-uniform for ptxas
     const int CS = gridDim.x;                                // cluster size = H/32
     const int cta = (int)cluster_ctarank();                  // == blockIdx.x
     const int dir = blockIdx.y, grp = blockIdx.z;
@@ -307,7 +310,7 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
     __syncthreads();
     cluster_sync_all();                                      // every CTA's barriers are initialised
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // uniform register: no R2UR waterfall per tcgen05 op
 
     if (warp == 4) {
         if (lane == 0) {
@@ -324,30 +327,39 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
             }
         }
     } else if (warp == 5) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(128, NB);
-            mbar_wait(wbar, 0);
-            if (p.a_tmem) { mbar_wait(abar, 0); tc_fence_after(); }
-            for (int s = 1; s < T; ++s) {
-                const int buf = (s - 1) & 1;
-                mbar_wait(&hfull[buf], (uint32_t)(((s - 1) >> 1) & 1));      // h_{s-1} from all CTAs
-                PK2_PROF(0);
+        // The whole warp runs this loop (warp-uniform control flow, operands in uniform registers); one elected
+        // lane issues.  Under `if (lane == 0)` every tcgen05.mma cost ~92 cycles of ELECT/R2UR waterfall.
+        const uint32_t idesc = make_idesc(128, NB);
+        mbar_wait(wbar, 0);
+        if (p.a_tmem) { mbar_wait(abar, 0); }
+        tc_fence_after();
+        const uint64_t ad0 = make_sw128_desc(smem_u32(Ws));
+        const bool a_tmem = p.a_tmem != 0;
+        for (int s = 1; s < T; ++s) {
+            const int buf = (s - 1) & 1;
+            mbar_wait(&hfull[buf], (uint32_t)(((s - 1) >> 1) & 1));      // h_{s-1} from all CTAs
+            if (lane == 0) PK2_PROF(0);
+            tc_fence_after();
+            // descriptors are affine in kk: bases built once, one 64-bit add per MMA
+            const uint64_t bd0 = make_nosw_desc(smem_u32(Hb + buf * hs_bytes), kChunk, 128);
+            if (elect_one()) {
                 if (s + 1 <= T - 2) mbar_expect_tx(&hfull[buf], step_bytes);  // re-arm for h_{s+1}
-                tc_fence_after();
-                // descriptors are affine in kk: build the bases once, add per MMA (a single thread issues
-                // these; ~20 dependent integer ops per MMA cost ~100 cycles each before -- the whole MMA phase)
-                const uint64_t bd0 = make_nosw_desc(smem_u32(Hb + buf * hs_bytes), kChunk, 128);
-                const uint64_t ad0 = make_sw128_desc(smem_u32(Ws));
+                if (a_tmem) {
 #pragma unroll 8
-                for (int kk = 0; kk < H / 16; ++kk) {
-                    const uint64_t bdesc = bd0 + (uint64_t)(kk * (2 * kChunk / 16));
-                    const uint32_t dq = tmem_base + (uint32_t)(kk & (kAcc - 1)) * NB;      // accumulator kk mod kAcc
-                    if (p.a_tmem) tc_mma_bf16_ts(dq, tmem_base + 256 + kk * 8, bdesc, idesc, (uint32_t)(kk >= kAcc));
-                    else tc_mma_bf16(dq, ad0 + (uint64_t)((kk >> 2) * (16384 / 16) + (kk & 3) * 2), bdesc, idesc, (uint32_t)(kk >= kAcc));
+                    for (int kk = 0; kk < H / 16; ++kk)
+                        tc_mma_bf16_ts(tmem_base + (uint32_t)(kk & (kAcc - 1)) * NB, tmem_base + 256 + kk * 8,
+                                       bd0 + (uint64_t)(kk * (2 * kChunk / 16)), idesc, (uint32_t)(kk >= kAcc));
+                } else {
+#pragma unroll 8
+                    for (int kk = 0; kk < H / 16; ++kk)
+                        tc_mma_bf16(tmem_base + (uint32_t)(kk & (kAcc - 1)) * NB,
+                                    ad0 + (uint64_t)((kk >> 2) * (16384 / 16) + (kk & 3) * 2),
+                                    bd0 + (uint64_t)(kk * (2 * kChunk / 16)), idesc, (uint32_t)(kk >= kAcc));
                 }
-                PK2_PROF(1);
                 tc_commit(mbar);
             }
+            __syncwarp();
+            if (lane == 0) PK2_PROF(1);
         }
     } else {
         const int r = threadIdx.x;
@@ -512,7 +524,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_constan
     uint64_t* aempty = afull + kRing;                        // [kRing]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + kRing);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // shfl: warp-uniform for ptxas
     const int cta = blockIdx.x, dir = blockIdx.y;
     const int nctas = gridDim.x;
     const int u0 = cta * 32;
@@ -534,7 +546,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_constan
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // uniform register: no R2UR waterfall per tcgen05 op
 
     if (warp == 4) {
         if (lane == 0) {
@@ -559,9 +571,10 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_constan
             }
         }
     } else if (warp == 5) {
-        if (lane == 0) {
+        {   // whole warp in the loop, one elected lane issues (see lstm_fwd_cluster_kernel)
             const uint32_t idesc = make_idesc(128, 32);
             mbar_wait(wbar, 0);
+            const uint64_t bdw = make_sw128_desc(smem_u32(Wt));
             uint32_t stage = 0, phase = 0;
             for (int s = 1; s < T; ++s) {
                 for (int g = 0; g < nga; ++g) {
@@ -569,17 +582,20 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_constan
                         mbar_wait(&afull[stage], phase);
                         tc_fence_after();
                         const uint64_t ad0 = make_sw128_desc(smem_u32(As + stage * kChunkBytes));
-                        const uint64_t bd0 = make_sw128_desc(smem_u32(Wt)) + (uint64_t)(c * CH * (4096 / 16));
-                        for (int q = 0; q < CH; ++q) {
+                        const uint64_t bd0 = bdw + (uint64_t)(c * CH * (4096 / 16));
+                        if (elect_one()) {
+                            for (int q = 0; q < CH; ++q) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                tc_mma_bf16(tmem_base + g * 32, ad0 + (uint64_t)(q * (NB * 128 / 16) + k * 2),
-                                            bd0 + (uint64_t)(q * (4096 / 16) + k * 2), idesc, (uint32_t)((c | q | k) != 0));
+                                for (int k = 0; k < 4; ++k)
+                                    tc_mma_bf16(tmem_base + g * 32, ad0 + (uint64_t)(q * (NB * 128 / 16) + k * 2),
+                                                bd0 + (uint64_t)(q * (4096 / 16) + k * 2), idesc, (uint32_t)((c | q | k) != 0));
+                            }
+                            tc_commit(&aempty[stage]);
+                            if (c == NCH - 1) tc_commit(&mbar[g]);
                         }
-                        tc_commit(&aempty[stage]);
+                        __syncwarp();
                         if (++stage == kRing) { stage = 0; phase ^= 1; }
                     }
-                    tc_commit(&mbar[g]);
                 }
             }
         }
@@ -695,7 +711,7 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap map_wt, BwdDev p) {
     uint64_t* afree = bars + 3;          // every receiver has released its A buffer (count = cluster size)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // shfl: warp-uniform for ptxas
     const int CS = gridDim.x;
     const int cta = (int)cluster_ctarank();
     const int dir = blockIdx.y, grp = blockIdx.z;
@@ -716,7 +732,7 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap map_wt, BwdDev p) {
     __syncthreads();
     cluster_sync_all();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // uniform register: no R2UR waterfall per tcgen05 op
 
     if (warp == 4) {
         if (lane == 0) {
@@ -725,21 +741,23 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap map_wt, BwdDev p) {
                 tma_load_2d(&map_wt, wbar, Wt + kb * 4096, kb * 64, dir * H + u0);
         }
     } else if (warp == 5) {
-        if (lane == 0) {
+        {   // whole warp in the loop, one elected lane issues (see lstm_fwd_cluster_kernel)
             const uint32_t idesc = make_idesc(64, 32);       // M = 64: only rows 0..15 are live
             mbar_wait(wbar, 0);
+            const uint64_t ad0 = make_nosw_desc(smem_u32(Ab), kChunk, 128);
+            const uint64_t bd0 = make_sw128_desc(smem_u32(Wt));
             for (int s = 1; s < T; ++s) {
                 mbar_wait(afull, (uint32_t)((s - 1) & 1));                    // dgates of step s-1 from all CTAs
-                if (s <= T - 2) mbar_expect_tx(afull, step_bytes);            // re-arm for the dgates of step s
                 tc_fence_after();
-                const uint32_t ab = smem_u32(Ab);
-                const uint64_t ad0 = make_nosw_desc(ab, kChunk, 128);
-                const uint64_t bd0 = make_sw128_desc(smem_u32(Wt));
+                if (elect_one()) {
+                    if (s <= T - 2) mbar_expect_tx(afull, step_bytes);        // re-arm for the dgates of step s
 #pragma unroll 8
-                for (int kk = 0; kk < 4 * H / 16; ++kk)
-                    tc_mma_bf16(tmem_base, ad0 + (uint64_t)(kk * (2 * kChunk / 16)),
-                                bd0 + (uint64_t)((kk >> 2) * (4096 / 16) + (kk & 3) * 2), idesc, (uint32_t)(kk != 0));
-                tc_commit(mbar);
+                    for (int kk = 0; kk < 4 * H / 16; ++kk)
+                        tc_mma_bf16(tmem_base, ad0 + (uint64_t)(kk * (2 * kChunk / 16)),
+                                    bd0 + (uint64_t)((kk >> 2) * (4096 / 16) + (kk & 3) * 2), idesc, (uint32_t)(kk != 0));
+                    tc_commit(mbar);
+                }
+                __syncwarp();
             }
         }
     } else {
@@ -837,147 +855,173 @@ lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap map_wt, BwdDev p) {
 }
 
 // ------------------------------------------- backward, cluster + DSMEM, K-split / reduce-scatter ----
-// dh_{t-1}[b, j] = sum_n dgates_t[b, n] W_hh[n, j].  Instead of all-gathering dgates (4H columns) and letting
-// every CTA contract over K = 4H for its 32 output units (128 A-read-bound MMAs per step), each CTA
+// dh_{t-1}[b, j] = sum_n dgates_t[b, n] W_hh[n, j].  Instead of all-gathering dgates (4H columns), each CTA
 // contracts ONLY over the 128 gate columns it has just produced itself, for ALL H output units:
-//     P_c[b, j] = sum_{n in slice c} dgates_t[b, n] W_hh[n, j]        (16 MMAs M128 x N256 x K16 per step)
-// and the partial sums are reduce-scattered through distributed shared memory: CTA c sends
-// P_c[:, units of CTA j] (bf16, 2 KB) to CTA j with one bulk copy per destination; CTA j adds the 16 tiles it
-// receives.  No operand is gathered, the A tile is 8 KB and local, W_hh[slice c, :] (128 KB) is the resident
-// B operand.  Receivers release their receive buffer to the senders with remote mbarrier arrives.
+//     P_c[j, b] = sum_{n in slice c} W_hh[n, j] dgates_t[b, n]
+// computed TRANSPOSED: A = W_hh[slice c, :]^T (resident, 128 KB, M = 128 output units per tile, H/128 tiles),
+// B = this step's dgates tile [32 batch rows x 128] (8 KB, local), N = 32: 8 x H/128 small MMAs (16 cycles each)
+// instead of 16 M128xN256 ones, and the accumulator has the output UNIT on the TMEM lane, so every epilogue
+// warp drains its own lane quadrant (with the batch on the lanes only warp 0 could, 2.1 k cycles per step).
+// The partial sums are reduce-scattered through distributed shared memory: tile (units of CTA d) x (32 rows)
+// goes to CTA d as one 2 KB bulk copy, issued by the warp that drained it; CTA d adds the CS tiles it receives.
+// Receivers release their receive buffer to the senders with remote mbarrier arrives (one per warp).
 constexpr int NBR = 32;                  // batch rows per cluster
+constexpr int kRsChunk = NBR / 8 * 128 + 16;   // B-tile K-chunk stride, +16 B: the 4 lane groups of a store hit different banks
 
-__global__ void __launch_bounds__(kThreads, 1)
+template <int EW>                        // epilogue warps: 4 or 8 (warps w and w+4 share a TMEM lane quadrant)
+__global__ void __launch_bounds__((EW + 2) * 32, 1)
 lstm_bwd_rs_kernel(const __grid_constant__ CUtensorMap map_wt, BwdDev p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int RPT = NBR / EW;                            // batch rows per thread (thread = unit lane, rows RPT*w ..)
+    constexpr int kChunk = kRsChunk;
+    constexpr int kBTile = 16 * kChunk;                      // [128 k' / 8][4 row groups][8][16 B] (+ padding)
+    constexpr int kTile = NBR * 32 * 2;                      // 2 KB: one [32 units x 32 rows] bf16 partial tile
     const int H = p.H, T = p.T, B = p.B;
-    const int NH = H / 256;                                  // N = 256 halves of the H output units (H = 512: 2)
-    constexpr int kChunk = NBR / 8 * 128;                    // 512 B: one 16-byte K-chunk over the 32 live rows
-    constexpr int kATile = 16 * kChunk;                      // 8 KB: [128 k' / 8][4 row groups][8][16 B]
-    constexpr int kTile = NBR * 32 * 2;                      // 2 KB: one [32 rows x 32 units] bf16 partial tile
+    const int NM = H / 128;                                  // M tiles of 128 output units
+    const int TPW = NM / (EW / 4);                           // tiles drained per warp
     const int CS = gridDim.x;
     uint8_t* Wb = smem;                                      // 2 k-blocks x [H rows x 64] bf16, SWIZZLE_128B
-    uint8_t* At = Wb + 2 * H * 128;                          // A tile + slack (the M=128 MMA reads rows >= 32)
-    uint8_t* stg = At + kATile + 2048;                       // [CS][32][32] bf16 outgoing partial tiles
-    uint8_t* rcv = stg + CS * kTile;                         // [CS][32][32] bf16 incoming partial tiles
+    uint8_t* Bt = Wb + 2 * H * 128;                          // dgates tile of the step (B operand)
+    uint8_t* stg = Bt + ((kBTile + 1023) & ~1023);           // [CS] outgoing partial tiles
+    uint8_t* rcv = stg + CS * kTile;                         // [CS] incoming partial tiles
     uint64_t* bars = reinterpret_cast<uint64_t*>(rcv + CS * kTile);
     uint64_t* wbar = bars + 0;
-    uint64_t* aready = bars + 1;         // A tile of the step written
+    uint64_t* aready = bars + 1;         // B tile of the step written
     uint64_t* dready = bars + 2;         // MMAs of the step retired
-    uint64_t* dfree = bars + 3;          // accumulator drained
+    uint64_t* dfree = bars + 3;          // accumulator drained (one arrival per epilogue warp)
     uint64_t* rfull = bars + 4;          // all partial tiles of the step landed
-    uint64_t* rfree = bars + 5;          // every receiver has consumed my tiles (count = cluster size)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    uint64_t* rfree = bars + 5;          // every receiver has consumed my tiles (one arrival per CTA)
+    uint64_t* abar = bars + 6;           // W_hh^T slice copied into tensor memory (one arrival per epilogue warp)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // shfl: warp-uniform for ptxas
     const int cta = (int)cluster_ctarank();
     const int dir = blockIdx.y, grp = blockIdx.z;
     const int u0 = cta * 32, b0 = grp * NBR;
     const int nbv = min(NBR, B - b0);
     const uint32_t step_bytes = (uint32_t)CS * kTile;
+    // accumulators: NM x 32 columns; A operand (W_hh^T slice, bf16 pairs): NM x 64 columns at column 128
+    const uint32_t tmem_cols = NM > 2 ? 512u : 256u;
 
     if (threadIdx.x == 0) {
-        mbar_init(wbar, 1); mbar_init(aready, 1); mbar_init(dready, 1); mbar_init(dfree, 1);
-        mbar_init(rfull, 1); mbar_init(rfree, (uint32_t)CS * 4u);   // rfree: one arrival per epilogue warp of every CTA
+        mbar_init(wbar, 1); mbar_init(aready, 1); mbar_init(dready, 1); mbar_init(dfree, EW);
+        mbar_init(rfull, 1); mbar_init(rfree, (uint32_t)CS); mbar_init(abar, EW);
         fence_barrier_init();
         if (T >= 2) mbar_expect_tx(rfull, step_bytes);
     }
-    for (int i = threadIdx.x; i < (kATile + 2048) / 16; i += kThreads)
-        reinterpret_cast<uint4*>(At)[i] = make_uint4(0u, 0u, 0u, 0u);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    if (warp == 5) tmem_alloc(tmem_slot, 512);
+    if (warp == EW + 1) tmem_alloc(tmem_slot, tmem_cols);
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // uniform register: no R2UR waterfall per tcgen05 op
+    const uint32_t tmem_a = tmem_base + 128;
 
-    if (warp == 4) {
+    if (warp == EW) {
         if (lane == 0) {
-            // W_hh[slice c, :] as B operand: rows j (all H), K = my 128 permuted gate columns
+            // W_hh[slice c, :]^T as A operand: rows j (all H), K = my 128 permuted gate columns
             mbar_expect_tx(wbar, (uint32_t)(2 * H * 128));
             for (int kb = 0; kb < 2; ++kb)
-                for (int h = 0; h < NH; ++h)
+                for (int h = 0; h < H / 256; ++h)
                     tma_load_2d(&map_wt, wbar, Wb + kb * H * 128 + h * 256 * 128, cta * 128 + kb * 64, dir * H + h * 256);
         }
-    } else if (warp == 5) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(128, 256);
-            mbar_wait(wbar, 0);
-            for (int s = 0; s + 1 < T; ++s) {
-                mbar_wait(aready, (uint32_t)(s & 1));
-                if (s > 0) mbar_wait(dfree, (uint32_t)((s - 1) & 1));
-                tc_fence_after();
-                const uint32_t at = smem_u32(At);
-                const uint64_t ad0 = make_nosw_desc(at, kChunk, 128);
-                const uint64_t bd0 = make_sw128_desc(smem_u32(Wb));
+    } else if (warp == EW + 1) {
+        // whole warp in the loop, one elected lane issues (see lstm_fwd_cluster_kernel)
+        const uint32_t idesc = make_idesc(128, NBR);
+        mbar_wait(abar, 0);                                      // W_hh^T slice is in tensor memory
+        tc_fence_after();
+        const uint64_t bd0 = make_nosw_desc(smem_u32(Bt), kChunk, 128);
+        for (int s = 0; s + 1 < T; ++s) {
+            mbar_wait(aready, (uint32_t)(s & 1));
+            if (s > 0) mbar_wait(dfree, (uint32_t)((s - 1) & 1));
+            tc_fence_after();
+            if (elect_one()) {
+                for (int m = 0; m < NM; ++m) {
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {                 // alternate the N halves: consecutive MMAs hit different accumulators
-                    for (int h = 0; h < NH; ++h)
-                        tc_mma_bf16(tmem_base + h * 256, ad0 + (uint64_t)(kk * (2 * kChunk / 16)),
-                                    bd0 + (uint64_t)(((kk >> 2) * H * 128 + h * 256 * 128) / 16 + (kk & 3) * 2), idesc,
-                                    (uint32_t)(kk != 0));
+                    for (int kk = 0; kk < 8; ++kk)
+                        tc_mma_bf16_ts(tmem_base + m * 32, tmem_a + m * 64 + kk * 8,
+                                       bd0 + (uint64_t)(kk * (2 * kChunk / 16)), idesc, (uint32_t)(kk != 0));
                 }
                 tc_commit(dready);
             }
+            __syncwarp();
         }
     } else {
-        // Epilogue mapping: thread = (row half rh, unit pair up) of warp w: units u0 + 2up, +1; batch rows
-        // (2w + rh) + 8k, k = 0..3  ->  8 elements per thread, every global / shared access is a bf16x2 or float2.
-        const int up = lane & 15, rh = lane >> 4;
-        float dcn[4][2];
+        // Epilogue mapping: lane = unit (u0 + lane), warp w owns batch rows RPT*w .. RPT*w + RPT - 1.
+        const int q = warp & 3;                                   // TMEM lane quadrant of this warp
+        const int t0 = (warp >> 2) * TPW;                         // first M tile this warp drains
+        {
+            // one-time: rows 128m + 32q + lane of the W_hh^T slice -> tensor memory lane, two bf16 per 32-bit
+            // column, read back out of the 128B-swizzled tiles the TMA wrote (A from TMEM: no per-MMA smem read of A)
+            mbar_wait(wbar, 0);
+            const int r = q * 32 + lane;
+            for (int m = t0; m < t0 + TPW; ++m)
+                for (int kb = 0; kb < 2; ++kb) {
+                    uint32_t w[32];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) dcn[k][0] = dcn[k][1] = 0.f;
+                    for (int ch = 0; ch < 8; ++ch) {
+                        const uint4 x = *reinterpret_cast<const uint4*>(Wb + kb * H * 128 + (m * 128 + r) * 128 + ((ch ^ (r & 7)) << 4));
+                        w[ch * 4 + 0] = x.x; w[ch * 4 + 1] = x.y; w[ch * 4 + 2] = x.z; w[ch * 4 + 3] = x.w;
+                    }
+                    tc_st_32x32b_x32(tmem_a + m * 64 + kb * 32 + ((uint32_t)(q * 32) << 16), w);
+                }
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(abar);
+        }
+        float dcn[RPT];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) dcn[i] = 0.f;
         long long* prof = (p.prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) ? p.prof : nullptr;
 #define PK2_PROF(e) do { if (prof && s >= 64 && s < 72) prof[(s - 64) * 16 + (e)] = clock64(); } while (0)
         // RAW operands of one step, fetched a whole step ahead.  Nothing touches these registers until the next
         // step (no conversion, no select): a dependent instruction right after the load would stall the warp for
         // the full HBM latency (measured: 7 k cycles per step, profiles/lstm_bwd_rs_trace_r1_v10_dbg.txt).
-        uint32_t q_g[4][4];
-        float2 q_c[4], q_cp[4], q_dy[4];
+        unsigned short q_g[RPT][4];
+        float q_c[RPT], q_cp[RPT], q_dy[RPT];
         auto fetch = [&](int s) {
             const int tt = dir ? s : (T - 1 - s);
             const int tfp = dir ? tt + 1 : tt - 1;
             const int tcp = (tfp >= 0 && tfp < T) ? tfp : tt;          // always a valid address; masked at use
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int b = min(2 * warp + rh + 8 * k, nbv - 1);
+            for (int i = 0; i < RPT; ++i) {
+                const int b = min(RPT * warp + i, nbv - 1);
                 const int64_t bb = b0 + b;
-                const __nv_bfloat16* gp = p.gates + ((((int64_t)dir * T + tt) * B + bb) * 4) * H + u0 + 2 * up;
+                const unsigned short* gp = reinterpret_cast<const unsigned short*>(p.gates) +
+                                           ((((int64_t)dir * T + tt) * B + bb) * 4) * H + u0 + lane;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) q_g[k][g] = *reinterpret_cast<const uint32_t*>(gp + g * H);
-                q_c[k] = *reinterpret_cast<const float2*>(p.cstate + (((int64_t)dir * T + tt) * B + bb) * H + u0 + 2 * up);
-                q_cp[k] = *reinterpret_cast<const float2*>(p.cstate + (((int64_t)dir * T + tcp) * B + bb) * H + u0 + 2 * up);
-                q_dy[k] = *reinterpret_cast<const float2*>(p.dy + (bb * T + tt) * 2 * H + dir * H + u0 + 2 * up);
+                for (int g = 0; g < 4; ++g) q_g[i][g] = gp[g * H];
+                q_c[i] = p.cstate[(((int64_t)dir * T + tt) * B + bb) * H + u0 + lane];
+                q_cp[i] = p.cstate[(((int64_t)dir * T + tcp) * B + bb) * H + u0 + lane];
+                q_dy[i] = p.dy[(bb * T + tt) * 2 * H + dir * H + u0 + lane];
             }
         };
         fetch(0);
+        const uint32_t swz = (uint32_t)((lane >> 1) & 3);        // 16-byte chunk swizzle of the partial tiles
+        const uint32_t hsw = (uint32_t)((lane >> 3) & 1);        // 8-byte half swap inside a chunk
         for (int s = 0; s < T; ++s) {
             const int tt = dir ? s : (T - 1 - s);
             const int tfp = dir ? tt + 1 : tt - 1;
             const float cpm = (tfp >= 0 && tfp < T) ? 1.f : 0.f;
-            float cO[4][2], a1[4][2], cI[4][2], cF[4][2], cG[4][2], fgv[4][2], dh[4][2];
+            float cO[RPT], a1[RPT], cI[RPT], cF[RPT], cG[RPT], fgv[RPT], dh[RPT];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float live = (2 * warp + rh + 8 * k < nbv) ? 1.f : 0.f;
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const float ig = __uint_as_float(e ? (q_g[k][0] & 0xffff0000u) : (q_g[k][0] << 16));
-                    const float fg = __uint_as_float(e ? (q_g[k][1] & 0xffff0000u) : (q_g[k][1] << 16));
-                    const float gg = __uint_as_float(e ? (q_g[k][2] & 0xffff0000u) : (q_g[k][2] << 16));
-                    const float og = __uint_as_float(e ? (q_g[k][3] & 0xffff0000u) : (q_g[k][3] << 16));
-                    const float c = e ? q_c[k].y : q_c[k].x;
-                    const float cp = (e ? q_cp[k].y : q_cp[k].x) * cpm;
-                    const float tc_ = tanh_approx(c);
-                    cO[k][e] = live * tc_ * og * (1.0f - og);
-                    a1[k][e] = live * og * (1.0f - tc_ * tc_);
-                    cI[k][e] = gg * ig * (1.0f - ig);
-                    cF[k][e] = cp * fg * (1.0f - fg);
-                    cG[k][e] = ig * (1.0f - gg * gg);
-                    fgv[k][e] = fg;
-                    dh[k][e] = live * (e ? q_dy[k].y : q_dy[k].x);
-                }
+            for (int i = 0; i < RPT; ++i) {
+                const float live = (RPT * warp + i < nbv) ? 1.f : 0.f;
+                const float ig = __uint_as_float((uint32_t)q_g[i][0] << 16);
+                const float fg = __uint_as_float((uint32_t)q_g[i][1] << 16);
+                const float gg = __uint_as_float((uint32_t)q_g[i][2] << 16);
+                const float og = __uint_as_float((uint32_t)q_g[i][3] << 16);
+                const float cp = q_cp[i] * cpm;
+                const float tc_ = tanh_approx(q_c[i]);
+                cO[i] = live * tc_ * og * (1.0f - og);
+                a1[i] = live * og * (1.0f - tc_ * tc_);
+                cI[i] = gg * ig * (1.0f - ig);
+                cF[i] = cp * fg * (1.0f - fg);
+                cG[i] = ig * (1.0f - gg * gg);
+                fgv[i] = fg;
+                dh[i] = live * q_dy[i];
             }
             if (s + 1 < T) fetch(s + 1);                 // in flight during this whole step
             if (s > 0) {
@@ -985,106 +1029,110 @@ lstm_bwd_rs_kernel(const __grid_constant__ CUtensorMap map_wt, BwdDev p) {
                 mbar_wait(rfull, (uint32_t)((s - 1) & 1));
                 PK2_PROF(0);
                 if (threadIdx.x == 0 && s + 1 < T) mbar_expect_tx(rfull, step_bytes);   // re-arm for this step's tiles
-                float acc[4][2];
+                float acc[RPT];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) acc[k][0] = acc[k][1] = 0.f;
+                for (int i = 0; i < RPT; ++i) acc[i] = 0.f;
+                if (EW == 4) {
+                    // rows 8w..8w+7 = chunk w of my unit's 64-byte row
+                    const uint8_t* rp = rcv + lane * 64 + (((uint32_t)warp ^ swz) << 4);
 #pragma unroll 4
-                for (int src = 0; src < CS; ++src) {
+                    for (int src = 0; src < CS; ++src) {
+                        uint4 v = *reinterpret_cast<const uint4*>(rp + src * kTile);
+                        if (hsw) { uint32_t t; t = v.x; v.x = v.z; v.z = t; t = v.y; v.y = v.w; v.w = t; }
+                        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int b = 2 * warp + rh + 8 * k;
-                        const uint32_t v = *reinterpret_cast<const uint32_t*>(rcv + src * kTile + (b * 32 + 2 * up) * 2);
-                        acc[k][0] += __uint_as_float(v << 16);
-                        acc[k][1] += __uint_as_float(v & 0xffff0000u);
+                        for (int j2 = 0; j2 < 4; ++j2) {
+                            acc[(2 * j2) % RPT] += __uint_as_float(wv[j2] << 16);
+                            acc[(2 * j2 + 1) % RPT] += __uint_as_float(wv[j2] & 0xffff0000u);
+                        }
+                    }
+                } else {
+                    // rows 4w..4w+3 = half (w & 1) of chunk w >> 1
+                    const uint8_t* rp = rcv + lane * 64 + ((((uint32_t)warp >> 1) ^ swz) << 4) + ((((uint32_t)warp & 1) ^ hsw) << 3);
+#pragma unroll 4
+                    for (int src = 0; src < CS; ++src) {
+                        const uint2 v = *reinterpret_cast<const uint2*>(rp + src * kTile);
+                        acc[0] += __uint_as_float(v.x << 16);
+                        acc[1 % RPT] += __uint_as_float(v.x & 0xffff0000u);
+                        acc[2 % RPT] += __uint_as_float(v.y << 16);
+                        acc[3 % RPT] += __uint_as_float(v.y & 0xffff0000u);
                     }
                 }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { dh[k][0] += acc[k][0]; dh[k][1] += acc[k][1]; }
+                for (int i = 0; i < RPT; ++i) dh[i] += acc[i];
                 PK2_PROF(6);
-                __syncwarp();                                        // this warp's reads of rcv are done
-                if (lane < CS) mbar_arrive_remote(mapa_u32(smem_u32(rfree), (uint32_t)lane));
-                PK2_PROF(1);
             }
-            uint32_t dg[4][4];                                       // bf16x2 per (row, gate)
+            unsigned short dg[RPT][4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int b = 2 * warp + rh + 8 * k;
-                float o[4][2];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const float dc = fmaf(dh[k][e], a1[k][e], dcn[k][e]);
-                    dcn[k][e] = dc * fgv[k][e];
-                    o[0][e] = dc * cI[k][e]; o[1][e] = dc * cF[k][e]; o[2][e] = dc * cG[k][e]; o[3][e] = dh[k][e] * cO[k][e];
-                }
+            for (int i = 0; i < RPT; ++i) {
+                const int b = RPT * warp + i;
+                const float dc = fmaf(dh[i], a1[i], dcn[i]);
+                dcn[i] = dc * fgv[i];
+                const float o[4] = {dc * cI[i], dc * cF[i], dc * cG[i], dh[i] * cO[i]};
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
-                    __nv_bfloat162 pr = __floats2bfloat162_rn(o[g][0], o[g][1]);
-                    dg[k][g] = *reinterpret_cast<uint32_t*>(&pr);
+                    dg[i][g] = __bfloat16_as_ushort(__float2bfloat16_rn(o[g]));
                     if (s + 1 < T) {
-                        const int col = g * 32 + 2 * up;              // k' within my slice = gate*32 + unit
-                        *reinterpret_cast<uint32_t*>(At + (col >> 3) * kChunk + (b >> 3) * 128 + (b & 7) * 16 + (col & 7) * 2) = dg[k][g];
+                        const int col = g * 32 + lane;                // k' within my slice = gate*32 + unit
+                        *reinterpret_cast<unsigned short*>(Bt + (col >> 3) * kChunk + (b >> 3) * 128 + (b & 7) * 16 + (col & 7) * 2) = dg[i][g];
                     }
                 }
             }
             if (s + 1 < T) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                named_bar_sync(1, kEpiThreads);
+                named_bar_sync(1, EW * 32);
                 if (threadIdx.x == 0) { PK2_PROF(2); mbar_arrive(aready); }
+                // every epilogue warp is past its reads of rcv: release it to the senders, one arrival per
+                // destination, spread over the warps (16 remote arrives from ONE warp serialise: 1.2 k cycles)
+                constexpr int kStride = EW * 32 / 16;
+                if (s > 0 && (threadIdx.x % kStride) == 0 && (int)(threadIdx.x / kStride) < CS)
+                    mbar_arrive_remote(mapa_u32(smem_u32(rfree), threadIdx.x / kStride));
+                PK2_PROF(1);
             }
             // off the critical path: dgates in the natural layout for the weight-gradient GEMMs
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int b = 2 * warp + rh + 8 * k;
+            for (int i = 0; i < RPT; ++i) {
+                const int b = RPT * warp + i;
                 if (b < nbv) {
-                    __nv_bfloat16* dp = p.dgates + (((int64_t)(b0 + b) * T + tt) * 2 + dir) * 4 * H + u0 + 2 * up;
+                    unsigned short* dp = reinterpret_cast<unsigned short*>(p.dgates) +
+                                         (((int64_t)(b0 + b) * T + tt) * 2 + dir) * 4 * H + u0 + lane;
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) *reinterpret_cast<uint32_t*>(dp + g * H) = dg[k][g];
+                    for (int g = 0; g < 4; ++g) dp[g * H] = dg[i][g];
                 }
             }
             if (s + 1 < T) {
-                // partial products of this step: TMEM rows 0..31 (lanes 0..31: warp 0) x H columns -> bf16 tiles
-                if (warp == 0) {
-                    mbar_wait(dready, (uint32_t)(s & 1));
-                    PK2_PROF(3);
-                    tc_fence_after();
-                    if (s > 0) mbar_wait_cluster(rfree, (uint32_t)((s - 1) & 1));   // receivers consumed my previous tiles
-                    for (int j = 0; j < CS; j += 4) {
-                        // four 32-column loads in flight per wait (128 accumulator columns per round); the four
-                        // tiles are sent as soon as they are staged, while the next round drains
-                        uint32_t v[4][32];
+                // partial sums of this step: TMEM lane = output unit, column = batch row
+                mbar_wait(dready, (uint32_t)(s & 1));
+                PK2_PROF(3);
+                tc_fence_after();
+                if (s > 0) mbar_wait_cluster(rfree, (uint32_t)((s - 1) & 1));   // receivers consumed my previous tiles
+                for (int t = t0; t < t0 + TPW; ++t) {
+                    uint32_t v[32];
+                    tc_ld_32x32b_x32(tmem_base + t * 32 + ((uint32_t)(q * 32) << 16), v);
+                    uint8_t* dstp = stg + (4 * t + q) * kTile + lane * 64;   // tile for CTA 4t+q: [unit = lane][32 rows]
 #pragma unroll
-                        for (int h2 = 0; h2 < 4; ++h2)
-                            if (j + h2 < CS) tc_ld_32x32b_x32_nowait(tmem_base + (j + h2) * 32, v[h2]);
-                        tc_wait_ld();
-#pragma unroll
-                        for (int h2 = 0; h2 < 4; ++h2) {
-                            if (j + h2 >= CS) break;
-                            uint4* dstp = reinterpret_cast<uint4*>(stg + (j + h2) * kTile + lane * 64);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                __nv_bfloat162 p0 = __floats2bfloat162_rn(__uint_as_float(v[h2][q * 8 + 0]), __uint_as_float(v[h2][q * 8 + 1]));
-                                __nv_bfloat162 p1 = __floats2bfloat162_rn(__uint_as_float(v[h2][q * 8 + 2]), __uint_as_float(v[h2][q * 8 + 3]));
-                                __nv_bfloat162 p2 = __floats2bfloat162_rn(__uint_as_float(v[h2][q * 8 + 4]), __uint_as_float(v[h2][q * 8 + 5]));
-                                __nv_bfloat162 p3 = __floats2bfloat162_rn(__uint_as_float(v[h2][q * 8 + 6]), __uint_as_float(v[h2][q * 8 + 7]));
-                                uint4 o;
-                                o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
-                                o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
-                                dstp[q] = o;
-                            }
-                        }
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        __syncwarp();
-                        if (lane < 4 && j + lane < CS) {
-                            // tile for CTA j+lane -> slot `cta` of its receive buffer; bytes counted on its rfull
-                            const uint32_t rank = (uint32_t)(j + lane);
-                            dsmem_bulk_copy(mapa_u32(smem_u32(rcv + cta * kTile), rank), smem_u32(stg + rank * kTile),
-                                            (uint32_t)kTile, mapa_u32(smem_u32(rfull), rank));
-                        }
+                    for (int c = 0; c < 4; ++c) {
+                        __nv_bfloat162 p0 = __floats2bfloat162_rn(__uint_as_float(v[c * 8 + 0]), __uint_as_float(v[c * 8 + 1]));
+                        __nv_bfloat162 p1 = __floats2bfloat162_rn(__uint_as_float(v[c * 8 + 2]), __uint_as_float(v[c * 8 + 3]));
+                        __nv_bfloat162 p2 = __floats2bfloat162_rn(__uint_as_float(v[c * 8 + 4]), __uint_as_float(v[c * 8 + 5]));
+                        __nv_bfloat162 p3 = __floats2bfloat162_rn(__uint_as_float(v[c * 8 + 6]), __uint_as_float(v[c * 8 + 7]));
+                        uint4 o;
+                        o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+                        o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+                        if (hsw) { uint32_t x; x = o.x; o.x = o.z; o.z = x; x = o.y; o.y = o.w; o.w = x; }
+                        *reinterpret_cast<uint4*>(dstp + (((uint32_t)c ^ swz) << 4)) = o;
                     }
-                    tc_fence_before();
-                    __syncwarp();
-                    PK2_PROF(4);
-                    if (lane == 0) mbar_arrive(dfree);
+                }
+                tc_fence_before();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                PK2_PROF(4);
+                if (lane == 0) mbar_arrive(dfree);
+                if (lane < TPW) {
+                    // tile for CTA `rank` -> slot `cta` of its receive buffer; bytes counted on its rfull
+                    const uint32_t rank = (uint32_t)(4 * (t0 + lane) + q);
+                    dsmem_bulk_copy(mapa_u32(smem_u32(rcv + cta * kTile), rank), smem_u32(stg + rank * kTile),
+                                    (uint32_t)kTile, mapa_u32(smem_u32(rfull), rank));
                 }
                 PK2_PROF(5);
             }
@@ -1094,7 +1142,7 @@ lstm_bwd_rs_kernel(const __grid_constant__ CUtensorMap map_wt, BwdDev p) {
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
-    if (warp == 5) tmem_dealloc(tmem_base, 512);
+    if (warp == EW + 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 // ------------------------------------------------------------------------------ host ----
@@ -1313,10 +1361,10 @@ int launch_bwd_cluster(const pk2_lstm_bwd_args* a, cudaStream_t st) {
 }
 
 // K-split / reduce-scatter backward on clusters; needs the permuted W_hh^T (a->whh_t_perm).
-int launch_bwd_rs(const pk2_lstm_bwd_args* a, cudaStream_t st) {
+template <int EW>
+int launch_bwd_rs_t(const pk2_lstm_bwd_args* a, cudaStream_t st) {
     const int H = a->H, T = a->T, B = a->B, CS = H / 32;
     const int G = (B + NBR - 1) / NBR;
-    if (CS > 16 || (CS & (CS - 1)) != 0 || H % 256 != 0 || a->whh_t_perm == nullptr) return -1;
     CUtensorMap mwt;
     {
         cuuint64_t dims[2] = {(cuuint64_t)(4 * H), (cuuint64_t)(2 * H)};
@@ -1324,12 +1372,12 @@ int launch_bwd_rs(const pk2_lstm_bwd_args* a, cudaStream_t st) {
         cuuint32_t box[2] = {64, 256};
         if (make_map(&mwt, a->whh_t_perm, 2, dims, str, box)) return 2;
     }
-    const size_t smem = (size_t)2 * H * 128 + 8192 + 2048 + 2 * (size_t)CS * 2048 + 128 + 1024;
+    const size_t smem = (size_t)2 * H * 128 + ((16 * kRsChunk + 1023) & ~1023) + 2 * (size_t)CS * 2048 + 128 + 1024;
     static bool attr_done = false, usable = true;
     if (!attr_done) {
         attr_done = true;
-        if (cudaFuncSetAttribute(lstm_bwd_rs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) != cudaSuccess ||
-            cudaFuncSetAttribute(lstm_bwd_rs_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        if (cudaFuncSetAttribute(lstm_bwd_rs_kernel<EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) != cudaSuccess ||
+            cudaFuncSetAttribute(lstm_bwd_rs_kernel<EW>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
             cudaGetLastError();
             usable = false;
         }
@@ -1337,7 +1385,7 @@ int launch_bwd_rs(const pk2_lstm_bwd_args* a, cudaStream_t st) {
     if (!usable || smem > 232448) return -1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CS, 2, G);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3((EW + 2) * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -1345,7 +1393,7 @@ int launch_bwd_rs(const pk2_lstm_bwd_args* a, cudaStream_t st) {
     attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     int max_clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, lstm_bwd_rs_kernel, &cfg) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, lstm_bwd_rs_kernel<EW>, &cfg) != cudaSuccess) {
         cudaGetLastError();
         return -1;
     }
@@ -1356,10 +1404,19 @@ int launch_bwd_rs(const pk2_lstm_bwd_args* a, cudaStream_t st) {
     d.cstate = a->cstate;
     d.dgates = static_cast<__nv_bfloat16*>(a->dgates);
     d.counters = a->sync; d.prof = g_prof_bwd;
-    { const char* e = getenv("PK2_LSTM_RS_DBG"); d.dbg = e ? atoi(e) : 0; }
-    PK2_CHECK(cudaLaunchKernelEx(&cfg, lstm_bwd_rs_kernel, mwt, d));
+    d.dbg = 0;
+    PK2_CHECK(cudaLaunchKernelEx(&cfg, lstm_bwd_rs_kernel<EW>, mwt, d));
     PK2_LAUNCHED();
     return 0;
+}
+
+int launch_bwd_rs(const pk2_lstm_bwd_args* a, cudaStream_t st) {
+    const int H = a->H, CS = H / 32;
+    // H = 256 (8 CTAs, 2 M tiles) or 512 (16 CTAs, 4 M tiles); the resident W_hh^T slice is 256*H bytes
+    if ((H != 256 && H != 512) || CS > 16 || a->whh_t_perm == nullptr) return -1;
+    static int ew = -1;
+    if (ew < 0) { const char* e = getenv("PK2_LSTM_RS_EW"); ew = (e && atoi(e) == 4) ? 4 : 8; }
+    return ew == 4 ? launch_bwd_rs_t<4>(a, st) : launch_bwd_rs_t<8>(a, st);
 }
 
 }  // namespace

@@ -46,7 +46,7 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     PipeBars* bars = reinterpret_cast<PipeBars*>(smem + kStages * kStageBytes);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // shfl: warp-uniform for ptxas
     const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
     const int num_tiles = num_m * num_n;
     const int num_kb = (K + BK - 1) / BK;
@@ -69,39 +69,41 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = bars->tmem_base;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, bars->tmem_base, 0);   // uniform register for the tcgen05 ops
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile % num_m) * BM, n0 = (tile / num_m) * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&bars->empty[stage], phase ^ 1);
+        // ===== TMA producer =====  (whole warp runs the loop, one elected lane issues: in a divergent
+        // `if (lane == 0)` region ptxas wraps every UTMALDG / UTCHMMA in an ELECT/R2UR waterfall loop)
+        uint32_t stage = 0, phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m0 = (tile % num_m) * BM, n0 = (tile / num_m) * BN;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&bars->empty[stage], phase ^ 1);
+                if (elect_one()) {
                     mbar_expect_tx(&bars->full[stage], kStageBytes);
                     uint8_t* sa = smem + stage * kStageBytes;
                     tma_load_2d(&map_a, &bars->full[stage], sa, kb * BK, m0);
                     tma_load_2d(&map_b, &bars->full[stage], sa + kStageBytesA, kb * BK, n0);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BM, BN);
-            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+        constexpr uint32_t idesc = make_idesc(BM, BN);
+        uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&bars->full[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&bars->full[stage], phase);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-                    const uint64_t adesc = make_sw128_desc(sa);
-                    const uint64_t bdesc = make_sw128_desc(sa + kStageBytesA);
+                const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+                const uint64_t adesc = make_sw128_desc(sa);
+                const uint64_t bdesc = make_sw128_desc(sa + kStageBytesA);
+                if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in 16 B units
@@ -110,10 +112,11 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     }
                     tc_commit(&bars->empty[stage]);           // frees the smem slot when the MMAs retire
                     if (kb == num_kb - 1) tc_commit(&bars->tmem_full[acc]);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> global =====

@@ -40,6 +40,15 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// One lane of a fully converged warp.  Issue tcgen05.mma / commit under this predicate from warp-uniform
+// code (NOT under `if (lane == 0)`): in a divergent region ptxas wraps every UTCHMMA in an
+// ELECT / R2UR / BRA.U.ANY waterfall loop, ~90 cycles per instruction (profiles/lstm_cluster_trace_r1_v15.txt).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"

@@ -48,7 +48,8 @@ def _ref_model(F, N, H, L, seed):
     return lstm, lin
 
 
-@pytest.mark.parametrize("B,T,F,N,H,L", [(3, 7, 16, 24, 64, 1), (5, 9, 80, 104, 128, 2), (64, 12, 80, 5768, 512, 3)])
+@pytest.mark.parametrize("B,T,F,N,H,L", [(3, 7, 16, 24, 64, 1), (5, 9, 80, 104, 128, 2), (40, 10, 40, 96, 256, 1),
+                                            (64, 12, 80, 5768, 512, 3)])
 def test_lstmam_forward_backward_vs_torch(dev, B, T, F, N, H, L):
     from pykaldi2_b200.models.lstm import LSTMAM
     lstm, lin = _ref_model(F, N, H, L, seed=B + T)
