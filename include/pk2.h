@@ -175,6 +175,9 @@ typedef struct {
 int pk2_lstm_layer_fwd(const pk2_lstm_fwd_args* a, void* stream);
 /* profiling aid: device int64[128] receiving clock64() stamps of 8 steps of one CTA; NULL = off */
 int pk2_lstm_set_profile_buffer(void* buf);
+/* profiling aid: device int64[128]; frames 64..71 of the first cluster of every pk2_denfb launch stamp clock64()
+ * at 7 points of the forward ([0,64)) and backward ([64,128)) frame loop; NULL = off */
+int pk2_den_set_profile_buffer(void* buf);
 
 typedef struct {
     int B, T, H;

@@ -1086,7 +1086,7 @@ lstm_bwd_rs_kernel(const __grid_constant__ CUtensorMap map_wt, BwdDev p) {
                 // destination, spread over the warps (16 remote arrives from ONE warp serialise: 1.2 k cycles)
                 constexpr int kStride = EW * 32 / 16;
                 if (s > 0 && (threadIdx.x % kStride) == 0 && (int)(threadIdx.x / kStride) < CS)
-                    mbar_arrive_remote(mapa_u32(smem_u32(rfree), threadIdx.x / kStride));
+                    mbar_arrive_remote_relaxed(mapa_u32(smem_u32(rfree), threadIdx.x / kStride));   // reads consumed before the barrier above
                 PK2_PROF(1);
             }
             // off the critical path: dgates in the natural layout for the weight-gradient GEMMs

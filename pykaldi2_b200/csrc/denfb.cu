@@ -278,6 +278,7 @@ struct DenArgs {
     double* logz;
     const int32_t* seq_map;   // sequence handled by cluster i (NULL = identity)
     int debug;                // profiling only (PK2_DEN_DEBUG): 1 = skip the arc loops, 2 = skip the passes
+    long long* prof;          // profiling only: clock64 stamps of frames 64..71 of cluster 0 (pk2_den_set_profile_buffer)
 };
 
 constexpr int kInitRegs = 8;     // init[] values a thread keeps in registers (covers S <= 8192)
@@ -410,7 +411,10 @@ __global__ void __launch_bounds__(kThreads, 1) den_forward_kernel(DenArgs a) {
     cluster_barrier<K>();           // peers' shared memory is live from here on; ev / cur complete
     if (T > 1) row_prefetch(lraw, ll + (int64_t)N, N);
 
+    long long* prof = (a.prof && blockIdx.x == 0 && threadIdx.x == 0) ? a.prof : nullptr;
+#define PK2_DPROF(e) do { if (prof && t >= 64 && t < 72) prof[(t - 64) * 8 + (e)] = clock64(); } while (0)
     for (int t = 0; t < T; ++t) {
+        PK2_DPROF(0);
         // cur = alpha'(t) (complete in every CTA), ev = e(t), lraw <- loglikes[t+1] in flight
         for (int j = r0 + threadIdx.x; j < r1; j += kThreads) aws[(int64_t)t * S + j] = cur[j];
         if (threadIdx.x == 0 && c == 0) asum[t] = A;
@@ -425,7 +429,9 @@ __global__ void __launch_bounds__(kThreads, 1) den_forward_kernel(DenArgs a) {
             nxt[row] = v;
             if (K > 1) stg[row - r0] = v;
         }, a.debug);
+        PK2_DPROF(1);
         const float An = cluster_exchange<K>(xs, nxt, stg, r0, r1, pk2::warp_sum(local), par, c);
+        PK2_DPROF(2);
         // alpha'(t+1) in place, e(t+1) from the prefetched row
         const float lk = a.leaky * An;
 #pragma unroll
@@ -435,16 +441,21 @@ __global__ void __launch_bounds__(kThreads, 1) den_forward_kernel(DenArgs a) {
         }
         for (int j = threadIdx.x + kInitRegs * kThreads; j < S; j += kThreads)
             nxt[j] = fmaf(lk, __ldg(&a.init[j]), nxt[j]);
+        PK2_DPROF(3);
         if (t + 1 < T) {
             cp_async_wait_all();
             __syncthreads();                          // lraw visible to all threads; nxt update done
+            PK2_DPROF(4);
             for (int p = threadIdx.x; p < N; p += kThreads) ev[p] = __expf(fminf(fmaxf(lraw[p], -30.f), 30.f));
         }
         A = An;
         float* tmp = cur; cur = nxt; nxt = tmp;
+        PK2_DPROF(5);
         __syncthreads();
         if (t + 2 < T) row_prefetch(lraw, ll + (int64_t)(t + 2) * N, N);
+        PK2_DPROF(6);
     }
+#undef PK2_DPROF
     // total probability: sum_j alpha'(T, j)
     float s2 = 0.f;
     for (int j = threadIdx.x; j < S; j += kThreads) s2 += cur[j];
@@ -546,9 +557,13 @@ __global__ void __launch_bounds__(kThreads, 1) den_backward_kernel(DenArgs a) {
     float* aln = kAl2 ? al2 : al;    // alpha'(t-1) being prefetched
     float asum_t = asum[T - 1];
 
+    long long* prof = (a.prof && blockIdx.x == 0 && threadIdx.x == 0) ? a.prof + 64 : nullptr;
+#define PK2_DPROF(e) do { if (prof && t >= 64 && t < 72) prof[(t - 64) * 8 + (e)] = clock64(); } while (0)
     for (int t = T - 1; t >= 0; --t) {
+        PK2_DPROF(0);
         cp_async_wait_all();
         __syncthreads();
+        PK2_DPROF(1);
         for (int p = threadIdx.x; p < N; p += kThreads)
             ev[p] = __expf(fminf(fmaxf(lraw[p], -30.f), 30.f));
         const float invA = 1.0f / asum_t;
@@ -558,6 +573,7 @@ __global__ void __launch_bounds__(kThreads, 1) den_backward_kernel(DenArgs a) {
             row_prefetch(lraw, ll + (int64_t)(t - 1) * N, N);
             if (kAl2) row_prefetch(aln, aws + (int64_t)(t - 1) * S, S);
         }
+        PK2_DPROF(2);
 
         // beta'(t, i) for this CTA's source states
         float local = 0.f;
@@ -566,20 +582,25 @@ __global__ void __launch_bounds__(kThreads, 1) den_backward_kernel(DenArgs a) {
             local = fmaf(v, init_row, local);
             nxt[row] = v;
         }, a.debug, a.init);
+        PK2_DPROF(3);
         // pdf occupancies gamma(t, p) for this CTA's pdf range
         const float gs = a.deriv_scale * invA;
         sell_pass<2>(tg, alc, cur, [&](int row, float acc, float acc2, float) {
             gbuf[row - p0] = fmaf(lk, acc2, acc) * ev[row] * gs;
         }, a.debug);
+        PK2_DPROF(4);
         const int par = t & 1;
         const float dot = cluster_exchange<K>(xs, nxt, nxt + r0, r0, r1, pk2::warp_sum(local), par, c);
+        PK2_DPROF(5);
         // (block barrier passed inside: gbuf / al reads of this frame are complete in this CTA)
         for (int p = p0 + threadIdx.x; p < p1; p += kThreads) grad[(int64_t)t * N + p] = gbuf[p - p0];
         if (kAl2) { float* t2 = alc; alc = aln; aln = t2; }
         else if (t > 0) row_prefetch(al, aws + (int64_t)(t - 1) * S, S);
         lk = a.leaky * dot;
         float* tmp = cur; cur = nxt; nxt = tmp;
+        PK2_DPROF(6);
     }
+#undef PK2_DPROF
     cluster_barrier<K>();
 }
 
@@ -597,6 +618,8 @@ size_t bwd_smem_bytes(int S, int N, int K) {
     return sizeof(float) * ((K > 1 ? 4 : 3) * Sp + 2 * Np + gcap + 2 * kMaxK * kWarps + kWarps + 4) +
            sizeof(int2) * ((S + 31) / 32 + (N + 31) / 32 + 4) + sizeof(uint16_t) * (rows_part + 64) + 64 + 16;
 }
+
+long long* g_den_prof = nullptr;     // pk2_den_set_profile_buffer (profiling only)
 
 template <int K>
 int launch_den(const DenArgs& args, int n_seq, cudaStream_t st) {
@@ -699,6 +722,11 @@ extern "C" int pk2_den_graph_create(int S, int N, const int32_t* fwd_off, const 
     return 0;
 }
 
+extern "C" int pk2_den_set_profile_buffer(void* buf) {
+    g_den_prof = static_cast<long long*>(buf);
+    return 0;
+}
+
 extern "C" int pk2_den_graph_destroy(void* graph) {
     if (!graph) return 0;
     DenGraph* g = static_cast<DenGraph*>(graph);
@@ -742,6 +770,7 @@ extern "C" int pk2_denfb(void* graph, const float* loglikes, const int32_t* num_
     int32_t* maps_dev = reinterpret_cast<int32_t*>(static_cast<char*>(workspace) + alpha + asum);
     a.grad = grad; a.logz = logz; a.seq_map = nullptr;
     { const char* e = getenv("PK2_DEN_DEBUG"); a.debug = e ? atoi(e) : 0; }
+    a.prof = g_den_prof;
 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);

@@ -189,6 +189,12 @@ __device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster, uint32_t s
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t mbar_cluster) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mbar_cluster) : "memory");
 }
+// Remote arrive WITHOUT the release fence.  The release form waits for every outstanding memory operation of
+// the thread (here: global prefetch loads ~1.2 k cycles).  Only valid when the accesses being released are
+// already complete (shared-memory reads whose values were consumed before a barrier the caller passed).
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t mbar_cluster) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(mbar_cluster) : "memory");
+}
 // wait with acquire at cluster scope (pairs with mbar_arrive_remote)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
     asm volatile(
