@@ -83,7 +83,7 @@ template <int NG>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_y, FwdDev p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     const int H = p.H, T = p.T, B = p.B;
     const int KB = H / 64;                                   // k-blocks of 64
     uint8_t* Ws = smem;                                      // KB x [128 x 64] bf16
@@ -260,15 +260,20 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
 // on the critical path.  The h operand uses the SWIZZLE_NONE K-major layout
 // [K/8 chunks][NB/8 row groups][8 rows][16 B] so that each sender's slice is one contiguous 2 KB block.
 // h tiles are double buffered (a sender may run one step ahead of a receiver's MMA).
-__global__ void __launch_bounds__(kThreads, 1)
+// EW epilogue warps (4 or 8): warps w and w+4 share TMEM lane quadrant w&3 (= gate) and split the batch
+// columns; ACC independent accumulators (1 or 4) summed in the epilogue.
+template <int EW, int ACC>
+__global__ void __launch_bounds__((EW + 2) * 32, 1)
 lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     const int H = p.H, T = p.T, B = p.B;
     const int KB = H / 64;
     constexpr int kChunk = NB / 8 * 128;                     // bytes of one 16-byte K-chunk over NB rows
-    constexpr int kAcc = 4;                                  // independent TMEM accumulators (summed in the epilogue)
     constexpr int kSlice = NB * 64;                          // bytes one CTA contributes per step
+    constexpr int CPW = NB / (EW / 4);                       // batch columns per epilogue warp in phase 1
+    constexpr int RPW = NB / EW;                             // batch rows per epilogue warp in phase 2
+    constexpr int kEpi = EW * 32;
     const int hs_bytes = H * NB * 2;
     uint8_t* Ws = smem;                                      // KB x [128 x 64] bf16, SWIZZLE_128B
     uint8_t* Hb = Ws + KB * 16384;                           // 2 x [H/8 chunks][NB/8][8][16 B]
@@ -295,24 +300,23 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
 
     if (threadIdx.x == 0) {
         mbar_init(wbar, 1); mbar_init(&hfull[0], 1); mbar_init(&hfull[1], 1);
-        mbar_init(gbar, 1); mbar_init(mbar, 1); mbar_init(gfree, 1); mbar_init(abar, 4);
+        mbar_init(gbar, 1); mbar_init(mbar, 1); mbar_init(gfree, 1); mbar_init(abar, EW);
         fence_barrier_init();
         if (T >= 2) mbar_expect_tx(&hfull[0], step_bytes);    // h_0
         if (T >= 3) mbar_expect_tx(&hfull[1], step_bytes);    // h_1
     }
-    for (int i = threadIdx.x; i < NB * 128; i += kThreads) gxs[i] = 0.f;   // padded batch rows stay finite
+    for (int i = threadIdx.x; i < NB * 128; i += (EW + 2) * 32) gxs[i] = 0.f;   // padded batch rows stay finite
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // before the bulk copies write gxs
-    // D: kAcc independent accumulators of 32 columns (dependent tcgen05.mma on ONE accumulator serialise at the
-    // full pipeline latency, ~97 cycles each: 4 accumulators let them pipeline); A: H/2 columns at column 256
+    // D: ACC accumulators of NB columns; A (W_hh slice, bf16 pairs): H/2 columns at column 256
     const uint32_t tmem_cols = p.a_tmem ? 512u : 128u;
-    if (warp == 5) tmem_alloc(tmem_slot, tmem_cols);
+    if (warp == EW + 1) tmem_alloc(tmem_slot, tmem_cols);
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                                      // every CTA's barriers are initialised
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // uniform register: no R2UR waterfall per tcgen05 op
 
-    if (warp == 4) {
+    if (warp == EW) {
         if (lane == 0) {
             mbar_expect_tx(wbar, (uint32_t)KB * 16384u);
             for (int kb = 0; kb < KB; ++kb)
@@ -326,7 +330,7 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
                 bulk_load(gxs, src, (uint32_t)nbv * 512u, gbar);
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == EW + 1) {
         // The whole warp runs this loop (warp-uniform control flow, operands in uniform registers); one elected
         // lane issues.  Under `if (lane == 0)` every tcgen05.mma cost ~92 cycles of ELECT/R2UR waterfall.
         const uint32_t idesc = make_idesc(128, NB);
@@ -347,14 +351,14 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
                 if (a_tmem) {
 #pragma unroll 8
                     for (int kk = 0; kk < H / 16; ++kk)
-                        tc_mma_bf16_ts(tmem_base + (uint32_t)(kk & (kAcc - 1)) * NB, tmem_base + 256 + kk * 8,
-                                       bd0 + (uint64_t)(kk * (2 * kChunk / 16)), idesc, (uint32_t)(kk >= kAcc));
+                        tc_mma_bf16_ts(tmem_base + (uint32_t)(kk & (ACC - 1)) * NB, tmem_base + 256 + kk * 8,
+                                       bd0 + (uint64_t)(kk * (2 * kChunk / 16)), idesc, (uint32_t)(kk >= ACC));
                 } else {
 #pragma unroll 8
                     for (int kk = 0; kk < H / 16; ++kk)
-                        tc_mma_bf16(tmem_base + (uint32_t)(kk & (kAcc - 1)) * NB,
+                        tc_mma_bf16(tmem_base + (uint32_t)(kk & (ACC - 1)) * NB,
                                     ad0 + (uint64_t)((kk >> 2) * (16384 / 16) + (kk & 3) * 2),
-                                    bd0 + (uint64_t)(kk * (2 * kChunk / 16)), idesc, (uint32_t)(kk >= kAcc));
+                                    bd0 + (uint64_t)(kk * (2 * kChunk / 16)), idesc, (uint32_t)(kk >= ACC));
                 }
                 tc_commit(mbar);
             }
@@ -362,23 +366,26 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
             if (lane == 0) PK2_PROF(1);
         }
     } else {
-        const int r = threadIdx.x;
-        const int gate = warp;
-        float cst[NB / 4];
+        const int gate = warp & 3;                               // TMEM lane quadrant = gate
+        const int r = gate * 32 + lane;                          // gate row of this thread (phase 1)
+        const int c0 = (warp >> 2) * CPW;                        // first batch column of this warp (phase 1)
+        float cst[RPW];
 #pragma unroll
-        for (int k = 0; k < NB / 4; ++k) cst[k] = 0.f;
+        for (int k = 0; k < RPW; ++k) cst[k] = 0.f;
         if (p.a_tmem) {
             // one-time: my gate row of the W_hh slice -> tensor memory lane r, two bf16 per 32-bit column,
-            // read back out of the 128B-swizzled shared-memory tiles the TMA wrote
+            // read back out of the 128B-swizzled shared-memory tiles the TMA wrote (warps sharing a quadrant
+            // split the k-blocks)
             mbar_wait(wbar, 0);
-            for (int kb = 0; kb < KB; ++kb) {
+            const int kpw = KB / (EW / 4);
+            for (int kb = (warp >> 2) * kpw; kb < (warp >> 2) * kpw + kpw; ++kb) {
                 uint32_t w[32];
 #pragma unroll
                 for (int ch = 0; ch < 8; ++ch) {
                     const uint4 q = *reinterpret_cast<const uint4*>(Ws + kb * 16384 + r * 128 + ((ch ^ (r & 7)) << 4));
                     w[ch * 4 + 0] = q.x; w[ch * 4 + 1] = q.y; w[ch * 4 + 2] = q.z; w[ch * 4 + 3] = q.w;
                 }
-                tc_st_32x32b_x32(tmem_base + 256 + kb * 32 + ((uint32_t)(warp * 32) << 16), w);
+                tc_st_32x32b_x32(tmem_base + 256 + kb * 32 + ((uint32_t)(gate * 32) << 16), w);
             }
             tc_wait_st();
             tc_fence_before();
@@ -388,70 +395,73 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
         uint32_t ph_g = 0, ph_m = 0;
         for (int s = 0; s < T; ++s) {
             const int tt = dir ? (T - 1 - s) : s;
-            float acc[NB];
+            float acc[CPW];
             if (s > 0) {
                 mbar_wait(mbar, ph_m); ph_m ^= 1;
                 if (threadIdx.x == 0) PK2_PROF(2);
                 tc_fence_after();
-                uint32_t v[kAcc][32];
+                uint32_t v[ACC][CPW];
 #pragma unroll
-                for (int q = 0; q < kAcc; ++q)
-                    tc_ld_32x32b_x32_nowait(tmem_base + q * NB + ((uint32_t)(warp * 32) << 16), v[q]);
+                for (int q = 0; q < ACC; ++q) {
+                    const uint32_t ta = tmem_base + q * NB + c0 + ((uint32_t)(gate * 32) << 16);
+                    if constexpr (CPW == 32) tc_ld_32x32b_x32_nowait(ta, v[q]);
+                    else tc_ld_32x32b_x16_nowait(ta, v[q]);
+                }
                 tc_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
+                for (int j = 0; j < CPW; ++j) {
                     float t = __uint_as_float(v[0][j]);
 #pragma unroll
-                    for (int q = 1; q < kAcc; ++q) t += __uint_as_float(v[q][j]);
+                    for (int q = 1; q < ACC; ++q) t += __uint_as_float(v[q][j]);
                     acc[j] = t;
                 }
                 tc_fence_before();
             } else {
 #pragma unroll
-                for (int j = 0; j < NB; ++j) acc[j] = 0.f;
+                for (int j = 0; j < CPW; ++j) acc[j] = 0.f;
             }
             if (threadIdx.x == 0) PK2_PROF(3);
             mbar_wait(gbar, ph_g); ph_g ^= 1;
             if (threadIdx.x == 0) PK2_PROF(4);
-            // all loads first, then 32 independent activations, then all stores (the in-place
+            // all loads first, then independent activations, then all stores (the in-place
             // read-modify-write loop serialised on the load->MUFU->store latency chain: 97 cycles/element)
             {
-                float gxr[NB];
+                float gxr[CPW];
 #pragma unroll
-                for (int b = 0; b < NB; ++b) gxr[b] = gxs[b * 128 + r];
+                for (int b = 0; b < CPW; ++b) gxr[b] = gxs[(c0 + b) * 128 + r];
                 if (gate == 2) {
 #pragma unroll
-                    for (int b = 0; b < NB; ++b) gxr[b] = tanh_approx(acc[b] + gxr[b]);
+                    for (int b = 0; b < CPW; ++b) gxr[b] = tanh_approx(acc[b] + gxr[b]);
                 } else {
 #pragma unroll
-                    for (int b = 0; b < NB; ++b) gxr[b] = sigmoid_approx(acc[b] + gxr[b]);
+                    for (int b = 0; b < CPW; ++b) gxr[b] = sigmoid_approx(acc[b] + gxr[b]);
                 }
 #pragma unroll
-                for (int b = 0; b < NB; ++b) gxs[b * 128 + r] = gxr[b];
+                for (int b = 0; b < CPW; ++b) gxs[(c0 + b) * 128 + r] = gxr[b];
             }
-            named_bar_sync(1, kEpiThreads);
+            named_bar_sync(1, kEpi);
             if (threadIdx.x == 0) PK2_PROF(5);
-            // cell update (lane = unit, warp w handles rows w, w+4, ...); h_t goes to the staging slice.
+            // cell update (lane = unit, warp w handles rows w, w+EW, ...); h_t goes to the staging slice.
             // The activations are copied to registers so the Gx buffer can be refilled right away.
-            __nv_bfloat16 hv[NB / 4];
-            __nv_bfloat16 gv[NB / 4][4];
+            __nv_bfloat16 hv[RPW];
+            __nv_bfloat16 gv[RPW][4];
             uint8_t* st = stg + (s & 1) * kSlice;
             {
-                float gi[NB / 4], gf[NB / 4], gg_[NB / 4], go[NB / 4], tc_[NB / 4];
+                float gi[RPW], gf[RPW], gg_[RPW], go[RPW], tc_[RPW];
 #pragma unroll
-                for (int k = 0; k < NB / 4; ++k) {
-                    const int b = warp + 4 * k;
+                for (int k = 0; k < RPW; ++k) {
+                    const int b = warp + EW * k;
                     gi[k] = gxs[b * 128 + lane]; gf[k] = gxs[b * 128 + 32 + lane];
                     gg_[k] = gxs[b * 128 + 64 + lane]; go[k] = gxs[b * 128 + 96 + lane];
                 }
 #pragma unroll
-                for (int k = 0; k < NB / 4; ++k) {
+                for (int k = 0; k < RPW; ++k) {
                     cst[k] = fmaf(gf[k], cst[k], gi[k] * gg_[k]);
                     tc_[k] = tanh_approx(cst[k]);
                 }
 #pragma unroll
-                for (int k = 0; k < NB / 4; ++k) {
-                    const int b = warp + 4 * k;
+                for (int k = 0; k < RPW; ++k) {
+                    const int b = warp + EW * k;
                     gv[k][0] = __float2bfloat16(gi[k]); gv[k][1] = __float2bfloat16(gf[k]);
                     gv[k][2] = __float2bfloat16(gg_[k]); gv[k][3] = __float2bfloat16(go[k]);
                     hv[k] = __float2bfloat16(go[k] * tc_[k]);
@@ -459,12 +469,13 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            named_bar_sync(1, kEpiThreads);
+            named_bar_sync(1, kEpi);
             if (threadIdx.x == 0) { PK2_PROF(6); mbar_arrive(gfree); }   // Gx buffer consumed: prefetch the next step now
-            if (s < T - 1 && (threadIdx.x & 7) == 0 && (threadIdx.x >> 3) < CS) {
+            constexpr int kStride = kEpi / 16;
+            if (s < T - 1 && (threadIdx.x % kStride) == 0 && (int)(threadIdx.x / kStride) < CS) {
                 // my slice -> CTA `rank` of the cluster (Hb[s&1] + cta*kSlice there); bytes are counted on its
-                // hfull[s&1].  The 16 copies are issued by 4 lanes of each of the 4 warps.
-                const uint32_t rank = threadIdx.x >> 3;
+                // hfull[s&1].  The copies are issued by 16 threads spread over the epilogue warps.
+                const uint32_t rank = threadIdx.x / kStride;
                 const uint32_t dst = mapa_u32(smem_u32(Hb + (s & 1) * hs_bytes + cta * kSlice), rank);
                 const uint32_t bar = mapa_u32(smem_u32(&hfull[s & 1]), rank);
                 dsmem_bulk_copy(dst, smem_u32(st), (uint32_t)kSlice, bar);
@@ -476,8 +487,8 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
                 float* co = p.cstate + (((int64_t)dir * T + tt) * B + b0) * H + u0 + lane;
                 __nv_bfloat16* gout = p.gates + (((int64_t)dir * T + tt) * B + b0) * 4 * H + u0 + lane;
 #pragma unroll
-                for (int k = 0; k < NB / 4; ++k) {
-                    const int b = warp + 4 * k;
+                for (int k = 0; k < RPW; ++k) {
+                    const int b = warp + EW * k;
                     if (b < nbv) {
                         yo[(int64_t)b * T * 2 * H] = hv[k];
                         co[(int64_t)b * H] = cst[k];
@@ -492,7 +503,7 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap map_w, FwdDev p) {
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                  // peers have consumed everything this CTA sent
-    if (warp == 5) tmem_dealloc(tmem_base, tmem_cols);
+    if (warp == EW + 1) tmem_dealloc(tmem_base, tmem_cols);
 #undef PK2_PROF
 }
 
@@ -507,7 +518,7 @@ template <int NG>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_bwd_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_constant__ CUtensorMap map_dg, BwdDev p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     const int H = p.H, T = p.T, B = p.B;
     const int KB = 4 * H / 64;                               // k-blocks over the 4H gate columns
     const int CH = min(kChunkBytes / (NB * 128), KB);        // k-blocks per chunk
@@ -694,7 +705,7 @@ constexpr int NBB = 16;
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap map_wt, BwdDev p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     const int H = p.H, T = p.T, B = p.B;
     const int KB = 4 * H / 64;
     constexpr int kChunk = NBB / 8 * 128;                    // 256 B: one 16-byte K-chunk over 16 rows
@@ -872,7 +883,7 @@ template <int EW>                        // epilogue warps: 4 or 8 (warps w and 
 __global__ void __launch_bounds__((EW + 2) * 32, 1)
 lstm_bwd_rs_kernel(const __grid_constant__ CUtensorMap map_wt, BwdDev p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     constexpr int RPT = NBR / EW;                            // batch rows per thread (thread = unit lane, rows RPT*w ..)
     constexpr int kChunk = kRsChunk;
     constexpr int kBTile = 16 * kChunk;                      // [128 k' / 8][4 row groups][8][16 B] (+ padding)
@@ -1228,10 +1239,10 @@ int launch_fwd(const pk2_lstm_fwd_args* a, cudaStream_t st) {
 }
 
 // Cluster/DSMEM forward: returns 0 on success, -1 if this device cannot co-schedule the clusters.
-int launch_fwd_cluster(const pk2_lstm_fwd_args* a, cudaStream_t st) {
+template <int EW, int ACC>
+int launch_fwd_cluster_t(const pk2_lstm_fwd_args* a, cudaStream_t st) {
     const int H = a->H, T = a->T, B = a->B, KB = H / 64, CS = H / 32;
     const int G = (B + NB - 1) / NB;
-    if (CS > 16 || (CS & (CS - 1)) != 0) return -1;
     CUtensorMap mw;
     {
         cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)(2 * 4 * H)};
@@ -1243,8 +1254,8 @@ int launch_fwd_cluster(const pk2_lstm_fwd_args* a, cudaStream_t st) {
     static bool attr_done = false, usable = true;
     if (!attr_done) {
         attr_done = true;
-        if (cudaFuncSetAttribute(lstm_fwd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) != cudaSuccess ||
-            cudaFuncSetAttribute(lstm_fwd_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        if (cudaFuncSetAttribute(lstm_fwd_cluster_kernel<EW, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) != cudaSuccess ||
+            cudaFuncSetAttribute(lstm_fwd_cluster_kernel<EW, ACC>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
             cudaGetLastError();
             usable = false;
         }
@@ -1252,7 +1263,7 @@ int launch_fwd_cluster(const pk2_lstm_fwd_args* a, cudaStream_t st) {
     if (!usable) return -1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CS, 2, G);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3((EW + 2) * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -1260,7 +1271,7 @@ int launch_fwd_cluster(const pk2_lstm_fwd_args* a, cudaStream_t st) {
     attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     int max_clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, lstm_fwd_cluster_kernel, &cfg) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, lstm_fwd_cluster_kernel<EW, ACC>, &cfg) != cudaSuccess) {
         cudaGetLastError();
         return -1;
     }
@@ -1271,10 +1282,23 @@ int launch_fwd_cluster(const pk2_lstm_fwd_args* a, cudaStream_t st) {
     d.gates = static_cast<__nv_bfloat16*>(a->gates);
     d.cstate = a->cstate; d.counters = a->sync; d.prof = g_prof;
     static const bool a_smem = getenv("PK2_LSTM_A_SMEM") != nullptr;       // debug: A operand from shared memory
-    d.a_tmem = (!a_smem && H <= 512) ? 1 : 0;
-    PK2_CHECK(cudaLaunchKernelEx(&cfg, lstm_fwd_cluster_kernel, mw, d));
+    d.a_tmem = (!a_smem && H <= 512 && (H / 64) % (EW / 4) == 0) ? 1 : 0;
+    PK2_CHECK(cudaLaunchKernelEx(&cfg, lstm_fwd_cluster_kernel<EW, ACC>, mw, d));
     PK2_LAUNCHED();
     return 0;
+}
+
+int launch_fwd_cluster(const pk2_lstm_fwd_args* a, cudaStream_t st) {
+    const int CS = a->H / 32;
+    if (CS > 16 || (CS & (CS - 1)) != 0) return -1;
+    // experiment knobs: PK2_LSTM_FWD_EW = 4 | 8 epilogue warps, PK2_LSTM_FWD_ACC = 1 | 4 accumulators
+    static int ew = -1, acc = -1;
+    if (ew < 0) {
+        const char* e = getenv("PK2_LSTM_FWD_EW"); ew = (e && atoi(e) == 4) ? 4 : 8;
+        const char* c = getenv("PK2_LSTM_FWD_ACC"); acc = (c && atoi(c) == 4) ? 4 : 1;
+    }
+    if (ew == 4) return acc == 4 ? launch_fwd_cluster_t<4, 4>(a, st) : launch_fwd_cluster_t<4, 1>(a, st);
+    return acc == 4 ? launch_fwd_cluster_t<8, 4>(a, st) : launch_fwd_cluster_t<8, 1>(a, st);
 }
 
 template <int NG>

@@ -19,37 +19,64 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64;      // BK * 2 B = 128 B = one swizzle row
-constexpr int kStages = 4;
+constexpr int BM = 128, BN = 256, BK = 64;      // per-CTA tile rows, tile columns; BK * 2 B = 128 B = one swizzle row
 constexpr int kAccStages = 2;
 constexpr int kThreads = 256;
-constexpr uint32_t kStageBytesA = BM * BK * 2, kStageBytesB = BN * BK * 2;
-constexpr uint32_t kStageBytes = kStageBytesA + kStageBytesB;
+constexpr int kMaxStages = 6;
+constexpr int kEpiLd = 36;                      // padded row of the epilogue transpose tile (floats)
+constexpr size_t kEpiSmem = 4 * 32 * kEpiLd * sizeof(float);
+constexpr uint32_t kStageBytesA = BM * BK * 2;
 constexpr uint32_t kTmemCols = kAccStages * BN;  // 512: the whole TMEM
 
 using namespace tc;
 
 struct __align__(8) PipeBars {
-    uint64_t full[kStages];
-    uint64_t empty[kStages];
+    uint64_t full[kMaxStages];
+    uint64_t empty[kMaxStages];
     uint64_t tmem_full[kAccStages];
     uint64_t tmem_empty[kAccStages];
     uint32_t tmem_base;
 };
 
+// CTAS = 1: one CTA per 128 x 256 tile, 4-stage ring of (A 16 KB + B 32 KB).
+// CTAS = 2: a CTA PAIR (2-CTA cluster, tcgen05 cta_group::2) per 256 x 256 tile: each CTA loads its own 128 rows
+//           of A and HALF of the B tile (128 of the 256 columns' rows), the leader CTA issues M=256 MMAs that read both
+//           CTAs' shared memory and write both CTAs' tensor memory.  Per CTA and k-block 32 KB arrive instead of
+//           48 KB (the L2->SM operand traffic was the limiter of the 1-CTA kernel on the M-long shapes:
+//           profiles/kernel_bench_r1_v2.jsonl) and the ring is 6 stages deep.
+// Tile rasterisation: bands of kBandRows rows of A are swept over ALL column tiles before the next band starts
+// (m fastest inside a band).  With the plain "all m for one n, then the next n" order every column pass streams the
+// whole of A from HBM again (A of the model's shapes is about the size of L2): 16 x 118 MB for the input projections.
+constexpr int kBandRows = 4096;
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int band, int* mt, int* nt) {
+    const int per_band = band * num_n;
+    const int b = tile / per_band, r = tile - b * per_band;
+    const int bs = min(band, num_m - b * band);          // the last band may be short
+    *nt = r / bs;
+    *mt = b * band + (r - *nt * bs);
+}
+
+template <int CTAS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     void* __restrict__ Cout, const float* __restrict__ bias, int M, int N, int K, int ldc,
                     int c_bf16, int lstm_T, int lstm_B, int lstm_H) {
+    constexpr int kStages = CTAS == 2 ? 6 : 4;
+    constexpr uint32_t kStageBytesB = (BN / CTAS) * BK * 2;
+    constexpr uint32_t kStageBytes = kStageBytesA + kStageBytesB;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment for SWIZZLE_128B tiles
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     PipeBars* bars = reinterpret_cast<PipeBars*>(smem + kStages * kStageBytes);
+    float* epi_smem = reinterpret_cast<float*>(smem + kStages * kStageBytes + ((sizeof(PipeBars) + 15) & ~15));   // 4 x [32][kEpiLd]
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // shfl: warp-uniform for ptxas
-    const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
+    const int rank = CTAS == 2 ? (int)cluster_ctarank() : 0;
+    const int num_m = (M + CTAS * BM - 1) / (CTAS * BM), num_n = (N + BN - 1) / BN;   // tiles of CTAS*128 x 256
     const int num_tiles = num_m * num_n;
     const int num_kb = (K + BK - 1) / BK;
+    const int tile0 = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;
+    constexpr int kBand = kBandRows / (CTAS * BM);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -57,17 +84,18 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
-        for (int i = 0; i < kAccStages; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], 4); }
+        // tmem_empty: one arrival per epilogue warp of every CTA of the pair (the peer arrives remotely on the leader's)
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], 4 * CTAS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     ::"r"(smem_u32(&bars->tmem_base)), "r"(kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (CTAS == 2) tmem_alloc_2cta(&bars->tmem_base, kTmemCols);
+        else tmem_alloc(&bars->tmem_base, kTmemCols);
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CTAS == 2) cluster_sync_all();          // the peer's barriers are initialised before anything lands on them
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, bars->tmem_base, 0);   // uniform register for the tcgen05 ops
 
@@ -75,128 +103,168 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         // ===== TMA producer =====  (whole warp runs the loop, one elected lane issues: in a divergent
         // `if (lane == 0)` region ptxas wraps every UTMALDG / UTCHMMA in an ELECT/R2UR waterfall loop)
         uint32_t stage = 0, phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m0 = (tile % num_m) * BM, n0 = (tile / num_m) * BN;
+        for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+            int mt, nt;
+            tile_coords(tile, num_m, num_n, kBand, &mt, &nt);
+            const int m0 = (mt * CTAS + rank) * BM, n0 = nt * BN;
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(&bars->empty[stage], phase ^ 1);
                 if (elect_one()) {
-                    mbar_expect_tx(&bars->full[stage], kStageBytes);
                     uint8_t* sa = smem + stage * kStageBytes;
-                    tma_load_2d(&map_a, &bars->full[stage], sa, kb * BK, m0);
-                    tma_load_2d(&map_b, &bars->full[stage], sa + kStageBytesA, kb * BK, n0);
+                    if constexpr (CTAS == 2) {
+                        // bytes of both CTAs' loads are counted on the leader's barrier; the leader arms it
+                        const uint32_t bar = mapa_u32(smem_u32(&bars->full[stage]), 0);
+                        if (rank == 0) mbar_expect_tx(&bars->full[stage], 2 * kStageBytes);
+                        tma_load_2d_2sm(&map_a, bar, sa, kb * BK, m0);
+                        tma_load_2d_2sm(&map_b, bar, sa + kStageBytesA, kb * BK, n0 + rank * (BN / 2));
+                    } else {
+                        mbar_expect_tx(&bars->full[stage], kStageBytes);
+                        tma_load_2d(&map_a, &bars->full[stage], sa, kb * BK, m0);
+                        tma_load_2d(&map_b, &bars->full[stage], sa + kStageBytesA, kb * BK, n0);
+                    }
                 }
                 __syncwarp();
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        constexpr uint32_t idesc = make_idesc(BM, BN);
-        uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * BN;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(&bars->full[stage], phase);
+        // ===== MMA issuer (pair: the leader CTA only) =====
+        if (CTAS == 1 || rank == 0) {
+            constexpr uint32_t idesc = make_idesc(CTAS * BM, BN);
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+                if constexpr (CTAS == 2) mbar_wait_cluster(&bars->tmem_empty[acc], acc_phase ^ 1);
+                else mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-                const uint64_t adesc = make_sw128_desc(sa);
-                const uint64_t bdesc = make_sw128_desc(sa + kStageBytesA);
-                if (elect_one()) {
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&bars->full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+                    const uint64_t adesc = make_sw128_desc(sa);
+                    const uint64_t bdesc = make_sw128_desc(sa + kStageBytesA);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in 16 B units
-                        tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                                    (uint32_t)((kb | k) != 0));
+                        for (int k = 0; k < BK / 16; ++k) {
+                            // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in 16 B units
+                            if constexpr (CTAS == 2)
+                                tc_mma_bf16_2cta(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                                 (uint32_t)((kb | k) != 0));
+                            else
+                                tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                            (uint32_t)((kb | k) != 0));
+                        }
+                        // frees the smem slot (in both CTAs of a pair) when the MMAs retire
+                        if constexpr (CTAS == 2) {
+                            tc_commit_2cta(&bars->empty[stage], 3);
+                            if (kb == num_kb - 1) tc_commit_2cta(&bars->tmem_full[acc], 3);
+                        } else {
+                            tc_commit(&bars->empty[stage]);
+                            if (kb == num_kb - 1) tc_commit(&bars->tmem_full[acc]);
+                        }
                     }
-                    tc_commit(&bars->empty[stage]);           // frees the smem slot when the MMAs retire
-                    if (kb == num_kb - 1) tc_commit(&bars->tmem_full[acc]);
+                    __syncwarp();
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                __syncwarp();
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
             }
-            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> global =====
         const int ew = warp - 4;                    // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
         uint32_t acc = 0, acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m0 = (tile % num_m) * BM, n0 = (tile / num_m) * BN;
+        for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+            int mt, nt;
+            tile_coords(tile, num_m, num_n, kBand, &mt, &nt);
+            const int m0 = (mt * CTAS + rank) * BM, n0 = nt * BN;
             mbar_wait(&bars->tmem_full[acc], acc_phase);
             tc_fence_after();
+            // Coalesced epilogue: the accumulator chunk arrives with lane = row (32 columns per lane); it is
+            // transposed through a per-warp shared-memory tile so that one store instruction writes 4 rows x 128 B
+            // (8 lanes x 16 B per row) instead of 32 rows x 16 B: the row-per-lane stores cost one sector
+            // transaction per lane and made the K = 1024 shapes epilogue-bound (profiles/kernel_bench_gemm_r1_v22).
             const int row = m0 + ew * 32 + lane;
+            float* tsm = epi_smem + ew * (32 * kEpiLd);
+            // destination of my row for column offset 0 of a chunk (element offset), or -1 for rows >= M
+            int64_t row_off = -1;
+            int lb = 0, lt = 0;
+            if (row < M) {
+                if (lstm_T > 0) { lb = row / lstm_T; lt = row - lb * lstm_T; }
+                row_off = (int64_t)row * ldc;
+            }
+            const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;      // transposed phase: rows sub_r + 4i, columns sub_c..+3
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t v[32];
                 const uint32_t taddr = tmem_base + acc * BN + c * 32 + ((uint32_t)(ew * 32) << 16);
                 tc_ld_32x32b_x32(taddr, v);
                 const int col0 = n0 + c * 32;
-                if (row < M && col0 < N) {
-                    if (col0 + 32 <= N) {
+                if (col0 >= N) continue;                               // warp-uniform
+                if (col0 + 32 <= N) {
+                    // per-row destination (element offset of column col0) in the layout of this launch
+                    int64_t off = row_off < 0 ? -1 : row_off + col0;
+                    if (lstm_T > 0 && row_off >= 0) {
+                        // LSTM gate layout [T][2][H/32][B][128]: row = b*T + t, col = dir*4H + gate*H + unit
+                        const int dir = col0 / (4 * lstm_H), r = col0 - dir * 4 * lstm_H;
+                        const int gate = r / lstm_H, unit = r - gate * lstm_H;
+                        off = ((((int64_t)lt * 2 + dir) * (lstm_H >> 5) + (unit >> 5)) * lstm_B + lb) * 128 + gate * 32;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(tsm + lane * kEpiLd + j) =
+                            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    __syncwarp();
+                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (bias) bv = make_float4(__ldg(&bias[col0 + sub_c]), __ldg(&bias[col0 + sub_c + 1]),
+                                               __ldg(&bias[col0 + sub_c + 2]), __ldg(&bias[col0 + sub_c + 3]));
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = sub_r + 4 * i;
+                        const int64_t o = __shfl_sync(0xffffffffu, off, r);
+                        float4 x = *reinterpret_cast<const float4*>(tsm + r * kEpiLd + sub_c);
+                        x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
+                        if (o < 0) continue;
                         if (c_bf16) {
-                            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(Cout) + (int64_t)row * ldc + col0;
-#pragma unroll
-                            for (int j = 0; j < 32; j += 8) {
-                                float f[8];
-#pragma unroll
-                                for (int q = 0; q < 8; ++q) f[q] = __uint_as_float(v[j + q]) + (bias ? __ldg(&bias[col0 + j + q]) : 0.f);
-                                uint4 o;
-                                __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]);
-                                __nv_bfloat162 p1 = __floats2bfloat162_rn(f[2], f[3]);
-                                __nv_bfloat162 p2 = __floats2bfloat162_rn(f[4], f[5]);
-                                __nv_bfloat162 p3 = __floats2bfloat162_rn(f[6], f[7]);
-                                o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
-                                o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
-                                if ((reinterpret_cast<uintptr_t>(dst + j) & 15) == 0) {
-                                    *reinterpret_cast<uint4*>(dst + j) = o;
-                                } else {
-#pragma unroll
-                                    for (int q = 0; q < 8; ++q) dst[j + q] = __float2bfloat16(f[q]);
-                                }
+                            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(Cout) + o + sub_c;
+                            __nv_bfloat162 p0 = __floats2bfloat162_rn(x.x, x.y), p1 = __floats2bfloat162_rn(x.z, x.w);
+                            if ((reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+                                uint2 w;
+                                w.x = *reinterpret_cast<uint32_t*>(&p0); w.y = *reinterpret_cast<uint32_t*>(&p1);
+                                *reinterpret_cast<uint2*>(dst) = w;
+                            } else {
+                                dst[0] = __float2bfloat16(x.x); dst[1] = __float2bfloat16(x.y);
+                                dst[2] = __float2bfloat16(x.z); dst[3] = __float2bfloat16(x.w);
                             }
                         } else {
-                            float* dst = reinterpret_cast<float*>(Cout) + (int64_t)row * ldc + col0;
-                            if (lstm_T > 0) {
-                                // LSTM gate layout [T][2][H/32][B][128]: row = b*T + t, col = dir*4H + gate*H + unit
-                                const int b = row / lstm_T, t = row - b * lstm_T;
-                                const int dir = col0 / (4 * lstm_H), r = col0 - dir * 4 * lstm_H;
-                                const int gate = r / lstm_H, unit = r - gate * lstm_H;
-                                dst = reinterpret_cast<float*>(Cout) +
-                                      ((((int64_t)t * 2 + dir) * (lstm_H >> 5) + (unit >> 5)) * lstm_B + b) * 128 + gate * 32;
-                            }
-                            const bool al = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                float4 o;
-                                o.x = __uint_as_float(v[j + 0]) + (bias ? __ldg(&bias[col0 + j + 0]) : 0.f);
-                                o.y = __uint_as_float(v[j + 1]) + (bias ? __ldg(&bias[col0 + j + 1]) : 0.f);
-                                o.z = __uint_as_float(v[j + 2]) + (bias ? __ldg(&bias[col0 + j + 2]) : 0.f);
-                                o.w = __uint_as_float(v[j + 3]) + (bias ? __ldg(&bias[col0 + j + 3]) : 0.f);
-                                if (al) *reinterpret_cast<float4*>(dst + j) = o;
-                                else { dst[j] = o.x; dst[j + 1] = o.y; dst[j + 2] = o.z; dst[j + 3] = o.w; }
-                            }
+                            float* dst = reinterpret_cast<float*>(Cout) + o + sub_c;
+                            if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) *reinterpret_cast<float4*>(dst) = x;
+                            else { dst[0] = x.x; dst[1] = x.y; dst[2] = x.z; dst[3] = x.w; }
                         }
-                    } else {
-                        for (int j = 0; j < 32 && col0 + j < N; ++j) {
-                            const float f = __uint_as_float(v[j]) + (bias ? __ldg(&bias[col0 + j]) : 0.f);
-                            if (c_bf16) reinterpret_cast<__nv_bfloat16*>(Cout)[(int64_t)row * ldc + col0 + j] = __float2bfloat16(f);
-                            else reinterpret_cast<float*>(Cout)[(int64_t)row * ldc + col0 + j] = f;
-                        }
+                    }
+                } else if (row < M) {
+                    for (int j = 0; j < 32 && col0 + j < N; ++j) {
+                        const float f = __uint_as_float(v[j]) + (bias ? __ldg(&bias[col0 + j]) : 0.f);
+                        if (c_bf16) reinterpret_cast<__nv_bfloat16*>(Cout)[(int64_t)row * ldc + col0 + j] = __float2bfloat16(f);
+                        else reinterpret_cast<float*>(Cout)[(int64_t)row * ldc + col0 + j] = f;
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+            if (lane == 0) {
+                if (CTAS == 2 && rank != 0) mbar_arrive_remote(mapa_u32(smem_u32(&bars->tmem_empty[acc]), 0));
+                else mbar_arrive(&bars->tmem_empty[acc]);
+            }
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CTAS == 2) cluster_sync_all();          // the leader's last MMAs / commits touch the peer
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        if constexpr (CTAS == 2) tmem_dealloc_2cta(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -254,17 +322,42 @@ extern "C" int pk2_gemm_bf16_nt(const void* A, const void* B, void* C, const flo
         PK2_CHECK(cudaGetDevice(&dev));
         PK2_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    const size_t smem = kStages * kStageBytes + sizeof(PipeBars) + 1024;
+    // CTA pairs (256 x 256 tiles) unless the problem is a single row of tiles or PK2_GEMM_1CTA is set
+    static const bool force1 = getenv("PK2_GEMM_1CTA") != nullptr;
+    const bool pair = !force1 && M > BM && g_num_sms >= 2;
     static bool attr = false;
     if (!attr) {
-        PK2_CHECK(cudaFuncSetAttribute(gemm_bf16_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PK2_CHECK(cudaFuncSetAttribute(gemm_bf16_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        PK2_CHECK(cudaFuncSetAttribute(gemm_bf16_nt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         attr = true;
     }
-    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-    int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    if (g_max_ctas > 0 && grid > g_max_ctas) grid = g_max_ctas;
-    gemm_bf16_nt_kernel<<<grid, kThreads, smem, pk2::as_stream(stream)>>>(ma, mb, C, bias, M, N, K, ldc, (flags >> 1) & 1,
-                                                                          g_lstm_T, g_lstm_B, g_lstm_H);
+    const int c_bf16 = (flags >> 1) & 1;
+    if (pair) {
+        CUtensorMap mb2;
+        if (make_map(&mb2, B, N, K, ldb, BN / 2)) return 2;
+        const size_t smem = 6 * (kStageBytesA + (BN / 2) * BK * 2) + sizeof(PipeBars) + 16 + kEpiSmem + 1024;
+        const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
+        int pairs = tiles < g_num_sms / 2 ? tiles : g_num_sms / 2;
+        if (g_max_ctas > 0 && pairs > g_max_ctas / 2) pairs = g_max_ctas / 2 > 0 ? g_max_ctas / 2 : 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = pk2::as_stream(stream);
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        PK2_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_nt_kernel<2>, ma, mb2, C, bias, M, N, K, ldc, c_bf16,
+                                     (int)g_lstm_T, (int)g_lstm_B, (int)g_lstm_H));
+    } else {
+        const size_t smem = 4 * (kStageBytesA + BN * BK * 2) + sizeof(PipeBars) + 16 + kEpiSmem + 1024;
+        const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+        int grid = tiles < g_num_sms ? tiles : g_num_sms;
+        if (g_max_ctas > 0 && grid > g_max_ctas) grid = g_max_ctas;
+        gemm_bf16_nt_kernel<1><<<grid, kThreads, smem, pk2::as_stream(stream)>>>(ma, mb, C, bias, M, N, K, ldc, c_bf16,
+                                                                                 g_lstm_T, g_lstm_B, g_lstm_H);
+    }
     PK2_POST_LAUNCH();
     return 0;
 }
