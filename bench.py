@@ -69,6 +69,25 @@ class ClockSampler(threading.Thread):
         self.index, self.rows, self._halt = index, [], threading.Event()
 
     def run(self):
+        # NVML in-process (what nvidia-smi reads) when available: spawning nvidia-smi every 0.2 s from a process with
+        # a large address space cost a 60 ms hiccup in the first timed step of one run (profiles/bench_r1_v25.json)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            bits = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+            while not self._halt.is_set():
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+                try:
+                    r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append([str(sm), str(mx)] + ["Active" if (r & b) else "Not Active" for _, b in bits])
+                self._halt.wait(0.05)
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self._halt.is_set():
@@ -260,14 +279,15 @@ def main():
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         return float(t.item())
 
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()                      # NVML initialisation happens during the warm-up, not in the timed region
     for _ in range(max(args.warmup, 3)):
         step(True)
     step(False)
     torch.cuda.synchronize()
-
-    sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
-        sampler.start()
+        del sampler.rows[:]                  # keep only the samples taken during the timed regions
     ops.DEN_TIMERS = []
     n0 = L.pk2_launch_count()
     t_res = timed(True, args.steps)

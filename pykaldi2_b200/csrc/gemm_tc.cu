@@ -21,10 +21,9 @@ namespace {
 
 constexpr int BM = 128, BN = 256, BK = 64;      // per-CTA tile rows, tile columns; BK * 2 B = 128 B = one swizzle row
 constexpr int kAccStages = 2;
-constexpr int kThreads = 256;
+constexpr int kThreads1 = 256, kThreads2 = 384;   // 4 control warps + 4 (single CTA) / 8 (pair) epilogue warps
 constexpr int kMaxStages = 6;
-constexpr int kEpiLd = 36;                      // padded row of the epilogue transpose tile (floats)
-constexpr size_t kEpiSmem = 4 * 32 * kEpiLd * sizeof(float);
+constexpr size_t kEpiTile = 32 * 32 * sizeof(float);   // per-warp epilogue transpose tile, 16-byte chunks XOR-swizzled by row
 constexpr uint32_t kStageBytesA = BM * BK * 2;
 constexpr uint32_t kTmemCols = kAccStages * BN;  // 512: the whole TMEM
 
@@ -57,7 +56,7 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int 
 }
 
 template <int CTAS>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(CTAS == 2 ? kThreads2 : kThreads1, 1)
 gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     void* __restrict__ Cout, const float* __restrict__ bias, int M, int N, int K, int ldc,
                     int c_bf16, int lstm_T, int lstm_B, int lstm_H) {
@@ -68,7 +67,8 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // 1024-byte alignment for SWIZZLE_128B tiles
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     PipeBars* bars = reinterpret_cast<PipeBars*>(smem + kStages * kStageBytes);
-    float* epi_smem = reinterpret_cast<float*>(smem + kStages * kStageBytes + ((sizeof(PipeBars) + 15) & ~15));   // 4 x [32][kEpiLd]
+    constexpr int EW = CTAS == 2 ? 8 : 4;              // epilogue warps: warps w and w+4 share a TMEM lane quadrant and split the columns
+    float* epi_smem = reinterpret_cast<float*>(smem + kStages * kStageBytes + ((sizeof(PipeBars) + 15) & ~15));   // EW x [32][32]
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // shfl: warp-uniform for ptxas
     const int rank = CTAS == 2 ? (int)cluster_ctarank() : 0;
@@ -85,7 +85,7 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
         // tmem_empty: one arrival per epilogue warp of every CTA of the pair (the peer arrives remotely on the leader's)
-        for (int i = 0; i < kAccStages; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], 4 * CTAS); }
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], EW * CTAS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -171,7 +171,8 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> global =====
-        const int ew = warp - 4;                    // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
+        const int ew = (warp - 4) & 3;              // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
+        const int c_begin = ((warp - 4) >> 2) * (BN / 32 / (EW / 4)), c_end = c_begin + BN / 32 / (EW / 4);
         uint32_t acc = 0, acc_phase = 0;
         for (int tile = tile0; tile < num_tiles; tile += tile_step) {
             int mt, nt;
@@ -184,62 +185,69 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             // (8 lanes x 16 B per row) instead of 32 rows x 16 B: the row-per-lane stores cost one sector
             // transaction per lane and made the K = 1024 shapes epilogue-bound (profiles/kernel_bench_gemm_r1_v22).
             const int row = m0 + ew * 32 + lane;
-            float* tsm = epi_smem + ew * (32 * kEpiLd);
-            // destination of my row for column offset 0 of a chunk (element offset), or -1 for rows >= M
-            int64_t row_off = -1;
-            int lb = 0, lt = 0;
-            if (row < M) {
-                if (lstm_T > 0) { lb = row / lstm_T; lt = row - lb * lstm_T; }
-                row_off = (int64_t)row * ldc;
+            float* tsm = epi_smem + (warp - 4) * (32 * 32);
+            // transposed phase: this lane stores rows sub_r + 4i (i < 8), columns sub_c..sub_c+3 of every 32-column
+            // chunk.  Destination = rowbase[i] + chunk term (both layouts are separable in row and column).
+            const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+            int64_t rowbase[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = m0 + ew * 32 + sub_r + 4 * i;
+                if (rr >= M) rowbase[i] = -1;
+                else if (lstm_T > 0) {
+                    // LSTM gate layout [T][2][H/32][B][128]: row = b*T + t
+                    const int lb = rr / lstm_T, lt = rr - lb * lstm_T;
+                    rowbase[i] = ((int64_t)lt * 2 * (lstm_H >> 5) * lstm_B + lb) * 128;
+                } else rowbase[i] = (int64_t)rr * ldc;
             }
-            const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;      // transposed phase: rows sub_r + 4i, columns sub_c..+3
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = c_begin; c < c_end; ++c) {
                 uint32_t v[32];
                 const uint32_t taddr = tmem_base + acc * BN + c * 32 + ((uint32_t)(ew * 32) << 16);
                 tc_ld_32x32b_x32(taddr, v);
                 const int col0 = n0 + c * 32;
                 if (col0 >= N) continue;                               // warp-uniform
                 if (col0 + 32 <= N) {
-                    // per-row destination (element offset of column col0) in the layout of this launch
-                    int64_t off = row_off < 0 ? -1 : row_off + col0;
-                    if (lstm_T > 0 && row_off >= 0) {
-                        // LSTM gate layout [T][2][H/32][B][128]: row = b*T + t, col = dir*4H + gate*H + unit
+                    int64_t cterm = col0;
+                    if (lstm_T > 0) {
+                        // col = dir*4H + gate*H + unit
                         const int dir = col0 / (4 * lstm_H), r = col0 - dir * 4 * lstm_H;
                         const int gate = r / lstm_H, unit = r - gate * lstm_H;
-                        off = ((((int64_t)lt * 2 + dir) * (lstm_H >> 5) + (unit >> 5)) * lstm_B + lb) * 128 + gate * 32;
+                        cterm = ((int64_t)(dir * (lstm_H >> 5) + (unit >> 5)) * lstm_B) * 128 + gate * 32;
                     }
                     __syncwarp();
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(tsm + lane * kEpiLd + j) =
+                        *reinterpret_cast<float4*>(tsm + lane * 32 + (((j >> 2) ^ (lane & 7)) << 2)) =
                             make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
                     __syncwarp();
                     float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (bias) bv = make_float4(__ldg(&bias[col0 + sub_c]), __ldg(&bias[col0 + sub_c + 1]),
                                                __ldg(&bias[col0 + sub_c + 2]), __ldg(&bias[col0 + sub_c + 3]));
+                    float4 x[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) x[i] = *reinterpret_cast<const float4*>(tsm + (sub_r + 4 * i) * 32 + ((((lane & 7)) ^ ((sub_r + 4 * i) & 7)) << 2));
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const int r = sub_r + 4 * i;
-                        const int64_t o = __shfl_sync(0xffffffffu, off, r);
-                        float4 x = *reinterpret_cast<const float4*>(tsm + r * kEpiLd + sub_c);
-                        x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
-                        if (o < 0) continue;
-                        if (c_bf16) {
-                            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(Cout) + o + sub_c;
-                            __nv_bfloat162 p0 = __floats2bfloat162_rn(x.x, x.y), p1 = __floats2bfloat162_rn(x.z, x.w);
-                            if ((reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
-                                uint2 w;
-                                w.x = *reinterpret_cast<uint32_t*>(&p0); w.y = *reinterpret_cast<uint32_t*>(&p1);
-                                *reinterpret_cast<uint2*>(dst) = w;
+                        x[i].x += bv.x; x[i].y += bv.y; x[i].z += bv.z; x[i].w += bv.w;
+                        if (rowbase[i] >= 0) {
+                            const int64_t o = rowbase[i] + cterm + sub_c;
+                            if (c_bf16) {
+                                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(Cout) + o;
+                                __nv_bfloat162 p0 = __floats2bfloat162_rn(x[i].x, x[i].y), p1 = __floats2bfloat162_rn(x[i].z, x[i].w);
+                                if ((reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+                                    uint2 w;
+                                    w.x = *reinterpret_cast<uint32_t*>(&p0); w.y = *reinterpret_cast<uint32_t*>(&p1);
+                                    *reinterpret_cast<uint2*>(dst) = w;
+                                } else {
+                                    dst[0] = __float2bfloat16(x[i].x); dst[1] = __float2bfloat16(x[i].y);
+                                    dst[2] = __float2bfloat16(x[i].z); dst[3] = __float2bfloat16(x[i].w);
+                                }
                             } else {
-                                dst[0] = __float2bfloat16(x.x); dst[1] = __float2bfloat16(x.y);
-                                dst[2] = __float2bfloat16(x.z); dst[3] = __float2bfloat16(x.w);
+                                float* dst = reinterpret_cast<float*>(Cout) + o;
+                                if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) *reinterpret_cast<float4*>(dst) = x[i];
+                                else { dst[0] = x[i].x; dst[1] = x[i].y; dst[2] = x[i].z; dst[3] = x[i].w; }
                             }
-                        } else {
-                            float* dst = reinterpret_cast<float*>(Cout) + o + sub_c;
-                            if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) *reinterpret_cast<float4*>(dst) = x;
-                            else { dst[0] = x.x; dst[1] = x.y; dst[2] = x.z; dst[3] = x.w; }
                         }
                     }
                 } else if (row < M) {
@@ -253,7 +261,9 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (CTAS == 2 && rank != 0) mbar_arrive_remote(mapa_u32(smem_u32(&bars->tmem_empty[acc]), 0));
+                // relaxed: only the tcgen05.ld reads (complete after wait::ld) must precede the leader's next MMAs; a
+                // release here would wait for all of this warp's global stores
+                if (CTAS == 2 && rank != 0) mbar_arrive_remote_relaxed(mapa_u32(smem_u32(&bars->tmem_empty[acc]), 0));
                 else mbar_arrive(&bars->tmem_empty[acc]);
             }
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
@@ -335,13 +345,14 @@ extern "C" int pk2_gemm_bf16_nt(const void* A, const void* B, void* C, const flo
     if (pair) {
         CUtensorMap mb2;
         if (make_map(&mb2, B, N, K, ldb, BN / 2)) return 2;
-        const size_t smem = 6 * (kStageBytesA + (BN / 2) * BK * 2) + sizeof(PipeBars) + 16 + kEpiSmem + 1024;
+        constexpr int EWH = 8;
+        const size_t smem = 6 * (kStageBytesA + (BN / 2) * BK * 2) + sizeof(PipeBars) + 16 + EWH * kEpiTile + 1024;
         const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
         int pairs = tiles < g_num_sms / 2 ? tiles : g_num_sms / 2;
         if (g_max_ctas > 0 && pairs > g_max_ctas / 2) pairs = g_max_ctas / 2 > 0 ? g_max_ctas / 2 : 1;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * pairs);
-        cfg.blockDim = dim3(kThreads);
+        cfg.blockDim = dim3(kThreads2);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = pk2::as_stream(stream);
         cudaLaunchAttribute at[1];
@@ -351,11 +362,12 @@ extern "C" int pk2_gemm_bf16_nt(const void* A, const void* B, void* C, const flo
         PK2_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_nt_kernel<2>, ma, mb2, C, bias, M, N, K, ldc, c_bf16,
                                      (int)g_lstm_T, (int)g_lstm_B, (int)g_lstm_H));
     } else {
-        const size_t smem = 4 * (kStageBytesA + BN * BK * 2) + sizeof(PipeBars) + 16 + kEpiSmem + 1024;
+        constexpr int EWH = 4;
+        const size_t smem = 4 * (kStageBytesA + BN * BK * 2) + sizeof(PipeBars) + 16 + EWH * kEpiTile + 1024;
         const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
         int grid = tiles < g_num_sms ? tiles : g_num_sms;
         if (g_max_ctas > 0 && grid > g_max_ctas) grid = g_max_ctas;
-        gemm_bf16_nt_kernel<1><<<grid, kThreads, smem, pk2::as_stream(stream)>>>(ma, mb, C, bias, M, N, K, ldc, c_bf16,
+        gemm_bf16_nt_kernel<1><<<grid, kThreads1, smem, pk2::as_stream(stream)>>>(ma, mb, C, bias, M, N, K, ldc, c_bf16,
                                                                                  g_lstm_T, g_lstm_B, g_lstm_H);
     }
     PK2_POST_LAUNCH();
