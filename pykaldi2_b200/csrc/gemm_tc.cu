@@ -15,6 +15,7 @@
 // epilogue so the epilogue of tile i overlaps the main loop of tile i+1.
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include <map>
 #include <mutex>
 
 namespace {
@@ -59,7 +60,9 @@ template <int CTAS>
 __global__ void __launch_bounds__(CTAS == 2 ? kThreads2 : kThreads1, 1)
 gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     void* __restrict__ Cout, const float* __restrict__ bias, int M, int N, int K, int ldc,
-                    int c_bf16, int lstm_T, int lstm_B, int lstm_H) {
+                    int c_bf16, int lstm_T, int lstm_B, int lstm_H, int splits) {
+    // splits > 1 (split-K): work item = (tile, K range); item s of a tile writes its fp32 partial product, plain
+    // layout [M][N], to Cout + s*M*N (a workspace); splitk_reduce_kernel adds the partials in a fixed order.
     constexpr int kStages = CTAS == 2 ? 6 : 4;
     constexpr uint32_t kStageBytesB = (BN / CTAS) * BK * 2;
     constexpr uint32_t kStageBytes = kStageBytesA + kStageBytesB;
@@ -73,8 +76,10 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // shfl: warp-uniform for ptxas
     const int rank = CTAS == 2 ? (int)cluster_ctarank() : 0;
     const int num_m = (M + CTAS * BM - 1) / (CTAS * BM), num_n = (N + BN - 1) / BN;   // tiles of CTAS*128 x 256
-    const int num_tiles = num_m * num_n;
-    const int num_kb = (K + BK - 1) / BK;
+    const int num_mn = num_m * num_n;
+    const int num_tiles = num_mn * splits;
+    const int num_kb_all = (K + BK - 1) / BK;
+    const int kb_per = (num_kb_all + splits - 1) / splits;
     const int tile0 = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;
     constexpr int kBand = kBandRows / (CTAS * BM);
 
@@ -105,9 +110,10 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         uint32_t stage = 0, phase = 0;
         for (int tile = tile0; tile < num_tiles; tile += tile_step) {
             int mt, nt;
-            tile_coords(tile, num_m, num_n, kBand, &mt, &nt);
+            tile_coords(tile % num_mn, num_m, num_n, kBand, &mt, &nt);
             const int m0 = (mt * CTAS + rank) * BM, n0 = nt * BN;
-            for (int kb = 0; kb < num_kb; ++kb) {
+            const int kb0 = (tile / num_mn) * kb_per, kb1 = min(num_kb_all, kb0 + kb_per);
+            for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(&bars->empty[stage], phase ^ 1);
                 if (elect_one()) {
                     uint8_t* sa = smem + stage * kStageBytes;
@@ -137,7 +143,8 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 else mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int kb0 = (tile / num_mn) * kb_per, kb1 = min(num_kb_all, kb0 + kb_per);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&bars->full[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * kStageBytes);
@@ -149,18 +156,18 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                             // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in 16 B units
                             if constexpr (CTAS == 2)
                                 tc_mma_bf16_2cta(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                                                 (uint32_t)((kb | k) != 0));
+                                                 (uint32_t)(((kb - kb0) | k) != 0));
                             else
                                 tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                                            (uint32_t)((kb | k) != 0));
+                                            (uint32_t)(((kb - kb0) | k) != 0));
                         }
                         // frees the smem slot (in both CTAs of a pair) when the MMAs retire
                         if constexpr (CTAS == 2) {
                             tc_commit_2cta(&bars->empty[stage], 3);
-                            if (kb == num_kb - 1) tc_commit_2cta(&bars->tmem_full[acc], 3);
+                            if (kb == kb1 - 1) tc_commit_2cta(&bars->tmem_full[acc], 3);
                         } else {
                             tc_commit(&bars->empty[stage]);
-                            if (kb == num_kb - 1) tc_commit(&bars->tmem_full[acc]);
+                            if (kb == kb1 - 1) tc_commit(&bars->tmem_full[acc]);
                         }
                     }
                     __syncwarp();
@@ -176,7 +183,7 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         uint32_t acc = 0, acc_phase = 0;
         for (int tile = tile0; tile < num_tiles; tile += tile_step) {
             int mt, nt;
-            tile_coords(tile, num_m, num_n, kBand, &mt, &nt);
+            tile_coords(tile % num_mn, num_m, num_n, kBand, &mt, &nt);
             const int m0 = (mt * CTAS + rank) * BM, n0 = nt * BN;
             mbar_wait(&bars->tmem_full[acc], acc_phase);
             tc_fence_after();
@@ -186,6 +193,7 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             // transaction per lane and made the K = 1024 shapes epilogue-bound (profiles/kernel_bench_gemm_r1_v22).
             const int row = m0 + ew * 32 + lane;
             float* tsm = epi_smem + (warp - 4) * (32 * 32);
+            void* Cout_t = splits > 1 ? static_cast<void*>(reinterpret_cast<float*>(Cout) + (int64_t)(tile / num_mn) * M * N) : Cout;
             // transposed phase: this lane stores rows sub_r + 4i (i < 8), columns sub_c..sub_c+3 of every 32-column
             // chunk.  Destination = rowbase[i] + chunk term (both layouts are separable in row and column).
             const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
@@ -233,7 +241,7 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         if (rowbase[i] >= 0) {
                             const int64_t o = rowbase[i] + cterm + sub_c;
                             if (c_bf16) {
-                                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(Cout) + o;
+                                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(Cout_t) + o;
                                 __nv_bfloat162 p0 = __floats2bfloat162_rn(x[i].x, x[i].y), p1 = __floats2bfloat162_rn(x[i].z, x[i].w);
                                 if ((reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
                                     uint2 w;
@@ -244,7 +252,7 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                                     dst[2] = __float2bfloat16(x[i].z); dst[3] = __float2bfloat16(x[i].w);
                                 }
                             } else {
-                                float* dst = reinterpret_cast<float*>(Cout) + o;
+                                float* dst = reinterpret_cast<float*>(Cout_t) + o;
                                 if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) *reinterpret_cast<float4*>(dst) = x[i];
                                 else { dst[0] = x[i].x; dst[1] = x[i].y; dst[2] = x[i].z; dst[3] = x[i].w; }
                             }
@@ -253,8 +261,8 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 } else if (row < M) {
                     for (int j = 0; j < 32 && col0 + j < N; ++j) {
                         const float f = __uint_as_float(v[j]) + (bias ? __ldg(&bias[col0 + j]) : 0.f);
-                        if (c_bf16) reinterpret_cast<__nv_bfloat16*>(Cout)[(int64_t)row * ldc + col0 + j] = __float2bfloat16(f);
-                        else reinterpret_cast<float*>(Cout)[(int64_t)row * ldc + col0 + j] = f;
+                        if (c_bf16) reinterpret_cast<__nv_bfloat16*>(Cout_t)[(int64_t)row * ldc + col0 + j] = __float2bfloat16(f);
+                        else reinterpret_cast<float*>(Cout_t)[(int64_t)row * ldc + col0 + j] = f;
                     }
                 }
             }
@@ -277,6 +285,24 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
+
+// C[m, n] = sum_s partial[s][m][n] (+ bias[n]), fixed order; fp32 or bf16 output with leading dimension ldc
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int64_t MN, int N, const float* __restrict__ bias,
+                                     void* __restrict__ C, int ldc, int c_bf16) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < MN; i += (int64_t)gridDim.x * blockDim.x) {
+        float acc = part[i];
+        for (int s2 = 1; s2 < splits; ++s2) acc += part[(int64_t)s2 * MN + i];
+        const int64_t m = i / N;
+        const int n = (int)(i - m * N);
+        if (bias) acc += bias[n];
+        if (c_bf16) reinterpret_cast<__nv_bfloat16*>(C)[m * ldc + n] = __float2bfloat16(acc);
+        else reinterpret_cast<float*>(C)[m * ldc + n] = acc;
+    }
+}
+
+struct SplitWs { float* ptr = nullptr; size_t bytes = 0; };
+std::map<cudaStream_t, SplitWs> g_split_ws;     // one workspace per stream (GEMMs on different streams overlap)
+std::mutex g_split_mu;
 
 // ---- host side -----------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -348,8 +374,33 @@ extern "C" int pk2_gemm_bf16_nt(const void* A, const void* B, void* C, const flo
         constexpr int EWH = 8;
         const size_t smem = 6 * (kStageBytesA + (BN / 2) * BK * 2) + sizeof(PipeBars) + 16 + EWH * kEpiTile + 1024;
         const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
-        int pairs = tiles < g_num_sms / 2 ? tiles : g_num_sms / 2;
-        if (g_max_ctas > 0 && pairs > g_max_ctas / 2) pairs = g_max_ctas / 2 > 0 ? g_max_ctas / 2 : 1;
+        int max_pairs = g_num_sms / 2;
+        if (g_max_ctas > 0 && max_pairs > g_max_ctas / 2) max_pairs = g_max_ctas / 2 > 0 ? g_max_ctas / 2 : 1;
+        // split-K: few tiles with a long contraction (the recurrent weight gradients: 16 tiles, K = B*T) would leave
+        // most SMs idle; partial products go to a per-stream workspace and are added in a fixed order
+        const int num_kb = (K + BK - 1) / BK;
+        int splits = 1;
+        static const bool no_split = getenv("PK2_GEMM_NO_SPLITK") != nullptr;
+        if (!no_split && g_lstm_T == 0 && tiles * 2 <= max_pairs && num_kb >= 64) {
+            splits = max_pairs / tiles;
+            if (splits > 8) splits = 8;
+            if (splits > num_kb / 16) splits = num_kb / 16;
+            if (splits < 1) splits = 1;
+        }
+        float* ws = nullptr;
+        if (splits > 1) {
+            const size_t need = (size_t)splits * M * N * sizeof(float);
+            std::lock_guard<std::mutex> lk(g_split_mu);
+            SplitWs& w = g_split_ws[pk2::as_stream(stream)];
+            if (need > w.bytes) {
+                if (w.ptr) { PK2_CHECK(cudaStreamSynchronize(pk2::as_stream(stream))); cudaFree(w.ptr); }
+                PK2_CHECK(cudaMalloc(&w.ptr, need));
+                w.bytes = need;
+            }
+            ws = w.ptr;
+        }
+        const int items = tiles * splits;
+        const int pairs = items < max_pairs ? items : max_pairs;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * pairs);
         cfg.blockDim = dim3(kThreads2);
@@ -359,8 +410,17 @@ extern "C" int pk2_gemm_bf16_nt(const void* A, const void* B, void* C, const flo
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        PK2_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_nt_kernel<2>, ma, mb2, C, bias, M, N, K, ldc, c_bf16,
-                                     (int)g_lstm_T, (int)g_lstm_B, (int)g_lstm_H));
+        if (splits > 1) {
+            PK2_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_nt_kernel<2>, ma, mb2, static_cast<void*>(ws),
+                                         static_cast<const float*>(nullptr), M, N, K, N, 0, 0, 0, 0, splits));
+            PK2_LAUNCHED();
+            const int64_t MN = (int64_t)M * N;
+            const int rb = (int)((MN + 255) / 256 < 2048 ? (MN + 255) / 256 : 2048);
+            splitk_reduce_kernel<<<rb, 256, 0, pk2::as_stream(stream)>>>(ws, splits, MN, N, bias, C, ldc, c_bf16);
+        } else {
+            PK2_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_nt_kernel<2>, ma, mb2, C, bias, M, N, K, ldc, c_bf16,
+                                         (int)g_lstm_T, (int)g_lstm_B, (int)g_lstm_H, 1));
+        }
     } else {
         constexpr int EWH = 4;
         const size_t smem = 4 * (kStageBytesA + BN * BK * 2) + sizeof(PipeBars) + 16 + EWH * kEpiTile + 1024;
@@ -368,7 +428,7 @@ extern "C" int pk2_gemm_bf16_nt(const void* A, const void* B, void* C, const flo
         int grid = tiles < g_num_sms ? tiles : g_num_sms;
         if (g_max_ctas > 0 && grid > g_max_ctas) grid = g_max_ctas;
         gemm_bf16_nt_kernel<1><<<grid, kThreads1, smem, pk2::as_stream(stream)>>>(ma, mb, C, bias, M, N, K, ldc, c_bf16,
-                                                                                 g_lstm_T, g_lstm_B, g_lstm_H);
+                                                                                 g_lstm_T, g_lstm_B, g_lstm_H, 1);
     }
     PK2_POST_LAUNCH();
     return 0;

@@ -24,7 +24,8 @@ def rel_err(a, b):
 
 @pytest.mark.parametrize("M,N,K,bias,bf16_out", [
     (128, 128, 64, False, False), (300, 200, 80, True, False), (1000, 5768, 1024, True, False),
-    (513, 80, 1000, False, False), (256, 4096, 4096, True, True), (130, 136, 72, False, True)])
+    (513, 80, 1000, False, False), (256, 4096, 4096, True, True), (130, 136, 72, False, True),
+    (2048, 512, 8192, True, False), (300, 100, 5000, False, True)])    # the last two take the split-K path
 def test_gemm_bf16_nt(dev, M, N, K, bias, bf16_out):
     from pykaldi2_b200.models import lstm as L
     torch.manual_seed(M + N + K)
