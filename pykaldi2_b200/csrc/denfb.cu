@@ -33,27 +33,30 @@ namespace {
 
 constexpr int kThreads = 1024;
 constexpr int kWarps = kThreads / 32;
-constexpr int kMaxK = 4;
+constexpr int kMaxK = 4;          // largest cluster of the streaming kernels
+constexpr int kMaxParts = 8;     // largest row partition of a table (register-resident kernels: clusters of 8)
 
 struct SellDev {
     const uint2* arcs;        // SELL arc records
     const int* slice_off;     // [n_slices + 1] offsets into arcs (multiple of 32)
     const int* slice_row;     // [n_slices * 32] row id or -1
-    int part_slice[kMaxK + 1];  // slices of part c: [part_slice[c], part_slice[c+1])
-    int part_row[kMaxK + 1];    // rows of part c
+    int part_slice[kMaxParts + 1];  // slices of part c: [part_slice[c], part_slice[c+1])
+    int part_row[kMaxParts + 1];    // rows of part c
 };
 
 struct SellHost {
     uint2* arcs = nullptr;
     int* slice_off = nullptr;
     int* slice_row = nullptr;
-    int part_slice[kMaxK + 1];
-    int part_row[kMaxK + 1];
+    int part_slice[kMaxParts + 1];
+    int part_row[kMaxParts + 1];
+    size_t n_arcs = 0;               // arc records (with padding)
+    std::vector<int> slice_len;      // host copy: arcs per lane of every slice
     void free_dev() { cudaFree(arcs); cudaFree(slice_off); cudaFree(slice_row); }
     SellDev dev() const {
         SellDev d;
         d.arcs = arcs; d.slice_off = slice_off; d.slice_row = slice_row;
-        for (int i = 0; i <= kMaxK; ++i) { d.part_slice[i] = part_slice[i]; d.part_row[i] = part_row[i]; }
+        for (int i = 0; i <= kMaxParts; ++i) { d.part_slice[i] = part_slice[i]; d.part_row[i] = part_row[i]; }
         return d;
     }
 };
@@ -71,7 +74,7 @@ int build_sell(const std::vector<std::vector<Arc3>>& rows, int K, SellHost* out)
     const int R = (int)rows.size();
     std::vector<uint2> arcs;
     std::vector<int> slice_off(1, 0), slice_row;
-    for (int i = 0; i <= kMaxK; ++i) { out->part_slice[i] = 0; out->part_row[i] = R; }
+    for (int i = 0; i <= kMaxParts; ++i) { out->part_slice[i] = 0; out->part_row[i] = R; }
     for (int c = 0; c < K; ++c) {
         const int r0 = part_bound(R, c, K), r1 = part_bound(R, c + 1, K);
         out->part_row[c] = r0;
@@ -121,7 +124,10 @@ int build_sell(const std::vector<std::vector<Arc3>>& rows, int K, SellHost* out)
             slice_off.push_back((int)arcs.size());
         }
     }
-    for (int c = K; c <= kMaxK; ++c) { out->part_slice[c] = (int)slice_off.size() - 1; out->part_row[c] = R; }
+    for (int c = K; c <= kMaxParts; ++c) { out->part_slice[c] = (int)slice_off.size() - 1; out->part_row[c] = R; }
+    out->n_arcs = arcs.size();
+    out->slice_len.clear();
+    for (size_t i = 0; i + 1 < slice_off.size(); ++i) out->slice_len.push_back((slice_off[i + 1] - slice_off[i]) / 32);
     if (arcs.empty()) arcs.push_back(make_uint2(0u, 0u));
     if (slice_row.empty()) slice_row.push_back(-1);
     PK2_CHECK(cudaMalloc(&out->arcs, sizeof(uint2) * arcs.size()));
@@ -133,15 +139,18 @@ int build_sell(const std::vector<std::vector<Arc3>>& rows, int K, SellHost* out)
     return 0;
 }
 
+struct RegSmemHost;
 struct DenGraph {
     int S = 0, N = 0;
     int64_t A = 0;
     std::vector<std::vector<Arc3>> rows_fwd, rows_bwd, rows_pdf;
     float* init = nullptr;          // device [S]
     float init_sum = 0.f;
-    bool built[kMaxK + 1] = {false, false, false, false, false};
-    SellHost t_fwd[kMaxK + 1], t_bwd[kMaxK + 1], t_pdf[kMaxK + 1];
+    bool built[kMaxParts + 1] = {};
+    SellHost t_fwd[kMaxParts + 1], t_bwd[kMaxParts + 1], t_pdf[kMaxParts + 1];
     std::mutex mu;
+    int reg_state = 0;               // register-resident path: 0 = not planned, 1 = usable, -1 = not usable
+    RegSmemHost* reg = nullptr;
     cudaStream_t side[2] = {nullptr, nullptr};     // side streams for the mixed-cluster schedule
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
 };
@@ -277,6 +286,9 @@ struct DenArgs {
     float* grad;
     double* logz;
     const int32_t* seq_map;   // sequence handled by cluster i (NULL = identity)
+    const float* e;           // register-resident kernels: exp(clamp(loglikes)) [n_seq][max_frames][N]
+    const int32_t* work;      // register-resident kernels: [n_clusters + 1] offsets, then sequence ids
+    int work_ids;             //   offset of the ids inside `work`
     int debug;                // profiling only (PK2_DEN_DEBUG): 1 = skip the arc loops, 2 = skip the passes
     long long* prof;          // profiling only: clock64 stamps of frames 64..71 of cluster 0 (pk2_den_set_profile_buffer)
 };
@@ -604,6 +616,603 @@ __global__ void __launch_bounds__(kThreads, 1) den_backward_kernel(DenArgs a) {
     cluster_barrier<K>();
 }
 
+// =====================================================================================================
+// Register-resident variant (clusters of 8 CTAs x 512 threads).
+//
+// The streaming kernels above re-read every arc record from L2 once per frame (3 x 0.6 MB per sequence and
+// frame): at 4 CTAs per sequence the three arc passes still take 21 k of the 32 k cycles of a frame pair
+// (profiles/den_trace_r1_v19.txt).  With 8 CTAs per sequence a CTA owns S/8 <= 1024 rows, i.e. two rows per
+// thread, and the ~8 arcs of a row fit the register file: the alpha and beta passes read no arc record from
+// memory at all (kRegArcs records per row live in registers for the whole kernel, longer rows keep the
+// remainder in shared memory), and the pdf-occupancy table of the CTA (~65 KB) is copied into shared memory
+// once.  What remains per frame is the two shared-memory gathers per arc (shared-memory bandwidth is the
+// bound of these kernels), one row exchange over DSMEM and two block barriers:
+//   * forward: the leaky-HMM term is applied lazily.  Peers exchange alpha(t) WITHOUT the leaky term and
+//     every row adds leaky*A(t) * z(t,j), z(t,j) = sum_arcs w*init[src]*e(t,pdf): one more register and FMA
+//     per arc instead of a pass over all S states in every CTA.
+//   * backward: the gamma pass is taken off the dependency chain: it runs while the beta rows travel.
+//   * the copies to the 7 peers are issued by 7 different warps (a single thread issuing 14 bulk copies
+//     costs ~2 k cycles).
+// A cluster is persistent over a LIST of sequences (host-side LPT assignment by length), so the 64
+// sequences of a batch are processed by the ~16 clusters that fit the GPU in one wave.
+constexpr int kRK = 8;             // CTAs per cluster
+constexpr int kRT = 512;           // threads per CTA
+constexpr int kRW = kRT / 32;      // warps per CTA
+constexpr int kRegArcs = 12;       // arc records per row held in registers
+constexpr int kRowsPerThread = 2;  // SELL slices per warp
+
+struct RegSlice {                  // one warp's slice of a SELL table
+    float w[kRegArcs];             // arc probability
+    uint32_t off[kRegArcs];        // byte offsets of the two gathers: (a * 4) | (b * 4) << 16
+    int len;                       // arcs per lane in this slice (warp-uniform); 0 = no slice
+    int row;                       // row of this lane, -1 = padding
+    const uint4* ovf;              // shared memory: records beyond kRegArcs, [len - kRegArcs][32] of {w, wi, off, -}
+};
+
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+// keep a loop-invariant address in a register: the compiler otherwise re-derives it (8-12 instructions) at every use
+__device__ __forceinline__ uint32_t pin_u32(uint32_t x) {
+    uint32_t y;
+    asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t prescale(uint32_t y) { return ((y & 0xffffu) << 2) | ((y >> 16) << 18); }
+
+// Load slices (warp, warp + kRW) of part c into registers; wi[] = w * init[a] when WI (forward table: a = source state).
+template <bool WI>
+__device__ __forceinline__ void load_reg_slices(const SellDev& tb, int c, const float* __restrict__ init,
+                                                RegSlice (&sl)[kRowsPerThread], float (&wi)[kRowsPerThread][kRegArcs],
+                                                uint4* ovf_area, int* wcnt) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s0 = tb.part_slice[c], nsl = tb.part_slice[c + 1] - s0;
+    int off[kRowsPerThread], extra[kRowsPerThread];
+#pragma unroll
+    for (int r = 0; r < kRowsPerThread; ++r) {
+        const int si = r == 0 ? warp : 2 * kRW - 1 - warp;       // slices are sorted by length: pair long with short
+        sl[r].len = 0; sl[r].row = -1; off[r] = 0;
+        if (si < nsl) {
+            off[r] = __ldg(&tb.slice_off[s0 + si]);
+            sl[r].len = (__ldg(&tb.slice_off[s0 + si + 1]) - off[r]) >> 5;
+            sl[r].row = __ldg(&tb.slice_row[(s0 + si) * 32 + lane]);
+        }
+#pragma unroll
+        for (int k = 0; k < kRegArcs; ++k) {
+            const uint2 rec = (k < sl[r].len) ? __ldg(tb.arcs + off[r] + k * 32 + lane) : make_uint2(0u, 0u);
+            sl[r].w[k] = __uint_as_float(rec.x);
+            sl[r].off[k] = prescale(rec.y);
+            wi[r][k] = WI ? sl[r].w[k] * __ldg(&init[rec.y & 0xffffu]) : 0.f;
+        }
+        extra[r] = max(sl[r].len - kRegArcs, 0);
+    }
+    if (lane == 0) { wcnt[warp] = extra[0] * 32; wcnt[2 * kRW - 1 - warp] = extra[1] * 32; }
+    __syncthreads();
+    // overflow area order: slice 0..2*kRW-1 (wcnt index = slice index inside the part)
+    const int c0 = wcnt[lane];
+#pragma unroll
+    for (int r = 0; r < kRowsPerThread; ++r) {
+        const int si = r == 0 ? warp : 2 * kRW - 1 - warp;
+        const int pre = warp_sum_i(lane < si ? c0 : 0);
+        for (int k = 0; k < extra[r]; ++k) {
+            const uint2 rec = __ldg(tb.arcs + off[r] + (kRegArcs + k) * 32 + lane);
+            const float w = __uint_as_float(rec.x);
+            const float x = WI ? w * __ldg(&init[rec.y & 0xffffu]) : 0.f;
+            ovf_area[pre + k * 32 + lane] = make_uint4(rec.x, __float_as_uint(x), prescale(rec.y), 0u);
+        }
+        sl[r].ovf = ovf_area + pre;
+    }
+    __syncwarp();
+}
+
+// One slice: acc += sum g_a * (w * g_b); accz += sum wz * g_b where wz = wi (forward: lazy leaky term) or
+// w (backward: lazy leaky term of beta).  base_a / base_b: shared-memory byte addresses of the gathered vectors.
+template <bool WI>
+__device__ __forceinline__ void reg_slice_pass(const RegSlice& s, const float (&wi)[kRegArcs], uint32_t base_a,
+                                               uint32_t base_b, float& acc, float& accz) {
+    const int lane = threadIdx.x & 31;
+    float a0 = 0.f, a1 = 0.f, z0 = 0.f, z1 = 0.f;
+#pragma unroll
+    for (int g = 0; g < kRegArcs; g += 4) {
+        if (g < s.len) {
+            float gb[4], ga[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                gb[u] = lds_f32(base_b + (s.off[g + u] >> 16));
+                ga[u] = lds_f32(base_a + (s.off[g + u] & 0xffffu));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float t = s.w[g + u] * gb[u];
+                if (u & 1) { a1 = fmaf(ga[u], t, a1); z1 = WI ? fmaf(wi[g + u], gb[u], z1) : z1 + t; }
+                else       { a0 = fmaf(ga[u], t, a0); z0 = WI ? fmaf(wi[g + u], gb[u], z0) : z0 + t; }
+            }
+        }
+    }
+    for (int k = kRegArcs; k < s.len; k += 4) {              // rows longer than the register slots (rare)
+        uint4 r[4];
+        float gb[4], ga[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            r[u] = (k + u < s.len) ? s.ovf[(k + u - kRegArcs) * 32 + lane] : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { gb[u] = lds_f32(base_b + (r[u].z >> 16)); ga[u] = lds_f32(base_a + (r[u].z & 0xffffu)); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float t = __uint_as_float(r[u].x) * gb[u];
+            if (u & 1) { a1 = fmaf(ga[u], t, a1); z1 = WI ? fmaf(__uint_as_float(r[u].y), gb[u], z1) : z1 + t; }
+            else       { a0 = fmaf(ga[u], t, a0); z0 = WI ? fmaf(__uint_as_float(r[u].y), gb[u], z0) : z0 + t; }
+        }
+    }
+    acc = a0 + a1;
+    accz = z0 + z1;
+}
+
+template <int NT>
+__device__ __forceinline__ void row_prefetch_nt(float* dst, const float* src, int n) {
+    const bool vec = ((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    if (vec) {
+        for (int i = threadIdx.x * 4; i < n; i += NT * 4) cp_async16(dst + i, src + i);
+    } else {
+        for (int i = threadIdx.x; i < n; i += NT) dst[i] = __ldg(src + i);
+    }
+    cp_async_commit();
+}
+// exp(clamp(x)) of a row: straight from global memory (first frame of a sequence) ...
+template <int NT>
+__device__ __forceinline__ void exp_row_direct(float* dst, const float* src, int n) {
+    for (int i = threadIdx.x; i < n; i += NT) dst[i] = __expf(fminf(fmaxf(__ldg(src + i), -30.f), 30.f));
+}
+// ... or in place on the chunks THIS thread fetched with row_prefetch_nt (same thread -> element mapping, so
+// no barrier is needed between the copy landing and the exp)
+template <int NT>
+__device__ __forceinline__ void exp_inplace_own(float* dst, const float* src, int n) {
+    const bool vec = ((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    if (vec) {
+        for (int i = threadIdx.x * 4; i < n; i += NT * 4) {
+            float4 x = *reinterpret_cast<float4*>(dst + i);
+            x.x = __expf(fminf(fmaxf(x.x, -30.f), 30.f)); x.y = __expf(fminf(fmaxf(x.y, -30.f), 30.f));
+            x.z = __expf(fminf(fmaxf(x.z, -30.f), 30.f)); x.w = __expf(fminf(fmaxf(x.w, -30.f), 30.f));
+            *reinterpret_cast<float4*>(dst + i) = x;
+        }
+    } else {
+        for (int i = threadIdx.x; i < n; i += NT) dst[i] = __expf(fminf(fmaxf(dst[i], -30.f), 30.f));
+    }
+}
+template <int NW>
+__device__ __forceinline__ float block_sum_nw(float v, float* red) {
+    v = pk2::warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    const float t = pk2::warp_sum(lane < NW ? red[lane] : 0.f);     // every warp: identical bits
+    __syncthreads();
+    return t;
+}
+
+// mbarrier wait with a watchdog: a protocol error traps (cudaErrorLaunchFailure) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = tc::smem_u32(bar);
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}\n" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return;
+        if (spin > (1u << 24)) __trap();
+    }
+}
+
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Row exchange: warp q (q = 0..6), one elected lane, pushes this CTA's row block and its 16-byte partial-sum
+// slot into peer (c + 1 + q) % 8; completion is counted on the peer's mbarrier.  Every issuing thread writes
+// the (identical) partial sum itself so that the write is ordered before its own copies.
+__device__ __forceinline__ void reg_send(const float* src_rows, float* dst_rows, int nrow, float* part_slot,
+                                         float own, uint64_t* bar, int c, int warp) {
+    *part_slot = own;
+    fence_async_smem();
+    const uint32_t peer = (uint32_t)((c + 1 + warp) % kRK);
+    const uint32_t bar_r = tc::mapa_u32(tc::smem_u32(bar), peer);
+    tc::dsmem_bulk_copy(tc::mapa_u32(tc::smem_u32(dst_rows), peer), tc::smem_u32(src_rows), (uint32_t)nrow * 4u, bar_r);
+    tc::dsmem_bulk_copy(tc::mapa_u32(tc::smem_u32(part_slot), peer), tc::smem_u32(part_slot), 16u, bar_r);
+}
+
+// cluster-wide sum of the 8 partial sums of a frame (16-byte slots); the own slot may not be visible yet
+__device__ __forceinline__ float sum_parts(uint32_t parts_s, int c, float own) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < kRK; ++k) {
+        const float v = lds_f32(parts_s + k * 16);
+        t += (k == c) ? own : v;
+    }
+    return t;
+}
+
+// e = exp(clamp(loglikes, -30, 30)) for the valid frames of every sequence, once per call: the frame loops
+// of the register-resident kernels then bulk-copy e rows straight into shared memory
+__global__ void __launch_bounds__(256) den_exp_kernel(const float* __restrict__ ll, float* __restrict__ e,
+                                                      const int32_t* __restrict__ num_frames, int64_t row_stride_b,
+                                                      int max_frames, int N) {
+    const int b = blockIdx.y, t = blockIdx.x;
+    if (t >= num_frames[b]) return;
+    const float* src = ll + ((int64_t)b * row_stride_b + t) * N;
+    float* dst = e + ((int64_t)b * max_frames + t) * N;
+    for (int i = threadIdx.x * 4; i < N; i += 256 * 4) {
+        float4 x = *reinterpret_cast<const float4*>(src + i);
+        x.x = __expf(fminf(fmaxf(x.x, -30.f), 30.f)); x.y = __expf(fminf(fmaxf(x.y, -30.f), 30.f));
+        x.z = __expf(fminf(fmaxf(x.z, -30.f), 30.f)); x.w = __expf(fminf(fmaxf(x.w, -30.f), 30.f));
+        *reinterpret_cast<float4*>(dst + i) = x;
+    }
+}
+
+struct RegSmem {                   // host-computed shared-memory carve-up (element counts)
+    int ovf_f, ovf_b;              // overflow records (forward / backward table)
+    int garcs;                     // pdf-table records per CTA
+    int nslg;                      // pdf-table slices per CTA
+    int gcap;                      // pdf rows per CTA
+};
+
+#define PK2_RPROF(e) do { if (prof && wi_ == w0 && t >= 64 && t < 72) prof[(t - 64) * 8 + (e)] = clock64(); } while (0)
+
+__global__ void __launch_bounds__(kRT, 1) den_forward_reg_kernel(DenArgs a, RegSmem rs) {
+    extern __shared__ __align__(16) float smem[];
+    const int S = a.S, N = a.N;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = (int)tc::cluster_ctarank();
+    const int q = blockIdx.x / kRK;
+    const int r0 = a.fwd.part_row[c], r1 = a.fwd.part_row[c + 1], nrow = r1 - r0;
+    float* buf = smem;                      // [2][S]  alpha (without the leaky term)
+    float* E = buf + 2 * S;                 // [2][N]  e(t), e(t+1)   (N % 4 == 0)
+    float* wsum = E + 2 * N;                // [2][32] per-warp partial sums, by frame parity
+    float* parts = wsum + 64;               // [2][kRK * 4]
+    float* red = parts + 2 * kRK * 4;       // [40]
+    int* wcnt = reinterpret_cast<int*>(red + 40);                  // [32]
+    double* dred = reinterpret_cast<double*>(wcnt + 32);           // [32]
+    uint64_t* xbar = reinterpret_cast<uint64_t*>(dred + 32);       // [2] row exchange
+    uint64_t* ebar = xbar + 2;                                     // [2] e rows
+    uint4* ovf = reinterpret_cast<uint4*>(xbar + 4);
+
+    RegSlice sl[kRowsPerThread];
+    float wi[kRowsPerThread][kRegArcs];
+    load_reg_slices<true>(a.fwd, c, a.init, sl, wi, ovf, wcnt);
+    float init_own[2];                      // init of the rows this thread stores to the alpha workspace
+    float s = 0.f;
+    for (int j = threadIdx.x; j < S; j += kRT) s += __ldg(&a.init[j]);
+#pragma unroll
+    for (int r = 0; r < 2; ++r) init_own[r] = (threadIdx.x + r * kRT < nrow) ? __ldg(&a.init[r0 + threadIdx.x + r * kRT]) : 0.f;
+    const float A0 = block_sum_nw<kRW>(s, red);
+    const uint32_t expect = (uint32_t)(S - nrow) * 4u + (uint32_t)(kRK - 1) * 16u;
+    const uint32_t ebytes = (uint32_t)N * 4u;
+    if (threadIdx.x == 0) {
+        tc::mbar_init(&xbar[0], 1); tc::mbar_init(&xbar[1], 1);
+        tc::mbar_init(&ebar[0], 1); tc::mbar_init(&ebar[1], 1);
+        tc::fence_barrier_init();
+        tc::mbar_expect_tx(&xbar[0], expect);
+        tc::mbar_expect_tx(&xbar[1], expect);
+    }
+    tc::cluster_sync_all();                 // every peer's barriers are armed before the first copy is sent
+
+    const int w0 = a.work[q], w1 = a.work[q + 1];
+    const int32_t* ids = a.work + a.work_ids;
+    long long* prof = (a.prof && blockIdx.x == 0 && threadIdx.x == 0) ? a.prof : nullptr;
+    const uint32_t buf_s = tc::smem_u32(buf), E_s = tc::smem_u32(E), parts_s = tc::smem_u32(parts);
+    uint32_t f = 0, phase = 0, ephase = 0;  // global frame counter: parity of buffers and barriers
+    for (int wi_ = w0; wi_ < w1; ++wi_) {
+        const int b = ids[wi_];
+        const int T = a.num_frames[b];
+        const float* e = a.e + (int64_t)b * a.max_frames * N;
+        float* aws = a.alpha_ws + (int64_t)b * a.max_frames * S;
+        float* asum = a.asum_ws + (int64_t)b * (a.max_frames + 2);
+        {
+            float* cur = buf + (f & 1) * S;             // alpha(0) = init
+            for (int j = threadIdx.x; j < S; j += kRT) cur[j] = __ldg(&a.init[j]);
+            if (threadIdx.x == 0) {
+                if (T > 0) { tc::mbar_expect_tx(&ebar[f & 1], ebytes); tc::bulk_load(E + (f & 1) * N, e, ebytes, &ebar[f & 1]); }
+                if (T > 1) { tc::mbar_expect_tx(&ebar[(f + 1) & 1], ebytes); tc::bulk_load(E + ((f + 1) & 1) * N, e + N, ebytes, &ebar[(f + 1) & 1]); }
+            }
+        }
+        float A = A0;
+        float lk = a.leaky * A0;                        // alpha'(t) = alpha(t) + lk * init
+        __syncthreads();
+        for (int t = 0; t < T; ++t, ++f) {
+            PK2_RPROF(0);
+            const int par = (int)(f & 1);
+            float* cur = buf + par * S;
+            float* nxt = buf + (par ^ 1) * S;
+            // alpha'(t) of this CTA's rows -> workspace (read by the backward kernel), coalesced
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int i = threadIdx.x + r * kRT;
+                if (i < nrow) aws[(int64_t)t * S + r0 + i] = fmaf(lk, init_own[r], cur[r0 + i]);
+            }
+            if (threadIdx.x == 0 && c == 0) asum[t] = A;
+            const float invA = 1.0f / A;
+            const uint32_t cur_s = pin_u32(buf_s + (uint32_t)(par * S) * 4u), Ec_s = pin_u32(E_s + (uint32_t)(par * N) * 4u);
+            mbar_wait_guard(&ebar[par], (ephase >> par) & 1u);          // e(t) has landed
+            ephase ^= (1u << par);
+            float vsum = 0.f;
+#pragma unroll
+            for (int r = 0; r < kRowsPerThread; ++r) {
+                float acc, z;
+                reg_slice_pass<true>(sl[r], wi[r], cur_s, Ec_s, acc, z);
+                if (sl[r].row >= 0) {
+                    const float v = fmaf(lk, z, acc) * invA;      // alpha(t+1, row)
+                    nxt[sl[r].row] = v;
+                    vsum += v;
+                }
+            }
+            const float ws = pk2::warp_sum(vsum);
+            if (lane == 0) wsum[par * 32 + warp] = ws;
+            fence_async_smem();                              // rows -> async proxy
+            PK2_RPROF(1);
+            __syncthreads();                                 // pass done in this CTA
+            const float own = pk2::warp_sum(lane < kRW ? wsum[par * 32 + lane] : 0.f);     // block total, bit-identical in every warp
+            if (lane == 0) {
+                if (warp < kRK - 1) {
+                    reg_send(nxt + r0, nxt + r0, nrow, parts + par * kRK * 4 + c * 4, own, &xbar[par], c, warp);
+                } else if (warp == kRK - 1 && t + 2 < T) {   // e(t+2) into the buffer the pass has just released
+                    tc::mbar_expect_tx(&ebar[par], ebytes);
+                    tc::bulk_load(E + par * N, e + (int64_t)(t + 2) * N, ebytes, &ebar[par]);
+                }
+            }
+            PK2_RPROF(2);
+            mbar_wait_guard(&xbar[par], (phase >> par) & 1u);
+            phase ^= (1u << par);
+            if (threadIdx.x == 0) tc::mbar_expect_tx(&xbar[par], expect);      // arm for frame f + 2
+            PK2_RPROF(3);
+            const float An = sum_parts(parts_s + (uint32_t)par * kRK * 16u, c, own);
+            lk = a.leaky * An;
+            A = An;
+            PK2_RPROF(4);
+        }
+        // total probability sum_j alpha'(T, j) = A(T) + lk * sum(init) and log Z
+        const float totp = fmaf(lk, A0, A);
+        if (c == 0) {
+            __threadfence_block();
+            __syncthreads();
+            double part = 0.0;
+            for (int t = threadIdx.x; t < T; t += kRT) part += log((double)asum[t]);
+            part = pk2::warp_sum_d(part);
+            if (lane == 0) dred[warp] = part;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double logsum = 0.0;
+                for (int w = 0; w < kRW; ++w) logsum += dred[w];
+                asum[T] = A;
+                asum[a.max_frames + 1] = totp;
+                a.logz[b] = log((double)totp) + logsum;
+            }
+        }
+        __syncthreads();
+    }
+    tc::cluster_sync_all();                 // no CTA exits while a peer may still copy into it
+}
+
+// Sum over the arcs of the rows of a SELL table held in SHARED memory (pdf-occupancy pass):
+// acc = sum ga[a] * (w * gb[b]), acc2 = sum ga[a] * w.  Slices are sorted by length: odd rounds go to the
+// warps in reverse order so that every warp gets about the same number of arcs.
+template <class Body>
+__device__ __forceinline__ void sell_pass_smem(const uint2* arcs, const int2* meta, const uint16_t* rows, int nsl,
+                                               uint32_t base_a, uint32_t base_b, Body&& body) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int rd = 0; rd * kRW < nsl; ++rd) {
+        const int i = rd * kRW + ((rd & 1) ? kRW - 1 - warp : warp);
+        if (i >= nsl) continue;
+        const int2 m = meta[i];
+        const uint2* p = arcs + m.x + lane;
+        const unsigned row = rows[i * 32 + lane];
+        float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
+        int k = 0;
+        for (; k + 4 <= m.y; k += 4) {
+            uint2 r[4];
+            float ga[4], gb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) r[u] = p[(k + u) * 32];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { ga[u] = lds_f32(base_a + (r[u].y & 0xffffu)); gb[u] = lds_f32(base_b + (r[u].y >> 16)); }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float w = __uint_as_float(r[u].x);
+                if (u & 1) { a1 = fmaf(ga[u], w * gb[u], a1); c1 = fmaf(ga[u], w, c1); }
+                else       { a0 = fmaf(ga[u], w * gb[u], a0); c0 = fmaf(ga[u], w, c0); }
+            }
+        }
+        for (; k < m.y; ++k) {
+            const uint2 r = p[k * 32];
+            const float w = __uint_as_float(r.x);
+            const float g = lds_f32(base_a + (r.y & 0xffffu));
+            a0 = fmaf(g, w * lds_f32(base_b + (r.y >> 16)), a0);
+            c0 = fmaf(g, w, c0);
+        }
+        if (row != 0xFFFFu) body((int)row, a0 + a1, c0 + c1);
+    }
+}
+
+__global__ void __launch_bounds__(kRT, 1) den_backward_reg_kernel(DenArgs a, RegSmem rs) {
+    extern __shared__ __align__(16) float smem[];
+    const int S = a.S, N = a.N;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = (int)tc::cluster_ctarank();
+    const int q = blockIdx.x / kRK;
+    const int r0 = a.bwd.part_row[c], r1 = a.bwd.part_row[c + 1], nrow = r1 - r0;
+    const int p0 = a.pdf.part_row[c], p1 = a.pdf.part_row[c + 1];
+    float* buf = smem;                      // [2][S]  beta' (without the leaky term)
+    float* al = buf + 2 * S;                // [S]     alpha'(t)
+    float* E = al + S;                      // [2][N]  e(t), e(t-1)
+    float* gbuf = E + 2 * N;                // [gcap]  gamma of this CTA's pdf range
+    float* wsum = gbuf + rs.gcap;           // [32]
+    float* parts = wsum + 32;               // [2][kRK * 4]
+    float* red = parts + 2 * kRK * 4;       // [40]
+    int* wcnt = reinterpret_cast<int*>(red + 40);                  // [32]
+    uint64_t* xbar = reinterpret_cast<uint64_t*>(wcnt + 32);       // [2] row exchange
+    uint64_t* cbar = xbar + 2;                                     // [2] credits
+    uint64_t* ebar = xbar + 4;                                     // [2] e rows
+    uint64_t* abar = xbar + 6;                                     // [1] alpha row (+1 pad)
+    uint4* ovf = reinterpret_cast<uint4*>(xbar + 8);               // [ovf_b]
+    uint2* garcs = reinterpret_cast<uint2*>(ovf + rs.ovf_b);       // [garcs]  (offsets pre-scaled)
+    int2* meta_g = reinterpret_cast<int2*>(garcs + rs.garcs);      // [nslg]
+    uint16_t* rows_g = reinterpret_cast<uint16_t*>(meta_g + rs.nslg);   // [nslg * 32]
+
+    RegSlice sl[kRowsPerThread];
+    float wi[kRowsPerThread][kRegArcs];     // unused (WI = false): optimised away
+    load_reg_slices<false>(a.bwd, c, a.init, sl, wi, ovf, wcnt);
+    float init_row[kRowsPerThread];
+#pragma unroll
+    for (int r = 0; r < kRowsPerThread; ++r) init_row[r] = sl[r].row >= 0 ? __ldg(&a.init[sl[r].row]) : 0.f;
+    // pdf table of this CTA -> shared memory (slice offsets relative to the CTA's first record)
+    const int gs0 = a.pdf.part_slice[c], nslg = a.pdf.part_slice[c + 1] - gs0;
+    const int gbase = __ldg(&a.pdf.slice_off[gs0]);
+    const int gcnt = __ldg(&a.pdf.slice_off[gs0 + nslg]) - gbase;
+    for (int i = threadIdx.x; i < nslg; i += kRT) {
+        const int off = __ldg(&a.pdf.slice_off[gs0 + i]);
+        meta_g[i] = make_int2(off - gbase, (__ldg(&a.pdf.slice_off[gs0 + i + 1]) - off) >> 5);
+    }
+    for (int i = threadIdx.x; i < nslg * 32; i += kRT) {
+        const int r = __ldg(&a.pdf.slice_row[gs0 * 32 + i]);
+        rows_g[i] = r < 0 ? (uint16_t)0xFFFFu : (uint16_t)r;
+    }
+    for (int i = threadIdx.x; i < gcnt; i += kRT) {
+        const uint2 rec = __ldg(a.pdf.arcs + gbase + i);
+        garcs[i] = make_uint2(rec.x, prescale(rec.y));
+    }
+    float s = 0.f;
+    for (int j = threadIdx.x; j < S; j += kRT) s += __ldg(&a.init[j]);
+    const float isum = block_sum_nw<kRW>(s, red);
+    const uint32_t expect = (uint32_t)(S - nrow) * 4u + (uint32_t)(kRK - 1) * 16u;
+    const uint32_t ebytes = (uint32_t)N * 4u, abytes = (uint32_t)S * 4u;
+    if (threadIdx.x == 0) {
+        tc::mbar_init(&xbar[0], 1); tc::mbar_init(&xbar[1], 1);
+        tc::mbar_init(&cbar[0], kRK - 1); tc::mbar_init(&cbar[1], kRK - 1);
+        tc::mbar_init(&ebar[0], 1); tc::mbar_init(&ebar[1], 1); tc::mbar_init(abar, 1);
+        tc::fence_barrier_init();
+        tc::mbar_expect_tx(&xbar[0], expect);
+        tc::mbar_expect_tx(&xbar[1], expect);
+    }
+    tc::cluster_sync_all();
+
+    const int w0 = a.work[q], w1 = a.work[q + 1];
+    const int32_t* ids = a.work + a.work_ids;
+    long long* prof = (a.prof && blockIdx.x == 0 && threadIdx.x == 0) ? a.prof + 64 : nullptr;
+    const uint32_t buf_s = tc::smem_u32(buf), E_s = tc::smem_u32(E), al_s = tc::smem_u32(al), parts_s = tc::smem_u32(parts);
+    uint32_t f = 0, phase = 0, ephase = 0, aphase = 0;
+    for (int wi_ = w0; wi_ < w1; ++wi_) {
+        const int b = ids[wi_];
+        const int T = a.num_frames[b];
+        const float* e = a.e + (int64_t)b * a.max_frames * N;
+        float* grad = a.grad + (int64_t)b * a.row_stride_b * N;
+        const float* aws = a.alpha_ws + (int64_t)b * a.max_frames * S;
+        const float* asum = a.asum_ws + (int64_t)b * (a.max_frames + 2);
+        for (int t = T; t < a.max_frames; ++t)
+            for (int p = p0 + threadIdx.x; p < p1; p += kRT) grad[(int64_t)t * N + p] = 0.f;
+        if (T <= 0) continue;               // uniform across the cluster
+        const float totp = asum[a.max_frames + 1];
+        const float bT = 1.0f / totp;
+        float lk = a.leaky * isum * bT;      // beta = beta' + lk (leaky term applied lazily)
+        {
+            float* cur = buf + (f & 1) * S;
+            for (int j = threadIdx.x; j < S; j += kRT) cur[j] = bT;
+            if (threadIdx.x == 0) {
+                tc::mbar_expect_tx(&ebar[f & 1], ebytes);
+                tc::bulk_load(E + (f & 1) * N, e + (int64_t)(T - 1) * N, ebytes, &ebar[f & 1]);
+                if (T > 1) {
+                    tc::mbar_expect_tx(&ebar[(f + 1) & 1], ebytes);
+                    tc::bulk_load(E + ((f + 1) & 1) * N, e + (int64_t)(T - 2) * N, ebytes, &ebar[(f + 1) & 1]);
+                }
+                tc::mbar_expect_tx(abar, abytes);
+                tc::bulk_load(al, aws + (int64_t)(T - 1) * S, abytes, abar);
+            }
+        }
+        float asum_t = asum[T - 1];
+        __syncthreads();
+        for (int t = T - 1; t >= 0; --t, ++f) {
+            PK2_RPROF(0);
+            const int par = (int)(f & 1);
+            float* nxt = buf + (par ^ 1) * S;   // beta'(t)
+            float* Ec = E + par * N;            // e(t)
+            const uint32_t cur_s = pin_u32(buf_s + (uint32_t)(par * S) * 4u), Ec_s = pin_u32(E_s + (uint32_t)(par * N) * 4u);
+            const float invA = 1.0f / asum_t;
+            if (t > 0) asum_t = asum[t - 1];
+            mbar_wait_guard(&ebar[par], (ephase >> par) & 1u);          // e(t) has landed
+            ephase ^= (1u << par);
+            float d = 0.f;
+#pragma unroll
+            for (int r = 0; r < kRowsPerThread; ++r) {
+                float acc, acc2;
+                reg_slice_pass<false>(sl[r], wi[r], cur_s, Ec_s, acc, acc2);
+                if (sl[r].row >= 0) {
+                    const float v = fmaf(lk, acc2, acc) * invA;
+                    nxt[sl[r].row] = v;
+                    d = fmaf(v, init_row[r], d);
+                }
+            }
+            const float ws = pk2::warp_sum(d);
+            if (lane == 0) wsum[warp] = ws;
+            fence_async_smem();
+            PK2_RPROF(1);
+            __syncthreads();                                 // [1] beta rows of this CTA complete
+            const float own = pk2::warp_sum(lane < kRW ? wsum[lane] : 0.f);
+            if (warp < kRK - 1 && lane == 0) {
+                // The peer's gamma pass of frame f-1 reads the buffer this frame's rows land in: wait for its
+                // credit.  Credits alternate between two barriers: a peer can give its credit for frame f
+                // before this CTA has looked at the credits of frame f-1 (it does not need our frame-f rows
+                // for that), and a single barrier two phases ahead would look "not complete" to a parity wait.
+                if (f > 0) mbar_wait_guard(&cbar[(f - 1) & 1u], ((f - 1) >> 1) & 1u);
+                reg_send(nxt + r0, nxt + r0, nrow, parts + par * kRK * 4 + c * 4, own, &xbar[par], c, warp);
+            }
+            PK2_RPROF(2);
+            // off the dependency chain, while the rows travel: pdf occupancies gamma(t, p) of this CTA's pdf range
+            mbar_wait_guard(abar, aphase & 1u);                         // alpha'(t) has landed
+            aphase ^= 1u;
+            const float gs = a.deriv_scale * invA;
+            sell_pass_smem(garcs, meta_g, rows_g, nslg, al_s, cur_s, [&](int row, float ac, float ac2) {
+                gbuf[row - p0] = fmaf(lk, ac2, ac) * Ec[row] * gs;
+            });
+            PK2_RPROF(3);
+            __syncthreads();                                 // [2] reads of al / cur / Ec done, gbuf complete
+            if (lane == 0) {
+                if (warp < kRK - 1) {
+                    tc::mbar_arrive_remote_relaxed(tc::mapa_u32(tc::smem_u32(&cbar[par]), (uint32_t)((c + 1 + warp) % kRK)));
+                } else if (warp == kRK - 1) {
+                    if (t > 0) { tc::mbar_expect_tx(abar, abytes); tc::bulk_load(al, aws + (int64_t)(t - 1) * S, abytes, abar); }
+                    if (t > 1) { tc::mbar_expect_tx(&ebar[par], ebytes); tc::bulk_load(Ec, e + (int64_t)(t - 2) * N, ebytes, &ebar[par]); }
+                }
+            }
+            for (int p = threadIdx.x; p < p1 - p0; p += kRT) grad[(int64_t)t * N + p0 + p] = gbuf[p];
+            PK2_RPROF(4);
+            mbar_wait_guard(&xbar[par], (phase >> par) & 1u);
+            phase ^= (1u << par);
+            if (threadIdx.x == 0) tc::mbar_expect_tx(&xbar[par], expect);
+            lk = a.leaky * sum_parts(parts_s + (uint32_t)par * kRK * 16u, c, own);
+            PK2_RPROF(5);
+        }
+        __syncthreads();
+    }
+    tc::cluster_sync_all();
+}
+#undef PK2_RPROF
+
+size_t reg_fwd_smem_bytes(int S, int N, const RegSmem& rs) {
+    return sizeof(float) * (2 * (size_t)S + 2 * (size_t)N + 64 + 2 * kRK * 4 + 40) +
+           sizeof(int) * 32 + sizeof(double) * 32 + sizeof(uint64_t) * 4 + sizeof(uint4) * (size_t)rs.ovf_f + 16;
+}
+size_t reg_bwd_smem_bytes(int S, int N, const RegSmem& rs) {
+    return sizeof(float) * (2 * (size_t)S + S + 2 * (size_t)N + rs.gcap + 32 + 2 * kRK * 4 + 40) +
+           sizeof(int) * 32 + sizeof(uint64_t) * 8 + sizeof(uint4) * (size_t)rs.ovf_b + sizeof(int2) * (size_t)rs.nslg +
+           sizeof(uint2) * (size_t)rs.garcs + sizeof(uint16_t) * (size_t)rs.nslg * 32 + 16;
+}
+
 size_t fwd_smem_bytes(int S, int N, int K) {
     const size_t Sp = (S + 3) & ~3, Np = (N + 3) & ~3;
     const size_t rows_part = (size_t)((S + K - 1) / K + 64);            // rows staged per CTA (+ slice padding)
@@ -688,6 +1297,97 @@ void plan_clusters(const int32_t* frames, int n, int budget, std::vector<int>* k
     }
 }
 
+
+struct RegSmemHost { RegSmem rs; size_t smem_f, smem_b; int max_clusters; };
+
+int launch_cluster8(void (*kern)(DenArgs, RegSmem), const DenArgs& args, const RegSmem& rs, int n_clusters,
+                    size_t smem, cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_clusters * kRK);
+    cfg.blockDim = dim3(kRT);
+    cfg.stream = st;
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kRK; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    PK2_CHECK(cudaLaunchKernelEx(&cfg, kern, args, rs));
+    PK2_LAUNCHED();
+    return 0;
+}
+
+// Decide once per graph whether the register-resident kernels apply: S splits into 8 parts of whole
+// 32-row slices with at most one row per thread, indices fit the packed records, and the backward
+// kernel's working set (beta x2, alpha, e x2, the CTA's pdf table) fits the 227 KB of shared memory.
+int plan_reg(DenGraph* g) {
+    if (g->reg_state != 0) return 0;
+    g->reg_state = -1;
+    const int S = g->S, N = g->N;
+    if (S % (kRK * 32) != 0 || S / kRK > kRT * kRowsPerThread || S >= 16384 || N >= 16384 || N % 4 != 0) return 0;
+    if (ensure_tables(g, kRK)) return 1;
+    RegSmem rs = {0, 0, 0, 0, 0};
+    const SellHost &tf = g->t_fwd[kRK], &tb = g->t_bwd[kRK], &tp = g->t_pdf[kRK];
+    for (int c = 0; c < kRK; ++c) {
+        int of = 0, ob = 0, ga = 0;
+        if (tf.part_slice[c + 1] - tf.part_slice[c] > kRW * kRowsPerThread || tb.part_slice[c + 1] - tb.part_slice[c] > kRW * kRowsPerThread) return 0;
+        for (int i = tf.part_slice[c]; i < tf.part_slice[c + 1]; ++i) of += std::max(tf.slice_len[i] - kRegArcs, 0) * 32;
+        for (int i = tb.part_slice[c]; i < tb.part_slice[c + 1]; ++i) ob += std::max(tb.slice_len[i] - kRegArcs, 0) * 32;
+        for (int i = tp.part_slice[c]; i < tp.part_slice[c + 1]; ++i) ga += tp.slice_len[i] * 32;
+        rs.ovf_f = std::max(rs.ovf_f, of); rs.ovf_b = std::max(rs.ovf_b, ob); rs.garcs = std::max(rs.garcs, ga);
+        rs.nslg = std::max(rs.nslg, tp.part_slice[c + 1] - tp.part_slice[c]);
+        rs.gcap = std::max(rs.gcap, tp.part_row[c + 1] - tp.part_row[c]);
+    }
+    rs.ovf_f = (rs.ovf_f + 1) & ~1; rs.ovf_b = (rs.ovf_b + 1) & ~1;
+    rs.nslg = (rs.nslg + 1) & ~1;
+    rs.gcap = (rs.gcap + 3) & ~3;
+    RegSmemHost* h = new RegSmemHost();
+    h->rs = rs;
+    h->smem_f = reg_fwd_smem_bytes(S, N, rs);
+    h->smem_b = reg_bwd_smem_bytes(S, N, rs);
+    if (h->smem_f > 227 * 1024 || h->smem_b > 227 * 1024) { delete h; return 0; }
+    PK2_CHECK(cudaFuncSetAttribute(den_forward_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_f));
+    PK2_CHECK(cudaFuncSetAttribute(den_backward_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_b));
+    // how many clusters of 8 can be resident at once (GPC granularity: fewer than SMs / 8)
+    int nmax = 1 << 30;
+    for (int pass = 0; pass < 2; ++pass) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(kRK * 64); cfg.blockDim = dim3(kRT);
+        cfg.dynamicSmemBytes = pass ? h->smem_b : h->smem_f;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kRK; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int n = 0;
+        PK2_CHECK(cudaOccupancyMaxActiveClusters(&n, pass ? den_backward_reg_kernel : den_forward_reg_kernel, &cfg));
+        nmax = std::min(nmax, n);
+    }
+    if (nmax < 1) { delete h; return 0; }
+    h->max_clusters = nmax;
+    g->reg = h;
+    g->reg_state = 1;
+    return 0;
+}
+
+// Work lists: longest sequence first onto the least loaded cluster (LPT).
+void plan_work(const int32_t* frames, int n, int ncl, std::vector<int32_t>* work) {
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    if (frames) std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return frames[x] > frames[y]; });
+    std::vector<std::vector<int>> lists(ncl);
+    std::vector<long long> load(ncl, 0);
+    for (int i : order) {
+        int best = 0;
+        for (int k = 1; k < ncl; ++k) if (load[k] < load[best]) best = k;
+        lists[best].push_back(i);
+        load[best] += (frames ? frames[i] : 1) + 8;      // + per-sequence set-up
+    }
+    work->assign(ncl + 1, 0);
+    for (int k = 0; k < ncl; ++k) {
+        (*work)[k + 1] = (*work)[k] + (int)lists[k].size();
+        for (int i : lists[k]) work->push_back(i);
+    }
+}
+
 }  // namespace
 
 extern "C" int pk2_den_graph_create(int S, int N, const int32_t* fwd_off, const float* fwd_prob,
@@ -730,9 +1430,10 @@ extern "C" int pk2_den_set_profile_buffer(void* buf) {
 extern "C" int pk2_den_graph_destroy(void* graph) {
     if (!graph) return 0;
     DenGraph* g = static_cast<DenGraph*>(graph);
-    for (int k = 1; k <= kMaxK; ++k)
+    for (int k = 1; k <= kMaxParts; ++k)
         if (g->built[k]) { g->t_fwd[k].free_dev(); g->t_bwd[k].free_dev(); g->t_pdf[k].free_dev(); }
     cudaFree(g->init);
+    delete g->reg;
     delete g;
     return 0;
 }
@@ -742,8 +1443,9 @@ extern "C" size_t pk2_denfb_workspace_bytes(void* graph, int n_seq, int max_fram
     DenGraph* g = static_cast<DenGraph*>(graph);
     size_t alpha = (size_t)n_seq * (size_t)max_frames * (size_t)g->S * sizeof(float);
     size_t asum = (size_t)n_seq * (size_t)(max_frames + 2) * sizeof(float);
-    size_t maps = (size_t)n_seq * sizeof(int32_t);
-    return ((alpha + 255) & ~(size_t)255) + ((asum + 255) & ~(size_t)255) + ((maps + 255) & ~(size_t)255);
+    size_t maps = ((size_t)n_seq + 256) * sizeof(int32_t);      // sequence map / work lists
+    size_t ebuf = (size_t)n_seq * (size_t)max_frames * (size_t)g->N * sizeof(float);   // exp(loglikes), register-resident path
+    return ((alpha + 255) & ~(size_t)255) + ((asum + 255) & ~(size_t)255) + ((maps + 255) & ~(size_t)255) + ebuf;
 }
 
 extern "C" int pk2_denfb(void* graph, const float* loglikes, const int32_t* num_frames,
@@ -753,8 +1455,8 @@ extern "C" int pk2_denfb(void* graph, const float* loglikes, const int32_t* num_
     PK2_REQUIRE(graph && loglikes && num_frames && workspace && grad && logz, "pk2_denfb: null argument");
     PK2_REQUIRE(n_seq > 0 && max_frames > 0, "pk2_denfb: empty batch");
     PK2_REQUIRE(row_stride_b >= max_frames, "pk2_denfb: row_stride_b < max_frames");
-    PK2_REQUIRE(cluster == 0 || cluster == 1 || cluster == 2 || cluster == 4,
-                "pk2_denfb: cluster must be 0, 1, 2 or 4 (got %d)", cluster);
+    PK2_REQUIRE(cluster == 0 || cluster == 1 || cluster == 2 || cluster == 4 || cluster == 8,
+                "pk2_denfb: cluster must be 0, 1, 2, 4 or 8 (got %d)", cluster);
     DenGraph* g = static_cast<DenGraph*>(graph);
     cudaStream_t st = pk2::as_stream(stream);
     DenArgs a;
@@ -768,7 +1470,9 @@ extern "C" int pk2_denfb(void* graph, const float* loglikes, const int32_t* num_
     a.alpha_ws = static_cast<float*>(workspace);
     a.asum_ws = reinterpret_cast<float*>(static_cast<char*>(workspace) + alpha);
     int32_t* maps_dev = reinterpret_cast<int32_t*>(static_cast<char*>(workspace) + alpha + asum);
-    a.grad = grad; a.logz = logz; a.seq_map = nullptr;
+    const size_t maps_bytes = ((((size_t)n_seq + 256) * sizeof(int32_t)) + 255) & ~(size_t)255;
+    float* e_dev = reinterpret_cast<float*>(static_cast<char*>(workspace) + alpha + asum + maps_bytes);
+    a.grad = grad; a.logz = logz; a.seq_map = nullptr; a.work = nullptr; a.work_ids = 0; a.e = nullptr;
     { const char* e = getenv("PK2_DEN_DEBUG"); a.debug = e ? atoi(e) : 0; }
     a.prof = g_den_prof;
 
@@ -776,6 +1480,31 @@ extern "C" int pk2_denfb(void* graph, const float* loglikes, const int32_t* num_
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 
+    // clusters of 8 with register-resident arcs (default where the graph fits, see plan_reg)
+    {
+        static const bool reg_off = []() { const char* e = getenv("PK2_DEN_REG"); return e && atoi(e) == 0; }();
+        if (cluster == 8 || (cluster == 0 && !reg_off)) {
+            if (plan_reg(g)) return 1;
+            if (g->reg_state == 1) {
+                const int ncl = std::min(n_seq, g->reg->max_clusters);
+                { static bool said = false; if (!said && getenv("PK2_DEN_VERBOSE")) { said = true;
+                    fprintf(stderr, "pk2_denfb: register-resident path, %d resident clusters of 8 (%d SMs), smem fwd %zu bwd %zu B\n",
+                            g->reg->max_clusters, sms, g->reg->smem_f, g->reg->smem_b); } }
+                std::vector<int32_t> work;
+                plan_work(num_frames_h, n_seq, ncl, &work);
+                PK2_CHECK(cudaMemcpyAsync(maps_dev, work.data(), sizeof(int32_t) * work.size(), cudaMemcpyHostToDevice, st));
+                a.fwd = g->t_fwd[kRK].dev(); a.bwd = g->t_bwd[kRK].dev(); a.pdf = g->t_pdf[kRK].dev();
+                a.work = maps_dev; a.work_ids = ncl + 1;
+                a.e = e_dev;
+                den_exp_kernel<<<dim3(max_frames, n_seq), 256, 0, st>>>(loglikes, e_dev, num_frames, row_stride_b, max_frames, g->N);
+                PK2_POST_LAUNCH();
+                if (launch_cluster8(den_forward_reg_kernel, a, g->reg->rs, ncl, g->reg->smem_f, st)) return 1;
+                return launch_cluster8(den_backward_reg_kernel, a, g->reg->rs, ncl, g->reg->smem_b, st);
+            }
+            PK2_REQUIRE(cluster != 8, "pk2_denfb: cluster = 8 needs num_states %% 256 == 0, num_states <= 8192, num_pdfs %% 4 == 0 and a graph "
+                        "whose per-CTA tables fit shared memory (S=%d N=%d)", g->S, g->N);
+        }
+    }
     if (g->S % 4 != 0) {            // the DSMEM row exchange moves 16-byte multiples: single-CTA clusters only
         PK2_REQUIRE(cluster == 0 || cluster == 1, "pk2_denfb: num_states %% 4 != 0 supports cluster = 1 only");
         cluster = 1;

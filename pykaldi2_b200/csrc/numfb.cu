@@ -10,12 +10,18 @@
 
 namespace {
 
-__global__ void __launch_bounds__(32)
+// 8 warps (sequences) per CTA: the kernel runs next to the denominator kernels, whose CTAs own a whole SM
+// each and are placed as clusters of 8 inside a GPC.  64 one-warp CTAs would be spread over 64 SMs and keep
+// most clusters from being placed until they finish; 8 CTAs take one SM in each GPC at most.
+constexpr int kNumWarps = 8;
+
+__global__ void __launch_bounds__(32 * kNumWarps)
 numfb_kernel(pk2_sup_batch sup, const float* __restrict__ loglikes, int N, int64_t row_stride_b,
              float deriv_scale, double* alpha, double* beta,
              float* __restrict__ grad, double* __restrict__ logz, float* __restrict__ arc_post) {
-    const int b = blockIdx.x;
-    const int lane = threadIdx.x;
+    const int b = blockIdx.x * kNumWarps + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= sup.n_seq) return;
     const int T = sup.num_frames[b];
     const int32_t* lvl = sup.level_off + sup.lvl_base[b];   // lvl[t]..lvl[t+1] = states of time t
     const float* ll = loglikes + (int64_t)b * row_stride_b * N;
@@ -91,7 +97,7 @@ extern "C" int pk2_numfb_post(const pk2_sup_batch* sup, const float* loglikes, i
                               double* ws_alpha, double* ws_beta, float* arc_post, double* logz, void* stream) {
     PK2_REQUIRE(sup && loglikes && ws_alpha && ws_beta && arc_post && logz, "pk2_numfb_post: null argument");
     PK2_REQUIRE(sup->n_seq > 0, "pk2_numfb_post: empty batch");
-    numfb_kernel<<<sup->n_seq, 32, 0, pk2::as_stream(stream)>>>(*sup, loglikes, num_pdfs, row_stride_b, 0.f, ws_alpha,
+    numfb_kernel<<<(sup->n_seq + kNumWarps - 1) / kNumWarps, 32 * kNumWarps, 0, pk2::as_stream(stream)>>>(*sup, loglikes, num_pdfs, row_stride_b, 0.f, ws_alpha,
                                                               ws_beta, nullptr, logz, arc_post);
     PK2_POST_LAUNCH();
     return 0;
@@ -114,7 +120,7 @@ extern "C" int pk2_numfb(const pk2_sup_batch* sup, const float* loglikes, int nu
                          float* grad, double* logz, void* stream) {
     PK2_REQUIRE(sup && loglikes && ws_alpha && ws_beta && grad && logz, "pk2_numfb: null argument");
     PK2_REQUIRE(sup->n_seq > 0, "pk2_numfb: empty batch");
-    numfb_kernel<<<sup->n_seq, 32, 0, pk2::as_stream(stream)>>>(*sup, loglikes, num_pdfs, row_stride_b,
+    numfb_kernel<<<(sup->n_seq + kNumWarps - 1) / kNumWarps, 32 * kNumWarps, 0, pk2::as_stream(stream)>>>(*sup, loglikes, num_pdfs, row_stride_b,
                                                               deriv_scale, ws_alpha, ws_beta, grad, logz, nullptr);
     PK2_POST_LAUNCH();
     return 0;

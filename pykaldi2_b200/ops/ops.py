@@ -60,23 +60,8 @@ def chain_objf_and_deriv(prediction, den_graph, sup_batch, chain_opts, cluster=0
     ws = th.empty(wsb, dtype=th.uint8, device=dev)
     logz = th.empty(2, B, dtype=th.float64, device=dev)
     nf = sup_batch._dev["num_frames"]
-    # The numerator forward-backward (latency-bound, a few warps) runs on a side stream while the
-    # denominator kernels occupy the SMs; its posteriors are added once the denominator has written grad.
-    main = th.cuda.current_stream(dev)
-    side = _side_stream(dev)
     ready = th.cuda.Event()
-    ready.record(main)
-    side.wait_event(ready)
-    with th.cuda.stream(side):
-        ab = th.empty(2, max(sup_batch.total_states, 1), dtype=th.float64, device=dev)
-        arc_post = th.empty(max(sup_batch.total_arcs, 1), dtype=th.float32, device=dev)
-        _lib.check(L.pk2_numfb_post(sup_batch.struct, _lib.ptr(prediction), N, Tmax, _lib.ptr(ab[0]), _lib.ptr(ab[1]),
-                                    _lib.ptr(arc_post), _lib.ptr(logz[1]), _lib.vp(side.cuda_stream)), "pk2_numfb_post")
-        num_done = th.cuda.Event()
-        num_done.record(side)
-    prediction.record_stream(side)
-    logz.record_stream(side)
-    arc_post.record_stream(main)
+    ready.record(th.cuda.current_stream(dev))
     if DEN_TIMERS is not None:
         e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
         e0.record()
@@ -89,6 +74,21 @@ def chain_objf_and_deriv(prediction, den_graph, sup_batch, chain_opts, cluster=0
     if DEN_TIMERS is not None:
         e1.record()
         DEN_TIMERS.append((e0, e1))
+    # The numerator forward-backward (latency-bound, one warp per sequence, 8 CTAs) runs on a side stream
+    # next to the denominator kernels, on SMs the denominator clusters leave free.
+    main = th.cuda.current_stream(dev)
+    side = _side_stream(dev)
+    side.wait_event(ready)
+    with th.cuda.stream(side):
+        ab = th.empty(2, max(sup_batch.total_states, 1), dtype=th.float64, device=dev)
+        arc_post = th.empty(max(sup_batch.total_arcs, 1), dtype=th.float32, device=dev)
+        _lib.check(L.pk2_numfb_post(sup_batch.struct, _lib.ptr(prediction), N, Tmax, _lib.ptr(ab[0]), _lib.ptr(ab[1]),
+                                    _lib.ptr(arc_post), _lib.ptr(logz[1]), _lib.vp(side.cuda_stream)), "pk2_numfb_post")
+        num_done = th.cuda.Event()
+        num_done.record(side)
+    prediction.record_stream(side)
+    logz.record_stream(side)
+    arc_post.record_stream(main)
     main.wait_event(num_done)
     scale = -float(w) * (1.0 + float(chain_opts.xent_regularize))
     _lib.check(L.pk2_numfb_scatter(sup_batch.struct, sup_batch.total_states, _lib.ptr(arc_post), N, Tmax, scale,

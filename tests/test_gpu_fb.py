@@ -140,6 +140,34 @@ def test_chain_objf_and_deriv_vs_oracle(dev, S, N, Ts, cluster):
         assert (grad[b, T:] == 0).all()
 
 
+@pytest.mark.parametrize("S,N,Ts,extra", [(256, 52, [20, 13, 1, 7, 33], 5),          # 5 clusters, one sequence each
+                                          (1024, 332, [37, 50], 14),                 # rows longer than the register slots
+                                          (256, 76, list(range(1, 41)), 5)])         # work lists: more sequences than clusters
+def test_chain_cluster8_register_resident(dev, S, N, Ts, extra):
+    """Clusters of 8 CTAs with register-resident arcs (denfb.cu: den_*_reg_kernel) against the oracle."""
+    from oracle import chain_ref
+    from pykaldi2_b200 import graphs
+    from pykaldi2_b200.ops import ops
+    fst, sup_fsts, pred = _chain_case(S, N, Ts, seed=S + 8, mean_extra=extra)
+    den = graphs.DenominatorGraph(fst, N)
+    oden = chain_ref.den_graph_from_fst(fst, N)
+    sups = [graphs.Supervision(f, T, N) for f, T in zip(sup_fsts, Ts)]
+    sb = graphs.SupervisionBatch(sups, device=dev)
+    opts = graphs.ChainTrainingOptions(leaky_hmm_coefficient=1e-4, xent_regularize=0.1)
+    p = torch.from_numpy(pred).to(dev)
+    objf, grad = ops.chain_objf_and_deriv(p, den, sb, opts, cluster=8)
+    objf = objf.cpu().numpy()
+    grad = grad.cpu().numpy()
+    for b, T in enumerate(Ts):
+        o, g, gx = chain_ref.chain_objf_and_deriv(pred[b, :T], oden, sup_fsts[b], leaky=1e-4, xent_regularize=0.1)
+        np.testing.assert_allclose(objf[b], o, rtol=1e-3)
+        np.testing.assert_allclose(grad[b, :T], -g, rtol=1e-3, atol=2e-6)
+        assert (grad[b, T:] == 0).all()
+    # the automatic choice (cluster = 0) takes the same kernels for this graph: bit-identical
+    objf0, grad0 = ops.chain_objf_and_deriv(p, den, sb, opts, cluster=0)
+    assert (objf0.cpu().numpy() == objf).all() and (grad0.cpu().numpy() == grad).all()
+
+
 def test_chain_function_per_utt_and_batch(dev):
     from oracle import chain_ref
     from pykaldi2_b200 import graphs
@@ -183,7 +211,7 @@ def test_denfb_full_size_properties(dev):
     opts = graphs.ChainTrainingOptions(leaky_hmm_coefficient=1e-4, xent_regularize=0.0)
     pred = torch.from_numpy(rng.normal(0, 2.0, (len(Ts), max(Ts), N)).astype(np.float32)).to(dev)
     res = {}
-    for K in (1, 2, 4):
+    for K in (1, 2, 4, 8):
         objf, grad = ops.chain_objf_and_deriv(pred, den, sb, opts, cluster=K)
         res[K] = (objf.cpu().numpy(), grad.cpu().numpy())
     o1, g1 = res[1]
@@ -192,7 +220,7 @@ def test_denfb_full_size_properties(dev):
         rows = g1[b, :T].astype(np.float64).sum(1)      # gamma_den - gamma_num rows sum to 0
         np.testing.assert_allclose(rows, 0.0, atol=2e-4)
         assert (g1[b, T:] == 0).all()
-    for K in (2, 4):                                    # cluster size does not change the answer
+    for K in (2, 4, 8):                                 # cluster size does not change the answer
         np.testing.assert_allclose(res[K][0], o1, rtol=1e-5)
         np.testing.assert_allclose(res[K][1], g1, rtol=1e-3, atol=1e-6)
     # shifting all loglikes of a frame by c shifts objf by 0 (num and den both move by c)

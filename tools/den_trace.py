@@ -19,7 +19,12 @@ pred = torch.randn(Bn, Tu, N, device=dev) * 2
 buf = torch.zeros(128, dtype=torch.int64, device=dev)
 fn = ["top", "pass done", "exchange done", "leaky done", "cp wait+sync", "exp done", "sync+prefetch"]
 bn = ["top", "cp wait+sync", "exp+sync+prefetch", "beta pass", "gamma pass", "exchange done", "grad store"]
-for K in (1, 2, 4):
+Ks = [int(k) for k in sys.argv[1:]] or [1, 2, 4, 8]
+fn8 = ["top", "alpha pass", "sync+send", "rows landed", "sum", "-", "-"]
+bn8 = ["top", "beta pass", "sync+send", "gamma pass", "sync+stores", "rows landed", "-"]
+for K in Ks:
+    if K == 8:
+        fn, bn = fn8, bn8
     ops.chain_objf_and_deriv(pred, den, sb, opts, cluster=K)
     L.pk2_den_set_profile_buffer(_lib.ptr(buf))
     ops.chain_objf_and_deriv(pred, den, sb, opts, cluster=K)
@@ -28,9 +33,9 @@ for K in (1, 2, 4):
     t = buf.cpu().view(2, 8, 8).numpy()
     print("K=%d forward (cycles after frame top):" % K)
     for f in (5, 6):
-        print("  frame %d:" % (64 + f), "  ".join("%s +%d" % (fn[e], t[0][f][e] - t[0][f][0]) for e in range(1, 7)),
+        print("  frame %d:" % (64 + f), "  ".join("%s +%d" % (fn[e], t[0][f][e] - t[0][f][0]) for e in range(1, 5 if K == 8 else 7)),
               " period %d" % (t[0][f + 1][0] - t[0][f][0]))
     print("K=%d backward:" % K)
     for f in (5, 6):      # backward runs t downwards: frame f+1 precedes frame f
-        print("  frame %d:" % (64 + f), "  ".join("%s +%d" % (bn[e], t[1][f][e] - t[1][f][0]) for e in range(1, 7)),
+        print("  frame %d:" % (64 + f), "  ".join("%s +%d" % (bn[e], t[1][f][e] - t[1][f][0]) for e in range(1, 6 if K == 8 else 7)),
               " period %d" % (t[1][f - 1][0] - t[1][f][0]))

@@ -52,16 +52,16 @@ def bench_den():
     sb = graphs.SupervisionBatch(sups, device=dev)
     pred = torch.randn(64, max(Ts), N, device=dev) * 2
     alg = sum(Ts) * (8 * N + 8 * S) + 24 * A
-    for K in (1, 2, 4, 0):
+    for K in (8, 4, 0):
         ms = timeit(lambda: ops.chain_objf_and_deriv(pred, den, sb, opts, cluster=K), iters=3, warm=1)
         # uniform T batch to get the per-frame cost of a cluster size
-        print(json.dumps({"kernel": "denfb+numfb", "cluster": K if K else "mixed", "ms": ms, "frames": sum(Ts),
+        print(json.dumps({"kernel": "denfb+numfb", "cluster": K if K else "auto", "ms": ms, "frames": sum(Ts),
                           "max_T": max(Ts), "alg_GBps": alg / ms / 1e6, "frac_hbm": alg / ms / 1e6 / peaks()["hbm_gbs"]}))
     Tu = 200
     supu = [graphs.Supervision(synth.make_supervision_fst(Tu, N, rng), Tu, N) for _ in range(16)]
     sbu = graphs.SupervisionBatch(supu, device=dev)
     predu = torch.randn(16, Tu, N, device=dev) * 2
-    for K in (1, 2, 4):
+    for K in (1, 2, 4, 8):
         ms = timeit(lambda: ops.chain_objf_and_deriv(predu, den, sbu, opts, cluster=K), iters=3, warm=1)
         print(json.dumps({"kernel": "denfb uniform T=200 B=16", "cluster": K, "ms": ms, "us_per_frame": 1e3 * ms / Tu}))
 
