@@ -149,6 +149,8 @@ struct DenGraph {
     bool built[kMaxParts + 1] = {};
     SellHost t_fwd[kMaxParts + 1], t_bwd[kMaxParts + 1], t_pdf[kMaxParts + 1];
     std::mutex mu;
+    int* start_flag = nullptr;       // device int, hybrid schedule
+    int epoch = 0;
     int reg_state = 0;               // register-resident path: 0 = not planned, 1 = usable, -1 = not usable
     RegSmemHost* reg = nullptr;
     cudaStream_t side[2] = {nullptr, nullptr};     // side streams for the mixed-cluster schedule
@@ -289,6 +291,8 @@ struct DenArgs {
     const float* e;           // register-resident kernels: exp(clamp(loglikes)) [n_seq][max_frames][N]
     const int32_t* work;      // register-resident kernels: [n_clusters + 1] offsets, then sequence ids
     int work_ids;             //   offset of the ids inside `work`
+    int* start_flag;          // hybrid schedule: set to `epoch` when the forward cluster kernel has started
+    int epoch;
     int debug;                // profiling only (PK2_DEN_DEBUG): 1 = skip the arc loops, 2 = skip the passes
     long long* prof;          // profiling only: clock64 stamps of frames 64..71 of cluster 0 (pk2_den_set_profile_buffer)
 };
@@ -352,7 +356,7 @@ __device__ __forceinline__ float cluster_exchange(XchgState& x, float* vec, cons
 
 // -------------------------------------------------------------------- forward ----
 template <int K>
-__global__ void __launch_bounds__(kThreads, 1) den_forward_kernel(DenArgs a) {
+__device__ __forceinline__ void den_forward_body(const DenArgs& a) {
     extern __shared__ __align__(16) float smem[];
     const int S = a.S, N = a.N;
     const int Sp = (S + 3) & ~3, Np = (N + 3) & ~3;
@@ -495,7 +499,10 @@ __global__ void __launch_bounds__(kThreads, 1) den_forward_kernel(DenArgs a) {
 
 // ------------------------------------------------------------------- backward ----
 template <int K>
-__global__ void __launch_bounds__(kThreads, 1) den_backward_kernel(DenArgs a) {
+__global__ void __launch_bounds__(kThreads, 1) den_forward_kernel(DenArgs a) { den_forward_body<K>(a); }
+
+template <int K>
+__device__ __forceinline__ void den_backward_body(const DenArgs& a) {
     extern __shared__ __align__(16) float smem[];
     const int S = a.S, N = a.N;
     const int Sp = (S + 3) & ~3, Np = (N + 3) & ~3;
@@ -614,6 +621,30 @@ __global__ void __launch_bounds__(kThreads, 1) den_backward_kernel(DenArgs a) {
     }
 #undef PK2_DPROF
     cluster_barrier<K>();
+}
+
+template <int K>
+__global__ void __launch_bounds__(kThreads, 1) den_backward_kernel(DenArgs a) { den_backward_body<K>(a); }
+
+// Forward and backward of single-CTA sequences in ONE launch (hybrid schedule: the shortest sequences of a
+// batch run on the SMs the clusters of 8 leave free; a single launch is placed once, so its CTAs can never
+// land on the SMs a cluster kernel is about to need).
+__global__ void __launch_bounds__(kThreads, 1) den_fb1_kernel(DenArgs a) {
+    den_forward_body<1>(a);
+    __threadfence();
+    __syncthreads();
+    den_backward_body<1>(a);
+}
+
+// Side-stream gate: returns once the cluster kernel of this call has started (its CTAs are placed), so that
+// the single-CTA kernel behind it only gets SMs the clusters do not use.  Bounded wait.
+__global__ void den_gate_kernel(const int* flag, int epoch) {
+    for (int i = 0; i < (1 << 20); ++i) {
+        int v;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v - epoch >= 0) return;
+        __nanosleep(200);
+    }
 }
 
 // =====================================================================================================
@@ -884,6 +915,9 @@ __global__ void __launch_bounds__(kRT, 1) den_forward_reg_kernel(DenArgs a, RegS
     uint64_t* ebar = xbar + 2;                                     // [2] e rows
     uint4* ovf = reinterpret_cast<uint4*>(xbar + 4);
 
+    if (a.start_flag && blockIdx.x == 0 && threadIdx.x == 0) {      // this kernel's CTAs are placed (hybrid schedule)
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.start_flag), "r"(a.epoch) : "memory");
+    }
     RegSlice sl[kRowsPerThread];
     float wi[kRowsPerThread][kRegArcs];
     load_reg_slices<true>(a.fwd, c, a.init, sl, wi, ovf, wcnt);
@@ -1368,24 +1402,54 @@ int plan_reg(DenGraph* g) {
     return 0;
 }
 
-// Work lists: longest sequence first onto the least loaded cluster (LPT).
-void plan_work(const int32_t* frames, int n, int ncl, std::vector<int32_t>* work) {
-    std::vector<int> order(n);
-    for (int i = 0; i < n; ++i) order[i] = i;
-    if (frames) std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return frames[x] > frames[y]; });
+// Work lists: longest sequence first onto the least loaded cluster (LPT).  Returns the largest load (frames).
+long long plan_work(const int32_t* frames, std::vector<int> ids, int ncl, std::vector<int32_t>* work) {
+    if (frames) std::stable_sort(ids.begin(), ids.end(), [&](int x, int y) { return frames[x] > frames[y]; });
     std::vector<std::vector<int>> lists(ncl);
     std::vector<long long> load(ncl, 0);
-    for (int i : order) {
+    for (int i : ids) {
         int best = 0;
         for (int k = 1; k < ncl; ++k) if (load[k] < load[best]) best = k;
         lists[best].push_back(i);
         load[best] += (frames ? frames[i] : 1) + 8;      // + per-sequence set-up
     }
-    work->assign(ncl + 1, 0);
-    for (int k = 0; k < ncl; ++k) {
-        (*work)[k + 1] = (*work)[k] + (int)lists[k].size();
-        for (int i : lists[k]) work->push_back(i);
+    if (work) {
+        work->assign(ncl + 1, 0);
+        for (int k = 0; k < ncl; ++k) {
+            (*work)[k + 1] = (*work)[k] + (int)lists[k].size();
+            for (int i : lists[k]) work->push_back(i);
+        }
     }
+    return *std::max_element(load.begin(), load.end());
+}
+
+// Hybrid schedule: the clusters of 8 leave `spare` SMs unused (GPC granularity).  The shortest sequences run
+// there as single-CTA streaming kernels (5.3x the per-frame time of a cluster, but on one SM instead of
+// eight) as long as they finish before the cluster pool does.
+constexpr double kSingleCost = 5.3;     // per-frame time of den_fb1_kernel / per-frame time of a cluster of 8
+void plan_hybrid(const int32_t* frames, int n, int ncl, int spare, std::vector<int>* pool, std::vector<int>* single) {
+    std::vector<int> asc(n);
+    for (int i = 0; i < n; ++i) asc[i] = i;
+    std::stable_sort(asc.begin(), asc.end(), [&](int x, int y) { return frames[x] < frames[y]; });
+    int best = 0;
+    for (int n1 = 1; n1 <= spare && n1 < n; ++n1) {
+        std::vector<int> rest(asc.begin() + n1, asc.end());
+        const long long pool_frames = plan_work(frames, rest, std::min(ncl, (int)rest.size()), nullptr);
+        if ((double)frames[asc[n1 - 1]] * kSingleCost <= (double)pool_frames) best = n1; else break;
+    }
+    single->assign(asc.begin(), asc.begin() + best);
+    pool->assign(asc.begin() + best, asc.end());
+}
+
+int ensure_side(DenGraph* g) {
+    if (!g->side[0]) {
+        for (int i = 0; i < 2; ++i) {
+            PK2_CHECK(cudaStreamCreateWithFlags(&g->side[i], cudaStreamNonBlocking));
+            PK2_CHECK(cudaEventCreateWithFlags(&g->ev_join[i], cudaEventDisableTiming));
+        }
+        PK2_CHECK(cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming));
+    }
+    return 0;
 }
 
 }  // namespace
@@ -1433,6 +1497,7 @@ extern "C" int pk2_den_graph_destroy(void* graph) {
     for (int k = 1; k <= kMaxParts; ++k)
         if (g->built[k]) { g->t_fwd[k].free_dev(); g->t_bwd[k].free_dev(); g->t_pdf[k].free_dev(); }
     cudaFree(g->init);
+    cudaFree(g->start_flag);
     delete g->reg;
     delete g;
     return 0;
@@ -1472,7 +1537,7 @@ extern "C" int pk2_denfb(void* graph, const float* loglikes, const int32_t* num_
     int32_t* maps_dev = reinterpret_cast<int32_t*>(static_cast<char*>(workspace) + alpha + asum);
     const size_t maps_bytes = ((((size_t)n_seq + 256) * sizeof(int32_t)) + 255) & ~(size_t)255;
     float* e_dev = reinterpret_cast<float*>(static_cast<char*>(workspace) + alpha + asum + maps_bytes);
-    a.grad = grad; a.logz = logz; a.seq_map = nullptr; a.work = nullptr; a.work_ids = 0; a.e = nullptr;
+    a.grad = grad; a.logz = logz; a.seq_map = nullptr; a.work = nullptr; a.work_ids = 0; a.e = nullptr; a.start_flag = nullptr; a.epoch = 0;
     { const char* e = getenv("PK2_DEN_DEBUG"); a.debug = e ? atoi(e) : 0; }
     a.prof = g_den_prof;
 
@@ -1486,20 +1551,65 @@ extern "C" int pk2_denfb(void* graph, const float* loglikes, const int32_t* num_
         if (cluster == 8 || (cluster == 0 && !reg_off)) {
             if (plan_reg(g)) return 1;
             if (g->reg_state == 1) {
-                const int ncl = std::min(n_seq, g->reg->max_clusters);
                 { static bool said = false; if (!said && getenv("PK2_DEN_VERBOSE")) { said = true;
                     fprintf(stderr, "pk2_denfb: register-resident path, %d resident clusters of 8 (%d SMs), smem fwd %zu bwd %zu B\n",
                             g->reg->max_clusters, sms, g->reg->smem_f, g->reg->smem_b); } }
+                static const bool hyb_off = []() { const char* e = getenv("PK2_DEN_HYBRID"); return e && atoi(e) == 0; }();
+                std::vector<int> pool, single;
+                // 8 of the spare SMs are left to the numerator kernel that runs next to this call (ops.py)
+                const int spare = sms - kRK * g->reg->max_clusters - 8;
+                if (cluster == 0 && !hyb_off && num_frames_h && spare > 0 && n_seq > g->reg->max_clusters &&
+                    fwd_smem_bytes(g->S, g->N, 1) <= 227 * 1024 && bwd_smem_bytes(g->S, g->N, 1) <= 227 * 1024) {
+                    plan_hybrid(num_frames_h, n_seq, g->reg->max_clusters, spare, &pool, &single);
+                } else {
+                    pool.resize(n_seq);
+                    for (int i = 0; i < n_seq; ++i) pool[i] = i;
+                }
+                const int ncl = std::min((int)pool.size(), g->reg->max_clusters);
                 std::vector<int32_t> work;
-                plan_work(num_frames_h, n_seq, ncl, &work);
+                plan_work(num_frames_h, pool, ncl, &work);
+                if (getenv("PK2_DEN_VERBOSE")) {
+                    static int said2 = 0;
+                    if (said2++ < 2) fprintf(stderr, "pk2_denfb: %d sequences on %d clusters, %d single-CTA sequences\n",
+                                             (int)pool.size(), ncl, (int)single.size());
+                }
+                const int single_off = (int)work.size();
+                for (int i : single) work.push_back(i);
                 PK2_CHECK(cudaMemcpyAsync(maps_dev, work.data(), sizeof(int32_t) * work.size(), cudaMemcpyHostToDevice, st));
                 a.fwd = g->t_fwd[kRK].dev(); a.bwd = g->t_bwd[kRK].dev(); a.pdf = g->t_pdf[kRK].dev();
                 a.work = maps_dev; a.work_ids = ncl + 1;
                 a.e = e_dev;
+                if (!single.empty()) {
+                    if (ensure_side(g) || ensure_tables(g, 1)) return 1;
+                    if (!g->start_flag) {
+                        PK2_CHECK(cudaMalloc(&g->start_flag, sizeof(int)));
+                        PK2_CHECK(cudaMemset(g->start_flag, 0, sizeof(int)));
+                    }
+                    a.start_flag = g->start_flag; a.epoch = ++g->epoch;
+                    PK2_CHECK(cudaEventRecord(g->ev_fork, st));          // work lists are on the device
+                }
                 den_exp_kernel<<<dim3(max_frames, n_seq), 256, 0, st>>>(loglikes, e_dev, num_frames, row_stride_b, max_frames, g->N);
                 PK2_POST_LAUNCH();
                 if (launch_cluster8(den_forward_reg_kernel, a, g->reg->rs, ncl, g->reg->smem_f, st)) return 1;
-                return launch_cluster8(den_backward_reg_kernel, a, g->reg->rs, ncl, g->reg->smem_b, st);
+                if (launch_cluster8(den_backward_reg_kernel, a, g->reg->rs, ncl, g->reg->smem_b, st)) return 1;
+                if (!single.empty()) {
+                    // single-CTA sequences: behind a gate that opens when the forward cluster kernel has started
+                    cudaStream_t ss = g->side[0];
+                    PK2_CHECK(cudaStreamWaitEvent(ss, g->ev_fork, 0));
+                    den_gate_kernel<<<1, 1, 0, ss>>>(g->start_flag, a.epoch);
+                    PK2_POST_LAUNCH();
+                    DenArgs a1 = a;
+                    a1.fwd = g->t_fwd[1].dev(); a1.bwd = g->t_bwd[1].dev(); a1.pdf = g->t_pdf[1].dev();
+                    a1.seq_map = maps_dev + single_off;
+                    a1.work = nullptr; a1.start_flag = nullptr;
+                    const size_t sm1 = std::max(fwd_smem_bytes(g->S, g->N, 1), bwd_smem_bytes(g->S, g->N, 1));
+                    PK2_CHECK(cudaFuncSetAttribute(den_fb1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+                    den_fb1_kernel<<<(int)single.size(), kThreads, sm1, ss>>>(a1);
+                    PK2_POST_LAUNCH();
+                    PK2_CHECK(cudaEventRecord(g->ev_join[0], ss));
+                    PK2_CHECK(cudaStreamWaitEvent(st, g->ev_join[0], 0));
+                }
+                return 0;
             }
             PK2_REQUIRE(cluster != 8, "pk2_denfb: cluster = 8 needs num_states %% 256 == 0, num_states <= 8192, num_pdfs %% 4 == 0 and a graph "
                         "whose per-CTA tables fit shared memory (S=%d N=%d)", g->S, g->N);
@@ -1531,13 +1641,7 @@ extern "C" int pk2_denfb(void* graph, const float* loglikes, const int32_t* num_
         count[K] = (int)idx.size();
     }
     PK2_CHECK(cudaMemcpyAsync(maps_dev, order.data(), sizeof(int32_t) * n_seq, cudaMemcpyHostToDevice, st));
-    if (!g->side[0]) {
-        for (int i = 0; i < 2; ++i) {
-            PK2_CHECK(cudaStreamCreateWithFlags(&g->side[i], cudaStreamNonBlocking));
-            PK2_CHECK(cudaEventCreateWithFlags(&g->ev_join[i], cudaEventDisableTiming));
-        }
-        PK2_CHECK(cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming));
-    }
+    if (ensure_side(g)) return 1;
     PK2_CHECK(cudaEventRecord(g->ev_fork, st));
     int off = 0, lane = 0;
     for (int K : {4, 2, 1}) {

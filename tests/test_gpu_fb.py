@@ -163,9 +163,11 @@ def test_chain_cluster8_register_resident(dev, S, N, Ts, extra):
         np.testing.assert_allclose(objf[b], o, rtol=1e-3)
         np.testing.assert_allclose(grad[b, :T], -g, rtol=1e-3, atol=2e-6)
         assert (grad[b, T:] == 0).all()
-    # the automatic choice (cluster = 0) takes the same kernels for this graph: bit-identical
+    # the automatic choice (cluster = 0): same kernels for the long sequences, the shortest ones of a large
+    # batch as single-CTA kernels on the SMs the clusters leave free (hybrid schedule)
     objf0, grad0 = ops.chain_objf_and_deriv(p, den, sb, opts, cluster=0)
-    assert (objf0.cpu().numpy() == objf).all() and (grad0.cpu().numpy() == grad).all()
+    np.testing.assert_allclose(objf0.cpu().numpy(), objf, rtol=1e-5)
+    np.testing.assert_allclose(grad0.cpu().numpy(), grad, rtol=1e-3, atol=1e-6)
 
 
 def test_chain_function_per_utt_and_batch(dev):
