@@ -757,7 +757,11 @@ __device__ __forceinline__ void reg_slice_pass(const RegSlice& s, const float (&
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 gb[u] = lds_f32(base_b + (s.off[g + u] >> 16));
-                ga[u] = lds_f32(base_a + (s.off[g + u] & 0xffffu));
+                uint32_t lo = s.off[g + u] & 0xffffu;
+                // forward kernels are short of registers: keep the compiler from hoisting 24 masked copies of the
+                // offsets out of the frame loop (one more LOP per arc instead)
+                if (WI) asm volatile("and.b32 %0, %1, 0xffff;" : "=r"(lo) : "r"(s.off[g + u]));
+                ga[u] = lds_f32(base_a + lo);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -1032,6 +1036,206 @@ __global__ void __launch_bounds__(kRT, 1) den_forward_reg_kernel(DenArgs a, RegS
         __syncthreads();
     }
     tc::cluster_sync_all();                 // no CTA exits while a peer may still copy into it
+}
+
+// ---- forward, two sequences interleaved per cluster -------------------------------------------------------
+// In den_forward_reg_kernel a third of the frame is spent waiting for the DSMEM row exchange (28 KB out and
+// in per CTA at ~17 B/clk) with nothing else to do.  Here a cluster works on TWO sequences ("slots", own
+// alpha / e buffers and mbarriers, the same arc registers): while the rows of one slot travel, the pass of
+// the other slot runs.  Each slot pulls the next sequence of the cluster's work list when its own ends.
+struct FSlot {
+    int b, T, t;                 // sequence, its frames, current frame; T < 0: slot idle (work list exhausted)
+    int pend;                    // rows of frame t have been sent, the exchange is not yet complete
+    float A, lk, own;
+    uint32_t f, phase, ephase;   // per-slot frame counter: parity of buffers and barriers
+};
+
+__global__ void __launch_bounds__(kRT, 1) den_forward_reg2_kernel(DenArgs a, RegSmem rs) {
+    extern __shared__ __align__(16) float smem[];
+    const int S = a.S, N = a.N;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = (int)tc::cluster_ctarank();
+    const int q = blockIdx.x / kRK;
+    const int r0 = a.fwd.part_row[c], r1 = a.fwd.part_row[c + 1], nrow = r1 - r0;
+    // slot block: buf [2][S] | E [2][N] | wsum [2][32] | parts [2][kRK*4] | xbar [2] | ebar [2]
+    const int slot_floats = 2 * S + 2 * N + 64 + 2 * kRK * 4 + 8;
+    float* red = smem + 2 * slot_floats;                           // [40]
+    int* wcnt = reinterpret_cast<int*>(red + 40);                  // [32]
+    double* dred = reinterpret_cast<double*>(wcnt + 32);           // [32]
+    uint4* ovf = reinterpret_cast<uint4*>(dred + 32);
+
+    if (a.start_flag && blockIdx.x == 0 && threadIdx.x == 0) {      // this kernel's CTAs are placed (hybrid schedule)
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.start_flag), "r"(a.epoch) : "memory");
+    }
+    RegSlice sl[kRowsPerThread];
+    float wi[kRowsPerThread][kRegArcs];
+    load_reg_slices<true>(a.fwd, c, a.init, sl, wi, ovf, wcnt);
+    float init_own[2];
+    float s0 = 0.f;
+    for (int j = threadIdx.x; j < S; j += kRT) s0 += __ldg(&a.init[j]);
+#pragma unroll
+    for (int r = 0; r < 2; ++r) init_own[r] = (threadIdx.x + r * kRT < nrow) ? __ldg(&a.init[r0 + threadIdx.x + r * kRT]) : 0.f;
+    const float A0 = block_sum_nw<kRW>(s0, red);
+    const uint32_t expect = (uint32_t)(S - nrow) * 4u + (uint32_t)(kRK - 1) * 16u;
+    const uint32_t ebytes = (uint32_t)N * 4u;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + s * slot_floats + 2 * S + 2 * N + 64 + 2 * kRK * 4);
+            tc::mbar_init(&xbar[0], 1); tc::mbar_init(&xbar[1], 1);
+            tc::mbar_init(&xbar[2], 1); tc::mbar_init(&xbar[3], 1);
+        }
+        tc::fence_barrier_init();
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + s * slot_floats + 2 * S + 2 * N + 64 + 2 * kRK * 4);
+            tc::mbar_expect_tx(&xbar[0], expect);
+            tc::mbar_expect_tx(&xbar[1], expect);
+        }
+    }
+    tc::cluster_sync_all();
+
+    const int w1 = a.work[q + 1];
+    int widx = a.work[q];
+    const int32_t* ids = a.work + a.work_ids;
+    const uint32_t smem_s = tc::smem_u32(smem);
+
+    FSlot st[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) { st[s].T = -1; st[s].t = 0; st[s].pend = 0; st[s].f = 0; st[s].phase = 0; st[s].ephase = 0;
+                                  st[s].b = 0; st[s].A = A0; st[s].lk = 0.f; st[s].own = 0.f; }
+
+    // log Z of a finished (or empty) sequence; all threads of the CTA call it
+    auto finish = [&](FSlot& z) {
+        float* asum = a.asum_ws + (int64_t)z.b * (a.max_frames + 2);
+        const float totp = fmaf(z.lk, A0, z.A);          // sum_j alpha'(T, j) = A(T) + lk * sum(init)
+        if (c == 0) {
+            __threadfence_block();
+            __syncthreads();
+            double part = 0.0;
+            for (int t = threadIdx.x; t < z.T; t += kRT) part += log((double)asum[t]);
+            part = pk2::warp_sum_d(part);
+            if (lane == 0) dred[warp] = part;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double logsum = 0.0;
+                for (int w = 0; w < kRW; ++w) logsum += dred[w];
+                asum[z.T] = z.A;
+                asum[a.max_frames + 1] = totp;
+                a.logz[z.b] = log((double)totp) + logsum;
+            }
+            __syncthreads();
+        }
+    };
+    // pull the next sequence of the work list into slot s (slot buffers are free: the caller has synchronised)
+    auto start_next = [&](FSlot& z, float* slot) {
+        for (;;) {
+            if (widx >= w1) { z.T = -1; return; }
+            z.b = ids[widx++];
+            z.T = a.num_frames[z.b];
+            z.t = 0; z.pend = 0;
+            z.A = A0; z.lk = a.leaky * A0;
+            if (z.T > 0) break;
+            finish(z);                                     // empty sequence: log Z = log sum alpha'(0)
+        }
+        float* cur = slot + (z.f & 1) * S;
+        for (int j = threadIdx.x; j < S; j += kRT) cur[j] = __ldg(&a.init[j]);
+        if (threadIdx.x == 0) {
+            const float* e = a.e + (int64_t)z.b * a.max_frames * N;
+            float* E = slot + 2 * S;
+            uint64_t* ebar = reinterpret_cast<uint64_t*>(slot + 2 * S + 2 * N + 64 + 2 * kRK * 4) + 2;
+            tc::mbar_expect_tx(&ebar[z.f & 1], ebytes);
+            tc::bulk_load(E + (z.f & 1) * N, e, ebytes, &ebar[z.f & 1]);
+            if (z.T > 1) {
+                tc::mbar_expect_tx(&ebar[(z.f + 1) & 1], ebytes);
+                tc::bulk_load(E + ((z.f + 1) & 1) * N, e + N, ebytes, &ebar[(z.f + 1) & 1]);
+            }
+        }
+    };
+
+#pragma unroll
+    for (int s = 0; s < 2; ++s) start_next(st[s], smem + s * slot_floats);
+    __syncthreads();
+
+    while (st[0].T >= 0 || st[1].T >= 0) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            FSlot& z = st[s];
+            if (z.T < 0) continue;
+            float* slot = smem + s * slot_floats;
+            const uint32_t slot_s = smem_s + (uint32_t)(s * slot_floats) * 4u;
+            float* wsum = slot + 2 * S + 2 * N;
+            float* parts = wsum + 64;
+            uint64_t* xbar = reinterpret_cast<uint64_t*>(parts + 2 * kRK * 4);
+            uint64_t* ebar = xbar + 2;
+            if (z.pend) {
+                // complete frame t of this slot: the peers' rows travelled while the other slot was computing
+                const int par = (int)(z.f & 1);
+                mbar_wait_guard(&xbar[par], (z.phase >> par) & 1u);
+                z.phase ^= (1u << par);
+                if (threadIdx.x == 0) tc::mbar_expect_tx(&xbar[par], expect);
+                const float An = sum_parts(slot_s + (uint32_t)(2 * S + 2 * N + 64 + par * kRK * 4) * 4u, c, z.own);
+                z.lk = a.leaky * An;
+                z.A = An;
+                ++z.t; ++z.f; z.pend = 0;
+                if (z.t == z.T) {
+                    finish(z);
+                    __syncthreads();
+                    start_next(z, slot);
+                    __syncthreads();
+                    if (z.T < 0) continue;
+                }
+            }
+            const int par = (int)(z.f & 1);
+            const int t = z.t;
+            float* cur = slot + par * S;
+            float* nxt = slot + (par ^ 1) * S;
+            float* aws = a.alpha_ws + (int64_t)z.b * a.max_frames * S;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int i = threadIdx.x + r * kRT;
+                if (i < nrow) aws[(int64_t)t * S + r0 + i] = fmaf(z.lk, init_own[r], cur[r0 + i]);
+            }
+            if (threadIdx.x == 0 && c == 0) a.asum_ws[(int64_t)z.b * (a.max_frames + 2) + t] = z.A;
+            const float invA = 1.0f / z.A;
+            const uint32_t cur_s = pin_u32(slot_s + (uint32_t)(par * S) * 4u);
+            const uint32_t Ec_s = pin_u32(slot_s + (uint32_t)(2 * S + par * N) * 4u);
+            mbar_wait_guard(&ebar[par], (z.ephase >> par) & 1u);          // e(t) has landed
+            z.ephase ^= (1u << par);
+            float vsum = 0.f;
+#pragma unroll
+            for (int r = 0; r < kRowsPerThread; ++r) {
+                float acc, zz;
+                reg_slice_pass<true>(sl[r], wi[r], cur_s, Ec_s, acc, zz);
+                if (sl[r].row >= 0) {
+                    const float v = fmaf(z.lk, zz, acc) * invA;
+                    nxt[sl[r].row] = v;
+                    vsum += v;
+                }
+            }
+            const float ws = pk2::warp_sum(vsum);
+            if (lane == 0) wsum[par * 32 + warp] = ws;
+            fence_async_smem();
+            __syncthreads();
+            z.own = pk2::warp_sum(lane < kRW ? wsum[par * 32 + lane] : 0.f);
+            if (lane == 0) {
+                if (warp < kRK - 1) {
+                    reg_send(nxt + r0, nxt + r0, nrow, parts + par * kRK * 4 + c * 4, z.own, &xbar[par], c, warp);
+                } else if (warp == kRK - 1 && t + 2 < z.T) {
+                    const float* e = a.e + (int64_t)z.b * a.max_frames * N;
+                    tc::mbar_expect_tx(&ebar[par], ebytes);
+                    tc::bulk_load(slot + 2 * S + par * N, e + (int64_t)(t + 2) * N, ebytes, &ebar[par]);
+                }
+            }
+            z.pend = 1;
+        }
+    }
+    tc::cluster_sync_all();
+}
+
+size_t reg_fwd2_smem_bytes(int S, int N, const RegSmem& rs) {
+    return sizeof(float) * (2 * (size_t)(2 * S + 2 * N + 64 + 2 * kRK * 4 + 8) + 40) + sizeof(int) * 32 +
+           sizeof(double) * 32 + sizeof(uint4) * (size_t)rs.ovf_f + 16;
 }
 
 // Sum over the arcs of the rows of a SELL table held in SHARED memory (pdf-occupancy pass):
@@ -1332,7 +1536,7 @@ void plan_clusters(const int32_t* frames, int n, int budget, std::vector<int>* k
 }
 
 
-struct RegSmemHost { RegSmem rs; size_t smem_f, smem_b; int max_clusters; };
+struct RegSmemHost { RegSmem rs; size_t smem_f, smem_b, smem_f2; int max_clusters; bool two_slot; };
 
 int launch_cluster8(void (*kern)(DenArgs, RegSmem), const DenArgs& args, const RegSmem& rs, int n_clusters,
                     size_t smem, cudaStream_t st) {
@@ -1378,6 +1582,10 @@ int plan_reg(DenGraph* g) {
     h->rs = rs;
     h->smem_f = reg_fwd_smem_bytes(S, N, rs);
     h->smem_b = reg_bwd_smem_bytes(S, N, rs);
+    h->smem_f2 = reg_fwd2_smem_bytes(S, N, rs);
+    h->two_slot = h->smem_f2 <= 227 * 1024;
+    if (h->two_slot)
+        PK2_CHECK(cudaFuncSetAttribute(den_forward_reg2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_f2));
     if (h->smem_f > 227 * 1024 || h->smem_b > 227 * 1024) { delete h; return 0; }
     PK2_CHECK(cudaFuncSetAttribute(den_forward_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_f));
     PK2_CHECK(cudaFuncSetAttribute(den_backward_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_b));
@@ -1590,7 +1798,10 @@ extern "C" int pk2_denfb(void* graph, const float* loglikes, const int32_t* num_
                 }
                 den_exp_kernel<<<dim3(max_frames, n_seq), 256, 0, st>>>(loglikes, e_dev, num_frames, row_stride_b, max_frames, g->N);
                 PK2_POST_LAUNCH();
-                if (launch_cluster8(den_forward_reg_kernel, a, g->reg->rs, ncl, g->reg->smem_f, st)) return 1;
+                static const bool two_off = []() { const char* e = getenv("PK2_DEN_FWD2"); return e && atoi(e) == 0; }();
+                if (g->reg->two_slot && !two_off) {
+                    if (launch_cluster8(den_forward_reg2_kernel, a, g->reg->rs, ncl, g->reg->smem_f2, st)) return 1;
+                } else if (launch_cluster8(den_forward_reg_kernel, a, g->reg->rs, ncl, g->reg->smem_f, st)) return 1;
                 if (launch_cluster8(den_backward_reg_kernel, a, g->reg->rs, ncl, g->reg->smem_b, st)) return 1;
                 if (!single.empty()) {
                     // single-CTA sequences: behind a gate that opens when the forward cluster kernel has started
