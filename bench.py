@@ -114,6 +114,9 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+DEN_TRAFFIC_BYTES = 5585641608      # ncu, profiles/ncu_den_full_r1_v24.md
+
+
 # ------------------------------------------------------------------------------ CPU arm ----
 def cpu_reference_sample(wavs, sup_fsts, den_fst, n_utts, threads=None):
     """The reference's CPU path on n_utts utterances; returns (audio seconds, wall seconds)."""
@@ -323,11 +326,15 @@ def main():
             "e2e": {"value": e2e, "unit": "hours audio per hour", "ms_per_step": 1e3 * t_e2e / args.steps,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8 * B + 8},
             "gpu_launches": int(n1 - n0),
-            "roofline": {"kernel": "den_forward_kernel+den_backward_kernel (pk2_denfb)", "bound": "hbm",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"kernel": "pk2_denfb: den_exp + den_forward_reg2 + den_backward_reg (15 clusters of 8) || den_fb1 (single CTAs)",
+                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "ms_per_launch_pair": den_s * 1e3,
-                         "algorithmic_bytes": int(alg_bytes), "traffic": None,
-                         "note": "binding bound is shared-memory gather bandwidth, not HBM (DESIGN.md section 5)"},
+                         "algorithmic_bytes": int(alg_bytes),
+                         # dram__bytes_read.sum + dram__bytes_write.sum of the four kernels of one pk2_denfb call at B = 64,
+                         # one `ncu --set full` capture (profiles/ncu_den_full_r1_v24.md); only valid for the default batch
+                         "traffic": DEN_TRAFFIC_BYTES if (B == BATCH and world == 1) else None,
+                         "note": "binding bound is shared-memory gather bandwidth + the DSMEM row exchange inside a chain of "
+                                 "dependent frames, not HBM (DESIGN.md section 4.4)"},
             "clocks": clocks,
         }
         if not args.no_cpu_baseline:

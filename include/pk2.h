@@ -74,9 +74,13 @@ size_t pk2_denfb_workspace_bytes(void* graph, int n_seq, int max_frames);
 /* loglikes/grad: row t of sequence b at base + (b*row_stride_b + t)*num_pdfs floats.
  * num_frames[b] (device int32) <= max_frames.  Writes grad[b,t,:] = deriv_scale *
  * gamma_den(t,:) for t < num_frames[b] and 0 for num_frames[b] <= t < max_frames,
- * logz[b] (double) = log Z_den.  cluster = CTAs per sequence (1, 2 or 4); 0 = auto: with the optional
- * host copy num_frames_h the batch is scheduled length-aware (long sequences get 4-CTA clusters, short
- * ones 1) as up to three concurrent launches that fill the SMs in one wave. */
+ * logz[b] (double) = log Z_den.  cluster = CTAs per sequence (1, 2, 4 or 8); 0 = auto.
+ * 8 (and auto, where the graph qualifies: num_states % 256 == 0, num_states <= 8192, num_pdfs % 4 == 0,
+ * per-CTA tables fit shared memory): persistent clusters of 8 CTAs with the arc records in registers, each
+ * working through a list of sequences; with the host copy num_frames_h, auto also runs the shortest
+ * sequences as single-CTA kernels on the SMs the clusters leave free.  Otherwise (1, 2, 4, or auto on other
+ * graphs): streaming kernels, one cluster per sequence; with num_frames_h, auto schedules length-aware
+ * (long sequences get 4-CTA clusters, short ones 1) as up to three concurrent launches. */
 int pk2_denfb(void* graph, const float* loglikes, const int32_t* num_frames,
               const int32_t* num_frames_h, int n_seq, int max_frames, int64_t row_stride_b,
               float leaky, float deriv_scale, void* workspace, float* grad, double* logz,

@@ -1634,7 +1634,7 @@ long long plan_work(const int32_t* frames, std::vector<int> ids, int ncl, std::v
 // Hybrid schedule: the clusters of 8 leave `spare` SMs unused (GPC granularity).  The shortest sequences run
 // there as single-CTA streaming kernels (5.3x the per-frame time of a cluster, but on one SM instead of
 // eight) as long as they finish before the cluster pool does.
-constexpr double kSingleCost = 5.3;     // per-frame time of den_fb1_kernel / per-frame time of a cluster of 8
+constexpr double kSingleCost = 6.2;     // per-frame time of den_fb1_kernel / per-frame time of a cluster of 8
 void plan_hybrid(const int32_t* frames, int n, int ncl, int spare, std::vector<int>* pool, std::vector<int>* single) {
     std::vector<int> asc(n);
     for (int i = 0; i < n; ++i) asc[i] = i;
