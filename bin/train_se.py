@@ -6,7 +6,7 @@ frame-level CE (reduction sum) for the CE-regularised objective, log-prior subtr
 ``ops.MMIFunction`` call per utterance, SGD with momentum, clip, rank-0 checkpoints
 ``model.se.<epoch>.tar``.  The decoder that would produce lattices on the fly (HCLG beam search on the
 CPU, :173-181) is replaced by ``SyntheticLatticeProvider`` (BASELINE.json config 3: synthetic decoding
-lattices); ``-criterion smbr/mpfe`` is SURVEY.md row 8f-1 and not built yet.
+lattices); ``-criterion smbr/mpfe`` switches to ``ops.sMBRFunction``.
 """
 import argparse
 import os
@@ -48,6 +48,7 @@ def main():
     parser.add_argument('-print_freq', default=10, type=int, metavar='N', help='print frequency (default: 10)')
     parser.add_argument('-save_freq', default=1000, type=int, metavar='N', help='save model frequency (default: 1000)')
     parser.add_argument('-synthetic', default=0, type=int, help="train on this many seeded synthetic utterances")
+    parser.add_argument('-silence_phones', default="1", type=str, help="colon separated silence phone ids (the reference reads <den_dir>/phones/silence.csl)")
     parser.add_argument('-batched_loss', default=1, type=int, help="0 = one MMIFunction call per utterance as the reference does")
     parser.add_argument('-seed', default=1234, type=int, help="random seed (model init, sampling)")
     parser.add_argument('-max_steps', default=0, type=int)
@@ -62,8 +63,6 @@ def main():
     rank, world, local = _common.init_distributed(True)
     if not th.cuda.is_available():
         raise SystemExit("train_se.py: the B200 build has no CPU path")
-    if args.criterion != "mmi":
-        raise SystemExit("train_se.py: -criterion %s is not built yet (SURVEY.md 8f-1)" % args.criterion)
     dev = th.device("cuda", local)
     os.makedirs(args.exp_dir, exist_ok=True)
     mc, dc = config["model_config"], config["data_config"]
@@ -88,7 +87,11 @@ def main():
 
     rng = np.random.default_rng(1234)
     tid2pdf = np.concatenate([[-1], np.repeat(np.arange(N), 2)]).astype(np.int32)
-    trans_model = graphs.TidPdfMap(tid2pdf)
+    # synthetic phone inventory: three pdfs per phone, phones numbered from 1 (phone 1 = silence); the reference reads
+    # the silence list from <den_dir>/phones/silence.csl (bin/train_se.py:147-162)
+    tid2phone = np.where(tid2pdf >= 0, tid2pdf // 3 + 1, 0).astype(np.int32)
+    trans_model = graphs.TidPdfMap(tid2pdf, tid2phone)
+    args.silence_ids = [int(i) for i in args.silence_phones.strip().split(':')]
     log_prior = th.from_numpy(synth.make_log_prior(N, rng)).to(dev)
     asr_decoder = graphs.SyntheticLatticeProvider()
 
@@ -125,14 +128,20 @@ def run_train_epoch(model, optimizer, averager, feat, log_prior, loader, epoch, 
             lat, _, _ = synth.make_lattice(int(num_frs[j]), N, rng, num_ali=trans_id)
             lats.append(graphs.Lattice(lat)); alis.append(trans_id)
         loglikes = prediction - log_prior                       # bin/train_se.py:241
+        mmi = args.criterion == "mmi"
         if args.batched_loss:
-            lb = graphs.LatticeBatch(lats, trans_model.tid2pdf, alis, device=x.device)
-            se_loss = ops.MMIFunction.apply_batch(loglikes, lb)
+            mpe = None if mmi else (args.criterion, trans_model.tid2phone, args.silence_ids)
+            lb = graphs.LatticeBatch(lats, trans_model.tid2pdf, alis, device=x.device, mpe=mpe)
+            se_loss = ops.MMIFunction.apply_batch(loglikes, lb) if mmi else ops.sMBRFunction.apply_batch(loglikes, lb)
         else:
             se_loss = 0.0
-            for j in range(B):
+            for j in range(B):                                  # the reference's calling pattern (bin/train_se.py:244-249)
                 asr_decoder.push(lats[j])
-                se_loss += ops.MMIFunction.apply(loglikes[j, :num_frs[j], :], asr_decoder, trans_model, alis[j].tolist())
+                if mmi:
+                    se_loss += ops.MMIFunction.apply(loglikes[j, :num_frs[j], :], asr_decoder, trans_model, alis[j].tolist())
+                else:
+                    se_loss += ops.sMBRFunction.apply(loglikes[j, :num_frs[j], :], asr_decoder, trans_model,
+                                                      alis[j].tolist(), args.criterion, args.silence_ids)
         loss = se_loss.cuda() + args.ce_ratio * ce_loss
         loss.backward()
         norm = pipeline.finish_step(model, optimizer, averager, args.max_grad_norm)

@@ -257,14 +257,23 @@ def _upload(host, device):
 
 
 class TidPdfMap(object):
-    """Minimal TransitionModel stand-in: transition-id -> pdf-id."""
+    """Minimal TransitionModel stand-in: transition-id -> pdf-id, and (for MPFE and the silence classes of
+    sMBR, ops/ops.py:130-147) transition-id -> phone."""
 
-    def __init__(self, tid2pdf):
+    def __init__(self, tid2pdf, tid2phone=None):
         self.tid2pdf = np.asarray(tid2pdf, np.int32)
         self._num_pdfs = int(self.tid2pdf.max()) + 1
+        self.tid2phone = None if tid2phone is None else np.asarray(tid2phone, np.int32)
+        if self.tid2phone is not None and len(self.tid2phone) != len(self.tid2pdf):
+            raise ValueError("tid2phone and tid2pdf must have one entry per transition id (index 0 unused)")
 
     def transition_id_to_pdf(self, tid):
         return int(self.tid2pdf[tid])
+
+    def transition_id_to_phone(self, tid):
+        if self.tid2phone is None:
+            raise RuntimeError("this TidPdfMap was built without a transition-id -> phone table")
+        return int(self.tid2phone[tid])
 
     def num_pdfs(self):
         return self._num_pdfs
@@ -326,6 +335,34 @@ class Lattice(object):
         # tids present on each frame (for the drop_frames test), as sorted unique (t, tid) keys
         self._frame_tid_keys = np.unique(times[s1].astype(np.int64) * (1 << 32) + t1)
 
+    def frame_acc(self, num_ali, tid2pdf, tid2phone, criterion, silence_phones, one_silence_class=True):
+        """Per-arc frame accuracy (uint8 0/1) of Kaldi's LatticeForwardBackwardMpeVariants for the non-epsilon
+        arcs, in in-arc and out-arc order: smbr compares the pdf of the arc with the pdf of the reference
+        alignment at the arc's frame, mpfe the phones; with one_silence_class (what ops/ops.py:138 passes) an
+        arc also counts when both phones are silence phones.  Pure index work (bit-exact)."""
+        if criterion not in ("smbr", "mpfe"):
+            raise ValueError("criterion must be 'smbr' or 'mpfe' (got %r)" % (criterion,))
+        num_ali = np.asarray(num_ali, np.int64)
+        if len(num_ali) != self.num_frames:
+            raise ValueError("alignment length %d != lattice frames %d" % (len(num_ali), self.num_frames))
+        tid2pdf = np.asarray(tid2pdf, np.int64)
+        tid2phone = np.asarray(tid2phone, np.int64)
+        sil = np.asarray(sorted(set(int(p) for p in silence_phones)), np.int64)
+        S = self.num_states
+        t_out = np.repeat(self.state_time[:S].astype(np.int64), np.diff(self.out_off))          # frame of each out-arc
+        t_in = np.repeat(self.state_time[:S].astype(np.int64), np.diff(self.in_off)) - 1        # in-arc: time of its source
+
+        def acc(tid, t):
+            tid = tid.astype(np.int64)
+            ref = num_ali[t]
+            ph, rph = tid2phone[tid], tid2phone[ref]
+            ph_sil = np.isin(ph, sil)
+            both = ph_sil & np.isin(rph, sil)
+            same = (ph == rph) if criterion == "mpfe" else (tid2pdf[tid] == tid2pdf[ref])
+            return ((same | both) if one_silence_class else (same & ~ph_sil)).astype(np.uint8)
+
+        return acc(self.in_tid, t_in), acc(self.out_tid, t_out)
+
     def keep_mask(self, num_ali):
         """1 where the alignment's tid occurs among the lattice's tids of that frame
         (frames where numerator and denominator posteriors are disjoint are dropped)."""
@@ -374,7 +411,9 @@ def _level_sort_lattice(S, src, dst, adv):
 class LatticeBatch(object):
     """Device-resident concatenation of lattices + alignments for pk2_latfb_mmi."""
 
-    def __init__(self, lats, tid2pdf, num_alis, device=None):
+    def __init__(self, lats, tid2pdf, num_alis, device=None, mpe=None):
+        """``mpe``: None, or (criterion, tid2phone, silence_phones) to also upload the per-arc frame accuracies
+        pk2_latfb_mpe needs (sMBR / MPFE)."""
         device = device or torch.device("cuda", torch.cuda.current_device())
         self.n_seq = len(lats)
         ns = np.array([l.num_states for l in lats], np.int64)
@@ -412,7 +451,15 @@ class LatticeBatch(object):
             "frame_base": np.concatenate([[0], np.cumsum(self.num_frames_host)]).astype(np.int32),
             "keep": np.concatenate(self.keep_host).astype(np.uint8),
         }
+        self.mpe = mpe
+        if mpe is not None:
+            criterion, tid2phone, silence = mpe
+            accs = [l.frame_acc(a, tid2pdf, tid2phone, criterion, silence) for l, a in zip(lats, num_alis)]
+            host["acc_in"] = np.concatenate([a[0] for a in accs] + [np.zeros(1, np.uint8)])
+            host["acc_out"] = np.concatenate([a[1] for a in accs] + [np.zeros(1, np.uint8)])
         self._dev, self._keep = _upload(host, device)
+        self.acc_in = self._dev.pop("acc_in", None)
+        self.acc_out = self._dev.pop("acc_out", None)
         self.struct = _lib.LatBatch()
         self.struct.n_seq = self.n_seq
         for k, t in self._dev.items():

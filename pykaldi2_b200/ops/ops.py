@@ -234,9 +234,89 @@ class MMIFunction(Function):
         return _MMIBatch.apply(prediction, lat_batch)
 
 
+def lattice_mpe(prediction, lat_batch, lm_scale=1.0, ac_scale=1.0):
+    """sMBR / MPFE over a padded minibatch.  prediction: cuda float32 [B, Tmax, N] log-likelihoods (log-prior
+    subtracted); lat_batch: LatticeBatch built with ``mpe=(criterion, tid2phone, silence_phones)``.
+    Returns (score [B] float64 = expected frame accuracy per utterance (what sMBRFunction.forward returns),
+    grad [B, Tmax, N] = -post_mat, the gradient the reference's backward hands to autograd
+    (ops/ops.py:149-156), tot_like [B]).  Scales default to 1: the reference calls no lattice_scale here."""
+    _lib.require_cuda(prediction, "prediction")
+    assert prediction.dtype == th.float32 and prediction.dim() == 3
+    if lat_batch.acc_in is None:
+        raise RuntimeError("LatticeBatch was built without mpe=(criterion, tid2phone, silence_phones)")
+    prediction = prediction.contiguous()
+    B, Tmax, N = prediction.shape
+    if B != lat_batch.n_seq:
+        raise RuntimeError("batch size %d != number of lattices %d" % (B, lat_batch.n_seq))
+    if max(lat_batch.num_frames_host) > Tmax:
+        raise RuntimeError("lattice longer than the network output")
+    dev = prediction.device
+    grad = th.empty_like(prediction)
+    out = th.empty(2, B, dtype=th.float64, device=dev)
+    ns = max(lat_batch.total_states, 1)
+    ws = th.empty(4, ns, dtype=th.float64, device=dev)
+    _lib.check(_lib.lib().pk2_latfb_mpe(lat_batch.struct, _lib.ptr(lat_batch.acc_in), _lib.ptr(lat_batch.acc_out),
+                                        _lib.ptr(prediction), N, Tmax, Tmax, float(lm_scale), float(ac_scale),
+                                        _lib.ptr(ws), ns, -1.0, _lib.ptr(grad), _lib.ptr(out[0]), _lib.ptr(out[1]),
+                                        _lib.stream()), "pk2_latfb_mpe")
+    return out[1], grad, out[0]
+
+
+def _tid2phone_of(trans_model):
+    t = getattr(trans_model, "tid2phone", None)
+    if t is None:
+        n = trans_model.num_transition_ids()
+        t = np.zeros(n + 1, np.int32)
+        for i in range(1, n + 1):
+            t[i] = trans_model.transition_id_to_phone(i)
+    return np.asarray(t, np.int32)
+
+
+class _MPEBatch(Function):
+    @staticmethod
+    def forward(ctx, prediction, lat_batch):
+        score, grad, _ = lattice_mpe(prediction.detach(), lat_batch)
+        ctx.save_for_backward(grad)
+        return th.tensor(float(score.sum().item()))
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        grad_input, = ctx.saved_tensors
+        return grad_input, None
+
+
 class sMBRFunction(Function):
-    """sMBR / MPFE (reference ops/ops.py:119-156) -- SURVEY.md section 8(f) row f1, not built yet."""
+    """
+        Args:
+        loglikes: log likelihoods from the nnet by forwarding the input data, cuda [T, N].
+                  Note, the log-prior should be substracted.
+        asr_decoder: object with .decode(loglikes) -> {"lattice": graphs.Lattice}
+        trans_model: hmm transition model (graphs.TidPdfMap with tid2phone, or anything with
+                     transition_id_to_pdf / transition_id_to_phone / num_transition_ids)
+        trans_ids:   alignments in the form of hmm transition ids
+        criterion: "smbr" or "mpfe"
+        silence_phones: slience phone indexes, in the form of list of int
+
+    Reference ops/ops.py:119-156: returns the expected frame accuracy (0-dim CPU tensor); backward hands
+    -post_mat to autograd ("flip the sign to maximize the frame accuracy"), grad_out ignored.
+    """
 
     @staticmethod
     def forward(ctx, loglikes, asr_decoder, trans_model, trans_ids, criterion, silence_phones):
-        raise NotImplementedError("sMBR/MPFE is a 'next' row (SURVEY.md 8f-1); use MMIFunction")
+        ll = loglikes.detach()
+        _lib.require_cuda(ll, "loglikes")
+        lattice = asr_decoder.decode(ll)["lattice"]
+        lb = LatticeBatch([lattice], _tid2pdf_of(trans_model), [np.asarray(trans_ids, np.int32)], device=ll.device,
+                          mpe=(criterion, _tid2phone_of(trans_model), list(silence_phones)))
+        score, grad, _ = lattice_mpe(ll.unsqueeze(0), lb)       # no lattice_scale on this path: ops/ops.py:133-143
+        ctx.save_for_backward(grad[0])
+        return th.tensor(float(score[0].item()))
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        grad_input, = ctx.saved_tensors
+        return grad_input, None, None, None, None, None
+
+    @staticmethod
+    def apply_batch(prediction, lat_batch):
+        return _MPEBatch.apply(prediction, lat_batch)

@@ -276,3 +276,65 @@ def test_mmi_function_reference_call_pattern(dev):
     rtot, post, drop, _ = lattice_ref.lattice_fb_mmi(ll, lat, tid2pdf, ali)
     np.testing.assert_allclose(loss.item(), rtot, rtol=1e-5)
     np.testing.assert_allclose(logits.grad.cpu().numpy(), -post, rtol=1e-3, atol=1e-6)
+
+
+# ------------------------------------------------------------------- sMBR / MPFE ----
+@pytest.mark.parametrize("criterion", ["smbr", "mpfe"])
+@pytest.mark.parametrize("eps", [0.0, 0.1])
+def test_lattice_mpe_vs_oracle(dev, eps, criterion):
+    from oracle import lattice_ref
+    from pykaldi2_b200 import graphs, synth
+    from pykaldi2_b200.ops import ops
+    rng = np.random.default_rng(17)
+    N, Ts = 200, [40, 23, 31]
+    lats, alis, olat = [], [], []
+    for T in Ts:
+        lat, tid2pdf, ali = synth.make_lattice(T, N, rng, kmin=8, kmax=20, ali_drop=0.2, eps_frac=eps)
+        olat.append(lat); alis.append(ali); lats.append(graphs.Lattice(lat))
+    tid2phone = np.where(np.asarray(tid2pdf) >= 0, np.asarray(tid2pdf) // 3 + 1, 0)
+    sil = [1, 2]
+    pred = rng.normal(0, 1.0, (len(Ts), max(Ts), N)).astype(np.float32)
+    lb = graphs.LatticeBatch(lats, tid2pdf, alis, device=dev, mpe=(criterion, tid2phone, sil))
+    score, grad, tot = ops.lattice_mpe(torch.from_numpy(pred).to(dev), lb)
+    score, grad, tot = score.cpu().numpy(), grad.cpu().numpy(), tot.cpu().numpy()
+    for b, T in enumerate(Ts):
+        rs, post, rtot = lattice_ref.lattice_fb_mpe(pred[b, :T], olat[b], tid2pdf, tid2phone, alis[b], criterion, sil)
+        # per-arc frame accuracies are index work: bit-exact against the oracle's per-arc function
+        L = lats[b]
+        t_out = np.repeat(L.state_time[:L.num_states], np.diff(L.out_off))
+        ref = [lattice_ref.mpe_frame_acc(int(t), int(alis[b][tt]), tid2pdf, tid2phone, criterion, set(sil))
+               for t, tt in zip(L.out_tid, t_out)]
+        assert (np.asarray(ref, np.uint8) == L.frame_acc(alis[b], tid2pdf, tid2phone, criterion, sil)[1]).all()
+        np.testing.assert_allclose(tot[b], rtot, rtol=1e-6)
+        np.testing.assert_allclose(score[b], rs, rtol=1e-5)
+        np.testing.assert_allclose(grad[b, :T], -post, rtol=1e-3, atol=1e-6)
+        assert (grad[b, T:] == 0).all()
+
+
+def test_smbr_function_reference_call_pattern(dev):
+    from oracle import lattice_ref
+    from pykaldi2_b200 import graphs, synth
+    from pykaldi2_b200.ops import ops
+    rng = np.random.default_rng(5)
+    N, T = 120, 35
+    lat, tid2pdf, ali = synth.make_lattice(T, N, rng, kmin=6, kmax=12)
+    tid2phone = np.where(np.asarray(tid2pdf) >= 0, np.asarray(tid2pdf) // 3 + 1, 0)
+    trans_model = graphs.TidPdfMap(tid2pdf, tid2phone)
+    decoder = graphs.SyntheticLatticeProvider([graphs.Lattice(lat)])
+    log_prior = torch.from_numpy(synth.make_log_prior(N, rng)).to(dev)
+    logits = torch.randn(T, N, device=dev, requires_grad=True)
+    loglike = logits - log_prior                       # bin/train_se.py:241
+    loss = ops.sMBRFunction.apply(loglike, decoder, trans_model, ali.tolist(), "smbr", [1])   # bin/train_se.py:249
+    assert loss.device.type == "cpu" and loss.dim() == 0
+    loss.backward()
+    ll = (logits.detach() - log_prior).cpu().numpy()
+    rs, post, _ = lattice_ref.lattice_fb_mpe(ll, lat, tid2pdf, tid2phone, ali, "smbr", [1])
+    np.testing.assert_allclose(loss.item(), rs, rtol=1e-5)
+    np.testing.assert_allclose(logits.grad.cpu().numpy(), -post, rtol=1e-3, atol=1e-6)
+    # batched entry used by bin/train_se.py -batched_loss 1
+    lb = graphs.LatticeBatch([graphs.Lattice(lat)], tid2pdf, [ali], device=dev, mpe=("smbr", tid2phone, [1]))
+    logits2 = logits.detach().clone().requires_grad_(True)
+    loss2 = ops.sMBRFunction.apply_batch((logits2 - log_prior).unsqueeze(0), lb)
+    loss2.backward()
+    np.testing.assert_allclose(loss2.item(), loss.item(), rtol=1e-6)
+    np.testing.assert_allclose(logits2.grad.cpu().numpy(), logits.grad.cpu().numpy(), rtol=1e-5, atol=1e-7)

@@ -60,3 +60,8 @@ def test_train_se_synthetic(tmp_path):
     out2 = run("train_se.py", ["-exp_dir", str(tmp_path), "-config", "configs/ce_test.yaml", "-batch_size", "2",
                                "-synthetic", "2", "-print_freq", "1", "-max_steps", "1", "-batched_loss", "0"], tmp_path)
     assert "Epoch: [0]" in out2
+    # -criterion switch (reference bin/train_se.py:62,216-219), the reference's per-utterance calling pattern
+    out3 = run("train_se.py", ["-exp_dir", str(tmp_path), "-config", "configs/ce_test.yaml", "-batch_size", "2",
+                               "-synthetic", "2", "-print_freq", "1", "-max_steps", "1", "-criterion", "mpfe",
+                               "-batched_loss", "0"], tmp_path)
+    assert "Epoch: [0]" in out3

@@ -62,6 +62,31 @@ def test_lattice_prep_index_tensors_bit_exact():
         assert len(L.out_dst) + len(L.eps_src) == len(lat["src"])
 
 
+def test_mpe_frame_accuracies_bit_exact():
+    """Host index work of sMBR / MPFE (graphs.Lattice.frame_acc) against the oracle's per-arc rule."""
+    from oracle import lattice_ref
+    from pykaldi2_b200 import graphs, synth
+    rng = np.random.default_rng(13)
+    lat, t2p, ali = synth.make_lattice(25, 60, rng, kmin=4, kmax=9, ali_drop=0.3, eps_frac=0.1)
+    t2ph = np.where(np.asarray(t2p) >= 0, np.asarray(t2p) // 3 + 1, 0)
+    L = graphs.Lattice(lat)
+    S = L.num_states
+    t_out = np.repeat(L.state_time[:S], np.diff(L.out_off))
+    t_in = np.repeat(L.state_time[:S], np.diff(L.in_off)) - 1
+    for crit in ("smbr", "mpfe"):
+        for sil in ([], [1, 3]):
+            a_in, a_out = L.frame_acc(ali, t2p, t2ph, crit, sil)
+            r_out = [lattice_ref.mpe_frame_acc(int(t), int(ali[tt]), t2p, t2ph, crit, set(sil)) for t, tt in zip(L.out_tid, t_out)]
+            r_in = [lattice_ref.mpe_frame_acc(int(t), int(ali[tt]), t2p, t2ph, crit, set(sil)) for t, tt in zip(L.in_tid, t_in)]
+            assert (a_out == np.asarray(r_out, np.uint8)).all() and (a_in == np.asarray(r_in, np.uint8)).all()
+    with pytest.raises(ValueError):
+        L.frame_acc(ali, t2p, t2ph, "mmi", [])
+    tm = graphs.TidPdfMap(t2p, t2ph)
+    assert tm.transition_id_to_phone(5) == int(t2ph[5])
+    with pytest.raises(RuntimeError):
+        graphs.TidPdfMap(t2p).transition_id_to_phone(1)
+
+
 def test_supervision_prep_and_generic_time_sort():
     from oracle import chain_ref
     from pykaldi2_b200 import graphs, synth

@@ -106,3 +106,78 @@ def test_merge_semantics_handbuilt():
     tot, post, drop, _ = lattice_ref.lattice_fb_mmi(ll, lat1, tid2pdf, [1])
     assert not drop[0] and (post == 0).all()
     np.testing.assert_allclose(tot, -0.3 - 0.1, rtol=1e-6)
+
+
+# ------------------------------------------------------------------ sMBR / MPFE ----
+def brute_mpe(ll, lat, tid2pdf, tid2phone, ali, criterion, sil, lm=1.0, ac=1.0):
+    """All paths: expected frame accuracy and sum_paths P(path) * (acc(path) - E[acc]) per (t, pdf)."""
+    T, N = ll.shape
+    S = lat["num_states"]
+    out = [[] for _ in range(S)]
+    for s, d, l, g in zip(lat["src"], lat["dst"], lat["tid"], lat["graph_cost"]):
+        out[s].append((int(d), int(l), float(g)))
+    paths = []
+
+    def rec(s, t, logp, lab):
+        if np.isfinite(lat["final_cost"][s]) and t == T:
+            paths.append((np.exp(logp - lm * lat["final_cost"][s]), list(lab)))
+        for (d, l, g) in out[s]:
+            if l == 0:
+                rec(d, t, logp - lm * g, lab)
+            elif t < T:
+                rec(d, t + 1, logp - lm * g + ac * ll[t, tid2pdf[l]], lab + [l])
+
+    rec(0, 0, 0.0, [])
+    Z = sum(p for p, _ in paths)
+    accs = [sum(lattice_ref.mpe_frame_acc(l, int(ali[t]), tid2pdf, tid2phone, criterion, sil) for t, l in enumerate(lab))
+            for _, lab in paths]
+    E = sum(p * a for (p, _), a in zip(paths, accs)) / Z
+    post = np.zeros((T, N))
+    for (p, lab), a in zip(paths, accs):
+        for t, l in enumerate(lab):
+            post[t, tid2pdf[l]] += p / Z * (a - E)
+    return E, post
+
+
+@pytest.mark.parametrize("criterion", ["smbr", "mpfe"])
+@pytest.mark.parametrize("seed,eps", [(0, 0.0), (1, 0.0), (2, 0.3), (3, 0.3)])
+def test_mpe_bruteforce(seed, eps, criterion):
+    rng = np.random.default_rng(100 + seed)
+    T, N = 4, 6
+    lat, tid2pdf, ali = synth.make_lattice(T, N, rng, kmin=2, kmax=3, dmin=1, dmax=3, ali_drop=0.3, eps_frac=eps)
+    tid2phone = np.asarray(tid2pdf) // 2 + 1            # 3 phones, phone 1 = silence
+    ll = rng.normal(0, 1, (T, N))
+    score, post, tot = lattice_ref.lattice_fb_mpe(ll, lat, tid2pdf, tid2phone, ali, criterion, [1])
+    E, pb = brute_mpe(ll, lat, tid2pdf, tid2phone, ali, criterion, {1})
+    np.testing.assert_allclose(score, E, rtol=1e-10)
+    np.testing.assert_allclose(post, pb, rtol=1e-8, atol=1e-12)
+    assert 0.0 <= score <= T
+
+
+def test_mpe_posterior_is_the_derivative_of_the_expected_accuracy():
+    """d E[acc] / d loglike[t, p] = acoustic_scale * post[t, p] (central differences)."""
+    rng = np.random.default_rng(7)
+    T, N = 5, 6
+    lat, tid2pdf, ali = synth.make_lattice(T, N, rng, kmin=2, kmax=4, dmin=1, dmax=3)
+    tid2phone = np.asarray(tid2pdf) // 2 + 1
+    ll = rng.normal(0, 1, (T, N))
+    ac = 0.7
+    f = lambda x: lattice_ref.lattice_fb_mpe(x, lat, tid2pdf, tid2phone, ali, "smbr", [1], ac_scale=ac)[0]
+    _, post, _ = lattice_ref.lattice_fb_mpe(ll, lat, tid2pdf, tid2phone, ali, "smbr", [1], ac_scale=ac)
+    h = 1e-5
+    for t in range(T):
+        for p in range(N):
+            d = np.zeros_like(ll); d[t, p] = h
+            np.testing.assert_allclose((f(ll + d) - f(ll - d)) / (2 * h), ac * post[t, p], rtol=1e-5, atol=1e-8)
+
+
+def test_mpe_silence_classes():
+    ph = np.array([0, 1, 1, 2, 3])            # tid -> phone; phones 1, 2 are silence
+    pdf = np.array([0, 0, 1, 2, 2])
+    acc = lattice_ref.mpe_frame_acc
+    assert acc(1, 2, pdf, ph, "smbr", {1, 2}) == 1.0            # different pdf, both silence
+    assert acc(1, 2, pdf, ph, "smbr", set()) == 0.0
+    assert acc(3, 4, pdf, ph, "smbr", {1}) == 1.0               # same pdf
+    assert acc(3, 4, pdf, ph, "mpfe", {1}) == 0.0               # different phones
+    assert acc(1, 3, pdf, ph, "mpfe", {1, 2}) == 1.0            # both silence phones
+    assert acc(1, 1, pdf, ph, "smbr", {1}, one_silence_class=False) == 0.0   # old behaviour: silence never counts
