@@ -24,6 +24,8 @@
 #include <algorithm>
 #include <vector>
 #include <mutex>
+#include <thread>
+#include <atomic>
 #include <string.h>
 #include <stdlib.h>
 
@@ -67,6 +69,57 @@ inline unsigned f2u(float f) { unsigned u; memcpy(&u, &f, sizeof(u)); return u; 
 inline int part_bound(int R, int c, int K) {
     if (c >= K) return R;
     return (int)(((int64_t)R * c / K) & ~31LL);
+}
+
+
+// Shared-memory wavefronts of one gather of a warp: the largest number of DISTINCT addresses that fall into
+// one of the 32 banks (same address = broadcast).  idx: the 32 lanes' word indices.
+inline int gather_wavefronts(const unsigned* idx) {
+    unsigned char cnt[32] = {0};
+    int worst = 0;
+    for (int l = 0; l < 32; ++l) {
+        bool dup = false;
+        for (int m = 0; m < l; ++m) if (idx[m] == idx[l]) { dup = true; break; }
+        if (dup) continue;
+        const int c = ++cnt[idx[l] & 31];
+        if (c > worst) worst = c;
+    }
+    return worst;
+}
+
+// Second pass over a slice after the greedy fill: hill-climb on the order of the arcs INSIDE each lane (any
+// order gives the same row sums; padding records may sit anywhere) to minimise the shared-memory wavefronts
+// of the two gathers of every step.  The greedy order alone leaves ~2.4 wavefronts per gather on the
+// BASELINE graph (3.4 unscheduled), this pass ~2.0 -- the arc passes are bound by the shared-memory pipe
+// (profiles/ncu_den_full_r1_v24.md).  Deterministic (fixed seed).
+inline void refine_slice(uint2* rec, int len) {
+    if (len < 2) return;
+    auto step_cost = [&](int k) {
+        unsigned a[32], b[32];
+        for (int l = 0; l < 32; ++l) { a[l] = rec[k * 32 + l].y & 0xffffu; b[l] = rec[k * 32 + l].y >> 16; }
+        return gather_wavefronts(a) + gather_wavefronts(b);
+    };
+    std::vector<int> cost(len);
+    for (int k = 0; k < len; ++k) cost[k] = step_cost(k);
+    uint64_t rng = 0x9E3779B97F4A7C15ull;
+    auto next = [&]() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return (unsigned)(rng >> 32); };
+    const int sweeps = 48;
+    for (int sw = 0; sw < sweeps; ++sw) {
+        for (int l = 0; l < 32; ++l) {
+            for (int rep = 0; rep < 2; ++rep) {
+                const int i = (int)(next() % (unsigned)len), j = (int)(next() % (unsigned)len);
+                if (i == j) continue;
+                uint2& x = rec[i * 32 + l];
+                uint2& y = rec[j * 32 + l];
+                if (x.x == y.x && x.y == y.y) continue;
+                const int old = cost[i] + cost[j];
+                std::swap(x, y);
+                const int ci = step_cost(i), cj = step_cost(j);
+                if (ci + cj <= old) { cost[i] = ci; cost[j] = cj; }
+                else std::swap(x, y);
+            }
+        }
+    }
 }
 
 // Build a SELL-32 table from per-row arc lists, partitioned into K contiguous row ranges.
@@ -123,6 +176,19 @@ int build_sell(const std::vector<std::vector<Arc3>>& rows, int K, SellHost* out)
             }
             slice_off.push_back((int)arcs.size());
         }
+    }
+    {   // second pass (independent per slice): host threads
+        const int nsl = (int)slice_off.size() - 1;
+        const int nth = std::max(1, std::min(16, (int)std::thread::hardware_concurrency()));
+        std::vector<std::thread> pool;
+        std::atomic<int> nextsl(0);
+        uint2* data = arcs.data();
+        for (int t = 0; t < nth; ++t)
+            pool.emplace_back([&]() {
+                for (int i = nextsl.fetch_add(1); i < nsl; i = nextsl.fetch_add(1))
+                    refine_slice(data + slice_off[i], (slice_off[i + 1] - slice_off[i]) / 32);
+            });
+        for (auto& th : pool) th.join();
     }
     for (int c = K; c <= kMaxParts; ++c) { out->part_slice[c] = (int)slice_off.size() - 1; out->part_row[c] = R; }
     out->n_arcs = arcs.size();
@@ -1610,20 +1676,51 @@ int plan_reg(DenGraph* g) {
     return 0;
 }
 
-// Work lists: longest sequence first onto the least loaded cluster (LPT).  Returns the largest load (frames).
+// Work lists: longest sequence first onto the least loaded cluster (LPT), then local search (move / swap
+// between the most loaded cluster and the others) -- with ~3 sequences per cluster plain LPT leaves the
+// largest load 5-10 % above the mean, the refinement ~2 %.  Returns the largest load (frames).
 long long plan_work(const int32_t* frames, std::vector<int> ids, int ncl, std::vector<int32_t>* work) {
     if (frames) std::stable_sort(ids.begin(), ids.end(), [&](int x, int y) { return frames[x] > frames[y]; });
+    auto cost = [&](int i) { return (long long)(frames ? frames[i] : 1) + 8; };      // + per-sequence set-up
     std::vector<std::vector<int>> lists(ncl);
     std::vector<long long> load(ncl, 0);
     for (int i : ids) {
         int best = 0;
         for (int k = 1; k < ncl; ++k) if (load[k] < load[best]) best = k;
         lists[best].push_back(i);
-        load[best] += (frames ? frames[i] : 1) + 8;      // + per-sequence set-up
+        load[best] += cost(i);
+    }
+    for (int it = 0; it < 1000; ++it) {
+        const int m = (int)(std::max_element(load.begin(), load.end()) - load.begin());
+        bool improved = false;
+        for (size_t x = 0; x < lists[m].size() && !improved; ++x) {
+            const int i = lists[m][x];
+            for (int k = 0; k < ncl && !improved; ++k) {
+                if (k == m) continue;
+                if (load[k] + cost(i) < load[m]) {                      // move i to cluster k
+                    lists[k].push_back(i); lists[m].erase(lists[m].begin() + x);
+                    load[k] += cost(i); load[m] -= cost(i);
+                    improved = true;
+                    break;
+                }
+                for (size_t y = 0; y < lists[k].size(); ++y) {          // swap i with a shorter sequence of k
+                    const int j = lists[k][y];
+                    const long long d = cost(i) - cost(j);
+                    if (d > 0 && load[k] + d < load[m]) {
+                        lists[m][x] = j; lists[k][y] = i;
+                        load[m] -= d; load[k] += d;
+                        improved = true;
+                        break;
+                    }
+                }
+            }
+        }
+        if (!improved) break;
     }
     if (work) {
         work->assign(ncl + 1, 0);
         for (int k = 0; k < ncl; ++k) {
+            if (frames) std::stable_sort(lists[k].begin(), lists[k].end(), [&](int x, int y) { return frames[x] > frames[y]; });
             (*work)[k + 1] = (*work)[k] + (int)lists[k].size();
             for (int i : lists[k]) work->push_back(i);
         }
@@ -1631,19 +1728,21 @@ long long plan_work(const int32_t* frames, std::vector<int> ids, int ncl, std::v
     return *std::max_element(load.begin(), load.end());
 }
 
-// Hybrid schedule: the clusters of 8 leave `spare` SMs unused (GPC granularity).  The shortest sequences run
-// there as single-CTA streaming kernels (5.3x the per-frame time of a cluster, but on one SM instead of
-// eight) as long as they finish before the cluster pool does.
-constexpr double kSingleCost = 6.2;     // per-frame time of den_fb1_kernel / per-frame time of a cluster of 8
+// Hybrid schedule: the clusters of 8 leave `spare` SMs unused (GPC granularity).  The n1 shortest sequences
+// run there as single-CTA streaming kernels (kSingleCost x the per-frame time of a cluster, but on one SM
+// instead of eight); n1 minimises max(time of the longest single sequence, time of the cluster pool).
+constexpr double kSingleCost = 5.6;     // per-frame time of den_fb1_kernel / per-frame time of a cluster of 8
 void plan_hybrid(const int32_t* frames, int n, int ncl, int spare, std::vector<int>* pool, std::vector<int>* single) {
     std::vector<int> asc(n);
     for (int i = 0; i < n; ++i) asc[i] = i;
     std::stable_sort(asc.begin(), asc.end(), [&](int x, int y) { return frames[x] < frames[y]; });
     int best = 0;
+    double best_t = (double)plan_work(frames, asc, std::min(ncl, n), nullptr);
     for (int n1 = 1; n1 <= spare && n1 < n; ++n1) {
         std::vector<int> rest(asc.begin() + n1, asc.end());
-        const long long pool_frames = plan_work(frames, rest, std::min(ncl, (int)rest.size()), nullptr);
-        if ((double)frames[asc[n1 - 1]] * kSingleCost <= (double)pool_frames) best = n1; else break;
+        const double tp = (double)plan_work(frames, rest, std::min(ncl, (int)rest.size()), nullptr);
+        const double t = std::max(tp, ((double)frames[asc[n1 - 1]] + 8.0) * kSingleCost);
+        if (t < best_t) { best_t = t; best = n1; }
     }
     single->assign(asc.begin(), asc.begin() + best);
     pool->assign(asc.begin() + best, asc.end());
