@@ -78,5 +78,52 @@ def main():
     print("golden vectors written to", OUT)
 
 
+
+def transformer_golden():
+    """Reference models/transformer.py::TransformerAM (stock nn.TransformerEncoder) on CPU fp32: weights,
+    input, masks and output of a tiny instance -> tests/golden/transformer_golden.npz."""
+    import importlib.util
+    import torch
+    spec = importlib.util.spec_from_file_location("ref_transformer", os.path.join(REF, "models", "transformer.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    torch.manual_seed(7)
+    m = mod.TransformerAM(8, 16, 2, 32, 2, 0.0, 10)
+    with torch.no_grad():                      # the reference's layers are deep copies: make them differ
+        for p in m.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    m.eval()
+    T, B = 9, 3
+    x = torch.randn(T, B, 8)
+    lens = [9, 6, 4]
+    kpm = torch.ones(B, T)
+    for i, n in enumerate(lens):
+        kpm[i, :n] = 0
+    kpm = kpm.bool()
+    keep = torch.tril(torch.ones(T, T), diagonal=2)
+    src_mask = keep.float().masked_fill(keep == 0, float("-inf")).masked_fill(keep == 1, 0.0)
+    out = {"x": x.numpy(), "kpm": kpm.numpy(), "src_mask": src_mask.numpy(), "lens": np.array(lens)}
+
+    def run(x, src_mask=None, kpm=None):
+        # TransformerAM.forward (models/transformer.py:86-93) with nn.TransformerEncoder.forward written out as
+        # what it was in the torch the reference targets (1.2): a loop over the layers and the final norm.  The
+        # container of torch 2.11 probes `layers[0].self_attn` for its fused fast path, which the reference's
+        # wrapper layer (TransformerEncoderLayerWithConv1d) does not have; the layers themselves are the reference's.
+        h = m.input_layer(x)
+        for layer in m.transformer.layers:
+            h = layer(h, src_mask, kpm)
+        return m.output_layer(m.transformer.norm(h))
+
+    with torch.no_grad():
+        out["y_nomask"] = run(x).numpy()
+        out["y_kpm"] = run(x, None, kpm).numpy()
+        out["y_both"] = run(x, src_mask, kpm).numpy()
+    for k, v in m.state_dict().items():
+        out["sd/" + k] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, "transformer_golden.npz"), **out)
+    print("transformer_golden.npz:", {k: v.shape for k, v in out.items() if not k.startswith("sd/")})
+
+
 if __name__ == "__main__":
     main()
+    transformer_golden()

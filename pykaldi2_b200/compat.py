@@ -3,6 +3,7 @@
     import pykaldi2_b200.compat; pykaldi2_b200.compat.install()
     from ops import ops                  # -> pykaldi2_b200.ops.ops       (reference ops/ops.py)
     from models import lstm              # -> pykaldi2_b200.models.lstm   (reference models/lstm.py)
+    from models import transformer       # -> pykaldi2_b200.models.transformer (reference models/transformer.py)
     from reader.preprocess import GlobalMeanVarianceNormalization         (unpickles transform.pkl)
     from utils import utils
     from data import ChunkDataloader, SeqDataloader
@@ -13,6 +14,7 @@ import sys
 _ALIASES = {
     "ops": "pykaldi2_b200.ops", "ops.ops": "pykaldi2_b200.ops.ops",
     "models": "pykaldi2_b200.models", "models.lstm": "pykaldi2_b200.models.lstm",
+    "models.transformer": "pykaldi2_b200.models.transformer",
     "reader": "pykaldi2_b200.reader", "reader.preprocess": "pykaldi2_b200.reader.preprocess",
     "utils": "pykaldi2_b200.utils", "utils.utils": "pykaldi2_b200.utils.utils",
     "data": "pykaldi2_b200.data", "data.dataloader": "pykaldi2_b200.data.dataloader",

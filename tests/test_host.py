@@ -177,3 +177,32 @@ def test_data_parallel_gloo_world2(tmp_path):
                        capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_transformer_am_matches_reference_golden():
+    """models.transformer.TransformerAM against outputs of the reference's own model on the same
+    weights (tests/golden/transformer_golden.npz, written by oracle/make_golden.py from /root/reference):
+    state-dict keys are interchangeable; no mask / key-padding mask / key-padding + look-ahead mask."""
+    from pykaldi2_b200.models import transformer
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "transformer_golden.npz"))
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd/")}
+    m = transformer.TransformerAM(8, 16, 2, 32, 2, 0.0, 10)
+    assert set(m.state_dict().keys()) == set(sd.keys())
+    m.load_state_dict(sd)
+    m.eval()
+    x = torch.from_numpy(g["x"])
+    kpm = torch.from_numpy(g["kpm"])
+    lens = g["lens"]
+    with torch.no_grad():
+        np.testing.assert_allclose(m(x).numpy(), g["y_nomask"], rtol=1e-4, atol=1e-5)
+        y = m(x, None, kpm).numpy()
+        y2 = m(x, torch.from_numpy(g["src_mask"]), kpm).numpy()
+        y3 = m(x, transformer.look_ahead_mask(x.size(0), 2), kpm).numpy()
+    for b, n in enumerate(lens):                     # valid frames (padded frames are never read by the losses)
+        np.testing.assert_allclose(y[:n, b], g["y_kpm"][:n, b], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(y2[:n, b], g["y_both"][:n, b], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(y3[:n, b], g["y_both"][:n, b], rtol=1e-4, atol=1e-5)
+    # fresh instance: every layer starts from the same weights, as nn.TransformerEncoder's deep copies do
+    m2 = transformer.TransformerAM(8, 16, 2, 32, 3, 0.1, 10)
+    s2 = m2.state_dict()
+    assert torch.equal(s2["transformer.layers.0.encoder_layer.linear1.weight"], s2["transformer.layers.2.encoder_layer.linear1.weight"])
