@@ -215,6 +215,7 @@ struct DenGraph {
     bool built[kMaxParts + 1] = {};
     SellHost t_fwd[kMaxParts + 1], t_bwd[kMaxParts + 1], t_pdf[kMaxParts + 1];
     std::mutex mu;
+    std::mutex launch_mu;            // the side streams / events / start flag of a graph serve one call at a time
     int* start_flag = nullptr;       // device int, hybrid schedule
     int epoch = 0;
     int reg_state = 0;               // register-resident path: 0 = not planned, 1 = usable, -1 = not usable
@@ -911,7 +912,7 @@ __device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t parity) 
             "selp.u32 %0, 1, 0, P1;\n"
             "}\n" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
         if (ok) return;
-        if (spin > (1u << 24)) __trap();
+        if (spin > (1u << 27)) __trap();      // seconds: far beyond any legitimate wait (micro-seconds)
     }
 }
 
@@ -1852,6 +1853,7 @@ extern "C" int pk2_denfb(void* graph, const float* loglikes, const int32_t* num_
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 
+    std::lock_guard<std::mutex> launch_lock(g->launch_mu);
     // clusters of 8 with register-resident arcs (default where the graph fits, see plan_reg)
     {
         static const bool reg_off = []() { const char* e = getenv("PK2_DEN_REG"); return e && atoi(e) == 0; }();

@@ -30,24 +30,79 @@ struct FbankPlan {
     int max_len;
 };
 
+struct cplx { float x, y; };
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return {a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return {a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+__device__ __forceinline__ cplx cshfl(cplx a, int lane) {
+    return {__shfl_sync(0xffffffffu, a.x, lane), __shfl_sync(0xffffffffu, a.y, lane)};
+}
+__device__ __forceinline__ cplx cshfl_xor(cplx a, int m) {
+    return {__shfl_xor_sync(0xffffffffu, a.x, m), __shfl_xor_sync(0xffffffffu, a.y, m)};
+}
+
+// 8-point DFT in registers (decimation in frequency, three radix-2 stages); a[k] = sum_n a[n] W8^(nk)
+__device__ __forceinline__ void dft8(cplx (&a)[8]) {
+    const float h = 0.70710678118654752f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const cplx u = cadd(a[i], a[i + 4]), d = csub(a[i], a[i + 4]);
+        a[i] = u;
+        if (i == 0) a[4] = d;
+        else if (i == 1) a[5] = {h * (d.x + d.y), h * (d.y - d.x)};          // * (1 - i)/sqrt2
+        else if (i == 2) a[6] = {d.y, -d.x};                                 // * -i
+        else a[7] = {h * (d.y - d.x), -h * (d.x + d.y)};                     // * (-1 - i)/sqrt2
+    }
+#pragma unroll
+    for (int base = 0; base < 8; base += 4) {
+        const cplx u0 = cadd(a[base], a[base + 2]), d0 = csub(a[base], a[base + 2]);
+        const cplx u1 = cadd(a[base + 1], a[base + 3]), d1 = csub(a[base + 1], a[base + 3]);
+        a[base] = u0; a[base + 1] = u1; a[base + 2] = d0; a[base + 3] = {d1.y, -d1.x};
+    }
+#pragma unroll
+    for (int base = 0; base < 8; base += 2) {
+        const cplx u = cadd(a[base], a[base + 1]), d = csub(a[base], a[base + 1]);
+        a[base] = u; a[base + 1] = d;
+    }
+    // bit-reversed -> natural order (register renaming)
+    cplx t = a[1]; a[1] = a[4]; a[4] = t;
+    t = a[3]; a[3] = a[6]; a[6] = t;
+}
+
+// One warp per frame, the FFT in registers: the 512-pt real FFT is a 256-pt complex FFT z[n] = x[2n] + i x[2n+1],
+// n = 32 n1 + lane: an 8-point DFT over n1 in the registers of each lane, the twiddle W256^(lane k1), and a 32-point
+// DFT ACROSS the lanes (five radix-2 decimation-in-frequency stages on warp shuffles); lane l then holds
+// Z[k1 + 8 bitrev5(l)], k1 = 0..7.  The split post-pass needs Z[256 - k], which sits in register 8 - k1 of lane
+// 31 - l (one shuffle).  Shared memory is only used for the 257 power values the mel filters read (padded
+// index k + k/32: conflict-free).  The first version kept the FFT in shared memory (8 stages x 4 butterflies x
+// 10 accesses per lane) and reached 3.6 % of the HBM roofline (profiles/README_r1.md).
 __global__ void __launch_bounds__(kWarps * 32)
 fbank_kernel(const float* __restrict__ wav, const int64_t* __restrict__ wav_off,
              const int32_t* __restrict__ frame_off, int n_utts, int total_frames,
              FbankPlan plan, float* __restrict__ out) {
-    __shared__ float s_re[kWarps][256];
-    __shared__ float s_im[kWarps][256];
-    __shared__ float s_p[kWarps][kBins + 3];
-    __shared__ float s_ham[kFrameLen];
-    __shared__ float2 s_tw[kBins];
+    __shared__ float s_p[kWarps][kBins + 12];
+    __shared__ float2 s_ham[kFrameLen / 2];
+    __shared__ float2 s_tw[kBins];          // W512^k
+    __shared__ float2 s_tw256[256];         // W256^m
 
-    for (int i = threadIdx.x; i < kFrameLen; i += blockDim.x) s_ham[i] = plan.hamming[i];
+    for (int i = threadIdx.x; i < kFrameLen / 2; i += blockDim.x) s_ham[i] = make_float2(plan.hamming[2 * i], plan.hamming[2 * i + 1]);
     for (int i = threadIdx.x; i < kBins; i += blockDim.x) s_tw[i] = plan.tw[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tw256[i] = (i <= 128) ? plan.tw[2 * i] : make_float2(plan.tw[512 - 2 * i].x, -plan.tw[512 - 2 * i].y);
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* re = s_re[warp];
-    float* im = s_im[warp];
     float* pw = s_p[warp];
+    // twiddles of the five cross-lane stages: W_{2 span}^(lane mod span), span = 16, 8, 4, 2, 1
+    cplx stw[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        const int span = 16 >> s;
+        float sn, cs;
+        sincospif(-(float)(lane & (span - 1)) / (float)span, &sn, &cs);
+        stw[s] = {cs, sn};
+    }
+    const int k2 = (int)(__brev((unsigned)lane) >> 27);                       // lane l ends up with k = k1 + 8 k2
+    const int lane_k0 = (int)(__brev((unsigned)((32 - k2) & 31)) >> 27);      // lane that holds Z[256 - 8 k2]
 
     for (int fr = blockIdx.x * kWarps + warp; fr < total_frames; fr += gridDim.x * kWarps) {
         // utterance of this frame: largest u with frame_off[u] <= fr
@@ -63,57 +118,54 @@ fbank_kernel(const float* __restrict__ wav, const int64_t* __restrict__ wav_off,
         const float* x = wav + w0;
         const int64_t base = (int64_t)t * kHop;
 
-        // pre-emphasis + window, scattered to bit-reversed complex order
+        // pre-emphasis + window: z[32 n1 + lane] = (v[2n], v[2n+1]), v[j] = (x[j+1] - .96 x[j]) * hamming[j]
+        cplx a[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int j = lane + 32 * i;
-            float v = 0.f;
+        for (int n1 = 0; n1 < 8; ++n1) {
+            const int j = 64 * n1 + 2 * lane;
+            a[n1] = {0.f, 0.f};
             if (j < kFrameLen) {
                 const int64_t m = base + j;                 // index into wav[1:] - .96 wav[:-1]
-                if (m < n - 1) {
-                    const float a = __ldg(&x[m + 1]);
-                    const float b = __ldg(&x[m]);
-                    v = __fmul_rn(__fsub_rn(a, __fmul_rn(0.96f, b)), s_ham[j]);
+                const float2 hw = s_ham[j >> 1];
+                if (m + 1 < n - 1) {
+                    const float x0 = __ldg(&x[m]), x1 = __ldg(&x[m + 1]), x2 = __ldg(&x[m + 2]);
+                    a[n1].x = __fmul_rn(__fsub_rn(x1, __fmul_rn(0.96f, x0)), hw.x);
+                    a[n1].y = __fmul_rn(__fsub_rn(x2, __fmul_rn(0.96f, x1)), hw.y);
+                } else if (m < n - 1) {
+                    a[n1].x = __fmul_rn(__fsub_rn(__ldg(&x[m + 1]), __fmul_rn(0.96f, __ldg(&x[m]))), hw.x);
                 }
             }
-            const int nn = j >> 1;
-            const int br = __brev((unsigned)nn) >> 24;
-            if (j & 1) im[br] = v; else re[br] = v;
         }
-        __syncwarp();
-        // 256-pt radix-2 DIT
+        dft8(a);
 #pragma unroll
-        for (int s = 0; s < 8; ++s) {
-            const int half = 1 << s;
-            const int tstep = 256 >> s;                     // index step into the 512-pt table
+        for (int k1 = 1; k1 < 8; ++k1) {
+            const float2 w = s_tw256[(lane * k1) & 255];
+            a[k1] = cmul(a[k1], cplx{w.x, w.y});
+        }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int b = lane + 32 * q;
-                const int pos = b & (half - 1);
-                const int i0 = ((b >> s) << (s + 1)) + pos;
-                const int i1 = i0 + half;
-                const float2 w = s_tw[pos * tstep];
-                const float xr = re[i1], xi = im[i1];
-                const float tr = xr * w.x - xi * w.y;
-                const float ti = xr * w.y + xi * w.x;
-                const float ur = re[i0], ui = im[i0];
-                re[i0] = ur + tr; im[i0] = ui + ti;
-                re[i1] = ur - tr; im[i1] = ui - ti;
+        for (int s = 0; s < 5; ++s) {
+            const int span = 16 >> s;
+            const bool upper = (lane & span) == 0;
+#pragma unroll
+            for (int k1 = 0; k1 < 8; ++k1) {
+                const cplx b = cshfl_xor(a[k1], span);
+                a[k1] = upper ? cadd(a[k1], b) : cmul(csub(b, a[k1]), stw[s]);
             }
-            __syncwarp();
         }
-        // split post-pass -> power spectrum
-        for (int k = lane; k < kBins; k += 32) {
-            const int k0 = k & 255, k1 = (256 - k) & 255;
-            const float zr = re[k0], zi = im[k0];
-            const float cr = re[k1], ci = -im[k1];
-            const float er = 0.5f * (zr + cr), ei = 0.5f * (zi + ci);   // Xe
-            const float dr = 0.5f * (zr - cr), di = 0.5f * (zi - ci);   // (Z - conj Z')/2
-            const float orr = di, oi = -dr;                              // / i  -> Xo
+        // split post-pass -> power spectrum of the 512-pt real FFT
+#pragma unroll
+        for (int k1 = 0; k1 < 8; ++k1) {
+            const int k = k1 + 8 * k2;
+            const cplx zm = (k1 == 0) ? cshfl(a[0], lane_k0) : cshfl(a[8 - k1], 31 - lane);   // Z[256 - k]
+            const cplx z = a[k1];
+            const float er = 0.5f * (z.x + zm.x), ei = 0.5f * (z.y - zm.y);      // (Z + conj Zm) / 2
+            const float dr = 0.5f * (z.x - zm.x), di = 0.5f * (z.y + zm.y);      // (Z - conj Zm) / 2
+            const float orr = di, oi = -dr;                                       // / i
             const float2 w = s_tw[k];
             const float xr = er + orr * w.x - oi * w.y;
             const float xi = ei + orr * w.y + oi * w.x;
-            pw[k] = xr * xr + xi * xi;
+            pw[k + (k >> 5)] = xr * xr + xi * xi;
+            if (k == 0) pw[256 + 8] = (z.x - z.y) * (z.x - z.y);                  // bin 256
         }
         __syncwarp();
         // mel + log
@@ -121,7 +173,7 @@ fbank_kernel(const float* __restrict__ wav, const int64_t* __restrict__ wav_off,
             const int st = plan.fstart[f], ln = plan.flen[f];
             const float* wv = plan.fw + plan.foff[f];
             float acc = 0.f;
-            for (int k = 0; k < ln; ++k) acc = fmaf(pw[st + k], __ldg(&wv[k]), acc);
+            for (int k = 0; k < ln; ++k) { const int b = st + k; acc = fmaf(pw[b + (b >> 5)], __ldg(&wv[k]), acc); }
             out[(int64_t)fr * kMel + f] = logf(acc + 1.0f);
         }
         __syncwarp();
