@@ -2,7 +2,7 @@
 //
 // Replaces nn.CrossEntropyLoss(ignore_index=-100) (reference bin/train_ce.py:134,189;
 // reduction='sum' at bin/train_se.py:214,235).  One CTA per row; the row is staged in
-// shared memory once (coalesced float4 loads), reduced (max, sum exp), and the gradient
+// shared memory once (coalesced float4 loads when n_cols % 4 == 0), reduced (max, sum exp), and the gradient
 // scale*(softmax - onehot) is written back.  HBM-bound: 4N B read + 4N B written per row.
 #include "common.cuh"
 
@@ -14,10 +14,12 @@ __global__ void __launch_bounds__(kThreads)
 ce_softmax_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels,
                   int64_t n_rows, int n_cols, float scale, float* __restrict__ loss_rows,
                   float* __restrict__ grad) {
-    extern __shared__ float row[];
+    extern __shared__ __align__(16) float row[];
     __shared__ float red[kThreads / 32];
     __shared__ float bc;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool vec = (n_cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0) &&
+                     (!grad || (reinterpret_cast<uintptr_t>(grad) & 15) == 0);
     for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
         const int64_t lab = labels[r];
         const float* src = logits + r * (int64_t)n_cols;
@@ -28,10 +30,18 @@ ce_softmax_kernel(const float* __restrict__ logits, const int64_t* __restrict__ 
             continue;
         }
         float m = -INFINITY;
-        for (int c = threadIdx.x; c < n_cols; c += kThreads) {
-            const float v = src[c];
-            row[c] = v;
-            m = fmaxf(m, v);
+        if (vec) {
+            for (int c = threadIdx.x * 4; c < n_cols; c += kThreads * 4) {
+                const float4 v = __ldcs(reinterpret_cast<const float4*>(src + c));     // streamed once: evict first
+                *reinterpret_cast<float4*>(row + c) = v;
+                m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+            }
+        } else {
+            for (int c = threadIdx.x; c < n_cols; c += kThreads) {
+                const float v = src[c];
+                row[c] = v;
+                m = fmaxf(m, v);
+            }
         }
         m = pk2::warp_max(m);
         if (lane == 0) red[warp] = m;
@@ -44,10 +54,19 @@ ce_softmax_kernel(const float* __restrict__ logits, const int64_t* __restrict__ 
         __syncthreads();
         m = bc;
         float s = 0.f;
-        for (int c = threadIdx.x; c < n_cols; c += kThreads) {
-            const float e = __expf(row[c] - m);
-            row[c] = e;
-            s += e;
+        if (vec) {
+            for (int c = threadIdx.x * 4; c < n_cols; c += kThreads * 4) {       // same thread -> element mapping as the load
+                float4 v = *reinterpret_cast<float4*>(row + c);
+                v.x = __expf(v.x - m); v.y = __expf(v.y - m); v.z = __expf(v.z - m); v.w = __expf(v.w - m);
+                *reinterpret_cast<float4*>(row + c) = v;
+                s += (v.x + v.y) + (v.z + v.w);
+            }
+        } else {
+            for (int c = threadIdx.x; c < n_cols; c += kThreads) {
+                const float e = __expf(row[c] - m);
+                row[c] = e;
+                s += e;
+            }
         }
         s = pk2::warp_sum(s);
         __syncthreads();
@@ -63,8 +82,18 @@ ce_softmax_kernel(const float* __restrict__ logits, const int64_t* __restrict__ 
         if (threadIdx.x == 0 && loss_rows) loss_rows[r] = logf(s) + m - src[lab];
         if (dst) {
             const float inv = scale / s;
-            for (int c = threadIdx.x; c < n_cols; c += kThreads)
-                dst[c] = row[c] * inv - (c == (int)lab ? scale : 0.f);
+            if (vec) {
+                for (int c = threadIdx.x * 4; c < n_cols; c += kThreads * 4) {
+                    float4 v = *reinterpret_cast<float4*>(row + c);
+                    v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+                    const int d = (int)lab - c;
+                    if (d == 0) v.x -= scale; else if (d == 1) v.y -= scale; else if (d == 2) v.z -= scale; else if (d == 3) v.w -= scale;
+                    *reinterpret_cast<float4*>(dst + c) = v;
+                }
+            } else {
+                for (int c = threadIdx.x; c < n_cols; c += kThreads)
+                    dst[c] = row[c] * inv - (c == (int)lab ? scale : 0.f);
+            }
         }
         __syncthreads();
     }

@@ -118,7 +118,23 @@ def bench_fbank():
                       "frac_hbm": byts / ms / 1e6 / peaks()["hbm_gbs"]}))
 
 
+def bench_ce():
+    """CE softmax + NLL forward/backward on BASELINE config 2 (256 chunks x 80 frames, N = 5768)."""
+    from pykaldi2_b200 import _lib
+    dev = torch.device("cuda", 0)
+    R, N = 256 * 80, 5768
+    logits = torch.randn(R, N, device=dev)
+    labels = torch.randint(0, N, (R,), device=dev)
+    loss = torch.empty(R, device=dev)
+    grad = torch.empty_like(logits)
+    L = _lib.lib()
+    ms = timeit(lambda: _lib.check(L.pk2_ce_softmax(_lib.ptr(logits), _lib.ptr(labels), R, N, 1.0, _lib.ptr(loss),
+                                                     _lib.ptr(grad), _lib.stream()), "ce"), iters=10, warm=3)
+    gbs = 2 * 4 * R * N / ms / 1e6
+    print(json.dumps({"kernel": "ce_softmax", "rows": R, "cols": N, "ms": ms, "GBps": gbs, "frac_hbm": gbs / peaks()["hbm_gbs"]}))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["den", "lstm", "gemm", "fbank"]
     for w in which:
-        {"den": bench_den, "lstm": bench_lstm, "gemm": bench_gemm, "fbank": bench_fbank}[w]()
+        {"den": bench_den, "lstm": bench_lstm, "gemm": bench_gemm, "fbank": bench_fbank, "ce": bench_ce}[w]()
