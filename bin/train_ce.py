@@ -2,7 +2,8 @@
 """Cross-entropy training of the BLSTM acoustic model on B200 (reference bin/train_ce.py).
 
 Same flags and YAML schema as the reference script; ``-hvd`` selects multi-GPU (NCCL via torchrun
-instead of Horovod).  ``-synthetic N`` trains on N seeded synthetic utterances (no zip corpus; the
+instead of Horovod).  ``-synthetic N`` trains on N seeded synthetic utterances; without it the corpus of ``-data_config`` (zip of wavs +
+label files, the reference's formats) is read by ``data.SpeechDataset`` (the
 reference's zip/wav ingestion is outside the hot path).  The loop body is
 bin/train_ce.py:177-208: features -> model -> CrossEntropyLoss(ignore_index=-100) -> backward ->
 clip -> Adam(amsgrad) step, with fbank/CMN/chunking, the BLSTM and the loss on libpk2.so kernels.
@@ -19,6 +20,7 @@ import _common
 from _common import pkdist
 from pykaldi2_b200 import pipeline
 from pykaldi2_b200.data.dataloader import SyntheticWaveDataset, WaveDataloader
+from pykaldi2_b200.data.speech_dataset import SpeechDataset
 from pykaldi2_b200.models import lstm
 from pykaldi2_b200.reader.preprocess import GlobalMeanVarianceNormalization
 from pykaldi2_b200.utils import utils
@@ -61,9 +63,10 @@ def main():
     os.makedirs(args.exp_dir, exist_ok=True)
 
     mc, dc = config["model_config"], config["data_config"]
-    if args.synthetic <= 0:
-        raise SystemExit("train_ce.py: only -synthetic data is wired in this build (zip corpora: SURVEY.md 8f-4)")
-    trainset = SyntheticWaveDataset(args.synthetic, mc["label_size"])
+    if args.synthetic > 0:
+        trainset = SyntheticWaveDataset(args.synthetic, mc["label_size"])
+    else:                                   # the reference's corpus description: zip of wavs + label text files
+        trainset = SpeechDataset(config)
     # the reference batches 80-frame chunks; here a minibatch of utterances is cut into chunks on the GPU
     utts_per_batch = max(1, args.batch_size * dc.get("seg_len", 80) // 1230)
     loader = WaveDataloader(trainset, utts_per_batch, num_workers=args.data_loader_threads, distributed=world > 1)

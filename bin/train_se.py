@@ -20,6 +20,7 @@ import _common
 from _common import pkdist
 from pykaldi2_b200 import graphs, pipeline, synth
 from pykaldi2_b200.data.dataloader import SyntheticWaveDataset, WaveDataloader
+from pykaldi2_b200.data.speech_dataset import SpeechDataset
 from pykaldi2_b200.models import lstm
 from pykaldi2_b200.ops import ops
 from pykaldi2_b200.utils import utils
@@ -66,11 +67,12 @@ def main():
     dev = th.device("cuda", local)
     os.makedirs(args.exp_dir, exist_ok=True)
     mc, dc = config["model_config"], config["data_config"]
-    if args.synthetic <= 0:
-        raise SystemExit("train_se.py: only -synthetic data is wired in this build")
     N = mc["label_size"]
 
-    dataset = SyntheticWaveDataset(args.synthetic, N)
+    if args.synthetic > 0:
+        dataset = SyntheticWaveDataset(args.synthetic, N)
+    else:                                   # zip of wavs + pdf-id / transition-id label files (example/librispeech/README.md)
+        dataset = SpeechDataset(config)
     loader = WaveDataloader(dataset, args.batch_size, num_workers=args.data_loader_threads, distributed=world > 1)
     feat = pipeline.FeaturePipeline(use_cmn=dc.get("use_cmn", True))
     print("Data loader set up successfully!")
@@ -112,7 +114,8 @@ def run_train_epoch(model, optimizer, averager, feat, log_prior, loader, epoch, 
     end = time.time()
     for i, batch in enumerate(loader):
         wav, woff, foff = feat.ex.pack(batch["wav"])
-        x, num_frs = feat.sequence_batch(wav, woff, foff)
+        n_fr = [min(int(foff[u + 1] - foff[u]), len(l)) for u, l in enumerate(batch["label"])]   # data/sr_dataset.py:358-363
+        x, num_frs = feat.sequence_batch(wav, woff, foff, n_frames=n_fr)
         B, Tmax = x.shape[0], x.shape[1]
         y = np.full((B, Tmax), -100, np.int64)
         for j, lab in enumerate(batch["label"]):

@@ -30,3 +30,4 @@ def install(force=False):
     dl = sys.modules["data.dataloader"]
     for name in ("ChunkDataloader", "SeqDataloader", "SyntheticWaveDataset", "WaveDataloader"):
         setattr(data, name, getattr(dl, name))
+    data.SpeechDataset = importlib.import_module("pykaldi2_b200.data.speech_dataset").SpeechDataset

@@ -7,9 +7,9 @@ SeqDataloader.collate_fn (:94-136): features zero padded, labels padded with -10
 constructor signatures; the distributed branch shards with torch.distributed's rank/size instead of
 Horovod's (data/dataloader.py:45-46,83-84).
 
-``SyntheticWaveDataset`` replaces zip/wav ingestion (reader/stream.py, out of scope) with seeded
-LibriSpeech-shaped waveforms + labels; its items are raw waveforms because the fbank now runs on the
-GPU (pipeline.FeaturePipeline), not in the DataLoader workers.
+``SyntheticWaveDataset`` yields seeded LibriSpeech-shaped waveforms + labels (corpora in the reference's zip /
+label-file formats: data/speech_dataset.py); items are raw waveforms because the fbank runs on the GPU
+(pipeline.FeaturePipeline), not in the DataLoader workers.
 """
 import numpy as np
 import torch

@@ -65,3 +65,17 @@ def test_train_se_synthetic(tmp_path):
                                "-synthetic", "2", "-print_freq", "1", "-max_steps", "1", "-criterion", "mpfe",
                                "-batched_loss", "0"], tmp_path)
     assert "Epoch: [0]" in out3
+
+
+def test_trainers_on_zip_corpus(tmp_path):
+    """train_ce.py / train_se.py on a corpus in the reference's formats (zip of wavs + label text
+    files + data yaml) instead of -synthetic."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_host import _make_corpus
+    data_yaml, wavs, labels = _make_corpus(str(tmp_path), n=6, seed=3)
+    out = run("train_ce.py", ["-exp_dir", str(tmp_path), "-train_config", "configs/ce_test.yaml", "-data_config", data_yaml,
+                              "-batch_size", "4", "-print_freq", "1", "-lr", "0.001", "-max_steps", "2"], tmp_path)
+    assert out.count("Epoch: [0]") >= 1 and os.path.exists(os.path.join(tmp_path, "model.0.tar"))
+    out = run("train_se.py", ["-exp_dir", str(tmp_path), "-config", "configs/ce_test.yaml", "-data", data_yaml,
+                              "-batch_size", "2", "-print_freq", "1", "-max_steps", "1"], tmp_path)
+    assert "Epoch: [0]" in out

@@ -206,3 +206,84 @@ def test_transformer_am_matches_reference_golden():
     m2 = transformer.TransformerAM(8, 16, 2, 32, 3, 0.1, 10)
     s2 = m2.state_dict()
     assert torch.equal(s2["transformer.layers.0.encoder_layer.linear1.weight"], s2["transformer.layers.2.encoder_layer.linear1.weight"])
+
+
+def _make_corpus(tmp_path, n=4, seed=0, label_dim=104):
+    """A tiny corpus in the reference's formats: zip of 16-bit wavs + pdf-id / transition-id text files + data yaml."""
+    import zipfile
+    from pykaldi2_b200.reader import zip_io
+    from pykaldi2_b200.data import fbank as fb
+    rng = np.random.default_rng(seed)
+    wavs, zpath = {}, os.path.join(tmp_path, "train.zip")
+    with zipfile.ZipFile(zpath, "w") as z:
+        for i in range(n):
+            utt = "100-%04d-%04d" % (seed, i)
+            x = (0.05 * rng.standard_normal(16000 + 3000 * i)).astype(np.float32)
+            wavs[utt] = x
+            z.writestr("wav/%s.wav" % utt, zip_io.write_wav(io_bytes(), x))
+        z.writestr("README.txt", "not audio")
+    pdf, tid = os.path.join(tmp_path, "pdf-ids.txt"), os.path.join(tmp_path, "trans-ids.txt")
+    labels = {}
+    with open(pdf, "w") as fp, open(tid, "w") as ft:
+        for utt, x in wavs.items():
+            if utt.endswith("0003"):
+                continue                                   # an utterance without labels is dropped
+            T = fb.num_frames(len(x)) - 1                  # Kaldi-style label count: one short of our frame count
+            lab = rng.integers(0, label_dim, T)
+            labels[utt] = lab
+            fp.write(utt + " " + " ".join(map(str, lab)) + "\n")
+            ft.write(utt + " " + " ".join(map(str, 2 * lab + 1)) + "\n")
+    data_yaml = os.path.join(tmp_path, "data.yaml")
+    with open(data_yaml, "w") as f:
+        f.write("clean_source:\n  1:\n    type: Librispeech\n    wav: %s\n    label: %s\n    aux_label: %s\n" % (zpath, pdf, tid))
+    return data_yaml, wavs, labels
+
+
+def io_bytes():
+    import io
+    return io.BytesIO()
+
+
+def test_zip_wav_label_ingestion(tmp_path):
+    """the reference's corpus formats (zip of wavs, `utt-id int int ...` label files, data yaml)."""
+    import struct
+    import yaml
+    from pykaldi2_b200.data.speech_dataset import SpeechDataset
+    from pykaldi2_b200.data.dataloader import WaveDataloader
+    from pykaldi2_b200.reader import zip_io
+    data_yaml, wavs, labels = _make_corpus(str(tmp_path))
+    with open(data_yaml) as f:
+        data = yaml.safe_load(f)
+    config = {"data_config": {"load_label": True}, "source_paths": [j for _, j in data["clean_source"].items()]}
+    ds = SpeechDataset(config)
+    assert len(ds) == 3                                     # 4 wavs, one without labels
+    for i in range(len(ds)):
+        wav, (utt,), pdf, (tid,) = ds[i]
+        ref = np.clip(np.round(wavs[utt].astype(np.float64) * 32768.0), -32768, 32767) / 32768.0   # 16-bit PCM -> [-1, 1)
+        assert wav.dtype == np.float32 and np.array_equal(wav, ref.astype(np.float32))
+        assert pdf.shape == (len(labels[utt]), 1) and (pdf[:, 0] == labels[utt]).all()
+        assert tid.shape == (1, len(labels[utt])) and (tid[0] == 2 * labels[utt] + 1).all()
+    batch = next(iter(WaveDataloader(ds, 2)))
+    assert set(batch) == {"utt_ids", "wav", "label", "aux"} and len(batch["wav"]) == 2
+    # other sample formats: 8 / 24 / 32-bit PCM, float32, stereo, odd-sized chunks before `data`
+    x = np.array([0.5, -0.25, 0.125, -1.0])
+
+    def riff(tag, ch, bits, payload, extra=b""):
+        fmt = struct.pack("<HHIIHH", tag, ch, 16000, 16000 * ch * bits // 8, ch * bits // 8, bits)
+        body = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt + extra + b"data" + struct.pack("<I", len(payload)) + payload
+        return b"RIFF" + struct.pack("<I", len(body)) + body
+    fs, y = zip_io.parse_wav(riff(1, 1, 32, (x * 2 ** 31).clip(-2 ** 31, 2 ** 31 - 1).astype("<i4").tobytes()))
+    assert fs == 16000 and np.allclose(y, x.clip(-1, 1 - 2 ** -31), atol=1e-6)
+    _, y = zip_io.parse_wav(riff(3, 1, 32, x.astype("<f4").tobytes(), extra=b"LIST" + struct.pack("<I", 3) + b"abc\0"))
+    assert np.array_equal(y, x.astype(np.float32))
+    v = (x * 2 ** 23).clip(-2 ** 23, 2 ** 23 - 1).astype(np.int32)
+    p24 = b"".join(struct.pack("<i", int(t))[:3] for t in v)
+    _, y = zip_io.parse_wav(riff(1, 1, 24, p24))
+    assert np.allclose(y, x.clip(-1, 1 - 2 ** -23), atol=1e-6)
+    _, y = zip_io.parse_wav(riff(1, 2, 16, (x * 32768).clip(-32768, 32767).astype("<i2").tobytes()))
+    assert y.shape == (2, 2)
+    with pytest.raises(ValueError):
+        zip_io.parse_wav(b"RIFFxxxxWAVEjunk")
+    with pytest.raises(ValueError):
+        zip_io.ZipWaveIO().read_wav(str(tmp_path) + "/a.flac")
+    assert zip_io.utt_id_of("/x/y.zip@/wav/100-121669-0001.wav") == "100-121669-0001"
