@@ -2,9 +2,9 @@
 """Cross-entropy training of the BLSTM acoustic model on B200 (reference bin/train_ce.py).
 
 Same flags and YAML schema as the reference script; ``-hvd`` selects multi-GPU (NCCL via torchrun
-instead of Horovod).  ``-synthetic N`` trains on N seeded synthetic utterances; without it the corpus of ``-data_config`` (zip of wavs +
-label files, the reference's formats) is read by ``data.SpeechDataset`` (the
-reference's zip/wav ingestion is outside the hot path).  The loop body is
+instead of Horovod).  ``-synthetic N`` trains on N seeded synthetic utterances; without it the
+corpus of ``-data_config`` (zip of wavs + label files, the reference's formats) is read by
+``data.SpeechDataset``.  The loop body is
 bin/train_ce.py:177-208: features -> model -> CrossEntropyLoss(ignore_index=-100) -> backward ->
 clip -> Adam(amsgrad) step, with fbank/CMN/chunking, the BLSTM and the loss on libpk2.so kernels.
 """
