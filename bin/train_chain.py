@@ -63,6 +63,7 @@ def main():
     parser.add_argument('-print_freq', default=10, type=int, metavar='N', help='print frequency (default: 10)')
     parser.add_argument('-save_freq', default=1000, type=int, metavar='N', help='save model frequency (default: 1000)')
     parser.add_argument('-synthetic', default=0, type=int, help="train on this many seeded synthetic utterances")
+    parser.add_argument('-den_fst', default='', type=str, help="denominator FST file (OpenFst binary vector/standard or fstprint text); default: synthetic")
     parser.add_argument('-den_states', default=8192, type=int, help="states of the synthetic denominator FST")
     parser.add_argument('-per_utt_loss', default=0, type=int, help="1 = one chain-objective call per utterance as the reference does")
     parser.add_argument('-seed', default=1234, type=int, help="random seed (model init, sampling)")
@@ -102,7 +103,10 @@ def main():
 
     supervision_opts = SupervisionOptions()
     chain_opts = graphs.ChainTrainingOptions(leaky_hmm_coefficient=1e-4, xent_regularize=args.xent_regularize)
-    den = graphs.DenominatorGraph(synth.make_den_fst(args.den_states, mc["label_size"], 7, seed=1234), mc["label_size"])
+    if args.den_fst:                      # a real denominator graph: OpenFst binary (Kaldi's den.fst) or fstprint text
+        den = graphs.DenominatorGraph.from_file(args.den_fst, mc["label_size"])
+    else:
+        den = graphs.DenominatorGraph(synth.make_den_fst(args.den_states, mc["label_size"], 7, seed=1234), mc["label_size"])
 
     model.train()
     for epoch in range(args.num_epochs):

@@ -93,6 +93,13 @@ class DenominatorGraph(object):
             cur = nxt / nxt.sum()
         return avg.astype(np.float32)
 
+    @classmethod
+    def from_file(cls, path, num_pdfs):
+        """``den.fst`` as Kaldi writes it (OpenFst binary, vector / standard) or in fstprint text form
+        (reference bin/train_chain.py:196-202 reads it through PyKaldi)."""
+        from .reader import fst_io
+        return cls(fst_io.read_fst(path), num_pdfs)
+
     def num_states(self):
         return self._S
 
@@ -188,6 +195,13 @@ class Supervision(object):
         self.in_src = src[i].astype(np.int32)
         self.in_pdf = pdf[i].astype(np.int32)
         self.in_w = w[i]
+
+    @classmethod
+    def from_file(cls, path, frames_per_sequence, label_dim, weight=1.0):
+        """Numerator FST of one utterance from a file (OpenFst binary vector / standard, or fstprint text):
+        epsilon-free, ilabel = pdf + 1, e.g. the ``fst`` member of a Kaldi chain Supervision dumped with fstprint."""
+        from .reader import fst_io
+        return cls(fst_io.read_fst(path), frames_per_sequence, label_dim, weight)
 
 
 def _cat_off(offs):

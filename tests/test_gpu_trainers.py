@@ -39,6 +39,14 @@ def test_train_chain_synthetic(tmp_path):
                                  "-synthetic", "16", "-den_states", "256", "-print_freq", "1", "-lr", "0.01",
                                  "-warmup_steps", "2", "-max_steps", "4"], tmp_path)
     assert out.count("Epoch: [0]") >= 3
+    # a denominator graph from a file (OpenFst binary as Kaldi writes den.fst) instead of the synthetic one
+    from pykaldi2_b200 import synth
+    from pykaldi2_b200.reader import fst_io
+    den_path = os.path.join(tmp_path, "den.fst")
+    fst_io.write_fst_binary(synth.make_den_fst(256, 104, 7, seed=1234), den_path)
+    o0 = run("train_chain.py", ["-exp_dir", str(tmp_path / "d"), "-config", "configs/ce_test.yaml", "-batch_size", "4",
+                                "-synthetic", "4", "-den_fst", den_path, "-print_freq", "1", "-max_steps", "1"], tmp_path)
+    assert "Epoch: [0]" in o0
     ck = torch.load(os.path.join(tmp_path, "chain.model.0.tar"), map_location="cpu")
     assert "output_layer.weight" in ck["model"]
     # per-utterance calling pattern of the reference gives the same first-step loss as the batched call

@@ -287,3 +287,35 @@ def test_zip_wav_label_ingestion(tmp_path):
     with pytest.raises(ValueError):
         zip_io.ZipWaveIO().read_wav(str(tmp_path) + "/a.flac")
     assert zip_io.utt_id_of("/x/y.zip@/wav/100-121669-0001.wav") == "100-121669-0001"
+
+
+def test_fst_readers_round_trip(tmp_path):
+    """SURVEY 8f-2 (reader half): OpenFst binary (vector / standard) and fstprint text forms of a denominator FST."""
+    from pykaldi2_b200 import synth
+    from pykaldi2_b200.reader import fst_io
+    fst = synth.make_den_fst(64, 20, 5, seed=3)
+    fst["final"][5] = 0.25
+    fst["final"][9] = 0.0
+    b = fst_io.write_fst_binary(fst, os.path.join(tmp_path, "den.fst"))
+    assert fst_io.FST_MAGIC == struct_unpack_i(b[:4])
+    r = fst_io.read_fst(os.path.join(tmp_path, "den.fst"))
+    for k in ("src", "dst", "ilabel"):
+        assert (r[k] == fst[k]).all(), k
+    assert r["num_states"] == 64 and r["start"] == 0
+    assert np.array_equal(r["weight"], fst["weight"]) and np.array_equal(r["final"], fst["final"])
+    fst_io.write_fst_text(fst, os.path.join(tmp_path, "den.txt"))
+    t = fst_io.read_fst(os.path.join(tmp_path, "den.txt"))
+    assert (t["src"] == fst["src"]).all() and (t["dst"] == fst["dst"]).all() and (t["ilabel"] == fst["ilabel"]).all()
+    np.testing.assert_allclose(t["weight"], fst["weight"], rtol=1e-6)
+    assert np.isinf(t["final"][0]) and t["final"][5] == np.float32(0.25) and t["final"][9] == 0.0
+    # hand-written fstprint text: start = source of the first line, default weights 0
+    h = fst_io.read_fst_text(["2 0 3 3 0.5", "0 1 1 1", "1 2 2 2 1.5", "1"])
+    assert h["start"] == 2 and h["num_states"] == 3 and list(h["src"]) == [0, 1, 2] and h["final"][1] == 0.0
+    assert h["weight"][list(h["src"]).index(0)] == 0.0
+    with pytest.raises(ValueError):
+        fst_io.read_fst_binary(b"\\0" * 64)
+
+
+def struct_unpack_i(b):
+    import struct
+    return struct.unpack("<i", b)[0]
