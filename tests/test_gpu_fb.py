@@ -232,6 +232,27 @@ def test_denfb_full_size_properties(dev):
     np.testing.assert_allclose(objf2.cpu().numpy(), o1, rtol=1e-4, atol=1e-3)
 
 
+def test_denfb_full_size_hybrid_schedule_matches_streaming(dev):
+    """BASELINE config 4 graph, more sequences than resident clusters: the automatic schedule (clusters of 8 with
+    work lists + single-CTA kernels on the spare SMs) against the streaming 4-CTA kernels."""
+    from pykaldi2_b200 import graphs, synth
+    from pykaldi2_b200.ops import ops
+    N, S = 5768, 8192
+    rng = np.random.default_rng(99)
+    den = graphs.DenominatorGraph(synth.make_den_fst(S, N, 7, seed=1234), N)
+    Ts = [int(t) for t in rng.integers(8, 60, size=26)]
+    sups = [graphs.Supervision(synth.make_supervision_fst(T, N, rng), T, N) for T in Ts]
+    sb = graphs.SupervisionBatch(sups, device=dev)
+    opts = graphs.ChainTrainingOptions(leaky_hmm_coefficient=1e-4, xent_regularize=0.0)
+    pred = torch.from_numpy(rng.normal(0, 2.0, (len(Ts), max(Ts), N)).astype(np.float32)).to(dev)
+    o0, g0 = ops.chain_objf_and_deriv(pred, den, sb, opts, cluster=0)
+    o4, g4 = ops.chain_objf_and_deriv(pred, den, sb, opts, cluster=4)
+    np.testing.assert_allclose(o0.cpu().numpy(), o4.cpu().numpy(), rtol=1e-5)
+    np.testing.assert_allclose(g0.cpu().numpy(), g4.cpu().numpy(), rtol=1e-3, atol=1e-6)
+    for b, T in enumerate(Ts):
+        assert (g0[b, T:] == 0).all()
+
+
 # ------------------------------------------------------------------- lattice MMI ----
 @pytest.mark.parametrize("eps", [0.0, 0.1])
 def test_lattice_mmi_vs_oracle(dev, eps):
