@@ -192,6 +192,11 @@ typedef struct {
 int pk2_lstm_layer_fwd(const pk2_lstm_fwd_args* a, void* stream);
 /* profiling aid: device int64[128] receiving clock64() stamps of 8 steps of one CTA; NULL = off */
 int pk2_lstm_set_profile_buffer(void* buf);
+/* Host-side schedule of pk2_denfb's register-resident path (no device work; used by the CPU tests):
+ * assign[i] = cluster that processes sequence i, or -1 = single-CTA kernel on one of `spare_sms` SMs.
+ * Returns the largest cluster load in frames, -1 on bad arguments. */
+long long pk2_den_plan(const int32_t* frames_h, int n_seq, int n_clusters, int spare_sms, int32_t* assign_h);
+
 /* profiling aid: device int64[128]; frames 64..71 of the first cluster of every pk2_denfb launch stamp clock64()
  * at 7 points of the forward ([0,64)) and backward ([64,128)) frame loop; NULL = off */
 int pk2_den_set_profile_buffer(void* buf);

@@ -75,6 +75,7 @@ _SIGS = {
     "pk2_lstm_layer_fwd": (C.c_int, [C.POINTER(LstmFwdArgs), vp]),
     "pk2_lstm_set_profile_buffer": (C.c_int, [vp]),
     "pk2_den_set_profile_buffer": (C.c_int, [vp]),
+    "pk2_den_plan": (C.c_longlong, [vp, C.c_int, C.c_int, C.c_int, vp]),
     "pk2_lstm_layer_bwd": (C.c_int, [C.POINTER(LstmBwdArgs), vp]),
 }
 

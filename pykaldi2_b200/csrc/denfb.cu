@@ -1794,6 +1794,24 @@ extern "C" int pk2_den_graph_create(int S, int N, const int32_t* fwd_off, const 
     return 0;
 }
 
+// Host-side schedule of one pk2_denfb call, exported for the CPU tests (no device work): assign[i] = cluster
+// (0 .. n_clusters-1) that processes sequence i, or -1 if it runs as a single-CTA kernel on a spare SM;
+// returns the largest cluster load in frames (incl. the per-sequence set-up allowance) or -1 on bad arguments.
+extern "C" long long pk2_den_plan(const int32_t* frames, int n_seq, int n_clusters, int spare_sms, int32_t* assign) {
+    if (!frames || !assign || n_seq <= 0 || n_clusters <= 0) return -1;
+    std::vector<int> pool, single;
+    if (spare_sms > 0 && n_seq > n_clusters) plan_hybrid(frames, n_seq, n_clusters, spare_sms, &pool, &single);
+    else { pool.resize(n_seq); for (int i = 0; i < n_seq; ++i) pool[i] = i; }
+    const int ncl = std::min((int)pool.size(), n_clusters);
+    std::vector<int32_t> work;
+    const long long worst = plan_work(frames, pool, ncl, &work);
+    for (int i = 0; i < n_seq; ++i) assign[i] = -2;
+    for (int k = 0; k < ncl; ++k)
+        for (int j = work[k]; j < work[k + 1]; ++j) assign[work[ncl + 1 + j]] = k;
+    for (int i : single) assign[i] = -1;
+    return worst;
+}
+
 extern "C" int pk2_den_set_profile_buffer(void* buf) {
     g_den_prof = static_cast<long long*>(buf);
     return 0;

@@ -319,3 +319,27 @@ def test_fst_readers_round_trip(tmp_path):
 def struct_unpack_i(b):
     import struct
     return struct.unpack("<i", b)[0]
+
+
+def test_den_schedule_host_planner():
+    """pk2_denfb's host-side schedule (clusters of 8 with work lists + single-CTA kernels on spare SMs): every
+    sequence is scheduled exactly once, the single-CTA set is the shortest sequences, loads are balanced."""
+    import ctypes as C
+    from pykaldi2_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(5)
+    T = np.clip(rng.gamma(6.0, 2.05, 64) * 100 / 3, 50, 1000).astype(np.int32)
+    for ncl, spare in ((15, 20), (15, 0), (4, 3), (80, 20)):
+        assign = np.full(len(T), -7, np.int32)
+        worst = L.pk2_den_plan(T.ctypes.data_as(_lib.vp), len(T), ncl, spare, assign.ctypes.data_as(_lib.vp))
+        assert worst > 0 and (assign >= -1).all() and (assign < ncl).all()
+        single = assign == -1
+        assert single.sum() <= max(spare, 0)
+        if single.any():
+            assert T[single].max() <= T[~single].min()                  # the shortest ones run on single SMs
+            assert T[single].max() * 5.6 <= worst * 1.25                 # and do not outlast the cluster pool by much
+        loads = np.array([(T[assign == k] + 8).sum() for k in range(min(ncl, (~single).sum()))])
+        assert loads.max() == worst
+        if (~single).sum() >= 3 * ncl:
+            assert loads.max() <= 1.06 * loads.mean()                    # LPT + local search: within a few percent
+    assert L.pk2_den_plan(None, 4, 2, 0, None) == -1
