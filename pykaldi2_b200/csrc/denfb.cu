@@ -1616,6 +1616,8 @@ int launch_cluster8(void (*kern)(DenArgs, RegSmem), const DenArgs& args, const R
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = kRK; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    // per launch, not per graph: the attribute belongs to the function, and graphs of different sizes share it
+    PK2_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PK2_CHECK(cudaLaunchKernelEx(&cfg, kern, args, rs));
     PK2_LAUNCHED();
     return 0;

@@ -253,6 +253,28 @@ def test_denfb_full_size_hybrid_schedule_matches_streaming(dev):
         assert (g0[b, T:] == 0).all()
 
 
+def test_denfb_random_batches_two_graphs_alternating(dev):
+    """Random batch sizes / lengths on two graphs of different size used alternately (the kernels' shared-memory
+    attribute is per function, not per graph): automatic and cluster-8 schedules against the streaming kernels."""
+    from pykaldi2_b200 import graphs, synth
+    from pykaldi2_b200.ops import ops
+    rng = np.random.default_rng(21)
+    opts = graphs.ChainTrainingOptions(leaky_hmm_coefficient=1e-4, xent_regularize=0.0)
+    dens = [(graphs.DenominatorGraph(synth.make_den_fst(S, N, 7, seed=S), N), N) for S, N in ((2048, 400), (256, 52))]
+    for trial in range(6):
+        den, N = dens[trial % 2]
+        B = int(rng.integers(1, 60))
+        Ts = [int(t) for t in rng.integers(1, 70, size=B)]
+        sups = [graphs.Supervision(synth.make_supervision_fst(T, N, rng), T, N) for T in Ts]
+        sb = graphs.SupervisionBatch(sups, device=dev)
+        pred = torch.from_numpy(rng.normal(0, 2.0, (B, max(Ts), N)).astype(np.float32)).to(dev)
+        o1, g1 = ops.chain_objf_and_deriv(pred, den, sb, opts, cluster=[1, 2, 4][trial % 3])
+        for K in (0, 8):
+            o, g = ops.chain_objf_and_deriv(pred, den, sb, opts, cluster=K)
+            np.testing.assert_allclose(o.cpu().numpy(), o1.cpu().numpy(), rtol=1e-5)
+            np.testing.assert_allclose(g.cpu().numpy(), g1.cpu().numpy(), rtol=1e-3, atol=1e-6)
+
+
 # ------------------------------------------------------------------- lattice MMI ----
 @pytest.mark.parametrize("eps", [0.0, 0.1])
 def test_lattice_mmi_vs_oracle(dev, eps):
