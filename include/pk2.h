@@ -112,6 +112,12 @@ typedef struct {
 int pk2_numfb(const pk2_sup_batch* sup, const float* loglikes, int num_pdfs, int64_t row_stride_b,
               float deriv_scale, double* ws_alpha, double* ws_beta, float* grad, double* logz,
               void* stream);
+/* Kaldi's fallback for sequences whose objective is not finite (derivatives <- 0; the caller sets
+ * objf <- -10 * weight * frames): zero grad[b, :, :] (row_elems = max_frames * num_pdfs floats per sequence)
+ * where logz_den[b] or logz_num[b] is not finite.  Device-side, no host synchronisation. */
+int pk2_chain_guard(const double* logz_den, const double* logz_num, int n_seq, int64_t row_elems,
+                    float* grad, void* stream);
+
 /* Split form, so that the numerator can run on a side stream while the denominator kernels run:
  * pk2_numfb_post computes log Z_num and the per-arc posteriors arc_post[A_tot] (no write to grad);
  * pk2_numfb_scatter adds deriv_scale * arc_post into grad afterwards (after pk2_denfb). */

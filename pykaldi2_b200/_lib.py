@@ -60,6 +60,7 @@ _SIGS = {
     "pk2_numfb": (C.c_int, [C.POINTER(SupBatch), vp, C.c_int, C.c_int64, C.c_float, vp, vp, vp, vp, vp]),
     "pk2_numfb_post": (C.c_int, [C.POINTER(SupBatch), vp, C.c_int, C.c_int64, vp, vp, vp, vp, vp]),
     "pk2_numfb_scatter": (C.c_int, [C.POINTER(SupBatch), C.c_int, vp, C.c_int, C.c_int64, C.c_float, vp, vp]),
+    "pk2_chain_guard": (C.c_int, [vp, vp, C.c_int, C.c_int64, vp, vp]),
     "pk2_latfb_mmi": (C.c_int, [C.POINTER(LatBatch), vp, C.c_int, C.c_int, C.c_int64, C.c_float,
                                 C.c_float, vp, vp, vp, vp, vp]),
     "pk2_latfb_mpe": (C.c_int, [C.POINTER(LatBatch), vp, vp, vp, C.c_int, C.c_int, C.c_int64, C.c_float, C.c_float,

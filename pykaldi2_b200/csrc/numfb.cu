@@ -91,7 +91,26 @@ __global__ void num_scatter_kernel(pk2_sup_batch sup, int total_states, const fl
     }
 }
 
+// Kaldi's fallback for a sequence whose objective is not finite (chain-training.cc: derivatives <- 0): zero its
+// gradient rows on the device, without a host round trip.  Blocks of healthy sequences return at once.
+__global__ void chain_guard_kernel(const double* __restrict__ logz_den, const double* __restrict__ logz_num,
+                                   int64_t row_elems, float* __restrict__ grad) {
+    const int b = blockIdx.y;
+    if (isfinite(logz_den[b]) && isfinite(logz_num[b])) return;
+    float* g = grad + (int64_t)b * row_elems;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < row_elems; i += (int64_t)gridDim.x * blockDim.x) g[i] = 0.f;
+}
+
 }  // namespace
+
+extern "C" int pk2_chain_guard(const double* logz_den, const double* logz_num, int n_seq, int64_t row_elems,
+                               float* grad, void* stream) {
+    PK2_REQUIRE(logz_den && logz_num && grad, "pk2_chain_guard: null argument");
+    if (n_seq <= 0 || row_elems <= 0) return 0;
+    chain_guard_kernel<<<dim3(32, n_seq), 256, 0, pk2::as_stream(stream)>>>(logz_den, logz_num, row_elems, grad);
+    PK2_POST_LAUNCH();
+    return 0;
+}
 
 extern "C" int pk2_numfb_post(const pk2_sup_batch* sup, const float* loglikes, int num_pdfs, int64_t row_stride_b,
                               double* ws_alpha, double* ws_beta, float* arc_post, double* logz, void* stream) {

@@ -10,7 +10,9 @@ the T x N matrix (ops/ops.py:55,64,255,261,269,271), no PyKaldi -- the forward-b
 runs in libpk2.so on the tensor's own device memory and stream.
 
 ``apply_batch`` entry points process a whole padded minibatch [B, Tmax, N] in one C-ABI
-call; the per-utterance form is the same code with B = 1.
+call; the per-utterance form is the same code with B = 1.  ``ChainObjtiveFunction.apply_batch`` returns its
+0-dim loss on the prediction's device and does not synchronise the host (the per-utterance forms keep the
+reference's 0-dim CPU tensor).
 There is no CPU fallback: CPU tensors raise.
 """
 import numpy as np
@@ -93,12 +95,12 @@ def chain_objf_and_deriv(prediction, den_graph, sup_batch, chain_opts, cluster=0
     scale = -float(w) * (1.0 + float(chain_opts.xent_regularize))
     _lib.check(L.pk2_numfb_scatter(sup_batch.struct, sup_batch.total_states, _lib.ptr(arc_post), N, Tmax, scale,
                                    _lib.ptr(grad), _lib.stream()), "pk2_numfb_scatter")
+    # Kaldi's fallback for a non-finite objective (derivs <- 0, objf <- -10 * weight * T), on the device: no host
+    # synchronisation between the loss kernels and the backward pass
+    _lib.check(L.pk2_chain_guard(_lib.ptr(logz[0]), _lib.ptr(logz[1]), B, Tmax * N, _lib.ptr(grad), _lib.stream()),
+               "pk2_chain_guard")
     objf = w * (logz[1] - logz[0])
-    bad = ~th.isfinite(objf)
-    if bool(bad.any()):            # Kaldi's fallback: derivs <- 0, objf <- -10 * weight * T
-        frames = nf.to(th.float64)
-        objf = th.where(bad, -10.0 * w * frames, objf)
-        grad[bad] = 0.0
+    objf = th.where(th.isfinite(objf), objf, -10.0 * w * nf.to(th.float64))
     return objf, grad
 
 
@@ -107,7 +109,9 @@ class _ChainBatch(Function):
     def forward(ctx, prediction, den_graph, sup_batch, chain_opts):
         objf, grad = chain_objf_and_deriv(prediction.detach(), den_graph, sup_batch, chain_opts)
         ctx.save_for_backward(grad)
-        return th.tensor(float(objf.sum().item()))
+        # 0-dim tensor on the prediction's device (the per-utterance ChainObjtiveFunction.apply keeps the reference's
+        # CPU scalar): reading it back here would stall the host between the loss kernels and the backward pass
+        return objf.sum().to(th.float32)
 
     @staticmethod
     def backward(ctx, grad_out):
