@@ -93,8 +93,18 @@ def main():
     # the silence list from <den_dir>/phones/silence.csl (bin/train_se.py:147-162)
     tid2phone = np.where(tid2pdf >= 0, tid2pdf // 3 + 1, 0).astype(np.int32)
     trans_model = graphs.TidPdfMap(tid2pdf, tid2phone)
+    if args.trans_model:                    # a Kaldi transition model in text form (copy-transition-model --binary=false)
+        trans_model = graphs.TidPdfMap.from_kaldi_text(args.trans_model)
+        if trans_model.num_pdfs() > N:
+            raise SystemExit("%s: the transition model has %d pdfs, the network %d outputs" % (args.trans_model, trans_model.num_pdfs(), N))
     args.silence_ids = [int(i) for i in args.silence_phones.strip().split(':')]
     log_prior = th.from_numpy(synth.make_log_prior(N, rng)).to(dev)
+    if args.prior_path:                     # final.occs in text form: log(occs / sum(occs)), bin/train_se.py:183-184
+        from pykaldi2_b200.reader import kaldi_io
+        lp = kaldi_io.log_prior_from_occs(args.prior_path)
+        if len(lp) != N:
+            raise SystemExit("%s: %d priors for %d network outputs" % (args.prior_path, len(lp), N))
+        log_prior = th.from_numpy(lp).to(dev)
     asr_decoder = graphs.SyntheticLatticeProvider()
 
     model.train()

@@ -281,6 +281,14 @@ class TidPdfMap(object):
         if self.tid2phone is not None and len(self.tid2phone) != len(self.tid2pdf):
             raise ValueError("tid2phone and tid2pdf must have one entry per transition id (index 0 unused)")
 
+    @classmethod
+    def from_kaldi_text(cls, path):
+        """From a text-form Kaldi transition model (``copy-transition-model --binary=false final.mdl -``);
+        the reference reads the binary model through PyKaldi (bin/train_se.py:164-170)."""
+        from .reader import kaldi_io
+        tm = kaldi_io.read_transition_model_text(path)
+        return cls(tm["tid2pdf"], tm["tid2phone"])
+
     def transition_id_to_pdf(self, tid):
         return int(self.tid2pdf[tid])
 

@@ -343,3 +343,64 @@ def test_den_schedule_host_planner():
         if (~single).sum() >= 3 * ncl:
             assert loads.max() <= 1.06 * loads.mean()                    # LPT + local search: within a few percent
     assert L.pk2_den_plan(None, 4, 2, 0, None) == -1
+
+
+KALDI_TM_TEXT = """<TransitionModel>
+<Topology>
+<TopologyEntry>
+<ForPhones>
+2 3
+</ForPhones>
+<State> 0 <PdfClass> 0 <Transition> 0 0.75 <Transition> 1 0.25 </State>
+<State> 1 <PdfClass> 1 <Transition> 1 0.75 <Transition> 2 0.25 </State>
+<State> 2 </State>
+</TopologyEntry>
+<TopologyEntry>
+<ForPhones>
+1
+</ForPhones>
+<State> 0 <PdfClass> 0 <Transition> 0 0.5 <Transition> 1 0.25 <Transition> 2 0.25 </State>
+<State> 1 <PdfClass> 1 <Transition> 1 0.5 <Transition> 2 0.5 </State>
+<State> 2 </State>
+</TopologyEntry>
+</Topology>
+<Triples> 6
+1 0 0
+1 1 1
+2 0 2
+2 1 3
+3 0 2
+3 1 4
+</Triples>
+<LogProbs>
+ [ 0 -0.69 -1.38 -1.38 -0.69 -0.69 -0.28 -1.38 -0.28 -1.38 -0.28 -1.38 -0.28 -1.38 ]
+</LogProbs>
+</TransitionModel>
+"""
+
+
+def test_kaldi_text_transition_model_and_occs(tmp_path):
+    """Transition ids as Kaldi's ComputeDerived enumerates them: tuples in order, one id per topology transition."""
+    from pykaldi2_b200 import graphs
+    from pykaldi2_b200.reader import kaldi_io
+    tm = kaldi_io.read_transition_model_text(KALDI_TM_TEXT)
+    #            tid:  1  2  3 | 4  5 | 6  7 | 8  9 | 10 11 | 12 13
+    assert list(tm["tid2pdf"]) == [-1, 0, 0, 0, 1, 1, 2, 2, 3, 3, 2, 2, 4, 4]
+    assert list(tm["tid2phone"]) == [0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3]
+    assert tm["num_pdfs"] == 5 and tm["phones"] == [1, 2, 3]
+    path = os.path.join(tmp_path, "final.mdl.txt")
+    with open(path, "w") as f:
+        f.write(KALDI_TM_TEXT)
+    t = graphs.TidPdfMap.from_kaldi_text(path)
+    assert t.num_transition_ids() == 13 and t.transition_id_to_pdf(9) == 3 and t.transition_id_to_phone(12) == 3
+    # newer models: <Tuples> with a separate self-loop pdf
+    tup = KALDI_TM_TEXT.replace("<Triples> 6", "<Tuples> 6").replace("</Triples>", "</Tuples>")
+    tup = re.sub(r"^(\d) (\d) (\d)$", lambda m: "%s %s %s %d" % (m.group(1), m.group(2), m.group(3), int(m.group(3)) + 10), tup, flags=re.M)
+    tm2 = kaldi_io.read_transition_model_text(tup)
+    assert list(tm2["tid2pdf"][1:6]) == [10, 0, 0, 11, 1]      # self-loop transitions take the self-loop pdf
+    with open(os.path.join(tmp_path, "bin.mdl"), "wb") as f:
+        f.write(b"\0B<TransitionModel>")
+    with pytest.raises(ValueError, match="binary"):
+        kaldi_io.read_transition_model_text(os.path.join(tmp_path, "bin.mdl"))
+    lp = kaldi_io.log_prior_from_occs(" [ 1 3 4 ]\n")
+    np.testing.assert_allclose(np.exp(lp), [0.125, 0.375, 0.5], rtol=1e-6)
