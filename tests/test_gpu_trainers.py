@@ -68,6 +68,23 @@ def test_train_se_synthetic(tmp_path):
     out2 = run("train_se.py", ["-exp_dir", str(tmp_path), "-config", "configs/ce_test.yaml", "-batch_size", "2",
                                "-synthetic", "2", "-print_freq", "1", "-max_steps", "1", "-batched_loss", "0"], tmp_path)
     assert "Epoch: [0]" in out2
+    # transition model / priors from Kaldi text files (-trans_model, -prior_path) instead of the synthetic maps:
+    # one emitting state with a self-loop and a forward transition per pdf gives the ids 2p+1, 2p+2 the synthetic
+    # alignments use
+    N = 104
+    mdl = ["<TransitionModel>", "<Topology>", "<TopologyEntry>", "<ForPhones>", " ".join(str(i) for i in range(1, N // 3 + 2)),
+           "</ForPhones>", "<State> 0 <PdfClass> 0 <Transition> 0 0.5 <Transition> 1 0.5 </State>", "<State> 1 </State>",
+           "</TopologyEntry>", "</Topology>", "<Triples> %d" % N] + ["%d 0 %d" % (p // 3 + 1, p) for p in range(N)] + \
+          ["</Triples>", "<LogProbs>", " [ 0 " + " ".join(["-0.69"] * (2 * N)) + " ]", "</LogProbs>", "</TransitionModel>"]
+    with open(os.path.join(tmp_path, "final.mdl.txt"), "w") as f:
+        f.write("\n".join(mdl) + "\n")
+    with open(os.path.join(tmp_path, "final.occs.txt"), "w") as f:
+        f.write(" [ " + " ".join(str(10 + (i % 7)) for i in range(N)) + " ]\n")
+    out4 = run("train_se.py", ["-exp_dir", str(tmp_path), "-config", "configs/ce_test.yaml", "-batch_size", "2",
+                               "-synthetic", "2", "-print_freq", "1", "-max_steps", "1", "-criterion", "smbr",
+                               "-trans_model", os.path.join(tmp_path, "final.mdl.txt"),
+                               "-prior_path", os.path.join(tmp_path, "final.occs.txt")], tmp_path)
+    assert "Epoch: [0]" in out4
     # -criterion switch (reference bin/train_se.py:62,216-219), the reference's per-utterance calling pattern
     out3 = run("train_se.py", ["-exp_dir", str(tmp_path), "-config", "configs/ce_test.yaml", "-batch_size", "2",
                                "-synthetic", "2", "-print_freq", "1", "-max_steps", "1", "-criterion", "mpfe",
