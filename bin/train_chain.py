@@ -5,8 +5,10 @@ Same flags as the reference script (bin/train_chain.py:60-83).  The loop body is
 subsampling with the epoch-dependent shift, model forward, the chain objective per utterance
 (``ops.ChainObjtiveFunction``), Noam learning rate, clip, Adam(amsgrad), rank-0 checkpoints
 ``chain.model.<i>.tar``.  ``-synthetic N`` supplies N seeded utterances, a synthetic denominator FST
-(``-den_states``) and synthetic time-constrained numerator FSTs: the reference builds those from Kaldi
-assets (den.fst, 0.trans_mdl, tree, alignments; :167-202,262-272), which is SURVEY.md row 8f-2.
+(``-den_states``) and synthetic time-constrained numerator FSTs.  Without it the corpus of ``-data`` (zip of wavs +
+pdf-id label file) is read, ``-den_fst`` takes Kaldi's den.fst (OpenFst binary or fstprint text) and the numerator
+graph of an utterance is built from its pdf alignment with a boundary tolerance (``-tolerance``); the reference's
+phone-level proto-supervision (0.trans_mdl, tree; :167-202,262-272) needs Kaldi's tree / topology.
 ``-per_utt_loss 1`` keeps the reference's one-call-per-utterance loop; the default batches the B
 calls into one C-ABI call (identical numbers, tests/test_gpu_fb.py).
 """
@@ -22,6 +24,7 @@ import _common
 from _common import pkdist
 from pykaldi2_b200 import graphs, pipeline, synth
 from pykaldi2_b200.data.dataloader import SyntheticWaveDataset, WaveDataloader
+from pykaldi2_b200.data.speech_dataset import SpeechDataset
 from pykaldi2_b200.models import lstm
 from pykaldi2_b200.ops import ops
 from pykaldi2_b200.utils import utils
@@ -63,6 +66,7 @@ def main():
     parser.add_argument('-print_freq', default=10, type=int, metavar='N', help='print frequency (default: 10)')
     parser.add_argument('-save_freq', default=1000, type=int, metavar='N', help='save model frequency (default: 1000)')
     parser.add_argument('-synthetic', default=0, type=int, help="train on this many seeded synthetic utterances")
+    parser.add_argument('-tolerance', default=2, type=int, help="boundary tolerance (output frames) of the alignment-derived numerator graphs")
     parser.add_argument('-den_fst', default='', type=str, help="denominator FST file (OpenFst binary vector/standard or fstprint text); default: synthetic")
     parser.add_argument('-den_states', default=8192, type=int, help="states of the synthetic denominator FST")
     parser.add_argument('-per_utt_loss', default=0, type=int, help="1 = one chain-objective call per utterance as the reference does")
@@ -82,10 +86,15 @@ def main():
     dev = th.device("cuda", local)
     os.makedirs(args.exp_dir, exist_ok=True)
     mc, dc = config["model_config"], config["data_config"]
-    if args.synthetic <= 0:
-        raise SystemExit("train_chain.py: only -synthetic data is wired in this build (Kaldi assets: SURVEY.md 8f-2)")
-
-    dataset = SyntheticWaveDataset(args.synthetic, mc["label_size"])
+    if args.synthetic > 0:
+        dataset = SyntheticWaveDataset(args.synthetic, mc["label_size"])
+    else:
+        # corpus in the reference's formats (zip of wavs + pdf-id label file, -data); the numerator graph of an utterance
+        # is built from its pdf alignment with a boundary tolerance (synth.alignment_to_supervision_fst) -- the
+        # reference's phone-level proto-supervision needs Kaldi's tree / topology
+        dataset = SpeechDataset(config)
+        if not args.den_fst:
+            print("WARNING: no -den_fst given: training against a synthetic denominator graph")
     loader = WaveDataloader(dataset, args.batch_size, num_workers=args.data_loader_threads, distributed=world > 1)
     feat = pipeline.FeaturePipeline(use_cmn=dc.get("use_cmn", True))
     print("Data loader set up successfully!")
@@ -127,14 +136,22 @@ def run_train_epoch(model, optimizer, averager, feat, loader, epoch, supervision
     for i, batch in enumerate(loader):
         wav, woff, foff = feat.ex.pack(batch["wav"])
         shift = epoch % factor                      # frame_shift = -(epoch % 3); x = roll(x, shift, 1)
-        x, num_frs = feat.sequence_batch(wav, woff, foff, factor=factor, shift=shift)
+        n_fr = None
+        if args.synthetic <= 0:                     # label trim (data/sr_dataset.py:358-363)
+            n_fr = [min(int(foff[u + 1] - foff[u]), len(l)) for u, l in enumerate(batch["label"])]
+        x, num_frs = feat.sequence_batch(wav, woff, foff, factor=factor, shift=shift, n_frames=n_fr)
         # numerator graphs: the reference derives them from the alignment (bin/train_chain.py:262-272);
         # synthetic stand-in, seeded per utterance
         sups = []
         for j, ids in enumerate(batch["utt_ids"]):
             t_sub = (int(num_frs[j]) - 1) // factor + 1
-            rng = np.random.default_rng(zlib.crc32(ids[0].encode()))
-            sups.append(graphs.Supervision(synth.make_supervision_fst(t_sub, den.num_pdfs(), rng), t_sub, den.num_pdfs()))
+            if args.synthetic > 0:
+                rng = np.random.default_rng(zlib.crc32(ids[0].encode()))
+                sup_fst = synth.make_supervision_fst(t_sub, den.num_pdfs(), rng)
+            else:
+                sup_fst = synth.alignment_to_supervision_fst(batch["label"][j][:, 0], factor, shift,
+                                                             slack=args.tolerance, n_out=t_sub)
+            sups.append(graphs.Supervision(sup_fst, t_sub, den.num_pdfs()))
         prediction = model(x)
         if args.per_utt_loss:
             loss = 0.0

@@ -75,6 +75,15 @@ def make_supervision_fst(T, num_pdfs, rng, slack=2, min_dur=2, max_dur=8):
         durs[-1] += T - sum(durs)
     K = len(durs)
     pdfs = rng.integers(0, num_pdfs, size=K)
+    return segments_to_supervision_fst(pdfs, durs, T, slack)
+
+
+def segments_to_supervision_fst(pdfs, durs, T, slack=2):
+    """Numerator FST of a segmentation: segment k carries pdf ``pdfs[k]`` for nominally ``durs[k]`` frames
+    (sum(durs) == T); every boundary may move by +-slack frames.  See make_supervision_fst for the state layout."""
+    T = int(T)
+    K = len(durs)
+    pdfs = np.asarray(pdfs)
     ends = np.cumsum(durs)                  # nominal end frame (exclusive) of segment k
     # segment k may be active at frame t iff start_k - slack <= t < end_k + slack
     starts = np.concatenate([[0], ends[:-1]])
@@ -115,6 +124,25 @@ def make_supervision_fst(T, num_pdfs, rng, slack=2, min_dur=2, max_dur=8):
     fst["final"][final_id] = 0.0
     fst["state_times"] = np.asarray([t for (t, k) in sid] + [T], np.int32)
     return _trim(fst)
+
+
+def alignment_to_supervision_fst(pdf_ali, factor=3, shift=0, slack=2, n_out=None):
+    """Numerator FST from a frame-level pdf alignment: the alignment is subsampled like the features
+    (frames shift, shift + factor, ...: bin/train_chain.py:251-255), run-length encoded into segments, and every
+    segment boundary may move by +-slack output frames.  A stand-in for the reference's
+    alignment -> phone/durations -> proto-supervision (tolerance) -> pdf FST chain (bin/train_chain.py:262-272), which
+    needs Kaldi's tree and topology: the time tolerance is applied at the pdf level instead of the phone level."""
+    ali = np.asarray(pdf_ali).reshape(-1)[shift::factor]
+    if n_out is not None:
+        ali = ali[:n_out]
+        if len(ali) < n_out:                # features may be a frame or two longer than the labels
+            ali = np.concatenate([ali, np.full(n_out - len(ali), ali[-1], ali.dtype)])
+    if len(ali) == 0:
+        raise ValueError("empty alignment")
+    change = np.flatnonzero(np.diff(ali)) + 1
+    starts = np.concatenate([[0], change])
+    durs = np.diff(np.concatenate([starts, [len(ali)]])).tolist()
+    return segments_to_supervision_fst(ali[starts].astype(np.int64), durs, len(ali), slack)
 
 
 def _trim(fst):

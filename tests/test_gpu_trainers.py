@@ -104,3 +104,11 @@ def test_trainers_on_zip_corpus(tmp_path):
     out = run("train_se.py", ["-exp_dir", str(tmp_path), "-config", "configs/ce_test.yaml", "-data", data_yaml,
                               "-batch_size", "2", "-print_freq", "1", "-max_steps", "1"], tmp_path)
     assert "Epoch: [0]" in out
+    # LF-MMI on the same corpus: denominator graph from a file, numerator graphs from the pdf alignments
+    from pykaldi2_b200 import synth
+    from pykaldi2_b200.reader import fst_io
+    den_path = os.path.join(tmp_path, "den.fst")
+    fst_io.write_fst_binary(synth.make_den_fst(256, 104, 7, seed=1234), den_path)
+    out = run("train_chain.py", ["-exp_dir", str(tmp_path), "-config", "configs/ce_test.yaml", "-data", data_yaml,
+                                 "-den_fst", den_path, "-batch_size", "2", "-print_freq", "1", "-max_steps", "2"], tmp_path)
+    assert out.count("Epoch: [0]") >= 2

@@ -404,3 +404,38 @@ def test_kaldi_text_transition_model_and_occs(tmp_path):
         kaldi_io.read_transition_model_text(os.path.join(tmp_path, "bin.mdl"))
     lp = kaldi_io.log_prior_from_occs(" [ 1 3 4 ]\n")
     np.testing.assert_allclose(np.exp(lp), [0.125, 0.375, 0.5], rtol=1e-6)
+
+
+def test_alignment_to_supervision_fst():
+    """Numerator graph from a frame-level pdf alignment (train_chain.py on a real corpus): the subsampled alignment
+    is a path of the FST, every path has T' labels, boundaries move by at most the tolerance."""
+    from oracle import chain_ref
+    from pykaldi2_b200 import graphs, synth
+    rng = np.random.default_rng(2)
+    ali = np.repeat(rng.integers(0, 40, 12), rng.integers(3, 15, 12))
+    for factor, shift, slack in ((3, 0, 2), (3, 1, 1), (1, 0, 0)):
+        sub = ali[shift::factor]
+        fst = synth.alignment_to_supervision_fst(ali, factor, shift, slack)
+        T = len(sub)
+        st = fst["state_times"]
+        assert (np.diff(st) >= 0).all() and st[-1] == T and np.isfinite(fst["final"]).sum() == 1
+        assert (st[fst["dst"]] == st[fst["src"]] + 1).all()                      # every arc advances one frame
+        # the alignment itself is accepted: follow it greedily through the FST
+        out = [[] for _ in range(fst["num_states"])]
+        for s, d, l in zip(fst["src"], fst["dst"], fst["ilabel"]):
+            out[s].append((int(d), int(l) - 1))
+        cur = {int(fst["start"])}
+        for t in range(T):
+            cur = {d for s in cur for d, p in out[s] if p == sub[t]}
+            assert cur, "alignment path lost at frame %d" % t
+        assert any(np.isfinite(fst["final"][s]) for s in cur)
+        if slack == 0:                                                           # no tolerance: exactly one path
+            assert len(fst["src"]) == T
+        sup = graphs.Supervision(fst, T, 40)
+        assert sup.frames_per_sequence == T
+        ll = rng.normal(0, 1, (T, 40))
+        logz = chain_ref.num_fb_log(ll, fst)[0]
+        assert np.isfinite(logz)
+    # labels shorter than the features: padded with the last label
+    f2 = synth.alignment_to_supervision_fst(ali[:30], 3, 0, 2, n_out=12)
+    assert f2["state_times"][-1] == 12
