@@ -180,7 +180,7 @@ def run_reference(args, rank):
         "unit": "hours audio per hour", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BLSTM 3x512 LF-MMI chain, batch 64 var-len utts, S=8192 den FST (C4)",
+        "config": {"workload": "BLSTM 3x512 LF-MMI chain, batch 64 var-len utts/GPU, S=8192 den FST (C4)",
                    "sample": "4 shortest utterances of the batch per step"},
         "cpu_baseline": {"value": irtf, "unit": "hours audio per hour", "cores": cores, "kind": "port",
                          "sample": "4 shortest utterances of the 64-utt batch: numpy fbank+CMN, torch-CPU nn.LSTM+Linear "
