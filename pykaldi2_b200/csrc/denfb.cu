@@ -1894,7 +1894,11 @@ extern "C" int pk2_denfb(void* graph, const float* loglikes, const int32_t* num_
                     pool.resize(n_seq);
                     for (int i = 0; i < n_seq; ++i) pool[i] = i;
                 }
-                const int ncl = std::min((int)pool.size(), g->reg->max_clusters);
+                int ncl = std::min((int)pool.size(), g->reg->max_clusters);
+                {   // experiments only (tools/exp_two_microbatches.py): leave SMs to kernels of other streams
+                    static const int cap = []() { const char* e = getenv("PK2_DEN_MAX_CLUSTERS"); return e ? atoi(e) : 0; }();
+                    if (cap > 0) ncl = std::min(ncl, cap);
+                }
                 std::vector<int32_t> work;
                 plan_work(num_frames_h, pool, ncl, &work);
                 if (getenv("PK2_DEN_VERBOSE")) {
