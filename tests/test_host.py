@@ -439,3 +439,36 @@ def test_alignment_to_supervision_fst():
     # labels shorter than the features: padded with the last label
     f2 = synth.alignment_to_supervision_fst(ali[:30], 3, 0, 2, n_out=12)
     assert f2["state_times"][-1] == 12
+
+
+def test_ingestion_directory_source_and_resampling(tmp_path):
+    """Directory corpora (no zip), several sources, and the resampling branch of the wav reader."""
+    from pykaldi2_b200.data.speech_dataset import SpeechDataset
+    from pykaldi2_b200.reader import zip_io
+    rng = np.random.default_rng(4)
+    srcs = []
+    for k in range(2):
+        d = os.path.join(tmp_path, "corpus%d" % k, "spk")
+        os.makedirs(d)
+        lab = os.path.join(tmp_path, "lab%d.txt" % k)
+        with open(lab, "w") as f:
+            for i in range(2):
+                utt = "u%d-%d" % (k, i)
+                zip_io.write_wav(os.path.join(d, utt + ".wav"), 0.1 * rng.standard_normal(8000))
+                f.write(utt + " " + " ".join(str(j % 7) for j in range(40)) + "\n")
+        srcs.append({"type": "Any", "wav": os.path.join(tmp_path, "corpus%d" % k), "label": lab})
+    ds = SpeechDataset({"source_paths": srcs, "data_config": {}})
+    assert len(ds) == 4 and sorted(ds[i][1][0] for i in range(4)) == ["u0-0", "u0-1", "u1-0", "u1-1"]
+    wav, _, pdf, tid = ds[0]
+    assert wav.shape == (8000,) and pdf.shape == (40, 1) and tid is None          # no aux_label given
+    assert len(SpeechDataset({"source_paths": srcs, "sweep_size": 0.005})) == 1   # sweep_size (hours) caps the epoch
+    # 8 kHz file read by a 16 kHz reader: polyphase resampling doubles the length
+    p8 = os.path.join(tmp_path, "eight.wav")
+    t = np.arange(4000) / 8000.0
+    zip_io.write_wav(p8, 0.5 * np.sin(2 * np.pi * 440 * t), fs=8000)
+    fs, x = zip_io.ZipWaveIO("float32", 16000).read_wav(p8)
+    assert fs == 16000 and abs(len(x) - 8000) <= 1
+    ref = 0.5 * np.sin(2 * np.pi * 440 * np.arange(len(x)) / 16000.0)
+    assert np.abs(x[200:-200] - ref[200:-200]).max() < 2e-2
+    with pytest.raises(ValueError):
+        SpeechDataset({"source_paths": []})
