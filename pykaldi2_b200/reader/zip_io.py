@@ -13,7 +13,6 @@ waveforms go to the GPU fbank as they are, no feature extraction happens on the 
 rejected with a clear error (no decoder in the image); a sample rate other than the target is resampled with
 scipy's polyphase filter (the reference uses resampy: not bit-identical, LibriSpeech never takes this branch).
 """
-import io
 import os
 import struct
 import zipfile

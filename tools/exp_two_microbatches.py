@@ -15,7 +15,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench
 from pykaldi2_b200 import graphs, pipeline, synth
-from pykaldi2_b200.data import fbank as fb
 from pykaldi2_b200.models.lstm import LSTMAM
 from pykaldi2_b200.ops import ops
 
