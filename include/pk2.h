@@ -203,6 +203,13 @@ int pk2_lstm_set_profile_buffer(void* buf);
  * Returns the largest cluster load in frames, -1 on bad arguments. */
 long long pk2_den_plan(const int32_t* frames_h, int n_seq, int n_clusters, int spare_sms, int32_t* assign_h);
 
+/* SM budget of later pk2_denfb calls on this graph (register-resident path): at most `max_clusters` resident
+ * clusters of 8 CTAs (0 = as many as fit) and `reserve_sms` SMs kept free of single-CTA kernels, so that kernels of
+ * OTHER streams (the 16-CTA BLSTM recurrence clusters of the other half-batch, pipeline.chain_step_overlapped) can
+ * run next to the denominator.  No reference counterpart: Kaldi's chain computation owns the GPU
+ * (reference ops/ops.py:255-269 is a blocking call). */
+int pk2_den_set_sm_budget(void* graph, int max_clusters, int reserve_sms);
+
 /* profiling aid: device int64[128]; frames 64..71 of the first cluster of every pk2_denfb launch stamp clock64()
  * at 7 points of the forward ([0,64)) and backward ([64,128)) frame loop; NULL = off */
 int pk2_den_set_profile_buffer(void* buf);

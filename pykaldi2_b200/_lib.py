@@ -77,6 +77,7 @@ _SIGS = {
     "pk2_lstm_set_profile_buffer": (C.c_int, [vp]),
     "pk2_den_set_profile_buffer": (C.c_int, [vp]),
     "pk2_den_plan": (C.c_longlong, [vp, C.c_int, C.c_int, C.c_int, vp]),
+    "pk2_den_set_sm_budget": (C.c_int, [vp, C.c_int, C.c_int]),
     "pk2_lstm_layer_bwd": (C.c_int, [C.POINTER(LstmBwdArgs), vp]),
 }
 

@@ -222,6 +222,8 @@ struct DenGraph {
     RegSmemHost* reg = nullptr;
     cudaStream_t side[2] = {nullptr, nullptr};     // side streams for the mixed-cluster schedule
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    int budget_clusters = 0;         // pk2_den_set_sm_budget: cap on resident clusters of 8 (0 = all that fit)
+    int budget_reserve = 0;          //                        SMs left to kernels of other streams
 };
 
 // ---------------------------------------------------------------- device helpers ----
@@ -1814,6 +1816,15 @@ extern "C" long long pk2_den_plan(const int32_t* frames, int n_seq, int n_cluste
     return worst;
 }
 
+extern "C" int pk2_den_set_sm_budget(void* graph, int max_clusters, int reserve_sms) {
+    PK2_REQUIRE(graph && max_clusters >= 0 && reserve_sms >= 0, "pk2_den_set_sm_budget: bad argument");
+    DenGraph* g = static_cast<DenGraph*>(graph);
+    std::lock_guard<std::mutex> launch_lock(g->launch_mu);
+    g->budget_clusters = max_clusters;
+    g->budget_reserve = reserve_sms;
+    return 0;
+}
+
 extern "C" int pk2_den_set_profile_buffer(void* buf) {
     g_den_prof = static_cast<long long*>(buf);
     return 0;
@@ -1886,19 +1897,17 @@ extern "C" int pk2_denfb(void* graph, const float* loglikes, const int32_t* num_
                 static const bool hyb_off = []() { const char* e = getenv("PK2_DEN_HYBRID"); return e && atoi(e) == 0; }();
                 std::vector<int> pool, single;
                 // 8 of the spare SMs are left to the numerator kernel that runs next to this call (ops.py)
-                const int spare = sms - kRK * g->reg->max_clusters - 8;
-                if (cluster == 0 && !hyb_off && num_frames_h && spare > 0 && n_seq > g->reg->max_clusters &&
+                int max_cl = g->reg->max_clusters;
+                if (g->budget_clusters > 0) max_cl = std::min(max_cl, g->budget_clusters);
+                const int spare = sms - kRK * max_cl - 8 - g->budget_reserve;
+                if (cluster == 0 && !hyb_off && num_frames_h && spare > 0 && n_seq > max_cl &&
                     fwd_smem_bytes(g->S, g->N, 1) <= 227 * 1024 && bwd_smem_bytes(g->S, g->N, 1) <= 227 * 1024) {
-                    plan_hybrid(num_frames_h, n_seq, g->reg->max_clusters, spare, &pool, &single);
+                    plan_hybrid(num_frames_h, n_seq, max_cl, spare, &pool, &single);
                 } else {
                     pool.resize(n_seq);
                     for (int i = 0; i < n_seq; ++i) pool[i] = i;
                 }
-                int ncl = std::min((int)pool.size(), g->reg->max_clusters);
-                {   // experiments only (tools/exp_two_microbatches.py): leave SMs to kernels of other streams
-                    static const int cap = []() { const char* e = getenv("PK2_DEN_MAX_CLUSTERS"); return e ? atoi(e) : 0; }();
-                    if (cap > 0) ncl = std::min(ncl, cap);
-                }
+                const int ncl = std::min((int)pool.size(), max_cl);
                 std::vector<int32_t> work;
                 plan_work(num_frames_h, pool, ncl, &work);
                 if (getenv("PK2_DEN_VERBOSE")) {

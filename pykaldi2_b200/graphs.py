@@ -110,6 +110,13 @@ class DenominatorGraph(object):
     def handle(self):
         return self._handle
 
+    def set_sm_budget(self, max_clusters=0, reserve_sms=0):
+        """Limit later forward-backward calls on this graph to ``max_clusters`` resident clusters of 8 CTAs
+        (0 = all that fit) and keep ``reserve_sms`` SMs free of single-CTA kernels, for callers that run
+        other kernels next to the denominator (pipeline.chain_step_overlapped)."""
+        _lib.check(_lib.lib().pk2_den_set_sm_budget(self._handle, int(max_clusters), int(reserve_sms)),
+                   "pk2_den_set_sm_budget")
+
     def __del__(self):
         try:
             if self._handle:

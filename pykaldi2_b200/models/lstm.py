@@ -21,6 +21,21 @@ from torch.autograd import Function
 from .. import _lib
 
 
+# Scheduling hooks for multi-stream callers (pipeline.chain_step_overlapped): optional callables invoked on the host
+# just BEFORE a launch is enqueued.  "fwd_recurrence_next": the first layer's recurrence kernel of a forward pass
+# comes next in the current stream; "bwd_recurrence_next": the top layer's backward recurrence kernel does.  A caller
+# records an event there (it completes when the preceding GEMM has finished, i.e. when the recurrence kernel starts)
+# so that kernels of another stream which would take all SMs (the denominator clusters) are held back until the
+# 16-CTA LSTM clusters, which need whole GPCs, have been placed.
+HOOKS = {}
+
+
+def _hook(name):
+    fn = HOOKS.get(name)
+    if fn is not None:
+        fn()
+
+
 def _pad8(n):
     return (n + 7) // 8 * 8
 
@@ -77,6 +92,8 @@ class _BlstmAM(Function):
             sync = th.empty(2 * ((B + 31) // 32), dtype=th.int32, device=dev)
             a = _lib.LstmFwdArgs(B, T, H, gx.data_ptr(), whh_p.data_ptr(), y.data_ptr(), gates.data_ptr(),
                                  cstate.data_ptr(), sync.data_ptr())
+            if l == 0:
+                _hook("fwd_recurrence_next")
             _lib.check(lib.pk2_lstm_layer_fwd(C.byref(a), _lib.stream()), "pk2_lstm_layer_fwd")
             saved["xin"].append(xin); saved["y"].append(y); saved["gates"].append(gates); saved["cstate"].append(cstate)
             if training and dropout_p > 0 and l < L - 1:
@@ -161,6 +178,8 @@ class _BlstmAM(Function):
             sync = th.empty(2 * ((B + 31) // 32), dtype=th.int32, device=dev)
             a = _lib.LstmBwdArgs(B, T, H, dy.data_ptr(), whh_t.data_ptr(), saved["gates"][l].data_ptr(),
                                  saved["cstate"][l].data_ptr(), dgates.data_ptr(), sync.data_ptr(), whh_tp.data_ptr())
+            if l == L - 1:
+                _hook("bwd_recurrence_next")
             _lib.check(lib.pk2_lstm_layer_bwd(C.byref(a), _lib.stream()), "pk2_lstm_layer_bwd")
             if pending is not None:               # gradients of the layer above: overlap with this recurrence
                 on_side(*pending)
@@ -204,8 +223,10 @@ class _BlstmAM(Function):
                 t.record_stream(main)
             grads[8 * l + 0] = d_wih[:4 * H]; grads[8 * l + 4] = d_wih[4 * H:]
             grads[8 * l + 1] = d_whh[0]; grads[8 * l + 5] = d_whh[1]
-            grads[8 * l + 2] = d_b[:4 * H]; grads[8 * l + 3] = d_b[:4 * H]
-            grads[8 * l + 6] = d_b[4 * H:]; grads[8 * l + 7] = d_b[4 * H:]
+            # bias_ih and bias_hh receive the same values but must not share storage: AccumulateGrad keeps the
+            # tensor it is handed, and in-place clipping would then scale the shared buffer once per parameter
+            grads[8 * l + 2] = d_b[:4 * H]; grads[8 * l + 3] = d_b[:4 * H].clone()
+            grads[8 * l + 6] = d_b[4 * H:]; grads[8 * l + 7] = d_b[4 * H:].clone()
         ctx.saved = None
         return (None, None, None, None, None, d_w_out, d_b_out) + tuple(grads)
 

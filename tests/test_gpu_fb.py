@@ -232,6 +232,38 @@ def test_denfb_full_size_properties(dev):
     np.testing.assert_allclose(objf2.cpu().numpy(), o1, rtol=1e-4, atol=1e-3)
 
 
+@pytest.mark.parametrize("cluster", [0, 8, 4, 1])
+def test_chain_full_size_vs_oracle(dev, cluster):
+    """BASELINE config 4 sizes (S = 8192, N = 5768, mean out-degree 8) against the fp64 oracle: objective and
+    derivatives of every sequence.  26 sequences of 30..150 frames: with cluster = 0 the automatic schedule puts the
+    long ones on clusters of 8 (register-resident arcs, two rows per thread) and the short ones on single-CTA
+    kernels; 8 / 4 / 1 force the register-resident, the 4-CTA streaming and the 1-CTA streaming kernels."""
+    from oracle import chain_ref
+    from pykaldi2_b200 import graphs, synth
+    from pykaldi2_b200.ops import ops
+    N, S = 5768, 8192
+    rng = np.random.default_rng(4321)
+    fst = synth.make_den_fst(S, N, 7, seed=1234)
+    den = graphs.DenominatorGraph(fst, N)
+    oden = chain_ref.den_graph_from_fst(fst, N)
+    for k in ("fwd_off", "fwd_pdf", "fwd_state", "bwd_off", "bwd_pdf", "bwd_state"):
+        assert (getattr(den, k) == oden[k]).all(), k
+    assert (den.fwd_prob == oden["fwd_prob"]).all() and (den.initial_probs == oden["initial_probs"]).all()
+    Ts = [150, 30] + [int(t) for t in rng.integers(30, 151, size=24)]
+    sup_fsts = [synth.make_supervision_fst(T, N, rng) for T in Ts]
+    sups = [graphs.Supervision(f, T, N) for f, T in zip(sup_fsts, Ts)]
+    sb = graphs.SupervisionBatch(sups, device=dev)
+    opts = graphs.ChainTrainingOptions(leaky_hmm_coefficient=1e-4, xent_regularize=0.0)
+    pred = rng.normal(0, 2.0, (len(Ts), max(Ts), N)).astype(np.float32)
+    objf, grad = ops.chain_objf_and_deriv(torch.from_numpy(pred).to(dev), den, sb, opts, cluster=cluster)
+    objf, grad = objf.cpu().numpy(), grad.cpu().numpy()
+    for b, T in enumerate(Ts):
+        o, g, _ = chain_ref.chain_objf_and_deriv(pred[b, :T], oden, sup_fsts[b], leaky=1e-4)
+        np.testing.assert_allclose(objf[b], o, rtol=1e-3, err_msg="sequence %d (T=%d)" % (b, T))
+        np.testing.assert_allclose(grad[b, :T], -g, rtol=1e-3, atol=2e-6, err_msg="sequence %d (T=%d)" % (b, T))
+        assert (grad[b, T:] == 0).all()
+
+
 def test_denfb_full_size_hybrid_schedule_matches_streaming(dev):
     """BASELINE config 4 graph, more sequences than resident clusters: the automatic schedule (clusters of 8 with
     work lists + single-CTA kernels on the spare SMs) against the streaming 4-CTA kernels."""
@@ -381,3 +413,59 @@ def test_smbr_function_reference_call_pattern(dev):
     loss2.backward()
     np.testing.assert_allclose(loss2.item(), loss.item(), rtol=1e-6)
     np.testing.assert_allclose(logits2.grad.cpu().numpy(), logits.grad.cpu().numpy(), rtol=1e-5, atol=1e-7)
+
+
+# ------------------------------------------------- lattice kernels at BASELINE config 3 scale ----
+def _c3_lattices(rng, N, Ts, eps):
+    from pykaldi2_b200 import graphs, synth
+    lats, alis, olat = [], [], []
+    for T in Ts:
+        lat, tid2pdf, ali = synth.make_lattice(T, N, rng, kmin=32, kmax=96, ali_drop=0.05, eps_frac=eps)
+        olat.append(lat); alis.append(ali); lats.append(graphs.Lattice(lat))
+    return lats, alis, olat, tid2pdf
+
+
+@pytest.mark.parametrize("eps", [0.0, 0.05])
+def test_lattice_mmi_c3_scale_vs_oracle(dev, eps):
+    """SURVEY 8d C3 shape: N = 5768, T >= 600, K_t ~ U{32..96} states per frame (about 250 arcs per frame), 5 % of
+    the frames without the alignment arc (drop_frames), optional 5 % epsilon arcs."""
+    from oracle import lattice_ref
+    from pykaldi2_b200 import graphs
+    from pykaldi2_b200.ops import ops
+    rng = np.random.default_rng(31)
+    N, Ts = 5768, [640, 905]
+    lats, alis, olat, tid2pdf = _c3_lattices(rng, N, Ts, eps)
+    pred = rng.normal(0, 3.0, (len(Ts), max(Ts), N)).astype(np.float32)
+    lb = graphs.LatticeBatch(lats, tid2pdf, alis, device=dev)
+    tot, grad = ops.lattice_mmi(torch.from_numpy(pred).to(dev), lb)
+    tot, grad = tot.cpu().numpy(), grad.cpu().numpy()
+    for b, T in enumerate(Ts):
+        rtot, post, drop, times = lattice_ref.lattice_fb_mmi(pred[b, :T], olat[b], tid2pdf, alis[b])
+        assert (lats[b].state_times_orig == times).all()
+        assert (lb.keep_host[b] == (~drop).astype(np.uint8)).all()
+        assert drop.any() and not drop.all()
+        np.testing.assert_allclose(tot[b], rtot, rtol=1e-6)
+        np.testing.assert_allclose(grad[b, :T], -post, rtol=1e-3, atol=1e-6)
+        assert (grad[b, T:] == 0).all()
+
+
+@pytest.mark.parametrize("criterion,eps", [("smbr", 0.0), ("smbr", 0.05), ("mpfe", 0.05)])
+def test_lattice_mpe_c3_scale_vs_oracle(dev, criterion, eps):
+    from oracle import lattice_ref
+    from pykaldi2_b200 import graphs
+    from pykaldi2_b200.ops import ops
+    rng = np.random.default_rng(37)
+    N, Ts = 5768, [600, 811]
+    lats, alis, olat, tid2pdf = _c3_lattices(rng, N, Ts, eps)
+    tid2phone = np.where(np.asarray(tid2pdf) >= 0, np.asarray(tid2pdf) // 40 + 1, 0)
+    sil = [1, 2]
+    pred = rng.normal(0, 1.0, (len(Ts), max(Ts), N)).astype(np.float32)
+    lb = graphs.LatticeBatch(lats, tid2pdf, alis, device=dev, mpe=(criterion, tid2phone, sil))
+    score, grad, tot = ops.lattice_mpe(torch.from_numpy(pred).to(dev), lb)
+    score, grad, tot = score.cpu().numpy(), grad.cpu().numpy(), tot.cpu().numpy()
+    for b, T in enumerate(Ts):
+        rs, post, rtot = lattice_ref.lattice_fb_mpe(pred[b, :T], olat[b], tid2pdf, tid2phone, alis[b], criterion, sil)
+        np.testing.assert_allclose(tot[b], rtot, rtol=1e-6)
+        np.testing.assert_allclose(score[b], rs, rtol=1e-5)
+        np.testing.assert_allclose(grad[b, :T], -post, rtol=1e-3, atol=1e-6)
+        assert (grad[b, T:] == 0).all()

@@ -1,13 +1,18 @@
 #!/usr/bin/env python
-"""EXPERIMENT (not measured yet): split the batch of one LF-MMI step into the shorter and
-the longer half and run them as two micro-batches on two CUDA streams, so that the denominator forward-backward of
-the short half (needs many SMs) overlaps the BLSTM recurrence of the long half (64 -> 32 CTAs, latency-bound) and the
-backward recurrence of the short half overlaps the denominator of the long half.  Gradients of the two halves
-accumulate into .grad; one optimizer step per 64 utterances, i.e. the same update as the single-batch step up to
-summation order.  Prints ms per step of the baseline (pipeline.chain_step) and of the two-stream variant.
+"""EXPERIMENT: run one LF-MMI step as two half-batches on two CUDA
+streams so that the denominator forward-backward of one half (wants many SMs) runs next to the BLSTM recurrence of
+the other half (2 clusters of 16 CTAs, latency-bound).
 
-Knobs to try with it: PK2_DEN_MAX_CLUSTERS (cap on resident denominator clusters, leaves SMs for the other stream's
-persistent GEMM CTAs and 16-CTA LSTM clusters), PK2_DEN_HYBRID=0.
+  baseline            pipeline.chain_step (one batch of 64)
+  two_streams         round-1 sketch: halves padded to their OWN longest member (not the same update as the batch of
+                      64: the reference's BLSTM also runs over the padding, so the padding length changes the result)
+  stag:<full|own>:<clusters>:<reserve>
+                      staggered schedule, long half first: fwd A | den A || fwd B | bwd A || den B | bwd B, the
+                      denominator limited to <clusters> clusters of 8 and <reserve> SMs kept free; "full" pads both
+                      halves to the batch's longest utterance => gradients equal to the single-batch step up to the
+                      order of summation (checked and printed)
+
+Prints ms per step and, for every variant, the largest relative gradient difference to the baseline.
 """
 import json, os, sys
 import numpy as np, torch
@@ -15,6 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench
 from pykaldi2_b200 import graphs, pipeline, synth
+from pykaldi2_b200.models import lstm as lstm_mod
 from pykaldi2_b200.models.lstm import LSTMAM
 from pykaldi2_b200.ops import ops
 
@@ -26,7 +32,8 @@ sups = [graphs.Supervision(f, t, bench.N_PDF) for f, t in zip(sup_fsts, sub)]
 torch.manual_seed(0)
 model = LSTMAM(bench.FEAT, bench.N_PDF, bench.HID, bench.LAYERS, 0.0, True).to(dev)
 model.train()
-opt = torch.optim.Adam(model.parameters(), lr=1e-4, amsgrad=True)
+params = list(model.parameters())
+opt = torch.optim.Adam(params, lr=1e-4, amsgrad=True)
 feat = pipeline.FeaturePipeline(use_cmn=True)
 wav_pinned, woff, foff = feat.ex.pack(wavs)
 wav = wav_pinned.to(dev)
@@ -40,35 +47,96 @@ t_half = [max((frames[i] - 1) // 3 + 1 for i in h) for h in halves]  # output fr
 streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
 
 
-def step_baseline():
-    return pipeline.chain_step(model, opt, None, feat, den, opts, wav, woff, foff, sb_all, epoch=0)
+def grads_baseline():
+    x, lens = feat.sequence_batch(wav, woff, foff, factor=3, shift=0)
+    loss = ops.ChainObjtiveFunction.apply_batch(model(x), den, sb_all, opts)
+    return loss, torch.autograd.grad(loss, params)
 
 
-def step_two_streams():
+def grads_two_streams():
     main = torch.cuda.current_stream(dev)
     x, lens = feat.sequence_batch(wav, woff, foff, factor=3, shift=0)        # [B, Tmax', 80]
     ready = torch.cuda.Event(); ready.record(main)
-    xs = []
+    xs, preds, losses, gs = [], [None, None], [None, None], [None, None]
     for k in (0, 1):
         streams[k].wait_event(ready)
         with torch.cuda.stream(streams[k]):
-            xk = x.index_select(0, idx_half[k])[:, :t_half[k]].contiguous()
+            xs.append(x.index_select(0, idx_half[k])[:, :t_half[k]].contiguous())
             x.record_stream(streams[k])
-            xs.append(xk)
-    preds, losses = [None, None], [None, None]
     with torch.cuda.stream(streams[1]):                                      # long half first: it is the critical path
         preds[1] = model(xs[1])
     with torch.cuda.stream(streams[0]):
         preds[0] = model(xs[0])
         losses[0] = ops.ChainObjtiveFunction.apply_batch(preds[0], den, sb_half[0], opts)
-        losses[0].backward()
+        gs[0] = torch.autograd.grad(losses[0], params)
     with torch.cuda.stream(streams[1]):
         losses[1] = ops.ChainObjtiveFunction.apply_batch(preds[1], den, sb_half[1], opts)
-        streams[1].wait_stream(streams[0])                                   # .grad of the short half is complete
-        losses[1].backward()
+        gs[1] = torch.autograd.grad(losses[1], params)
     main.wait_stream(streams[0]); main.wait_stream(streams[1])
+    for g in gs[0] + gs[1]:
+        g.record_stream(main)
+    torch._foreach_add_(list(gs[0]), list(gs[1]))
+    return losses[0] + losses[1], gs[0]
+
+
+def make_staggered(fullpad, clusters, reserve):
+    def run():
+        main = torch.cuda.current_stream(dev)
+        sA, sB = streams
+        x, lens = feat.sequence_batch(wav, woff, foff, factor=3, shift=0)
+        Tfull = x.shape[1]
+        ready = torch.cuda.Event(); ready.record(main)
+        A, B = 1, 0                                                           # long half first
+        tA = Tfull if fullpad else t_half[A]
+        tB = Tfull if fullpad else t_half[B]
+        ev = {}
+
+        def mark(name):
+            def fn():
+                e = torch.cuda.Event(); e.record(torch.cuda.current_stream(dev)); ev[name] = e
+            return fn
+        den.set_sm_budget(clusters, reserve)
+        try:
+            sA.wait_event(ready); sB.wait_event(ready)
+            x.record_stream(sA); x.record_stream(sB)
+            with torch.cuda.stream(sA):
+                xA = x.index_select(0, idx_half[A])[:, :tA].contiguous()
+                predA = model(xA)
+                mark("fwdA")()
+            with torch.cuda.stream(sB):
+                xB = x.index_select(0, idx_half[B])[:, :tB].contiguous()
+                sB.wait_event(ev["fwdA"])
+                lstm_mod.HOOKS["fwd_recurrence_next"] = mark("recB")
+                predB = model(xB)
+                lstm_mod.HOOKS.pop("fwd_recurrence_next")
+            with torch.cuda.stream(sA):
+                sA.wait_event(ev["recB"])                                     # B's LSTM clusters are placed first
+                lossA = ops.ChainObjtiveFunction.apply_batch(predA, den, sb_half[A], opts)
+                lstm_mod.HOOKS["bwd_recurrence_next"] = mark("brecA")
+                gA = torch.autograd.grad(lossA, params)
+                lstm_mod.HOOKS.pop("bwd_recurrence_next")
+            with torch.cuda.stream(sB):
+                sB.wait_event(ev["brecA"])                                    # A's backward clusters are placed first
+                lossB = ops.ChainObjtiveFunction.apply_batch(predB, den, sb_half[B], opts)
+                gB = torch.autograd.grad(lossB, params)
+        finally:
+            lstm_mod.HOOKS.clear()
+            den.set_sm_budget(0, 0)
+        main.wait_stream(sA); main.wait_stream(sB)
+        for g in gA + gB:
+            g.record_stream(main)
+        lossB = lossB.clone(); lossB.record_stream(main)
+        torch._foreach_add_(list(gA), list(gB))
+        return lossA + lossB, gA
+    return run
+
+
+def full_step(gfn):
+    loss, gs = gfn()
+    for p, g in zip(params, gs):
+        p.grad = g
     pipeline.finish_step(model, opt, None, 5.0)
-    return float(losses[0].item()) + float(losses[1].item())
+    return float(loss.item())
 
 
 def timeit(fn, steps=6, warm=3):
@@ -84,8 +152,27 @@ def timeit(fn, steps=6, warm=3):
     return e0.elapsed_time(e1) / steps, v
 
 
+def variant(name):
+    if name == "baseline":
+        return grads_baseline
+    if name == "two_streams":
+        return grads_two_streams
+    _, pad, cl, rs = name.split(":")
+    return make_staggered(pad == "full", int(cl), int(rs))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["baseline", "two_streams"]
+    which = sys.argv[1:] or ["baseline", "two_streams", "stag:full:12:32", "stag:full:0:0", "stag:own:12:32"]
+    state0 = {k: v.clone() for k, v in model.state_dict().items()}
+    _, gref = grads_baseline()
+    gref = [g.clone() for g in gref]
+    torch.cuda.synchronize()
     for w in which:
-        ms, v = timeit({"baseline": step_baseline, "two_streams": step_two_streams}[w])
-        print(json.dumps({"variant": w, "ms_per_step": round(ms, 3), "objf": v}), flush=True)
+        model.load_state_dict(state0)
+        gfn = variant(w)
+        _, gs = gfn()
+        torch.cuda.synchronize()
+        diff = max(float((a - b).norm() / (b.norm() + 1e-30)) for a, b in zip(gs, gref))
+        ms, v = timeit(lambda: full_step(gfn))
+        print(json.dumps({"variant": w, "ms_per_step": round(ms, 3), "objf": v, "max_rel_grad_diff_vs_baseline": diff}),
+              flush=True)

@@ -1,0 +1,23 @@
+#!/bin/bash
+# One gpurun call = several measurements, each under its own timeout, everything logged under gpurun_out/.
+#   tools/gpu_session.sh <tag> <step> [<step> ...]     steps: pytest kb:<which...> exp bench bench_ref launches
+set -u
+TAG=$1; shift
+OUT=gpurun_out
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $OUT/gpu_$TAG.txt 2>&1
+for step in "$@"; do
+  case "$step" in
+    pytest)      timeout 900 python -m pytest tests -m gpu -x -q -s > $OUT/pytest_$TAG.log 2>&1; echo "pytest rc=$?"; tail -5 $OUT/pytest_$TAG.log ;;
+    pytestall)   timeout 1200 python -m pytest tests -m gpu -q -s > $OUT/pytest_$TAG.log 2>&1; echo "pytest rc=$?"; tail -15 $OUT/pytest_$TAG.log ;;
+    pytest:*)    timeout 900 python -m pytest tests -m gpu -x -q -s -k "${step#pytest:}" > $OUT/pytest_$TAG.log 2>&1; echo "pytest rc=$?"; tail -5 $OUT/pytest_$TAG.log ;;
+    kb:*)        for w in $(echo "${step#kb:}" | tr ',' ' '); do timeout 600 python tools/kernel_bench.py $w >> $OUT/kb_$TAG.jsonl 2>> $OUT/kb_$TAG.err; done; cat $OUT/kb_$TAG.jsonl ;;
+    exp)         timeout 600 python tools/exp_two_microbatches.py > $OUT/exp2mb_$TAG.jsonl 2> $OUT/exp2mb_$TAG.err; cat $OUT/exp2mb_$TAG.jsonl; tail -3 $OUT/exp2mb_$TAG.err ;;
+    exp:*)       timeout 600 python tools/exp_two_microbatches.py $(echo "${step#exp:}" | tr ',' ' ') > $OUT/exp2mb_$TAG.jsonl 2> $OUT/exp2mb_$TAG.err; cat $OUT/exp2mb_$TAG.jsonl; tail -3 $OUT/exp2mb_$TAG.err ;;
+    bench)       timeout 600 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; cat $OUT/bench_$TAG.json; tail -3 $OUT/bench_$TAG.err ;;
+    bench_ref)   timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_${TAG}_reference.json 2> $OUT/bench_${TAG}_reference.err; cat $OUT/bench_${TAG}_reference.json ;;
+    launches)    timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $OUT/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/launches_$TAG.log 2>&1; echo "launches rc=$?" ;;
+    py:*)        timeout 900 python ${step#py:} > $OUT/py_$TAG.log 2>&1; echo "py rc=$?"; tail -30 $OUT/py_$TAG.log ;;
+    *)           echo "unknown step $step" ;;
+  esac
+done

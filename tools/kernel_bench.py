@@ -5,6 +5,7 @@
   python tools/kernel_bench.py lstm     # recurrent kernels: us per step, forward and backward
   python tools/kernel_bench.py gemm     # tcgen05 GEMM TFLOP/s on the model's shapes
   python tools/kernel_bench.py fbank    # fbank GB/s
+  python tools/kernel_bench.py cudnn    # the reference model on cuDNN/cuBLAS (fp32 / tf32 / bf16) vs LSTMAM, fwd and fwd+bwd
 Prints one JSON object per measurement (copied into profiles/ by hand).
 """
 import json
@@ -88,11 +89,62 @@ def bench_lstm():
                           "fwd_us_per_step_layer": 1e3 * mf / (3 * T), "train_TFLOPs": flops / mfb / 1e9}))
 
 
+def bench_cudnn():
+    """The bar SURVEY 2.3 sets for row a8: the reference model itself -- torch.nn.LSTM (cuDNN) + nn.Linear (cuBLAS),
+    reference models/lstm.py:46-58 with cudnn.benchmark as bin/train_ce.py:118 sets it -- on the same box and shapes,
+    fp32 (what the reference runs), fp32 with TF32 allowed, and bf16 parameters; next to this repo's LSTMAM."""
+    import torch.nn as nn
+    from pykaldi2_b200.models.lstm import LSTMAM
+    dev = torch.device("cuda", 0)
+    torch.backends.cudnn.benchmark = True
+
+    class Ref(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lstm = nn.LSTM(80, 512, 3, batch_first=True, dropout=0.0, bidirectional=True)
+            self.output_layer = nn.Linear(1024, 5768)
+
+        def forward(self, x):
+            return self.output_layer(self.lstm(x)[0])
+
+    for B, T in ((64, 882), (256, 80), (4, 1500)):
+        x = torch.randn(B, T, 80, device=dev)
+        g = torch.randn(B, T, 5768, device=dev) * 1e-3
+        rows = {}
+        for name in ("cudnn_fp32", "cudnn_tf32", "cudnn_bf16", "ours_bf16"):
+            torch.backends.cuda.matmul.allow_tf32 = name == "cudnn_tf32"
+            torch.backends.cudnn.allow_tf32 = name == "cudnn_tf32"
+            torch.manual_seed(0)
+            if name == "ours_bf16":
+                model, xx, gg = LSTMAM(80, 5768, 512, 3, 0.0, True).to(dev), x, g
+            elif name == "cudnn_bf16":
+                model, xx, gg = Ref().to(dev).to(torch.bfloat16), x.to(torch.bfloat16), g.to(torch.bfloat16)
+            else:
+                model, xx, gg = Ref().to(dev), x, g
+            model.train()
+
+            def fwd():
+                with torch.no_grad():
+                    model(xx)
+
+            def fwdbwd():
+                model(xx).backward(gg)
+                for p in model.parameters():
+                    p.grad = None
+            rows[name] = (timeit(fwd, 3, 2), timeit(fwdbwd, 3, 2))
+            del model
+        print(json.dumps({"kernel": "BLSTM 3x512 + Linear 5768", "B": B, "T": T,
+                          **{k + "_fwd_ms": round(v[0], 3) for k, v in rows.items()},
+                          **{k + "_fwd_bwd_ms": round(v[1], 3) for k, v in rows.items()},
+                          "speedup_vs_cudnn_fp32_fwd_bwd": round(rows["cudnn_fp32"][1] / rows["ours_bf16"][1], 2),
+                          "speedup_vs_cudnn_bf16_fwd_bwd": round(rows["cudnn_bf16"][1] / rows["ours_bf16"][1], 2)}), flush=True)
+
+
 def bench_gemm():
     from pykaldi2_b200.models import lstm as L
     dev = torch.device("cuda", 0)
     pk = peaks()
-    for M, N, K in ((57600, 4096, 1024), (57600, 5768, 1024), (57600, 1024, 5768), (4096, 1024, 57600),
+    for M, N, K in ((56448, 4096, 1024), (56448, 5768, 1024), (56448, 1024, 5768), (5768, 1024, 56448), (4096, 1024, 56448), (57600, 4096, 1024), (57600, 5768, 1024), (57600, 1024, 5768), (4096, 1024, 57600),
                     (5768, 1024, 57600), (2048, 512, 57600), (57600, 1024, 4096), (20480, 4096, 1024), (8192, 8192, 8192)):
         a = torch.randn(M, K, device=dev).to(torch.bfloat16)
         b = torch.randn(N, K, device=dev).to(torch.bfloat16)
@@ -137,4 +189,5 @@ def bench_ce():
 if __name__ == "__main__":
     which = sys.argv[1:] or ["den", "lstm", "gemm", "fbank"]
     for w in which:
-        {"den": bench_den, "lstm": bench_lstm, "gemm": bench_gemm, "fbank": bench_fbank, "ce": bench_ce}[w]()
+        {"den": bench_den, "lstm": bench_lstm, "gemm": bench_gemm, "fbank": bench_fbank, "ce": bench_ce,
+         "cudnn": bench_cudnn}[w]()
