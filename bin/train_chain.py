@@ -152,7 +152,7 @@ def run_train_epoch(model, optimizer, averager, feat, loader, epoch, supervision
                 sup_fst = synth.alignment_to_supervision_fst(batch["label"][j][:, 0], factor, shift,
                                                              slack=args.tolerance, n_out=t_sub)
             sups.append(graphs.Supervision(sup_fst, t_sub, den.num_pdfs()))
-        prediction = model(x)
+        prediction = model(x, valid_lengths=[s.frames_per_sequence for s in sups])   # no output layer on the padding
         if args.per_utt_loss:
             loss = 0.0
             for j, sup in enumerate(sups):

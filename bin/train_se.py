@@ -131,7 +131,7 @@ def run_train_epoch(model, optimizer, averager, feat, log_prior, loader, epoch, 
         for j, lab in enumerate(batch["label"]):
             y[j, :num_frs[j]] = lab[:num_frs[j], 0]
         y = th.from_numpy(y).cuda(non_blocking=True)
-        prediction = model(x)
+        prediction = model(x, valid_lengths=num_frs)          # padded frames: zero logits, ignored by both losses
         ce_loss = pipeline.ce_loss(prediction.view(-1, N), y.view(-1), reduction="sum")
         # synthetic decoding lattices around the alignment, seeded per utterance
         lats, alis = [], []

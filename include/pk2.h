@@ -178,6 +178,16 @@ int pk2_latfb_mpe(const pk2_lat_batch* lat, const uint8_t* acc_in, const uint8_t
 int pk2_gemm_set_max_ctas(int n);
 int pk2_gemm_bf16_nt(const void* A, const void* B, void* C, const float* bias,
                      int M, int N, int K, int lda, int ldb, int ldc, int flags, void* stream);
+/* Extended form.  flags bit2 (PK2_GEMM_TN): C[M,N] = At[K,M]^T * Bt[K,N] -- both operands are stored with the
+ * contraction index as the row (lda / ldb = row strides >= M / N) and are consumed in place through MN-major tcgen05
+ * descriptors: the weight gradients dW = dY^T X of nn.Linear / nn.LSTM backward (reference models/lstm.py:46-61 ->
+ * cuBLAS gemm with op(A) = T), whose operands are the activation matrices [frames, features] as they lie in memory.
+ * c_row_map (device int32[M], may be NULL): row r of the product goes to row c_row_map[r] of C -- the output layer is
+ * evaluated on the valid (unpadded) frames only and scattered back into the padded [B, Tmax, N] layout. */
+#define PK2_GEMM_BF16_OUT 2
+#define PK2_GEMM_TN 4
+int pk2_gemm_bf16_ex(const void* A, const void* B, void* C, const float* bias,
+                     int M, int N, int K, int lda, int ldb, int ldc, int flags, const int32_t* c_row_map, void* stream);
 
 /* x[B*T, I] (bf16, row stride ldx) * W_ih_cat[8H, I]^T + bias[8H] -> gx in the recurrent kernel's
  * layout [T][2][H/32][B][128] fp32 (128 = 4 gates x 32 units of one CTA).  W_ih_cat = [W_ih_fwd; W_ih_bwd],
@@ -233,6 +243,14 @@ int pk2_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
 int pk2_transpose_bf16(const void* src, int src_bf16, void* dst, int R, int C, int lds, int ldd, void* stream);
 /* hprevT[dir][j][b*T+t] = y[b][t -/+ 1][dir*H + j] (0 at the sequence boundary): the h_{t-1} operand of dW_hh */
 int pk2_lstm_hprev_t(const void* y, void* hprev_t, int B, int T, int H, int ldd, void* stream);
+/* hprev[b*T+t][dir*H + j] = y[b][t -/+ 1][dir*H + j] (0 at the sequence boundary), bf16 [B*T, 2H]: the h_{t-1} operand
+ * of dW_hh in the layout the TN GEMM consumes in place */
+int pk2_lstm_hprev(const void* y, void* hprev, int B, int T, int H, void* stream);
+/* dst[r, :] = bf16(src[rows[r], :]), src fp32 or bf16 [*, C] contiguous rows, rows device int32[R] or NULL (identity):
+ * compaction of the valid (unpadded) frames of dlogits / the top layer's output for the output-layer GEMMs */
+int pk2_gather_rows_bf16(const void* src, int src_bf16, const int32_t* rows, void* dst, int64_t R, int C, void* stream);
+/* zero rows t >= lengths[b] of p[B][T][row_bytes] (lengths device int32[B], row_bytes % 16 == 0) */
+int pk2_zero_pad_rows(void* p, const int32_t* lengths, int B, int T, int64_t row_bytes, void* stream);
 /* out[c] = sum_r src[r, c]  (bf16 src [R, C], fp32 out) */
 int pk2_colsum_bf16(const void* src, float* out, int64_t R, int C, void* stream);
 

@@ -67,11 +67,16 @@ _SIGS = {
                                 vp, C.c_int64, C.c_float, vp, vp, vp, vp]),
     "pk2_gemm_bf16_nt": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_int, vp]),
+    "pk2_gemm_bf16_ex": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, vp, vp]),
     "pk2_gemm_set_max_ctas": (C.c_int, [C.c_int]),
     "pk2_cast_bf16": (C.c_int, [vp, vp, C.c_int64, vp]),
     "pk2_transpose_bf16": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "pk2_lstm_hprev_t": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "pk2_colsum_bf16": (C.c_int, [vp, vp, C.c_int64, C.c_int, vp]),
+    "pk2_lstm_hprev": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "pk2_gather_rows_bf16": (C.c_int, [vp, C.c_int, vp, vp, C.c_int64, C.c_int, vp]),
+    "pk2_zero_pad_rows": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int64, vp]),
     "pk2_lstm_input_proj": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "pk2_lstm_layer_fwd": (C.c_int, [C.POINTER(LstmFwdArgs), vp]),
     "pk2_lstm_set_profile_buffer": (C.c_int, [vp]),
@@ -112,8 +117,15 @@ def ptr(t):
     """Device (or host) pointer of a tensor as c_void_p; None -> NULL."""
     if t is None:
         return vp(0)
+    if isinstance(t, vp):
+        return t
     assert t.is_contiguous(), "pk2: tensor must be contiguous"
     return vp(t.data_ptr())
+
+
+def ptr_at(t, elems):
+    """Pointer to element ``elems`` of a tensor's storage view (operand sub-matrices with a leading dimension)."""
+    return vp(t.data_ptr() + int(elems) * t.element_size())
 
 
 def stream():

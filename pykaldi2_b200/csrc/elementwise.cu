@@ -68,6 +68,56 @@ __global__ void hprev_t_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat1
     }
 }
 
+// hprev[b*T + t, dir*H + j] = y[b, t -/+ 1, dir*H + j] (0 at the sequence boundary); 8 bf16 per thread
+__global__ void hprev_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ out, int B, int T, int H) {
+    const int vec_per_row = 2 * H / 8;
+    const int64_t total = (int64_t)B * T * vec_per_row;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = i / vec_per_row;
+        const int c8 = (int)(i - m * vec_per_row);
+        const int b = (int)(m / T), t = (int)(m - (int64_t)b * T);
+        const int tp = (c8 * 8 >= H) ? t + 1 : t - 1;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (tp >= 0 && tp < T) v = reinterpret_cast<const uint4*>(y)[((int64_t)b * T + tp) * vec_per_row + c8];
+        reinterpret_cast<uint4*>(out)[i] = v;
+    }
+}
+
+// dst[r, :] = bf16(src[rows[r], :])   (rows == nullptr: identity); one warp-stride loop over 4-column groups
+template <bool SRC_BF16>
+__global__ void gather_rows_bf16_kernel(const void* __restrict__ src, const int32_t* __restrict__ rows,
+                                        __nv_bfloat16* __restrict__ dst, int64_t R, int C) {
+    const int c4n = C >> 2;
+    for (int64_t r = blockIdx.x; r < R; r += gridDim.x) {
+        const int64_t sr = rows ? (int64_t)__ldg(&rows[r]) : r;
+        if (SRC_BF16) {
+            const uint2* s2 = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(src) + sr * C);
+            uint2* d2 = reinterpret_cast<uint2*>(dst + r * C);
+            for (int c = threadIdx.x; c < c4n; c += blockDim.x) d2[c] = s2[c];
+        } else {
+            const float4* s4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + sr * C);
+            uint2* d2 = reinterpret_cast<uint2*>(dst + r * C);
+            for (int c = threadIdx.x; c < c4n; c += blockDim.x) {
+                const float4 v = s4[c];
+                __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+                uint2 o;
+                o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
+                d2[c] = o;
+            }
+        }
+    }
+}
+
+// zero rows t >= lengths[b] of a [B, T, row_bytes] tensor (row_bytes % 16 == 0)
+__global__ void zero_pad_rows_kernel(uint4* __restrict__ p, const int32_t* __restrict__ lengths, int T, int vec_per_row) {
+    const int b = blockIdx.y;
+    const int len = lengths[b];
+    for (int t = len + blockIdx.x; t < T; t += gridDim.x) {
+        uint4* row = p + ((int64_t)b * T + t) * vec_per_row;
+        for (int c = threadIdx.x; c < vec_per_row; c += blockDim.x) row[c] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
 __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ partial, int64_t R, int C,
                                    int rows_per_block) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -125,6 +175,41 @@ extern "C" int pk2_lstm_hprev_t(const void* y, void* hprev_t, int B, int T, int 
     PK2_REQUIRE(grid.y <= 65535, "pk2_lstm_hprev_t: too many rows (%d)", M);
     hprev_t_kernel<<<grid, block, 0, pk2::as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(y),
                                                             static_cast<__nv_bfloat16*>(hprev_t), B, T, H, ldd);
+    PK2_POST_LAUNCH();
+    return 0;
+}
+
+extern "C" int pk2_lstm_hprev(const void* y, void* hprev, int B, int T, int H, void* stream) {
+    PK2_REQUIRE(y && hprev, "pk2_lstm_hprev: null argument");
+    PK2_REQUIRE(H % 8 == 0 && B > 0 && T > 0, "pk2_lstm_hprev: H must be a multiple of 8");
+    hprev_kernel<<<148 * 8, 256, 0, pk2::as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(y),
+                                                            static_cast<__nv_bfloat16*>(hprev), B, T, H);
+    PK2_POST_LAUNCH();
+    return 0;
+}
+
+extern "C" int pk2_gather_rows_bf16(const void* src, int src_bf16, const int32_t* rows, void* dst, int64_t R, int C,
+                                    void* stream) {
+    PK2_REQUIRE(src && dst, "pk2_gather_rows_bf16: null argument");
+    if (R <= 0 || C <= 0) return 0;
+    PK2_REQUIRE(C % 4 == 0, "pk2_gather_rows_bf16: row length must be a multiple of 4 (got %d)", C);
+    PK2_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0,
+                "pk2_gather_rows_bf16: misaligned pointers");
+    const int grid = (int)(R < 148 * 16 ? R : 148 * 16);
+    const int threads = C >= 1024 ? 256 : 128;
+    if (src_bf16) gather_rows_bf16_kernel<true><<<grid, threads, 0, pk2::as_stream(stream)>>>(src, rows, static_cast<__nv_bfloat16*>(dst), R, C);
+    else gather_rows_bf16_kernel<false><<<grid, threads, 0, pk2::as_stream(stream)>>>(src, rows, static_cast<__nv_bfloat16*>(dst), R, C);
+    PK2_POST_LAUNCH();
+    return 0;
+}
+
+extern "C" int pk2_zero_pad_rows(void* p, const int32_t* lengths, int B, int T, int64_t row_bytes, void* stream) {
+    PK2_REQUIRE(p && lengths, "pk2_zero_pad_rows: null argument");
+    if (B <= 0 || T <= 0 || row_bytes <= 0) return 0;
+    PK2_REQUIRE(row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0, "pk2_zero_pad_rows: rows must be 16-byte multiples");
+    PK2_REQUIRE(B <= 65535, "pk2_zero_pad_rows: batch too large");
+    dim3 grid(T < 64 ? T : 64, B);
+    zero_pad_rows_kernel<<<grid, 256, 0, pk2::as_stream(stream)>>>(static_cast<uint4*>(p), lengths, T, (int)(row_bytes / 16));
     PK2_POST_LAUNCH();
     return 0;
 }

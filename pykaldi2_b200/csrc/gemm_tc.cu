@@ -1,6 +1,11 @@
 // bf16 GEMM on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), sm_100a.
 //
 //   C[M,N] = A[M,K] * B[N,K]^T (+ bias[N])     A, B bf16 row-major (K contiguous), fp32 accumulate
+//   C[M,N] = At[K,M]^T * Bt[K,N]               "TN" form (PK2_GEMM_TN): both operands stored with the contraction
+//                                              index as the ROW (M / N contiguous) and consumed in place through
+//                                              MN-major UMMA descriptors -- the weight gradients dW = dY^T X, whose
+//                                              operands are activations [frames, features]; no transposed copies
+//   optional c_row_map: row r of the product is stored to row c_row_map[r] of C (scatter of compacted rows)
 //
 // This is the dense contraction of the BLSTM acoustic model (reference models/lstm.py:46-61,
 // which reaches cuDNN/cuBLAS through nn.LSTM / nn.Linear): input projections X*W_ih^T,
@@ -56,11 +61,11 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int 
     *mt = b * band + (r - *nt * bs);
 }
 
-template <int CTAS>
+template <int CTAS, bool TN>
 __global__ void __launch_bounds__(CTAS == 2 ? kThreads2 : kThreads1, 1)
 gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     void* __restrict__ Cout, const float* __restrict__ bias, int M, int N, int K, int ldc,
-                    int c_bf16, int lstm_T, int lstm_B, int lstm_H, int splits) {
+                    int c_bf16, int lstm_T, int lstm_B, int lstm_H, int splits, const int32_t* __restrict__ c_row_map) {
     // splits > 1 (split-K): work item = (tile, K range); item s of a tile writes its fp32 partial product, plain
     // layout [M][N], to Cout + s*M*N (a workspace); splitk_reduce_kernel adds the partials in a fixed order.
     constexpr int kStages = CTAS == 2 ? 6 : 4;
@@ -121,12 +126,29 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         // bytes of both CTAs' loads are counted on the leader's barrier; the leader arms it
                         const uint32_t bar = mapa_u32(smem_u32(&bars->full[stage]), 0);
                         if (rank == 0) mbar_expect_tx(&bars->full[stage], 2 * kStageBytes);
-                        tma_load_2d_2sm(&map_a, bar, sa, kb * BK, m0);
-                        tma_load_2d_2sm(&map_b, bar, sa + kStageBytesA, kb * BK, n0 + rank * (BN / 2));
+                        if constexpr (TN) {
+                            // MN-major tiles: one box = 64 contiguous m (128 B swizzle row) x BK k-rows = 8 KB
+#pragma unroll
+                            for (int c = 0; c < BM / 64; ++c) tma_load_2d_2sm(&map_a, bar, sa + c * 8192, m0 + c * 64, kb * BK);
+#pragma unroll
+                            for (int c = 0; c < BN / 2 / 64; ++c)
+                                tma_load_2d_2sm(&map_b, bar, sa + kStageBytesA + c * 8192, n0 + rank * (BN / 2) + c * 64, kb * BK);
+                        } else {
+                            tma_load_2d_2sm(&map_a, bar, sa, kb * BK, m0);
+                            tma_load_2d_2sm(&map_b, bar, sa + kStageBytesA, kb * BK, n0 + rank * (BN / 2));
+                        }
                     } else {
                         mbar_expect_tx(&bars->full[stage], kStageBytes);
-                        tma_load_2d(&map_a, &bars->full[stage], sa, kb * BK, m0);
-                        tma_load_2d(&map_b, &bars->full[stage], sa + kStageBytesA, kb * BK, n0);
+                        if constexpr (TN) {
+#pragma unroll
+                            for (int c = 0; c < BM / 64; ++c) tma_load_2d(&map_a, &bars->full[stage], sa + c * 8192, m0 + c * 64, kb * BK);
+#pragma unroll
+                            for (int c = 0; c < BN / 64; ++c)
+                                tma_load_2d(&map_b, &bars->full[stage], sa + kStageBytesA + c * 8192, n0 + c * 64, kb * BK);
+                        } else {
+                            tma_load_2d(&map_a, &bars->full[stage], sa, kb * BK, m0);
+                            tma_load_2d(&map_b, &bars->full[stage], sa + kStageBytesA, kb * BK, n0);
+                        }
                     }
                 }
                 __syncwarp();
@@ -136,7 +158,10 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     } else if (warp == 1) {
         // ===== MMA issuer (pair: the leader CTA only) =====
         if (CTAS == 1 || rank == 0) {
-            constexpr uint32_t idesc = make_idesc(CTAS * BM, BN);
+            constexpr uint32_t idesc = make_idesc(CTAS * BM, BN) | (TN ? ((1u << 15) | (1u << 16)) : 0u);   // a_major / b_major = MN
+            // descriptor advance per K = 16 step, in 16-byte units: 32 B inside the swizzle row (K-major) or
+            // two 8-row groups of 1024 B (MN-major)
+            constexpr uint64_t kstep = TN ? 128 : 2;
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 if constexpr (CTAS == 2) mbar_wait_cluster(&bars->tmem_empty[acc], acc_phase ^ 1);
@@ -148,17 +173,16 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     mbar_wait(&bars->full[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-                    const uint64_t adesc = make_sw128_desc(sa);
-                    const uint64_t bdesc = make_sw128_desc(sa + kStageBytesA);
+                    const uint64_t adesc = TN ? make_sw128_mn_desc(sa, 8192, 1024) : make_sw128_desc(sa);
+                    const uint64_t bdesc = TN ? make_sw128_mn_desc(sa + kStageBytesA, 8192, 1024) : make_sw128_desc(sa + kStageBytesA);
                     if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
-                            // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in 16 B units
                             if constexpr (CTAS == 2)
-                                tc_mma_bf16_2cta(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                tc_mma_bf16_2cta(d_tmem, adesc + (uint64_t)k * kstep, bdesc + (uint64_t)k * kstep, idesc,
                                                  (uint32_t)(((kb - kb0) | k) != 0));
                             else
-                                tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                tc_mma_bf16(d_tmem, adesc + (uint64_t)k * kstep, bdesc + (uint64_t)k * kstep, idesc,
                                             (uint32_t)(((kb - kb0) | k) != 0));
                         }
                         // frees the smem slot (in both CTAs of a pair) when the MMAs retire
@@ -206,7 +230,7 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     // LSTM gate layout [T][2][H/32][B][128]: row = b*T + t
                     const int lb = rr / lstm_T, lt = rr - lb * lstm_T;
                     rowbase[i] = ((int64_t)lt * 2 * (lstm_H >> 5) * lstm_B + lb) * 128;
-                } else rowbase[i] = (int64_t)rr * ldc;
+                } else rowbase[i] = (int64_t)((c_row_map && splits == 1) ? __ldg(&c_row_map[rr]) : rr) * ldc;
             }
 #pragma unroll 1
             for (int c = c_begin; c < c_end; ++c) {
@@ -259,10 +283,11 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         }
                     }
                 } else if (row < M) {
+                    const int64_t orow = (c_row_map && splits == 1) ? __ldg(&c_row_map[row]) : row;
                     for (int j = 0; j < 32 && col0 + j < N; ++j) {
                         const float f = __uint_as_float(v[j]) + (bias ? __ldg(&bias[col0 + j]) : 0.f);
-                        if (c_bf16) reinterpret_cast<__nv_bfloat16*>(Cout_t)[(int64_t)row * ldc + col0 + j] = __float2bfloat16(f);
-                        else reinterpret_cast<float*>(Cout_t)[(int64_t)row * ldc + col0 + j] = f;
+                        if (c_bf16) reinterpret_cast<__nv_bfloat16*>(Cout_t)[orow * ldc + col0 + j] = __float2bfloat16(f);
+                        else reinterpret_cast<float*>(Cout_t)[orow * ldc + col0 + j] = f;
                     }
                 }
             }
@@ -288,12 +313,13 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
 // C[m, n] = sum_s partial[s][m][n] (+ bias[n]), fixed order; fp32 or bf16 output with leading dimension ldc
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int64_t MN, int N, const float* __restrict__ bias,
-                                     void* __restrict__ C, int ldc, int c_bf16) {
+                                     void* __restrict__ C, int ldc, int c_bf16, const int32_t* __restrict__ c_row_map) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < MN; i += (int64_t)gridDim.x * blockDim.x) {
         float acc = part[i];
         for (int s2 = 1; s2 < splits; ++s2) acc += part[(int64_t)s2 * MN + i];
-        const int64_t m = i / N;
+        int64_t m = i / N;
         const int n = (int)(i - m * N);
+        if (c_row_map) m = c_row_map[m];
         if (bias) acc += bias[n];
         if (c_bf16) reinterpret_cast<__nv_bfloat16*>(C)[m * ldc + n] = __float2bfloat16(acc);
         else reinterpret_cast<float*>(C)[m * ldc + n] = acc;
@@ -340,37 +366,16 @@ int g_num_sms = 0;
 thread_local int g_lstm_T = 0, g_lstm_B = 0, g_lstm_H = 0;
 thread_local int g_max_ctas = 0;      // 0 = all SMs; set to leave SMs to a concurrently running persistent kernel
 
-}  // namespace
-
-extern "C" int pk2_gemm_bf16_nt(const void* A, const void* B, void* C, const float* bias, int M, int N, int K,
-                                int lda, int ldb, int ldc, int flags, void* stream) {
-    PK2_REQUIRE(A && B && C, "pk2_gemm_bf16_nt: null argument");
-    PK2_REQUIRE(M > 0 && N > 0 && K > 0, "pk2_gemm_bf16_nt: empty problem %dx%dx%d", M, N, K);
-    PK2_REQUIRE((flags & 1) == 0, "pk2_gemm_bf16_nt: accumulate flag not supported");
-    PK2_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "pk2_gemm_bf16_nt: lda/ldb must be multiples of 8 elements (16 B)");
-    PK2_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
-                "pk2_gemm_bf16_nt: A/B must be 16-byte aligned");
-    CUtensorMap ma, mb;
-    if (make_map(&ma, A, M, K, lda, BM)) return 2;
-    if (make_map(&mb, B, N, K, ldb, BN)) return 2;
-    if (g_num_sms == 0) {
-        int dev = 0;
-        PK2_CHECK(cudaGetDevice(&dev));
-        PK2_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    // CTA pairs (256 x 256 tiles) unless the problem is a single row of tiles or PK2_GEMM_1CTA is set
-    static const bool force1 = getenv("PK2_GEMM_1CTA") != nullptr;
-    const bool pair = !force1 && M > BM && g_num_sms >= 2;
+template <bool TN>
+int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, bool pair, void* C, const float* bias,
+                int M, int N, int K, int ldc, int c_bf16, const int32_t* c_row_map, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        PK2_CHECK(cudaFuncSetAttribute(gemm_bf16_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        PK2_CHECK(cudaFuncSetAttribute(gemm_bf16_nt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        PK2_CHECK(cudaFuncSetAttribute(gemm_bf16_nt_kernel<1, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        PK2_CHECK(cudaFuncSetAttribute(gemm_bf16_nt_kernel<2, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         attr = true;
     }
-    const int c_bf16 = (flags >> 1) & 1;
     if (pair) {
-        CUtensorMap mb2;
-        if (make_map(&mb2, B, N, K, ldb, BN / 2)) return 2;
         constexpr int EWH = 8;
         const size_t smem = 6 * (kStageBytesA + (BN / 2) * BK * 2) + sizeof(PipeBars) + 16 + EWH * kEpiTile + 1024;
         const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
@@ -391,9 +396,9 @@ extern "C" int pk2_gemm_bf16_nt(const void* A, const void* B, void* C, const flo
         if (splits > 1) {
             const size_t need = (size_t)splits * M * N * sizeof(float);
             std::lock_guard<std::mutex> lk(g_split_mu);
-            SplitWs& w = g_split_ws[pk2::as_stream(stream)];
+            SplitWs& w = g_split_ws[st];
             if (need > w.bytes) {
-                if (w.ptr) { PK2_CHECK(cudaStreamSynchronize(pk2::as_stream(stream))); cudaFree(w.ptr); }
+                if (w.ptr) { PK2_CHECK(cudaStreamSynchronize(st)); cudaFree(w.ptr); }
                 PK2_CHECK(cudaMalloc(&w.ptr, need));
                 w.bytes = need;
             }
@@ -405,21 +410,22 @@ extern "C" int pk2_gemm_bf16_nt(const void* A, const void* B, void* C, const flo
         cfg.gridDim = dim3(2 * pairs);
         cfg.blockDim = dim3(kThreads2);
         cfg.dynamicSmemBytes = smem;
-        cfg.stream = pk2::as_stream(stream);
+        cfg.stream = st;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         if (splits > 1) {
-            PK2_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_nt_kernel<2>, ma, mb2, static_cast<void*>(ws),
-                                         static_cast<const float*>(nullptr), M, N, K, N, 0, 0, 0, 0, splits));
+            PK2_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_nt_kernel<2, TN>, ma, mb2, static_cast<void*>(ws),
+                                         static_cast<const float*>(nullptr), M, N, K, N, 0, 0, 0, 0, splits,
+                                         static_cast<const int32_t*>(nullptr)));
             PK2_LAUNCHED();
             const int64_t MN = (int64_t)M * N;
             const int rb = (int)((MN + 255) / 256 < 2048 ? (MN + 255) / 256 : 2048);
-            splitk_reduce_kernel<<<rb, 256, 0, pk2::as_stream(stream)>>>(ws, splits, MN, N, bias, C, ldc, c_bf16);
+            splitk_reduce_kernel<<<rb, 256, 0, st>>>(ws, splits, MN, N, bias, C, ldc, c_bf16, c_row_map);
         } else {
-            PK2_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_nt_kernel<2>, ma, mb2, C, bias, M, N, K, ldc, c_bf16,
-                                         (int)g_lstm_T, (int)g_lstm_B, (int)g_lstm_H, 1));
+            PK2_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_nt_kernel<2, TN>, ma, mb2, C, bias, M, N, K, ldc, c_bf16,
+                                         (int)g_lstm_T, (int)g_lstm_B, (int)g_lstm_H, 1, c_row_map));
         }
     } else {
         constexpr int EWH = 4;
@@ -427,11 +433,53 @@ extern "C" int pk2_gemm_bf16_nt(const void* A, const void* B, void* C, const flo
         const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
         int grid = tiles < g_num_sms ? tiles : g_num_sms;
         if (g_max_ctas > 0 && grid > g_max_ctas) grid = g_max_ctas;
-        gemm_bf16_nt_kernel<1><<<grid, kThreads1, smem, pk2::as_stream(stream)>>>(ma, mb, C, bias, M, N, K, ldc, c_bf16,
-                                                                                 g_lstm_T, g_lstm_B, g_lstm_H, 1);
+        gemm_bf16_nt_kernel<1, TN><<<grid, kThreads1, smem, st>>>(ma, mb, C, bias, M, N, K, ldc, c_bf16,
+                                                                  g_lstm_T, g_lstm_B, g_lstm_H, 1, c_row_map);
     }
     PK2_POST_LAUNCH();
     return 0;
+}
+
+}  // namespace
+
+extern "C" int pk2_gemm_bf16_ex(const void* A, const void* B, void* C, const float* bias, int M, int N, int K,
+                                int lda, int ldb, int ldc, int flags, const int32_t* c_row_map, void* stream) {
+    PK2_REQUIRE(A && B && C, "pk2_gemm_bf16: null argument");
+    PK2_REQUIRE(M > 0 && N > 0 && K > 0, "pk2_gemm_bf16: empty problem %dx%dx%d", M, N, K);
+    PK2_REQUIRE((flags & 1) == 0, "pk2_gemm_bf16: accumulate flag not supported");
+    PK2_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "pk2_gemm_bf16: lda/ldb must be multiples of 8 elements (16 B)");
+    PK2_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+                "pk2_gemm_bf16: A/B must be 16-byte aligned");
+    const bool tn = (flags & PK2_GEMM_TN) != 0;
+    PK2_REQUIRE(!tn || g_lstm_T == 0, "pk2_gemm_bf16: TN form has no LSTM gate-layout epilogue");
+    PK2_REQUIRE(!tn || (lda >= M && ldb >= N), "pk2_gemm_bf16: TN form needs lda >= M and ldb >= N (row strides of At[K,M], Bt[K,N])");
+    if (g_num_sms == 0) {
+        int dev = 0;
+        PK2_CHECK(cudaGetDevice(&dev));
+        PK2_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    // CTA pairs (256 x 256 tiles) unless the problem is a single row of tiles or PK2_GEMM_1CTA is set
+    static const bool force1 = getenv("PK2_GEMM_1CTA") != nullptr;
+    const bool pair = !force1 && M > BM && g_num_sms >= 2;
+    const int c_bf16 = (flags >> 1) & 1;
+    CUtensorMap ma, mb, mb2;
+    cudaStream_t st = pk2::as_stream(stream);
+    if (tn) {
+        // operands [K rows][M or N contiguous]: boxes of 64 contiguous elements x BK rows
+        if (make_map(&ma, A, K, M, lda, BK)) return 2;
+        if (make_map(&mb, B, K, N, ldb, BK)) return 2;
+        mb2 = mb;
+        return launch_gemm<true>(ma, mb, mb2, pair, C, bias, M, N, K, ldc, c_bf16, c_row_map, st);
+    }
+    if (make_map(&ma, A, M, K, lda, BM)) return 2;
+    if (make_map(&mb, B, N, K, ldb, BN)) return 2;
+    if (pair && make_map(&mb2, B, N, K, ldb, BN / 2)) return 2;
+    return launch_gemm<false>(ma, mb, mb2, pair, C, bias, M, N, K, ldc, c_bf16, c_row_map, st);
+}
+
+extern "C" int pk2_gemm_bf16_nt(const void* A, const void* B, void* C, const float* bias, int M, int N, int K,
+                                int lda, int ldb, int ldc, int flags, void* stream) {
+    return pk2_gemm_bf16_ex(A, B, C, bias, M, N, K, lda, ldb, ldc, flags & ~PK2_GEMM_TN, nullptr, stream);
 }
 
 // Cap the number of CTAs of subsequent GEMM launches from this thread (0 = no cap): used when weight-gradient

@@ -152,6 +152,19 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
+// MN-major, SWIZZLE_128B descriptor (cute make_umma_desc<Major::MN>, canonical layout in 16-byte units
+// ((8,n),(8,k)):((1,LBO),(8,SBO))): a swizzle atom is 8 k-rows x 128 B (64 contiguous M/N elements); LBO = byte
+// distance between 64-element M/N chunks, SBO = byte distance between 8-row k groups.  A TMA box of
+// [64 elements x R rows] with SWIZZLE_128B lands exactly in this layout with SBO = 1024.
+__device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32=1 [4,6) | a_format BF16=1 [7,10)
 // | b_format BF16=1 [10,13) | a_major K=0 [15] | b_major K=0 [16] | N>>3 [17,23) | M>>4 [24,29)
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {

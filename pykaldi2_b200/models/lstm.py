@@ -11,6 +11,15 @@ gradients, and the persistent tcgen05 recurrence kernels of csrc/blstm.cu.  Arit
 operands, fp32 accumulation, fp32 cell state, fp32 master weights (the reference is all-fp32 on
 cuDNN; parity budget 1e-3 relative on log-posteriors, see tests/test_gpu_blstm.py).
 No CPU fallback: CPU inputs raise.
+
+Three things keep the GEMM part of a step short:
+  * the bf16 / per-CTA-packed / transposed copies of the weights are cached on the module and rebuilt only when a
+    parameter changed (optimizer step, load_state_dict): one packing per step however many times forward runs;
+  * ``forward(data, valid_lengths=...)``: the output layer and its two gradient GEMMs run on the valid (unpadded)
+    frames only -- the logits of padded frames are never read by the sequence losses and their gradient is exactly
+    zero -- compacted by a row gather and scattered back by the GEMM epilogue; padded logit rows are zero;
+  * the weight gradients dW = dY^T X read dY and X where they lie (TN form of the tcgen05 GEMM, MN-major
+    descriptors): no transposed copies of the activations.
 """
 import ctypes as C
 
@@ -40,9 +49,13 @@ def _pad8(n):
     return (n + 7) // 8 * 8
 
 
-def _gemm(a, b, c, bias, M, N, K, lda, ldb, ldc, bf16_out=False):
-    _lib.check(_lib.lib().pk2_gemm_bf16_nt(_lib.ptr(a), _lib.ptr(b), _lib.ptr(c), _lib.ptr(bias), M, N, K,
-                                           lda, ldb, ldc, 2 if bf16_out else 0, _lib.stream()), "pk2_gemm_bf16_nt")
+TN_GEMM = True          # weight gradients through the TN form (False: transposed copies + NT form, the round-1 path)
+
+
+def _gemm(a, b, c, bias, M, N, K, lda, ldb, ldc, bf16_out=False, tn=False, row_map=None):
+    flags = (2 if bf16_out else 0) | (4 if tn else 0)
+    _lib.check(_lib.lib().pk2_gemm_bf16_ex(_lib.ptr(a), _lib.ptr(b), _lib.ptr(c), _lib.ptr(bias), M, N, K,
+                                           lda, ldb, ldc, flags, _lib.ptr(row_map), _lib.stream()), "pk2_gemm_bf16_ex")
 
 
 def _cast(src):
@@ -60,11 +73,48 @@ def _transpose(src, R, Cc, lds):
     return dst, ldd
 
 
+def _gather_rows(src, rows, R, Cc):
+    """bf16 [R, Cc] = src[rows] (src fp32 or bf16 [*, Cc]); rows None = all rows in order (a plain cast)."""
+    dst = th.empty(R, Cc, dtype=th.bfloat16, device=src.device)
+    _lib.check(_lib.lib().pk2_gather_rows_bf16(_lib.ptr(src), 1 if src.dtype == th.bfloat16 else 0, _lib.ptr(rows),
+                                               _lib.ptr(dst), R, Cc, _lib.stream()), "pk2_gather_rows_bf16")
+    return dst
+
+
+class _Packed(object):
+    """bf16 operand copies of the weights in the layouts the kernels read.  Built once per parameter version."""
+
+    def __init__(self, w_out, b_out, lstm_params, L, H):
+        self.layers = []
+        for l in range(L):
+            wih_f, whh_f, bih_f, bhh_f, wih_b, whh_b, bih_b, bhh_b = lstm_params[8 * l:8 * l + 8]
+            I = wih_f.shape[1]
+            d = {"I": I}
+            wih_cat32 = th.cat([wih_f, wih_b], 0).contiguous()                      # [8H, I]
+            d["wih_cat"] = _cast(wih_cat32)
+            d["bias_cat"] = th.cat([bih_f + bhh_f, bih_b + bhh_b], 0).contiguous()  # [8H] fp32
+            # recurrent weights packed per CTA: [dir][cta][gate][32][H]
+            whh = th.stack([whh_f, whh_b], 0).view(2, 4, H // 32, 32, H).permute(0, 2, 1, 3, 4).contiguous()
+            d["whh_p"] = _cast(whh.view(2 * 4 * H, H))
+            d["whh_t"] = _cast(th.cat([whh_f.t(), whh_b.t()], 0).contiguous())      # [2H, 4H]
+            # same matrix with the 4H index permuted to cta*128 + gate*32 + unit (cluster/DSMEM backward kernel)
+            d["whh_tp"] = _cast(whh.reshape(2, 4 * H, H).transpose(1, 2).reshape(2 * H, 4 * H).contiguous())
+            if l > 0:
+                d["wih_t"], d["ldk"] = _transpose(wih_cat32, 8 * H, I, I)           # [I, 8H]
+            self.layers.append(d)
+        w = w_out.contiguous()
+        self.w_out = _cast(w)                                                       # [N, 2H]
+        self.w_out_t, self.ldw = _transpose(w, w.shape[0], 2 * H, 2 * H)            # [2H, pad8(N)]
+        self.b_out = b_out.contiguous()
+        self.ready = th.cuda.Event()
+        self.ready.record(th.cuda.current_stream(w_out.device))
+
+
 class _BlstmAM(Function):
     """x[B,T,F] fp32 -> logits[B,T,N] fp32 through L bidirectional LSTM layers + Linear."""
 
     @staticmethod
-    def forward(ctx, x, num_layers, hidden, dropout_p, training, w_out, b_out, *lstm_params):
+    def forward(ctx, x, num_layers, hidden, dropout_p, training, packed, valid, w_out, b_out, *lstm_params):
         _lib.require_cuda(x, "x")
         L, H = num_layers, hidden
         B, T, F = x.shape
@@ -73,24 +123,20 @@ class _BlstmAM(Function):
         lib = _lib.lib()
         if F % 8 != 0:
             raise RuntimeError("feature dim must be a multiple of 8 (got %d)" % F)
+        th.cuda.current_stream(dev).wait_event(packed.ready)
         xin = _cast(x.contiguous().view(M, F))
-        saved = {"xin": [], "y": [], "gates": [], "cstate": [], "mask": [], "whh_t": [], "wih_t": []}
+        saved = {"xin": [], "y": [], "gates": [], "cstate": [], "mask": []}
         for l in range(L):
-            wih_f, whh_f, bih_f, bhh_f, wih_b, whh_b, bih_b, bhh_b = lstm_params[8 * l:8 * l + 8]
-            I = wih_f.shape[1]
-            wih_cat = _cast(th.cat([wih_f, wih_b], 0).contiguous())                 # [8H, I]
-            bias_cat = th.cat([bih_f + bhh_f, bih_b + bhh_b], 0).contiguous()       # [8H]
+            pk = packed.layers[l]
+            I = pk["I"]
             gx = th.empty(T, 2, H // 32, B, 128, dtype=th.float32, device=dev)
-            _lib.check(lib.pk2_lstm_input_proj(_lib.ptr(xin), _lib.ptr(wih_cat), _lib.ptr(bias_cat), _lib.ptr(gx),
+            _lib.check(lib.pk2_lstm_input_proj(_lib.ptr(xin), _lib.ptr(pk["wih_cat"]), _lib.ptr(pk["bias_cat"]), _lib.ptr(gx),
                                                B, T, I, H, I, _lib.stream()), "pk2_lstm_input_proj")
-            # recurrent weights packed per CTA: [dir][cta][gate][32][H]
-            whh = th.stack([whh_f, whh_b], 0).view(2, 4, H // 32, 32, H).permute(0, 2, 1, 3, 4).contiguous()
-            whh_p = _cast(whh.view(2 * 4 * H, H))
             y = th.empty(B, T, 2 * H, dtype=th.bfloat16, device=dev)
             gates = th.empty(2, T, B, 4, H, dtype=th.bfloat16, device=dev)
             cstate = th.empty(2, T, B, H, dtype=th.float32, device=dev)
             sync = th.empty(2 * ((B + 31) // 32), dtype=th.int32, device=dev)
-            a = _lib.LstmFwdArgs(B, T, H, gx.data_ptr(), whh_p.data_ptr(), y.data_ptr(), gates.data_ptr(),
+            a = _lib.LstmFwdArgs(B, T, H, gx.data_ptr(), pk["whh_p"].data_ptr(), y.data_ptr(), gates.data_ptr(),
                                  cstate.data_ptr(), sync.data_ptr())
             if l == 0:
                 _hook("fwd_recurrence_next")
@@ -104,26 +150,32 @@ class _BlstmAM(Function):
                 xin = y.view(M, 2 * H)
             saved["mask"].append(mask)
             del gx
-        N = w_out.shape[0]
-        w_out_bf = _cast(w_out.contiguous())
+        N = packed.w_out.shape[0]
         logits = th.empty(B, T, N, dtype=th.float32, device=dev)
-        _gemm(xin, w_out_bf, logits, b_out.contiguous(), M, N, 2 * H, 2 * H, 2 * H, N)
+        if valid is None:
+            top, Mv, rows = xin, M, None
+        else:
+            rows, lens_dev, Mv = valid
+            top = _gather_rows(xin, rows, Mv, 2 * H)                    # valid frames only, compact
+            _lib.check(lib.pk2_zero_pad_rows(_lib.ptr(logits), _lib.ptr(lens_dev), B, T, 4 * N, _lib.stream()),
+                       "pk2_zero_pad_rows")
+        _gemm(top, packed.w_out, logits, packed.b_out, Mv, N, 2 * H, 2 * H, 2 * H, N, row_map=rows)
         ctx.saved = saved
-        ctx.top_in = xin
-        ctx.dims = (B, T, F, L, H, N)
-        ctx.save_for_backward(w_out, *lstm_params)
+        ctx.top = top
+        ctx.rows = rows
+        ctx.packed = packed
+        ctx.dims = (B, T, F, L, H, N, Mv)
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
         """Backward pass.  The recurrence kernels of a layer own 64 of the 148 SMs for ~4 ms; the weight /
-        bias gradients of the layer ABOVE (transposes + K-long GEMMs, needed only by the optimizer) run on a
-        side stream on the remaining SMs meanwhile.  The recurrence is always launched first so that its
-        16-CTA clusters get whole GPCs; the side-stream GEMMs are capped to the SMs that are left."""
-        B, T, F, L, H, N = ctx.dims
+        bias gradients of the layer ABOVE (K-long TN GEMMs, needed only by the optimizer) run on a side stream on
+        the remaining SMs meanwhile.  The recurrence is always launched first so that its 16-CTA clusters get
+        whole GPCs; the side-stream GEMMs are capped to the SMs that are left."""
+        B, T, F, L, H, N, Mv = ctx.dims
         M = B * T
-        w_out, *lstm_params = ctx.saved_tensors
-        saved = ctx.saved
+        saved, packed, rows, top = ctx.saved, ctx.packed, ctx.rows, ctx.top
         dev = dlogits.device
         lib = _lib.lib()
         if N % 8 != 0:
@@ -147,37 +199,42 @@ class _BlstmAM(Function):
             ev.record(main)
             return ev
 
-        dl = _cast(dlogits.contiguous().view(M, N))                      # [M, N] bf16
-        w_out_t, ldw = _transpose(w_out.contiguous(), N, 2 * H, 2 * H)   # [2H, pad8(N)]
-        dy = th.empty(M, 2 * H, dtype=th.float32, device=dev)
-        _gemm(dl, w_out_t, dy, None, M, 2 * H, N, N, ldw, 2 * H)
-        top_in = ctx.top_in
+        def wgrad(dY, ldy, X, ldx, rows_k, m, n):
+            """dW[m, n] = dY[rows_k, m]^T X[rows_k, n] (bf16 operands as they lie in memory)."""
+            dW = th.empty(m, n, dtype=th.float32, device=dev)
+            if TN_GEMM:
+                _gemm(dY, X, dW, None, m, n, rows_k, ldy, ldx, n, tn=True)
+            else:
+                dY_t, ldm = _transpose(dY, rows_k, m, ldy)
+                X_t, _ = _transpose(X, rows_k, n, ldx)
+                _gemm(dY_t, X_t, dW, None, m, n, rows_k, ldm, ldm, n)
+            return dW
+
+        dl = _gather_rows(dlogits.contiguous().view(M, N), rows, Mv, N)  # [Mv, N] bf16, valid frames only
+        if rows is None:
+            dy = th.empty(M, 2 * H, dtype=th.float32, device=dev)
+        else:
+            dy = th.zeros(M, 2 * H, dtype=th.float32, device=dev)        # padded frames: zero gradient
+        _gemm(dl, packed.w_out_t, dy, None, Mv, 2 * H, N, N, packed.ldw, 2 * H, row_map=rows)
 
         def out_layer_grads():
-            dl.record_stream(side); top_in.record_stream(side)
-            dl_t, ldm = _transpose(dl, M, N, N)                          # [N, pad8(M)]
-            top_t, _ = _transpose(top_in, M, 2 * H, 2 * H)               # [2H, pad8(M)]
-            d_w_out = th.empty(N, 2 * H, dtype=th.float32, device=dev)
-            _gemm(dl_t, top_t, d_w_out, None, N, 2 * H, M, ldm, ldm, 2 * H)
+            dl.record_stream(side); top.record_stream(side)
+            d_w_out = wgrad(dl, N, top, 2 * H, Mv, N, 2 * H)
             d_b_out = th.empty(N, dtype=th.float32, device=dev)
-            _lib.check(lib.pk2_colsum_bf16(_lib.ptr(dl), _lib.ptr(d_b_out), M, N, _lib.stream()), "pk2_colsum_bf16")
+            _lib.check(lib.pk2_colsum_bf16(_lib.ptr(dl), _lib.ptr(d_b_out), Mv, N, _lib.stream()), "pk2_colsum_bf16")
             results["out"] = (d_w_out, d_b_out)
 
         pending = (mark_ready(), out_layer_grads)
         grads = [None] * (8 * L)
         for l in range(L - 1, -1, -1):
-            wih_f, whh_f, _, _, wih_b, whh_b, _, _ = lstm_params[8 * l:8 * l + 8]
-            I = wih_f.shape[1]
+            pk = packed.layers[l]
+            I = pk["I"]
             if saved["mask"][l] is not None:
                 dy = dy * saved["mask"][l].view(M, 2 * H).float()
-            whh_t = _cast(th.cat([whh_f.t(), whh_b.t()], 0).contiguous())        # [2H, 4H]
-            # same matrix with the 4H index permuted to cta*128 + gate*32 + unit (cluster/DSMEM kernel)
-            whh_tp = _cast(th.stack([whh_f, whh_b], 0).view(2, 4, H // 32, 32, H).permute(0, 2, 1, 3, 4)
-                           .reshape(2, 4 * H, H).transpose(1, 2).reshape(2 * H, 4 * H).contiguous())
             dgates = th.empty(B, T, 2, 4 * H, dtype=th.bfloat16, device=dev)
             sync = th.empty(2 * ((B + 31) // 32), dtype=th.int32, device=dev)
-            a = _lib.LstmBwdArgs(B, T, H, dy.data_ptr(), whh_t.data_ptr(), saved["gates"][l].data_ptr(),
-                                 saved["cstate"][l].data_ptr(), dgates.data_ptr(), sync.data_ptr(), whh_tp.data_ptr())
+            a = _lib.LstmBwdArgs(B, T, H, dy.data_ptr(), pk["whh_t"].data_ptr(), saved["gates"][l].data_ptr(),
+                                 saved["cstate"][l].data_ptr(), dgates.data_ptr(), sync.data_ptr(), pk["whh_tp"].data_ptr())
             if l == L - 1:
                 _hook("bwd_recurrence_next")
             _lib.check(lib.pk2_lstm_layer_bwd(C.byref(a), _lib.stream()), "pk2_lstm_layer_bwd")
@@ -186,23 +243,30 @@ class _BlstmAM(Function):
                 pending = None
             dg2 = dgates.view(M, 8 * H)
             if l > 0:
-                wih_t, ldk = _transpose(th.cat([wih_f, wih_b], 0).contiguous(), 8 * H, I, I)   # [I, 8H]
                 dy_next = th.empty(M, I, dtype=th.float32, device=dev)
-                _gemm(dg2, wih_t, dy_next, None, M, I, 8 * H, 8 * H, ldk, I)
+                _gemm(dg2, pk["wih_t"], dy_next, None, M, I, 8 * H, 8 * H, pk["ldk"], I)
             xin_l, y_l = saved["xin"][l], saved["y"][l]
 
             def layer_grads(l=l, dg2=dg2, xin_l=xin_l, y_l=y_l, I=I):
                 dg2.record_stream(side); xin_l.record_stream(side); y_l.record_stream(side)
-                dg_t, ldm = _transpose(dg2, M, 8 * H, 8 * H)                          # [8H, pad8(M)]
-                x_t, _ = _transpose(xin_l, M, I, I)                                    # [I, pad8(M)]
-                d_wih = th.empty(8 * H, I, dtype=th.float32, device=dev)
-                _gemm(dg_t, x_t, d_wih, None, 8 * H, I, M, ldm, ldm, I)
-                hp_t = th.empty(2 * H, ldm, dtype=th.bfloat16, device=dev)
-                _lib.check(lib.pk2_lstm_hprev_t(_lib.ptr(y_l), _lib.ptr(hp_t), B, T, H, ldm, _lib.stream()),
-                           "pk2_lstm_hprev_t")
-                d_whh = th.empty(2, 4 * H, H, dtype=th.float32, device=dev)
-                for d in range(2):
-                    _gemm(dg_t[d * 4 * H:(d + 1) * 4 * H], hp_t[d * H:(d + 1) * H], d_whh[d], None, 4 * H, H, M, ldm, ldm, H)
+                d_wih = wgrad(dg2, 8 * H, xin_l, I, M, 8 * H, I)
+                d_whh = []
+                if TN_GEMM:
+                    hp = th.empty(M, 2 * H, dtype=th.bfloat16, device=dev)
+                    _lib.check(lib.pk2_lstm_hprev(_lib.ptr(y_l), _lib.ptr(hp), B, T, H, _lib.stream()), "pk2_lstm_hprev")
+                    for d in range(2):
+                        dW = th.empty(4 * H, H, dtype=th.float32, device=dev)
+                        _gemm(_lib.ptr_at(dg2, d * 4 * H), _lib.ptr_at(hp, d * H), dW, None, 4 * H, H, M, 8 * H, 2 * H, H, tn=True)
+                        d_whh.append(dW)
+                else:
+                    dg_t, ldm = _transpose(dg2, M, 8 * H, 8 * H)
+                    hp_t = th.empty(2 * H, ldm, dtype=th.bfloat16, device=dev)
+                    _lib.check(lib.pk2_lstm_hprev_t(_lib.ptr(y_l), _lib.ptr(hp_t), B, T, H, ldm, _lib.stream()),
+                               "pk2_lstm_hprev_t")
+                    for d in range(2):
+                        dW = th.empty(4 * H, H, dtype=th.float32, device=dev)
+                        _gemm(dg_t[d * 4 * H:(d + 1) * 4 * H], hp_t[d * H:(d + 1) * H], dW, None, 4 * H, H, M, ldm, ldm, H)
+                        d_whh.append(dW)
                 d_b = th.empty(8 * H, dtype=th.float32, device=dev)
                 _lib.check(lib.pk2_colsum_bf16(_lib.ptr(dg2), _lib.ptr(d_b), M, 8 * H, _lib.stream()), "pk2_colsum_bf16")
                 results[l] = (d_wih, d_whh, d_b)
@@ -219,7 +283,7 @@ class _BlstmAM(Function):
         d_w_out.record_stream(main); d_b_out.record_stream(main)
         for l in range(L):
             d_wih, d_whh, d_b = results[l]
-            for t in (d_wih, d_whh, d_b):
+            for t in [d_wih, d_b] + d_whh:
                 t.record_stream(main)
             grads[8 * l + 0] = d_wih[:4 * H]; grads[8 * l + 4] = d_wih[4 * H:]
             grads[8 * l + 1] = d_whh[0]; grads[8 * l + 5] = d_whh[1]
@@ -227,8 +291,8 @@ class _BlstmAM(Function):
             # tensor it is handed, and in-place clipping would then scale the shared buffer once per parameter
             grads[8 * l + 2] = d_b[:4 * H]; grads[8 * l + 3] = d_b[:4 * H].clone()
             grads[8 * l + 6] = d_b[4 * H:]; grads[8 * l + 7] = d_b[4 * H:].clone()
-        ctx.saved = None
-        return (None, None, None, None, None, d_w_out, d_b_out) + tuple(grads)
+        ctx.saved = ctx.top = ctx.packed = ctx.rows = None
+        return (None, None, None, None, None, None, None, d_w_out, d_b_out) + tuple(grads)
 
 
 _SIDE = {}
@@ -270,6 +334,8 @@ class LSTMAM(nn.Module):
                             batch_first=True,
                             dropout=self.dropout,
                             bidirectional=self.bidirectional)
+        self._pack, self._pack_key = None, None
+        self._valid_cache = {}
 
     def _flat_params(self):
         out = []
@@ -279,9 +345,46 @@ class LSTMAM(nn.Module):
                     out.append(getattr(self.lstm, "%s_l%d%s" % (name, l, sfx)))
         return out
 
-    def forward(self, data):
+    def _packed(self, flat):
+        """Operand copies of the weights, rebuilt only when a parameter changed (in-place updates bump _version,
+        .to() / load_state_dict change the storage or the version)."""
+        ps = [self.output_layer.weight, self.output_layer.bias] + flat
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if key != self._pack_key:
+            with th.no_grad():
+                self._pack = _Packed(ps[0].detach(), ps[1].detach(), [p.detach() for p in flat], self.num_layers,
+                                     self.hidden_size)
+            self._pack_key = key
+        return self._pack
+
+    def _valid_rows(self, valid_lengths, B, T, dev):
+        lens = tuple(int(v) for v in valid_lengths)
+        if len(lens) != B or min(lens) < 0 or max(lens) > T:
+            raise RuntimeError("valid_lengths must hold one length in [0, T] per sequence")
+        key = (lens, T, dev.index)
+        hit = self._valid_cache.get(key)
+        if hit is None:
+            import numpy as np
+            rows = np.concatenate([b * T + np.arange(n, dtype=np.int32) for b, n in enumerate(lens)]).astype(np.int32)
+            if len(self._valid_cache) > 64:
+                self._valid_cache.clear()
+            hit = (th.from_numpy(rows).to(dev), th.tensor(lens, dtype=th.int32, device=dev), int(rows.shape[0]))
+            self._valid_cache[key] = hit
+        return hit
+
+    def forward(self, data, valid_lengths=None):
+        """data [B, T, F] -> logits [B, T, N].  ``valid_lengths`` (optional, one int per sequence, in output frames):
+        the caller promises to read only logits[b, :valid_lengths[b]] (the sequence losses do); the output layer is
+        then evaluated on those frames only and the other rows of the result are zero.  The recurrent layers always
+        run over the padding, as the reference's nn.LSTM on the padded batch does (models/lstm.py:58)."""
         if not data.is_cuda:
             raise RuntimeError("pykaldi2_b200.models.lstm.LSTMAM has no CPU path; move the model and data to CUDA")
+        flat = self._flat_params()
+        valid = None
+        if valid_lengths is not None:
+            valid = self._valid_rows(valid_lengths, data.shape[0], data.shape[1], data.device)
+            if valid[2] == 0 or valid[2] == data.shape[0] * data.shape[1]:
+                valid = None
         return _BlstmAM.apply(data.to(th.float32), self.num_layers, self.hidden_size, float(self.dropout),
-                              self.training, self.output_layer.weight, self.output_layer.bias,
-                              *self._flat_params())
+                              self.training, self._packed(flat), valid, self.output_layer.weight, self.output_layer.bias,
+                              *flat)

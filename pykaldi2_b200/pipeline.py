@@ -96,7 +96,10 @@ def chain_step(model, optimizer, averager, feat, den_graph, chain_opts, wav, wof
     ``after_backward``: host callback run once the backward pass is enqueued (e.g. prefetch of the next batch)."""
     shift = epoch % factor                                   # frame_shift = -(epoch % 3) then roll
     x, lens = feat.sequence_batch(wav, woff, foff, factor=factor, shift=shift)
-    prediction = model(x)
+    # the output layer runs on the frames the loss reads (one supervision frame per output frame), not on the padding
+    valid = supervisions.num_frames_host if hasattr(supervisions, "num_frames_host") else \
+        [s.frames_per_sequence for s in supervisions]
+    prediction = model(x, valid_lengths=valid)
     loss = ops.ChainObjtiveFunction.apply_batch(prediction, den_graph, supervisions, chain_opts)
     loss.backward()
     if after_backward is not None:

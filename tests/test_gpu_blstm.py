@@ -201,3 +201,105 @@ def test_lstm_bias_grads_do_not_share_storage(dev):
     ref_params = dict(lstm.named_parameters())
     for name, p in model.lstm.named_parameters():
         assert rel_err(p.grad.cpu(), ref_params[name].grad) < 3e-2, name
+
+
+@pytest.mark.parametrize("M,N,K,lda_pad,ldb_pad", [
+    (128, 256, 64, 0, 0), (200, 80, 300, 0, 0), (5768, 1024, 1000, 0, 0), (4096, 80, 777, 0, 0),
+    (2048, 512, 5000, 2048, 512),      # split-K path; operands are column blocks of wider matrices (d_whh)
+    (136, 72, 130, 8, 8)])
+def test_gemm_bf16_tn(dev, M, N, K, lda_pad, ldb_pad):
+    """TN form: C[M,N] = At[K,M]^T Bt[K,N], operands consumed in place through MN-major descriptors."""
+    from pykaldi2_b200 import _lib
+    from pykaldi2_b200.models import lstm as L
+    torch.manual_seed(M + N + K)
+    lda, ldb = M + lda_pad, N + ldb_pad
+    at = torch.randn(K, lda, device=dev).to(torch.bfloat16)
+    bt = torch.randn(K, ldb, device=dev).to(torch.bfloat16)
+    oa, ob = (lda_pad // 2) // 8 * 8, (ldb_pad // 2) // 8 * 8         # sub-matrix column offsets (16-byte aligned)
+    c = torch.full((M, N), float("nan"), device=dev)
+    L._gemm(_lib.ptr_at(at, oa), _lib.ptr_at(bt, ob), c, None, M, N, K, lda, ldb, N, tn=True)
+    ref = at[:, oa:oa + M].double().t() @ bt[:, ob:ob + N].double()
+    assert torch.isfinite(c).all()
+    assert rel_err(c, ref) < 2e-5
+
+
+def test_gemm_row_map_scatter(dev):
+    """Rows of the product scattered through c_row_map (compacted valid frames -> padded layout)."""
+    from pykaldi2_b200.models import lstm as L
+    torch.manual_seed(5)
+    M, N, K, Mfull = 777, 520, 192, 1500
+    a = torch.randn(M, K, device=dev).to(torch.bfloat16)
+    b = torch.randn(N, K, device=dev).to(torch.bfloat16)
+    bias = torch.randn(N, device=dev)
+    rows = torch.sort(torch.randperm(Mfull, device=dev)[:M]).values.to(torch.int32)
+    c = torch.zeros(Mfull, N, device=dev)
+    L._gemm(a, b, c, bias, M, N, K, K, K, N, row_map=rows)
+    ref = torch.zeros(Mfull, N, device=dev, dtype=torch.float64)
+    ref[rows.long()] = a.double() @ b.double().t() + bias.double()
+    assert rel_err(c, ref) < 2e-5
+    untouched = torch.ones(Mfull, dtype=torch.bool, device=dev)
+    untouched[rows.long()] = False
+    assert (c[untouched] == 0).all()
+
+
+@pytest.mark.parametrize("tn", [True, False])
+def test_lstmam_valid_lengths(dev, tn):
+    """forward(x, valid_lengths): the output layer runs on the valid frames only.  Valid rows of the logits and all
+    parameter gradients must equal the full computation under a loss that ignores the padding; padded rows are 0.
+    Both weight-gradient paths (TN GEMM in place / transposed copies) against the fp32 reference."""
+    from pykaldi2_b200.models import lstm as lstm_mod
+    from pykaldi2_b200.models.lstm import LSTMAM
+    B, T, F, N, H, L = 9, 41, 80, 200, 128, 2
+    lstm, lin = _ref_model(F, N, H, L, seed=21)
+    model = LSTMAM(F, N, H, L, 0.0, True)
+    model.lstm.load_state_dict(lstm.state_dict())
+    model.output_layer.load_state_dict(lin.state_dict())
+    model = model.to(dev)
+    x, lens = _varlen_batch(B, T, F, seed=22)
+    labels = torch.randint(0, N, (B, T))
+    for b in range(B):
+        labels[b, int(lens[b]):] = -100
+    loss_ref = torch.nn.functional.cross_entropy(lin(lstm(x)[0]).view(-1, N), labels.view(-1), reduction="sum",
+                                                 ignore_index=-100)
+    loss_ref.backward()
+    old = lstm_mod.TN_GEMM
+    lstm_mod.TN_GEMM = tn
+    try:
+        full = model(x.to(dev)).detach()
+        logits = model(x.to(dev), valid_lengths=[int(v) for v in lens])
+        for b in range(B):
+            n = int(lens[b])
+            assert torch.equal(logits[b, :n], full[b, :n])
+            assert (logits[b, n:] == 0).all()
+        loss = torch.nn.functional.cross_entropy(logits.view(-1, N), labels.view(-1).to(dev), reduction="sum",
+                                                 ignore_index=-100)
+        loss.backward()
+    finally:
+        lstm_mod.TN_GEMM = old
+    np.testing.assert_allclose(loss.item(), loss_ref.item(), rtol=1e-3)
+    ref_params = dict(lstm.named_parameters())
+    for name, p in model.lstm.named_parameters():
+        assert rel_err(p.grad.cpu(), ref_params[name].grad) < 3e-2, name
+    assert rel_err(model.output_layer.weight.grad.cpu(), lin.weight.grad) < 3e-2
+    assert rel_err(model.output_layer.bias.grad.cpu(), lin.bias.grad) < 3e-2
+
+
+def test_lstmam_weight_cache_follows_updates(dev):
+    """The packed bf16 operand copies are rebuilt after an in-place parameter update and after load_state_dict."""
+    from pykaldi2_b200.models.lstm import LSTMAM
+    B, T, F, N, H, L = 4, 6, 16, 24, 64, 1
+    model = LSTMAM(F, N, H, L, 0.0, True).to(dev)
+    x = torch.randn(B, T, F, device=dev)
+    out0 = model(x).detach().clone()
+    pack0 = model._pack
+    assert model(x) is not None and model._pack is pack0            # unchanged parameters: same pack
+    with torch.no_grad():
+        model.output_layer.bias.add_(1.0)
+    out1 = model(x).detach()
+    assert model._pack is not pack0
+    torch.testing.assert_close(out1, out0 + 1.0, rtol=1e-5, atol=1e-5)
+    lstm, lin = _ref_model(F, N, H, L, seed=9)
+    model.lstm.load_state_dict(lstm.state_dict())
+    model.output_layer.load_state_dict(lin.state_dict())
+    ref = lin(lstm(x.cpu())[0]).detach()
+    assert rel_err(model(x).detach().cpu(), ref) < 2e-2

@@ -45,11 +45,12 @@ sb_half = [graphs.SupervisionBatch([sups[i] for i in h], device=dev) for h in ha
 idx_half = [torch.as_tensor(h, device=dev) for h in halves]
 t_half = [max((frames[i] - 1) // 3 + 1 for i in h) for h in halves]  # output frames of the longest member
 streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+v_half = [[sub[i] for i in h] for h in halves]
 
 
 def grads_baseline():
     x, lens = feat.sequence_batch(wav, woff, foff, factor=3, shift=0)
-    loss = ops.ChainObjtiveFunction.apply_batch(model(x), den, sb_all, opts)
+    loss = ops.ChainObjtiveFunction.apply_batch(model(x, valid_lengths=sub), den, sb_all, opts)
     return loss, torch.autograd.grad(loss, params)
 
 
@@ -64,9 +65,9 @@ def grads_two_streams():
             xs.append(x.index_select(0, idx_half[k])[:, :t_half[k]].contiguous())
             x.record_stream(streams[k])
     with torch.cuda.stream(streams[1]):                                      # long half first: it is the critical path
-        preds[1] = model(xs[1])
+        preds[1] = model(xs[1], valid_lengths=v_half[1])
     with torch.cuda.stream(streams[0]):
-        preds[0] = model(xs[0])
+        preds[0] = model(xs[0], valid_lengths=v_half[0])
         losses[0] = ops.ChainObjtiveFunction.apply_batch(preds[0], den, sb_half[0], opts)
         gs[0] = torch.autograd.grad(losses[0], params)
     with torch.cuda.stream(streams[1]):
@@ -101,13 +102,13 @@ def make_staggered(fullpad, clusters, reserve):
             x.record_stream(sA); x.record_stream(sB)
             with torch.cuda.stream(sA):
                 xA = x.index_select(0, idx_half[A])[:, :tA].contiguous()
-                predA = model(xA)
+                predA = model(xA, valid_lengths=v_half[A])
                 mark("fwdA")()
             with torch.cuda.stream(sB):
                 xB = x.index_select(0, idx_half[B])[:, :tB].contiguous()
                 sB.wait_event(ev["fwdA"])
                 lstm_mod.HOOKS["fwd_recurrence_next"] = mark("recB")
-                predB = model(xB)
+                predB = model(xB, valid_lengths=v_half[B])
                 lstm_mod.HOOKS.pop("fwd_recurrence_next")
             with torch.cuda.stream(sA):
                 sA.wait_event(ev["recB"])                                     # B's LSTM clusters are placed first
@@ -162,7 +163,8 @@ def variant(name):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["baseline", "two_streams", "stag:full:12:32", "stag:full:0:0", "stag:own:12:32"]
+    which = sys.argv[1:] or ["baseline", "two_streams", "stag:full:12:32", "stag:full:0:0", "stag:full:10:48", "stag:own:12:32"]
+    print(json.dumps({"CUDA_DEVICE_MAX_CONNECTIONS": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS")}), flush=True)
     state0 = {k: v.clone() for k, v in model.state_dict().items()}
     _, gref = grads_baseline()
     gref = [g.clone() for g in gref]

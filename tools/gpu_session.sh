@@ -13,6 +13,7 @@ for step in "$@"; do
     pytest:*)    timeout 900 python -m pytest tests -m gpu -x -q -s -k "${step#pytest:}" > $OUT/pytest_$TAG.log 2>&1; echo "pytest rc=$?"; tail -5 $OUT/pytest_$TAG.log ;;
     kb:*)        for w in $(echo "${step#kb:}" | tr ',' ' '); do timeout 600 python tools/kernel_bench.py $w >> $OUT/kb_$TAG.jsonl 2>> $OUT/kb_$TAG.err; done; cat $OUT/kb_$TAG.jsonl ;;
     exp)         timeout 600 python tools/exp_two_microbatches.py > $OUT/exp2mb_$TAG.jsonl 2> $OUT/exp2mb_$TAG.err; cat $OUT/exp2mb_$TAG.jsonl; tail -3 $OUT/exp2mb_$TAG.err ;;
+    exp8)        CUDA_DEVICE_MAX_CONNECTIONS=8 timeout 600 python tools/exp_two_microbatches.py baseline stag:full:12:32 > $OUT/exp2mb_${TAG}_conn8.jsonl 2> $OUT/exp2mb_${TAG}_conn8.err; cat $OUT/exp2mb_${TAG}_conn8.jsonl; tail -3 $OUT/exp2mb_${TAG}_conn8.err ;;
     exp:*)       timeout 600 python tools/exp_two_microbatches.py $(echo "${step#exp:}" | tr ',' ' ') > $OUT/exp2mb_$TAG.jsonl 2> $OUT/exp2mb_$TAG.err; cat $OUT/exp2mb_$TAG.jsonl; tail -3 $OUT/exp2mb_$TAG.err ;;
     bench)       timeout 600 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; cat $OUT/bench_$TAG.json; tail -3 $OUT/bench_$TAG.err ;;
     bench_ref)   timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_${TAG}_reference.json 2> $OUT/bench_${TAG}_reference.err; cat $OUT/bench_${TAG}_reference.json ;;
