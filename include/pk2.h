@@ -151,21 +151,26 @@ typedef struct {
     const int32_t* frame_base;  /* [n_seq+1] */
     const uint8_t* keep;        /* [sum T] 1 = frame kept, 0 = dropped */
 } pk2_lat_batch;
+/* ws: pk2_latfb_workspace_bytes(total_states, total_arcs, mpe) bytes of device memory (alpha / beta per state,
+ * per-arc scores in in-arc and out-arc order, per-arc pdf); total_arcs = number of non-epsilon arcs
+ * (= in_off[total_states]), total_frames = sum of num_frames. */
+size_t pk2_latfb_workspace_bytes(int64_t total_states, int64_t total_arcs, int mpe);
 int pk2_latfb_mmi(const pk2_lat_batch* lat, const float* loglikes, int num_pdfs, int max_frames,
                   int64_t row_stride_b, float lm_scale, float ac_scale,
-                  double* ws_alpha, double* ws_beta, float* grad, double* tot, void* stream);
+                  void* ws, int64_t total_states, int64_t total_arcs, int64_t total_frames,
+                  float* grad, double* tot, void* stream);
 
 /* sMBR / MPFE.  Replaces lattice_forward_backward_mpe_variants(trans_model, silence_phones,
  * lattice, trans_ids, criterion, one_silence_class=True) + Posterior.to_pdf_matrix of sMBRFunction.forward
  * (reference ops/ops.py:130-147; Kaldi lat/lattice-functions.cc LatticeForwardBackwardMpeVariants on the CPU).
  * acc_in / acc_out: per non-epsilon arc frame accuracy (0/1) in the order of lat->in_* / lat->out_* (host index
- * work: graphs.Lattice.frame_acc).  ws: 4 * total_states doubles.  grad (zeroed by the call)[b,t,pdf] =
+ * work: graphs.Lattice.frame_acc).  ws: pk2_latfb_workspace_bytes(total_states, total_arcs, 1) bytes.  grad (zeroed by the call)[b,t,pdf] =
  * deriv_scale * sum over the arcs (t, pdf) of posterior * (accuracy through the arc - expected accuracy);
  * tot_like[b] = lattice log-likelihood, tot_score[b] = expected frame accuracy (the op's return value).
  * The reference applies no lattice_scale on this path: pass lm_scale = ac_scale = 1. */
 int pk2_latfb_mpe(const pk2_lat_batch* lat, const uint8_t* acc_in, const uint8_t* acc_out,
                   const float* loglikes, int num_pdfs, int max_frames, int64_t row_stride_b,
-                  float lm_scale, float ac_scale, double* ws, int64_t total_states,
+                  float lm_scale, float ac_scale, void* ws, int64_t total_states, int64_t total_arcs,
                   float deriv_scale, float* grad, double* tot_like, double* tot_score, void* stream);
 
 /* ------------------------------------------------------------------ BLSTM --

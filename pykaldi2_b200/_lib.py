@@ -61,10 +61,11 @@ _SIGS = {
     "pk2_numfb_post": (C.c_int, [C.POINTER(SupBatch), vp, C.c_int, C.c_int64, vp, vp, vp, vp, vp]),
     "pk2_numfb_scatter": (C.c_int, [C.POINTER(SupBatch), C.c_int, vp, C.c_int, C.c_int64, C.c_float, vp, vp]),
     "pk2_chain_guard": (C.c_int, [vp, vp, C.c_int, C.c_int64, vp, vp]),
+    "pk2_latfb_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int]),
     "pk2_latfb_mmi": (C.c_int, [C.POINTER(LatBatch), vp, C.c_int, C.c_int, C.c_int64, C.c_float,
-                                C.c_float, vp, vp, vp, vp, vp]),
+                                C.c_float, vp, C.c_int64, C.c_int64, C.c_int64, vp, vp, vp]),
     "pk2_latfb_mpe": (C.c_int, [C.POINTER(LatBatch), vp, vp, vp, C.c_int, C.c_int, C.c_int64, C.c_float, C.c_float,
-                                vp, C.c_int64, C.c_float, vp, vp, vp, vp]),
+                                vp, C.c_int64, C.c_int64, C.c_float, vp, vp, vp, vp]),
     "pk2_gemm_bf16_nt": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_int, vp]),
     "pk2_gemm_bf16_ex": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

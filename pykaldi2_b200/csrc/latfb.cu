@@ -4,11 +4,25 @@
 // cancel=True) + Posterior.to_pdf_matrix (reference ops/ops.py:57-62; Kaldi
 // lat/lattice-functions.cc + hmm/posterior.cc on the CPU) and removes the per-utterance
 // D2H/H2D copies of ops/ops.py:55,64.  Recursion: SURVEY.md Appendix B, alpha/beta in double.
-// Lattice states are time-stamped, so the recursion is level-synchronous: one CTA per
-// utterance walks the time levels, one thread per state of the level; same-level epsilon
-// arcs (rare) are applied serially in topological order between levels.  The arc's acoustic
-// score is gathered from the loglike row already on the device.  Output: dense gradient
+// Lattice states are time-stamped, so the recursion is level-synchronous.  Output: dense gradient
 // rows  grad[t,:] = den_post(t,:) - num_post(t,:)  for kept frames, 0 for dropped frames.
+//
+// Round-2 structure (three launches, the serial part reduced to what is serial):
+//   lat_arc_like_kernel   one thread per state, all SMs: per-arc score  -lm*graph + ac*loglike[t, pdf(tid)]  for the
+//                         in-arc and the out-arc order and the arc's pdf -- the only part that touches the T x N
+//                         log-likelihood matrix (random 4-byte gathers, independent of the recursion)
+//   lat_chain_kernel      TWO CTAs per utterance, running concurrently: the alpha chain (levels 0..T, in-arc CSR) and the
+//                         beta chain (levels T..0, out-arc CSR) do not depend on each other.  Per level a thread owns one
+//                         state; its arcs (source / destination state, score) were prefetched into registers one level
+//                         ahead and the CSR offsets two levels ahead, so the per-level critical path is: alpha of the
+//                         previous level from L1 -> max / expf / logf -> store -> one block barrier.  Values are kept
+//                         in double, the transcendental part of each log-sum-exp runs in fp32 on the shifted terms
+//                         (|error| ~1e-7 per level).  Same-level epsilon arcs (rare) are applied serially in
+//                         topological order between levels.
+//   lat_post_kernel       one thread per state, all SMs: arc posteriors exp(alpha + score + beta - tot) scattered into
+//                         the dense gradient rows (atomicAdd: two arcs of a frame may share a pdf), numerator -1
+// The round-1 kernels (one CTA per utterance doing everything, fp64 transcendental per arc, 4 dependent global loads
+// per level) are kept behind PK2_LATFB_V0=1 for A/B timing.
 #include "common.cuh"
 
 namespace {
@@ -290,27 +304,392 @@ latfb_mpe_kernel(pk2_lat_batch lat, const uint8_t* __restrict__ acc_in, const ui
     }
 }
 
+
+// =================================================================== round-2 kernels ====
+constexpr int kChain = 128;      // threads of a chain CTA (one state per thread and level; wider levels loop)
+constexpr int kPF = 6;           // arcs per state prefetched into registers
+
+__device__ __forceinline__ int seq_of_state(const pk2_lat_batch& lat, int s) {
+    int lo = 0, hi = lat.n_seq - 1;                   // largest b with seq_state_off[b] <= s
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(&lat.seq_state_off[mid]) <= s) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256)
+lat_arc_like_kernel(pk2_lat_batch lat, const float* __restrict__ loglikes, int N, int64_t row_stride_b, float lm, float ac,
+                    double* __restrict__ like_in, double* __restrict__ like_out, int32_t* __restrict__ pdf_out,
+                    int total_states) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= total_states) return;
+    const int b = seq_of_state(lat, s);
+    const int t = lat.state_time[s];
+    const float* ll = loglikes + (int64_t)b * row_stride_b * N;
+    if (t < lat.num_frames[b]) {
+        const float* row = ll + (int64_t)t * N;
+        for (int k = lat.out_off[s]; k < lat.out_off[s + 1]; ++k) {
+            const int p = __ldg(&lat.tid2pdf[lat.out_tid[k]]);
+            like_out[k] = -(double)(lm * lat.out_gc[k]) + (double)ac * (double)__ldg(&row[p]);
+            pdf_out[k] = p;
+        }
+    }
+    if (t >= 1) {
+        const float* row = ll + (int64_t)(t - 1) * N;
+        for (int k = lat.in_off[s]; k < lat.in_off[s + 1]; ++k)
+            like_in[k] = -(double)(lm * lat.in_gc[k]) + (double)ac * (double)__ldg(&row[lat.tid2pdf[lat.in_tid[k]]]);
+    }
+}
+
+// One direction of the recursion for one utterance.  FWD: level t from the in-arcs (sources at level t-1);
+// !FWD: level t from the out-arcs (destinations at level t+1).  `val` = alpha or beta, `val_s` = the expected-accuracy
+// recursion of sMBR / MPFE (MPE only).
+template <bool FWD, bool MPE>
+__device__ void lat_chain(const pk2_lat_batch& lat, int b, const int32_t* __restrict__ arc_off,
+                          const int32_t* __restrict__ arc_peer, const double* __restrict__ arc_like,
+                          const uint8_t* __restrict__ arc_acc, float lm, double* val, double* val_s,
+                          double* __restrict__ tot_out, double* __restrict__ score_out, int* s_lvl, int* s_eoff) {
+    __shared__ double s_red[kChain / 32], s_red2[kChain / 32];
+    __shared__ double s_tot;
+    const int T = lat.num_frames[b];
+    const int tid = threadIdx.x;
+    {
+        const int32_t* lvl_g = lat.level_off + lat.lvl_base[b];
+        const int32_t* eoff_g = lat.eps_off + lat.lvl_base[b];
+        for (int i = tid; i < T + 2; i += kChain) { s_lvl[i] = lvl_g[i]; s_eoff[i] = eoff_g[i]; }
+    }
+    __syncthreads();
+
+    // same-level epsilon arcs, serial in (reverse) topological order; first the log-domain value, then, with those
+    // final, the accuracy recursion
+    auto eps = [&](int t) {
+        if (s_eoff[t + 1] > s_eoff[t]) {
+            if (tid == 0) {
+                if (FWD) {
+                    for (int k = s_eoff[t]; k < s_eoff[t + 1]; ++k) {
+                        const int d = lat.eps_dst[k];
+                        val[d] = pk2::log_add(val[d], val[lat.eps_src[k]] - (double)(lm * lat.eps_gc[k]));
+                    }
+                } else {
+                    for (int k = s_eoff[t + 1] - 1; k >= s_eoff[t]; --k) {
+                        const int u = lat.eps_src[k];
+                        val[u] = pk2::log_add(val[u], val[lat.eps_dst[k]] - (double)(lm * lat.eps_gc[k]));
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    };
+    auto eps_s = [&](int t) {
+        if (MPE && s_eoff[t + 1] > s_eoff[t]) {
+            if (tid == 0) {
+                if (FWD) {
+                    for (int k = s_eoff[t]; k < s_eoff[t + 1]; ++k) {
+                        const int u = lat.eps_src[k], d = lat.eps_dst[k];
+                        val_s[d] += exp(val[u] - (double)(lm * lat.eps_gc[k]) - val[d]) * val_s[u];
+                    }
+                } else {
+                    for (int k = s_eoff[t + 1] - 1; k >= s_eoff[t]; --k) {
+                        const int u = lat.eps_src[k], d = lat.eps_dst[k];
+                        val_s[u] += exp(val[d] - (double)(lm * lat.eps_gc[k]) - val[u]) * val_s[d];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    };
+    // a state without register-resident arcs (levels wider than the CTA): everything from memory
+    auto slow_state = [&](int s) {
+        const int k0 = arc_off[s], k1 = arc_off[s + 1];
+        double m = -INFINITY;
+        for (int k = k0; k < k1; ++k) m = fmax(m, val[arc_peer[k]] + arc_like[k]);
+        float sum = 0.f;
+        if (m > -INFINITY) for (int k = k0; k < k1; ++k) sum += expf((float)(val[arc_peer[k]] + arc_like[k] - m));
+        val[s] = (m > -INFINITY) ? m + (double)logf(sum) : -INFINITY;
+    };
+    auto slow_state_s = [&](int s) {
+        const int k0 = arc_off[s], k1 = arc_off[s + 1];
+        const double v = val[s];
+        double sc = 0.0;
+        if (v > -INFINITY)
+            for (int k = k0; k < k1; ++k) {
+                const int u = arc_peer[k];
+                sc += (double)expf((float)(val[u] + arc_like[k] - v)) * (val_s[u] + (double)arc_acc[k]);
+            }
+        val_s[s] = sc;
+    };
+
+    // ---- first level
+    const int t_first = FWD ? 0 : T;
+    if (FWD) {
+        const int s_begin = lat.seq_state_off[b];
+        for (int s = s_lvl[0] + tid; s < s_lvl[1]; s += kChain) { val[s] = (s == s_begin) ? 0.0 : -INFINITY; if (MPE) val_s[s] = 0.0; }
+    } else {
+        for (int s = s_lvl[T] + tid; s < s_lvl[T + 1]; s += kChain) {
+            const float fc = lat.final_cost[s];
+            val[s] = (fc < INFINITY) ? -(double)(lm * fc) : -INFINITY;
+            if (MPE) val_s[s] = 0.0;
+        }
+    }
+    __syncthreads();
+    eps(t_first);
+    eps_s(t_first);
+
+    // ---- software pipeline: offsets two levels ahead, arcs one level ahead
+    const int step = FWD ? 1 : -1;
+    auto in_range = [&](int t) { return FWD ? (t <= T) : (t >= 0); };
+    auto load_off = [&](int t, int& k0, int& k1) {
+        k0 = k1 = 0;
+        if (in_range(t)) {
+            const int s = s_lvl[t] + tid;
+            if (s < s_lvl[t + 1]) { k0 = arc_off[s]; k1 = arc_off[s + 1]; }
+        }
+    };
+    int c_k0, c_n, c_peer[kPF];
+    double c_like[kPF];
+    uint8_t c_acc[kPF];
+    int n_k0, n_k1;
+    {
+        int k1;
+        load_off(t_first + step, c_k0, k1);
+        c_n = k1 - c_k0;
+#pragma unroll
+        for (int i = 0; i < kPF; ++i) {
+            c_peer[i] = 0; c_like[i] = 0.0; c_acc[i] = 0;
+            if (i < c_n) { c_peer[i] = arc_peer[c_k0 + i]; c_like[i] = arc_like[c_k0 + i]; if (MPE) c_acc[i] = arc_acc[c_k0 + i]; }
+        }
+        load_off(t_first + 2 * step, n_k0, n_k1);
+    }
+    for (int t = t_first + step; in_range(t); t += step) {
+        // prefetch: arcs of the next level, offsets of the one after (independent of the values computed below)
+        int p_peer[kPF];
+        double p_like[kPF];
+        uint8_t p_acc[kPF];
+        const int p_n = n_k1 - n_k0;
+#pragma unroll
+        for (int i = 0; i < kPF; ++i) {
+            p_peer[i] = 0; p_like[i] = 0.0; p_acc[i] = 0;
+            if (i < p_n) { p_peer[i] = arc_peer[n_k0 + i]; p_like[i] = arc_like[n_k0 + i]; if (MPE) p_acc[i] = arc_acc[n_k0 + i]; }
+        }
+        int f_k0, f_k1;
+        load_off(t + 2 * step, f_k0, f_k1);
+
+        const int lv0 = s_lvl[t], lv1 = s_lvl[t + 1];
+        const int s = lv0 + tid;
+        double x[kPF];
+        if (s < lv1) {
+            double m = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < kPF; ++i) {
+                x[i] = -INFINITY;
+                if (i < c_n) { x[i] = val[c_peer[i]] + c_like[i]; m = fmax(m, x[i]); }
+            }
+            for (int k = c_k0 + kPF; k < c_k0 + c_n; ++k) m = fmax(m, val[arc_peer[k]] + arc_like[k]);
+            float sum = 0.f;
+            if (m > -INFINITY) {
+#pragma unroll
+                for (int i = 0; i < kPF; ++i) if (i < c_n) sum += expf((float)(x[i] - m));
+                for (int k = c_k0 + kPF; k < c_k0 + c_n; ++k) sum += expf((float)(val[arc_peer[k]] + arc_like[k] - m));
+            }
+            val[s] = (m > -INFINITY) ? m + (double)logf(sum) : -INFINITY;
+        }
+        for (int s2 = s + kChain; s2 < lv1; s2 += kChain) slow_state(s2);
+        __syncthreads();
+        eps(t);
+        if (MPE) {
+            if (s < lv1) {
+                const double v = val[s];
+                double sc = 0.0;
+                if (v > -INFINITY) {
+#pragma unroll
+                    for (int i = 0; i < kPF; ++i)
+                        if (i < c_n) sc += (double)expf((float)(val[c_peer[i]] + c_like[i] - v)) * (val_s[c_peer[i]] + (double)c_acc[i]);
+                    for (int k = c_k0 + kPF; k < c_k0 + c_n; ++k) {
+                        const int u = arc_peer[k];
+                        sc += (double)expf((float)(val[u] + arc_like[k] - v)) * (val_s[u] + (double)arc_acc[k]);
+                    }
+                }
+                val_s[s] = sc;
+            }
+            for (int s2 = s + kChain; s2 < lv1; s2 += kChain) slow_state_s(s2);
+            __syncthreads();
+            eps_s(t);
+        }
+        c_k0 = n_k0; c_n = p_n;
+#pragma unroll
+        for (int i = 0; i < kPF; ++i) { c_peer[i] = p_peer[i]; c_like[i] = p_like[i]; c_acc[i] = p_acc[i]; }
+        n_k0 = f_k0; n_k1 = f_k1;
+    }
+
+    if (FWD) {
+        // ---- total log-likelihood (and expected accuracy) from the final states
+        double z = -INFINITY;
+        for (int s = s_lvl[T] + tid; s < s_lvl[T + 1]; s += kChain) {
+            const float fc = lat.final_cost[s];
+            if (fc < INFINITY) z = pk2::log_add(z, val[s] - (double)(lm * fc));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) z = pk2::log_add(z, __shfl_xor_sync(0xffffffffu, z, o));
+        if ((tid & 31) == 0) s_red[tid >> 5] = z;
+        __syncthreads();
+        if (tid == 0) {
+            double zz = s_red[0];
+            for (int i = 1; i < kChain / 32; ++i) zz = pk2::log_add(zz, s_red[i]);
+            s_tot = zz;
+            tot_out[b] = zz;
+        }
+        __syncthreads();
+        if (MPE) {
+            const double tot = s_tot;
+            double sc = 0.0;
+            for (int s = s_lvl[T] + tid; s < s_lvl[T + 1]; s += kChain) {
+                const float fc = lat.final_cost[s];
+                if (fc < INFINITY) sc += exp(val[s] - (double)(lm * fc) - tot) * val_s[s];
+            }
+            sc = pk2::warp_sum_d(sc);
+            if ((tid & 31) == 0) s_red2[tid >> 5] = sc;
+            __syncthreads();
+            if (tid == 0) {
+                double zz = 0.0;
+                for (int i = 0; i < kChain / 32; ++i) zz += s_red2[i];
+                score_out[b] = zz;
+            }
+        }
+    }
+}
+
+struct LatWs {
+    double *alpha, *beta, *alpha_s, *beta_s, *like_in, *like_out;
+    int32_t* pdf_out;
+};
+
+template <bool MPE>
+__global__ void __launch_bounds__(kChain)
+lat_chain_kernel(pk2_lat_batch lat, LatWs w, const uint8_t* __restrict__ acc_in, const uint8_t* __restrict__ acc_out,
+                 float lm, double* __restrict__ tot_out, double* __restrict__ score_out, int max_frames) {
+    extern __shared__ int s_dyn[];
+    int* s_lvl = s_dyn;
+    int* s_eoff = s_dyn + (max_frames + 2);
+    const int b = blockIdx.x >> 1;
+    if ((blockIdx.x & 1) == 0)
+        lat_chain<true, MPE>(lat, b, lat.in_off, lat.in_src, w.like_in, acc_in, lm, w.alpha, w.alpha_s, tot_out, score_out, s_lvl, s_eoff);
+    else
+        lat_chain<false, MPE>(lat, b, lat.out_off, lat.out_dst, w.like_out, acc_out, lm, w.beta, w.beta_s, tot_out, score_out, s_lvl, s_eoff);
+}
+
+template <bool MPE>
+__global__ void __launch_bounds__(256)
+lat_post_kernel(pk2_lat_batch lat, LatWs w, const uint8_t* __restrict__ acc_out, int N, int64_t row_stride_b,
+                float deriv_scale, const double* __restrict__ tot_in, const double* __restrict__ score_in,
+                float* __restrict__ grad, int total_states, int total_frames) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < total_states) {
+        const int b = seq_of_state(lat, s);
+        const int t = lat.state_time[s];
+        if (t < lat.num_frames[b] && (MPE || lat.keep[lat.frame_base[b] + t] != 0)) {
+            float* grow = grad + ((int64_t)b * row_stride_b + t) * N;
+            const double a = w.alpha[s] - tot_in[b];
+            if (a > -INFINITY) {
+                const double as = MPE ? (w.alpha_s[s] - score_in[b]) : 0.0;
+                for (int k = lat.out_off[s]; k < lat.out_off[s + 1]; ++k) {
+                    const int d = lat.out_dst[k];
+                    const float post = expf((float)(a + w.like_out[k] + w.beta[d]));
+                    if (MPE) {
+                        const float v = post * (float)(as + (double)acc_out[k] + w.beta_s[d]);
+                        if (v != 0.f) atomicAdd(&grow[w.pdf_out[k]], deriv_scale * v);
+                    } else if (post > 0.f) {
+                        atomicAdd(&grow[w.pdf_out[k]], post);
+                    }
+                }
+            }
+        }
+    }
+    if (!MPE && s < total_frames) {
+        // numerator: -1 at (t, pdf(num_ali[t])) on kept frames; s enumerates the frames of the batch
+        if (lat.keep[s]) {
+            int lo = 0, hi = lat.n_seq - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (__ldg(&lat.frame_base[mid]) <= s) lo = mid; else hi = mid - 1;
+            }
+            const int t = s - lat.frame_base[lo];
+            atomicAdd(&grad[((int64_t)lo * row_stride_b + t) * N + lat.tid2pdf[lat.num_ali[s]]], -1.0f);
+        }
+    }
+}
+
+size_t lat_ws_layout(int64_t S, int64_t A, bool mpe, void* base, LatWs* w) {
+    const size_t nd = (size_t)(mpe ? 4 : 2) * S + 2 * (size_t)A;
+    if (w) {
+        double* d = static_cast<double*>(base);
+        w->alpha = d; w->beta = d + S;
+        w->alpha_s = mpe ? d + 2 * S : nullptr; w->beta_s = mpe ? d + 3 * S : nullptr;
+        double* arcs = d + (size_t)(mpe ? 4 : 2) * S;
+        w->like_in = arcs; w->like_out = arcs + A;
+        w->pdf_out = reinterpret_cast<int32_t*>(arcs + 2 * A);
+    }
+    return nd * sizeof(double) + (size_t)A * sizeof(int32_t) + 16;
+}
+
+template <bool MPE>
+int launch_lat_v1(const pk2_lat_batch* lat, const uint8_t* acc_in, const uint8_t* acc_out, const float* loglikes,
+                  int num_pdfs, int max_frames, int64_t row_stride_b, float lm, float ac, void* ws, int64_t S, int64_t A,
+                  float deriv_scale, float* grad, double* tot, double* score, int total_frames, cudaStream_t st) {
+    LatWs w;
+    lat_ws_layout(S, A, MPE, ws, &w);
+    const int nb = (int)((S + 255) / 256);
+    lat_arc_like_kernel<<<nb, 256, 0, st>>>(*lat, loglikes, num_pdfs, row_stride_b, lm, ac, w.like_in, w.like_out, w.pdf_out, (int)S);
+    PK2_POST_LAUNCH();
+    const size_t smem = 2 * (size_t)(max_frames + 2) * sizeof(int);
+    PK2_REQUIRE(smem <= 200 * 1024, "pk2_latfb: utterances of more than %d frames are not supported", (int)(200 * 1024 / 8 - 2));
+    PK2_CHECK(cudaFuncSetAttribute(lat_chain_kernel<MPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lat_chain_kernel<MPE><<<2 * lat->n_seq, kChain, smem, st>>>(*lat, w, acc_in, acc_out, lm, tot, score, max_frames);
+    PK2_POST_LAUNCH();
+    const int64_t np = S > total_frames ? S : total_frames;
+    lat_post_kernel<MPE><<<(int)((np + 255) / 256), 256, 0, st>>>(*lat, w, acc_out, num_pdfs, row_stride_b, deriv_scale, tot, score,
+                                                                grad, (int)S, total_frames);
+    PK2_POST_LAUNCH();
+    return 0;
+}
+
 }  // namespace
+
+extern "C" size_t pk2_latfb_workspace_bytes(int64_t total_states, int64_t total_arcs, int mpe) {
+    if (total_states <= 0 || total_arcs < 0) return 0;
+    return lat_ws_layout(total_states, total_arcs, mpe != 0, nullptr, nullptr);
+}
+
+static bool latfb_v0() {
+    static const bool v0 = []() { const char* e = getenv("PK2_LATFB_V0"); return e && atoi(e) != 0; }();
+    return v0;
+}
 
 extern "C" int pk2_latfb_mmi(const pk2_lat_batch* lat, const float* loglikes, int num_pdfs,
                              int max_frames, int64_t row_stride_b, float lm_scale, float ac_scale,
-                             double* ws_alpha, double* ws_beta, float* grad, double* tot, void* stream) {
-    PK2_REQUIRE(lat && loglikes && ws_alpha && ws_beta && grad && tot, "pk2_latfb_mmi: null argument");
-    PK2_REQUIRE(lat->n_seq > 0 && max_frames > 0, "pk2_latfb_mmi: empty batch");
+                             void* ws, int64_t total_states, int64_t total_arcs, int64_t total_frames,
+                             float* grad, double* tot, void* stream) {
+    PK2_REQUIRE(lat && loglikes && ws && grad && tot, "pk2_latfb_mmi: null argument");
+    PK2_REQUIRE(lat->n_seq > 0 && max_frames > 0 && total_states > 0, "pk2_latfb_mmi: empty batch");
     PK2_REQUIRE(row_stride_b >= max_frames, "pk2_latfb_mmi: row_stride_b < max_frames");
     cudaStream_t st = pk2::as_stream(stream);
     // rows are addressed as b*row_stride_b + t: zero everything up to the last sequence's max_frames
     const size_t rows = (size_t)(lat->n_seq - 1) * (size_t)row_stride_b + (size_t)max_frames;
     PK2_CHECK(cudaMemsetAsync(grad, 0, rows * (size_t)num_pdfs * sizeof(float), st));
-    latfb_kernel<<<lat->n_seq, kThreads, 0, st>>>(*lat, loglikes, num_pdfs, row_stride_b, lm_scale,
-                                                 ac_scale, ws_alpha, ws_beta, grad, tot);
-    PK2_POST_LAUNCH();
-    return 0;
+    if (latfb_v0()) {
+        double* a = static_cast<double*>(ws);
+        latfb_kernel<<<lat->n_seq, kThreads, 0, st>>>(*lat, loglikes, num_pdfs, row_stride_b, lm_scale,
+                                                     ac_scale, a, a + total_states, grad, tot);
+        PK2_POST_LAUNCH();
+        return 0;
+    }
+    return launch_lat_v1<false>(lat, nullptr, nullptr, loglikes, num_pdfs, max_frames, row_stride_b, lm_scale, ac_scale, ws,
+                                total_states, total_arcs, 1.0f, grad, tot, nullptr, (int)total_frames, st);
 }
 
 extern "C" int pk2_latfb_mpe(const pk2_lat_batch* lat, const uint8_t* acc_in, const uint8_t* acc_out,
                              const float* loglikes, int num_pdfs, int max_frames, int64_t row_stride_b,
-                             float lm_scale, float ac_scale, double* ws /* [4][total_states] */, int64_t total_states,
+                             float lm_scale, float ac_scale, void* ws, int64_t total_states, int64_t total_arcs,
                              float deriv_scale, float* grad, double* tot_like, double* tot_score, void* stream) {
     PK2_REQUIRE(lat && acc_in && acc_out && loglikes && ws && grad && tot_like && tot_score, "pk2_latfb_mpe: null argument");
     PK2_REQUIRE(lat->n_seq > 0 && max_frames > 0 && total_states > 0, "pk2_latfb_mpe: empty batch");
@@ -318,9 +697,14 @@ extern "C" int pk2_latfb_mpe(const pk2_lat_batch* lat, const uint8_t* acc_in, co
     cudaStream_t st = pk2::as_stream(stream);
     const size_t rows = (size_t)(lat->n_seq - 1) * (size_t)row_stride_b + (size_t)max_frames;
     PK2_CHECK(cudaMemsetAsync(grad, 0, rows * (size_t)num_pdfs * sizeof(float), st));
-    latfb_mpe_kernel<<<lat->n_seq, kThreads, 0, st>>>(*lat, acc_in, acc_out, loglikes, num_pdfs, row_stride_b, lm_scale,
-                                                     ac_scale, ws, ws + total_states, ws + 2 * total_states,
-                                                     ws + 3 * total_states, deriv_scale, grad, tot_like, tot_score);
-    PK2_POST_LAUNCH();
-    return 0;
+    if (latfb_v0()) {
+        double* a = static_cast<double*>(ws);
+        latfb_mpe_kernel<<<lat->n_seq, kThreads, 0, st>>>(*lat, acc_in, acc_out, loglikes, num_pdfs, row_stride_b, lm_scale,
+                                                         ac_scale, a, a + total_states, a + 2 * total_states,
+                                                         a + 3 * total_states, deriv_scale, grad, tot_like, tot_score);
+        PK2_POST_LAUNCH();
+        return 0;
+    }
+    return launch_lat_v1<true>(lat, acc_in, acc_out, loglikes, num_pdfs, max_frames, row_stride_b, lm_scale, ac_scale, ws,
+                               total_states, total_arcs, deriv_scale, grad, tot_like, tot_score, 0, st);
 }

@@ -448,7 +448,22 @@ class LatticeBatch(object):
         ns = np.array([l.num_states for l in lats], np.int64)
         sbase = np.concatenate([[0], np.cumsum(ns)])
         self.total_states = int(sbase[-1])
+        self.total_arcs = int(sum(len(l.in_src) for l in lats))
         self.num_frames_host = [l.num_frames for l in lats]
+        self.total_frames = int(sum(self.num_frames_host))
+        # every index the kernels dereference is validated here, once, on the host: transition ids
+        # within the tid -> pdf map, pdfs within the prediction's columns (checked against N at call time)
+        t2p = np.asarray(tid2pdf, np.int64)
+        self.max_pdf = -1
+        for l, a in zip(lats, num_alis):
+            for name, tids in (("lattice arc", l.out_tid), ("alignment", np.asarray(a, np.int64))):
+                if len(tids) and (tids.min() < 1 or tids.max() >= len(t2p)):
+                    raise ValueError("%s transition id outside 1..%d" % (name, len(t2p) - 1))
+                if len(tids):
+                    pd = t2p[np.asarray(tids, np.int64)]
+                    if pd.min() < 0:
+                        raise ValueError("%s transition id maps to no pdf" % name)
+                    self.max_pdf = max(self.max_pdf, int(pd.max()))
         for l, a in zip(lats, num_alis):
             if len(a) != l.num_frames:
                 raise ValueError("alignment length %d != lattice frames %d" % (len(a), l.num_frames))

@@ -182,13 +182,16 @@ def lattice_mmi(prediction, lat_batch, lm_scale=1.0, ac_scale=0.2):
         raise RuntimeError("batch size %d != number of lattices %d" % (B, lat_batch.n_seq))
     if max(lat_batch.num_frames_host) > Tmax:
         raise RuntimeError("lattice longer than the network output")
+    if lat_batch.max_pdf >= N:
+        raise RuntimeError("the transition model maps to pdf %d but the prediction has %d columns" % (lat_batch.max_pdf, N))
     dev = prediction.device
     grad = th.empty_like(prediction)
     tot = th.empty(B, dtype=th.float64, device=dev)
-    ab = th.empty(2, max(lat_batch.total_states, 1), dtype=th.float64, device=dev)
-    _lib.check(_lib.lib().pk2_latfb_mmi(lat_batch.struct, _lib.ptr(prediction), N, Tmax, Tmax,
-                                        float(lm_scale), float(ac_scale), _lib.ptr(ab[0]),
-                                        _lib.ptr(ab[1]), _lib.ptr(grad), _lib.ptr(tot), _lib.stream()),
+    L = _lib.lib()
+    ws = th.empty(L.pk2_latfb_workspace_bytes(lat_batch.total_states, lat_batch.total_arcs, 0), dtype=th.uint8, device=dev)
+    _lib.check(L.pk2_latfb_mmi(lat_batch.struct, _lib.ptr(prediction), N, Tmax, Tmax,
+                               float(lm_scale), float(ac_scale), _lib.ptr(ws), lat_batch.total_states,
+                               lat_batch.total_arcs, lat_batch.total_frames, _lib.ptr(grad), _lib.ptr(tot), _lib.stream()),
                "pk2_latfb_mmi")
     return tot, grad
 
@@ -254,15 +257,17 @@ def lattice_mpe(prediction, lat_batch, lm_scale=1.0, ac_scale=1.0):
         raise RuntimeError("batch size %d != number of lattices %d" % (B, lat_batch.n_seq))
     if max(lat_batch.num_frames_host) > Tmax:
         raise RuntimeError("lattice longer than the network output")
+    if lat_batch.max_pdf >= N:
+        raise RuntimeError("the transition model maps to pdf %d but the prediction has %d columns" % (lat_batch.max_pdf, N))
     dev = prediction.device
     grad = th.empty_like(prediction)
     out = th.empty(2, B, dtype=th.float64, device=dev)
-    ns = max(lat_batch.total_states, 1)
-    ws = th.empty(4, ns, dtype=th.float64, device=dev)
-    _lib.check(_lib.lib().pk2_latfb_mpe(lat_batch.struct, _lib.ptr(lat_batch.acc_in), _lib.ptr(lat_batch.acc_out),
-                                        _lib.ptr(prediction), N, Tmax, Tmax, float(lm_scale), float(ac_scale),
-                                        _lib.ptr(ws), ns, -1.0, _lib.ptr(grad), _lib.ptr(out[0]), _lib.ptr(out[1]),
-                                        _lib.stream()), "pk2_latfb_mpe")
+    L = _lib.lib()
+    ws = th.empty(L.pk2_latfb_workspace_bytes(lat_batch.total_states, lat_batch.total_arcs, 1), dtype=th.uint8, device=dev)
+    _lib.check(L.pk2_latfb_mpe(lat_batch.struct, _lib.ptr(lat_batch.acc_in), _lib.ptr(lat_batch.acc_out),
+                               _lib.ptr(prediction), N, Tmax, Tmax, float(lm_scale), float(ac_scale),
+                               _lib.ptr(ws), lat_batch.total_states, lat_batch.total_arcs, -1.0, _lib.ptr(grad),
+                               _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.stream()), "pk2_latfb_mpe")
     return out[1], grad, out[0]
 
 

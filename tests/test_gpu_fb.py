@@ -469,3 +469,50 @@ def test_lattice_mpe_c3_scale_vs_oracle(dev, criterion, eps):
         np.testing.assert_allclose(score[b], rs, rtol=1e-5)
         np.testing.assert_allclose(grad[b, :T], -post, rtol=1e-3, atol=1e-6)
         assert (grad[b, T:] == 0).all()
+
+
+@pytest.mark.parametrize("eps", [0.0, 0.1])
+def test_lattice_wide_levels_vs_oracle(dev, eps):
+    """Levels wider than a chain CTA (more than 128 states per frame) and states with more arcs than the register
+    prefetch holds: the kernels' memory path, MMI and sMBR."""
+    from oracle import lattice_ref
+    from pykaldi2_b200 import graphs, synth
+    from pykaldi2_b200.ops import ops
+    rng = np.random.default_rng(41)
+    N, Ts = 300, [23, 9, 1]
+    lats, alis, olat = [], [], []
+    for T in Ts:
+        lat, tid2pdf, ali = synth.make_lattice(T, N, rng, kmin=140, kmax=300, ali_drop=0.2, eps_frac=eps)
+        olat.append(lat); alis.append(ali); lats.append(graphs.Lattice(lat))
+    assert max(int(np.diff(l.level_off).max()) for l in lats) > 128
+    assert max(int(np.diff(l.in_off).max()) for l in lats) > 6
+    tid2phone = np.where(np.asarray(tid2pdf) >= 0, np.asarray(tid2pdf) // 3 + 1, 0)
+    pred = rng.normal(0, 2.0, (len(Ts), max(Ts), N)).astype(np.float32)
+    p = torch.from_numpy(pred).to(dev)
+    lb = graphs.LatticeBatch(lats, tid2pdf, alis, device=dev, mpe=("smbr", tid2phone, [1, 2]))
+    tot, grad = ops.lattice_mmi(p, lb)
+    score, grad_s, tot_s = ops.lattice_mpe(p, lb)
+    tot, grad, score, grad_s, tot_s = (x.cpu().numpy() for x in (tot, grad, score, grad_s, tot_s))
+    for b, T in enumerate(Ts):
+        rtot, post, drop, _ = lattice_ref.lattice_fb_mmi(pred[b, :T], olat[b], tid2pdf, alis[b])
+        np.testing.assert_allclose(tot[b], rtot, rtol=1e-6)
+        np.testing.assert_allclose(grad[b, :T], -post, rtol=1e-3, atol=1e-6)
+        rs, post_s, rtot_s = lattice_ref.lattice_fb_mpe(pred[b, :T], olat[b], tid2pdf, tid2phone, alis[b], "smbr", [1, 2])
+        np.testing.assert_allclose(tot_s[b], rtot_s, rtol=1e-6)
+        np.testing.assert_allclose(score[b], rs, rtol=1e-5)
+        np.testing.assert_allclose(grad_s[b, :T], -post_s, rtol=1e-3, atol=1e-6)
+
+
+def test_lattice_batch_validates_indices(dev):
+    """Transition ids outside the tid -> pdf map and pdfs outside the prediction's columns are refused on the host
+    (the kernels index with them)."""
+    from pykaldi2_b200 import graphs, synth
+    from pykaldi2_b200.ops import ops
+    rng = np.random.default_rng(2)
+    N, T = 50, 12
+    lat, tid2pdf, ali = synth.make_lattice(T, N, rng, kmin=4, kmax=8)
+    with pytest.raises(ValueError):
+        graphs.LatticeBatch([graphs.Lattice(lat)], tid2pdf[:20], [ali], device=dev)
+    lb = graphs.LatticeBatch([graphs.Lattice(lat)], tid2pdf, [ali], device=dev)
+    with pytest.raises(RuntimeError):
+        ops.lattice_mmi(torch.zeros(1, T, N - 10, device=dev), lb)

@@ -31,7 +31,7 @@ for it in range(steps + 3):
     ev[0].record()
     x, lens = feat.sequence_batch(wav, woff, foff, factor=3, shift=0)
     ev[1].record()
-    pred = model(x)
+    pred = model(x, valid_lengths=sub)
     ev[2].record()
     loss = ops.ChainObjtiveFunction.apply_batch(pred, den, sb, opts)
     ev[3].record()
