@@ -48,6 +48,9 @@ def main():
     parser.add_argument('-synthetic', default=0, type=int, help="train on this many seeded synthetic utterances")
     parser.add_argument('-seed', default=1234, type=int, help="random seed (model init, sampling)")
     parser.add_argument('-max_steps', default=0, type=int, help="stop after this many minibatches (0 = whole epoch)")
+    parser.add_argument('-chunk_buffer', default=20000, type=int,
+                        help="chunks kept in the shuffle buffer before minibatches are drawn at random from it "
+                             "(the reference's DataBuffer holds 20000 samples)")
     args = parser.parse_args()
 
     th.manual_seed(args.seed)
@@ -67,7 +70,8 @@ def main():
         trainset = SyntheticWaveDataset(args.synthetic, mc["label_size"])
     else:                                   # the reference's corpus description: zip of wavs + label text files
         trainset = SpeechDataset(config)
-    # the reference batches 80-frame chunks; here a minibatch of utterances is cut into chunks on the GPU
+    # the reference batches 80-frame chunks drawn at random from a sample buffer; here groups of utterances are cut
+    # into chunks on the GPU and pooled in a device-side shuffle buffer (pipeline.ChunkPool)
     utts_per_batch = max(1, args.batch_size * dc.get("seg_len", 80) // 1230)
     loader = WaveDataloader(trainset, utts_per_batch, num_workers=args.data_loader_threads, distributed=world > 1)
     feat = pipeline.FeaturePipeline(use_cmn=dc.get("use_cmn", True))
@@ -105,6 +109,9 @@ def main():
         if epoch > args.anneal_lr_epoch:
             for g in optimizer.param_groups:
                 g['lr'] *= args.anneal_lr_ratio
+        loader.set_epoch(epoch)
+        if hasattr(trainset, "set_epoch"):
+            trainset.set_epoch(epoch)               # chunk mode: this epoch's random sweep of the corpus
         run_train_epoch(model, optimizer, averager, feat, loader, epoch, args, dc)
         if rank == 0:
             _common.save_checkpoint(args.exp_dir + '/model.' + str(epoch) + '.tar', model, optimizer, epoch)
@@ -117,14 +124,13 @@ def run_train_epoch(model, optimizer, averager, feat, loader, epoch, args, dc):
     progress = utils.ProgressMeter(len(loader), batch_time, losses, grad_norm, prefix="Epoch: [{}]".format(epoch))
     rtf = utils.RTFMeter()
     seg_len, seg_shift = dc.get("seg_len", 80), dc.get("seg_shift", 80)
-    end = time.time()
-    for i, data in enumerate(loader):
-        wav, woff, foff = feat.ex.pack(data["wav"])
-        n_fr = [min(int(foff[u + 1] - foff[u]), len(l)) for u, l in enumerate(data["label"])]   # label trim
-        x, cu, cs = feat.chunk_batch(wav, woff, foff, seg_len, seg_shift, n_fr)
-        x = x[:args.batch_size]
-        y = np.stack([data["label"][u][s:s + seg_len, 0] for u, s in zip(cu, cs)])[:args.batch_size]
-        y = th.from_numpy(y).cuda(non_blocking=True)
+    dev = next(model.parameters()).device
+    # room for the buffer plus the chunks of one more group of utterances (30 s utterance = 37 chunks)
+    pool = pipeline.ChunkPool(args.chunk_buffer + args.batch_size + 64 * loader_group_size(loader), seg_len,
+                              model.input_size, dev, seed=args.seed + epoch)
+    state = {"step": 0, "end": time.time()}
+
+    def train_step(x, y):
         prediction = model(x)
         loss = pipeline.ce_loss(prediction.view(-1, prediction.shape[2]), y.view(-1))
         loss.backward()
@@ -132,13 +138,35 @@ def run_train_epoch(model, optimizer, averager, feat, loader, epoch, args, dc):
         grad_norm.update(float(norm))
         losses.update(loss.item(), x.size(0))
         rtf.update(x.size(0) * seg_len)
-        batch_time.update(time.time() - end)
-        end = time.time()
-        if i % args.print_freq == 0:
-            progress.print(i)
+        batch_time.update(time.time() - state["end"])
+        state["end"] = time.time()
+        if state["step"] % args.print_freq == 0:
+            progress.print(state["step"])
             print("iRTF {:.1f}".format(rtf.irtf), flush=True)
-        if args.max_steps and i + 1 >= args.max_steps:
-            break
+        state["step"] += 1
+        return bool(args.max_steps) and state["step"] >= args.max_steps
+
+    done = False
+    for data in loader:
+        wav, woff, foff = feat.ex.pack(data["wav"])
+        n_fr = [min(int(foff[u + 1] - foff[u]), len(l)) for u, l in enumerate(data["label"])]   # label trim
+        x, cu, cs = feat.chunk_batch(wav, woff, foff, seg_len, seg_shift, n_fr)
+        if x.shape[0] == 0:
+            continue
+        y = np.stack([data["label"][u][s:s + seg_len, 0] for u, s in zip(cu, cs)])
+        pool.add(x, th.from_numpy(y).to(dev, non_blocking=True))
+        # the reference pops samples once the buffer holds buffer_size of them (data/sr_dataset.py:70-73)
+        while not done and pool.n >= max(args.chunk_buffer, args.batch_size):
+            done = train_step(*pool.draw(args.batch_size))
+        if done:
+            return
+    while not done and pool.n > 0:                  # end of the sweep: drain the buffer, nothing is discarded
+        done = train_step(*pool.draw(args.batch_size))
+
+
+def loader_group_size(loader):
+    bs = getattr(loader, "batch_size", None)
+    return int(bs) if bs else 64
 
 
 if __name__ == '__main__':

@@ -95,7 +95,8 @@ def main():
         dataset = SpeechDataset(config)
         if not args.den_fst:
             print("WARNING: no -den_fst given: training against a synthetic denominator graph")
-    loader = WaveDataloader(dataset, args.batch_size, num_workers=args.data_loader_threads, distributed=world > 1)
+    loader = WaveDataloader(dataset, args.batch_size, num_workers=args.data_loader_threads, distributed=world > 1,
+                            balanced=True, seed=args.seed)
     feat = pipeline.FeaturePipeline(use_cmn=dc.get("use_cmn", True))
     print("Data loader set up successfully!")
     print("Number of minibatches: {}".format(len(loader)))

@@ -73,7 +73,8 @@ def main():
         dataset = SyntheticWaveDataset(args.synthetic, N)
     else:                                   # zip of wavs + pdf-id / transition-id label files (example/librispeech/README.md)
         dataset = SpeechDataset(config)
-    loader = WaveDataloader(dataset, args.batch_size, num_workers=args.data_loader_threads, distributed=world > 1)
+    loader = WaveDataloader(dataset, args.batch_size, num_workers=args.data_loader_threads, distributed=world > 1,
+                            balanced=True, seed=args.seed)
     feat = pipeline.FeaturePipeline(use_cmn=dc.get("use_cmn", True))
     print("Data loader set up successfully!")
     print("Number of minibatches: {}".format(len(loader)))

@@ -307,7 +307,12 @@ latfb_mpe_kernel(pk2_lat_batch lat, const uint8_t* __restrict__ acc_in, const ui
 
 // =================================================================== round-2 kernels ====
 constexpr int kChain = 128;      // threads of a chain CTA (one state per thread and level; wider levels loop)
-constexpr int kPF = 6;           // arcs per state prefetched into registers
+constexpr int kPF = 6;           // arcs per state staged in shared memory ahead of time
+constexpr int kDepth = 8;        // levels the asynchronous arc copies run ahead of the recursion
+constexpr int kValW = 1024;      // states per level whose value is exchanged through shared memory
+
+// one arc as the chain and posterior kernels read it: score, state at the other end, frame accuracy (sMBR / MPFE)
+struct __align__(16) ArcRec { double like; int peer; int acc; };
 
 __device__ __forceinline__ int seq_of_state(const pk2_lat_batch& lat, int s) {
     int lo = 0, hi = lat.n_seq - 1;                   // largest b with seq_state_off[b] <= s
@@ -319,8 +324,9 @@ __device__ __forceinline__ int seq_of_state(const pk2_lat_batch& lat, int s) {
 }
 
 __global__ void __launch_bounds__(256)
-lat_arc_like_kernel(pk2_lat_batch lat, const float* __restrict__ loglikes, int N, int64_t row_stride_b, float lm, float ac,
-                    double* __restrict__ like_in, double* __restrict__ like_out, int32_t* __restrict__ pdf_out,
+lat_arc_like_kernel(pk2_lat_batch lat, const uint8_t* __restrict__ acc_in, const uint8_t* __restrict__ acc_out,
+                    const float* __restrict__ loglikes, int N, int64_t row_stride_b, float lm, float ac,
+                    ArcRec* __restrict__ rec_in, ArcRec* __restrict__ rec_out, int32_t* __restrict__ pdf_out,
                     int total_states) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= total_states) return;
@@ -331,35 +337,75 @@ lat_arc_like_kernel(pk2_lat_batch lat, const float* __restrict__ loglikes, int N
         const float* row = ll + (int64_t)t * N;
         for (int k = lat.out_off[s]; k < lat.out_off[s + 1]; ++k) {
             const int p = __ldg(&lat.tid2pdf[lat.out_tid[k]]);
-            like_out[k] = -(double)(lm * lat.out_gc[k]) + (double)ac * (double)__ldg(&row[p]);
+            ArcRec r;
+            r.like = -(double)(lm * lat.out_gc[k]) + (double)ac * (double)__ldg(&row[p]);
+            r.peer = lat.out_dst[k];
+            r.acc = acc_out ? (int)acc_out[k] : 0;
+            rec_out[k] = r;
             pdf_out[k] = p;
         }
     }
     if (t >= 1) {
         const float* row = ll + (int64_t)(t - 1) * N;
-        for (int k = lat.in_off[s]; k < lat.in_off[s + 1]; ++k)
-            like_in[k] = -(double)(lm * lat.in_gc[k]) + (double)ac * (double)__ldg(&row[lat.tid2pdf[lat.in_tid[k]]]);
+        for (int k = lat.in_off[s]; k < lat.in_off[s + 1]; ++k) {
+            ArcRec r;
+            r.like = -(double)(lm * lat.in_gc[k]) + (double)ac * (double)__ldg(&row[lat.tid2pdf[lat.in_tid[k]]]);
+            r.peer = lat.in_src[k];
+            r.acc = acc_in ? (int)acc_in[k] : 0;
+            rec_in[k] = r;
+        }
     }
 }
 
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+// shared-memory carve-up of a chain CTA
+struct ChainSmem {
+    int* lvl;          // [T + 2] first state of every level
+    int* eoff;         // [T + 2] first epsilon arc of every level
+    double* sv;        // [2][kValW] value (alpha / beta) of the previous and the current level
+    double* sv_s;      // [2][kValW] accuracy recursion (sMBR / MPFE)
+    int2* off;         // [2 * kDepth][kChain] CSR range of the thread's state, 2 * kDepth levels ahead
+    ArcRec* rec;       // [kDepth + 1][kPF][kChain] the state's first kPF arcs, kDepth levels ahead
+};
+
 // One direction of the recursion for one utterance.  FWD: level t from the in-arcs (sources at level t-1);
 // !FWD: level t from the out-arcs (destinations at level t+1).  `val` = alpha or beta, `val_s` = the expected-accuracy
-// recursion of sMBR / MPFE (MPE only).
+// recursion of sMBR / MPFE (MPE only).  The arcs of level t are copied into the thread's private shared-memory slots
+// kDepth levels ahead with cp.async (the CSR offsets they depend on 2 * kDepth levels ahead), so the loads never sit
+// on the dependency chain; the previous level's values come from shared memory.
 template <bool FWD, bool MPE>
 __device__ void lat_chain(const pk2_lat_batch& lat, int b, const int32_t* __restrict__ arc_off,
-                          const int32_t* __restrict__ arc_peer, const double* __restrict__ arc_like,
-                          const uint8_t* __restrict__ arc_acc, float lm, double* val, double* val_s,
-                          double* __restrict__ tot_out, double* __restrict__ score_out, int* s_lvl, int* s_eoff) {
+                          const ArcRec* __restrict__ arc_rec, float lm, double* val, double* val_s,
+                          double* __restrict__ tot_out, double* __restrict__ score_out, const ChainSmem& sm) {
     __shared__ double s_red[kChain / 32], s_red2[kChain / 32];
     __shared__ double s_tot;
     const int T = lat.num_frames[b];
     const int tid = threadIdx.x;
+    int* s_lvl = sm.lvl;
+    int* s_eoff = sm.eoff;
     {
         const int32_t* lvl_g = lat.level_off + lat.lvl_base[b];
         const int32_t* eoff_g = lat.eps_off + lat.lvl_base[b];
         for (int i = tid; i < T + 2; i += kChain) { s_lvl[i] = lvl_g[i]; s_eoff[i] = eoff_g[i]; }
     }
     __syncthreads();
+
+    // value of a state of level `lt` (the level being computed, or its neighbour): shared memory for the first kValW
+    // states of a level, global memory beyond
+    auto sv_slot = [&](int lt) { return (lt & 1) * kValW; };
+    auto get = [&](int s, int lt) { const int li = s - s_lvl[lt]; return li < kValW ? sm.sv[sv_slot(lt) + li] : val[s]; };
+    auto get_s = [&](int s, int lt) { const int li = s - s_lvl[lt]; return li < kValW ? sm.sv_s[sv_slot(lt) + li] : val_s[s]; };
+    auto put = [&](int s, int lt, double v) { const int li = s - s_lvl[lt]; if (li < kValW) sm.sv[sv_slot(lt) + li] = v; val[s] = v; };
+    auto put_s = [&](int s, int lt, double v) { const int li = s - s_lvl[lt]; if (li < kValW) sm.sv_s[sv_slot(lt) + li] = v; val_s[s] = v; };
 
     // same-level epsilon arcs, serial in (reverse) topological order; first the log-domain value, then, with those
     // final, the accuracy recursion
@@ -368,13 +414,13 @@ __device__ void lat_chain(const pk2_lat_batch& lat, int b, const int32_t* __rest
             if (tid == 0) {
                 if (FWD) {
                     for (int k = s_eoff[t]; k < s_eoff[t + 1]; ++k) {
-                        const int d = lat.eps_dst[k];
-                        val[d] = pk2::log_add(val[d], val[lat.eps_src[k]] - (double)(lm * lat.eps_gc[k]));
+                        const int u = lat.eps_src[k], d = lat.eps_dst[k];
+                        put(d, t, pk2::log_add(get(d, t), get(u, t) - (double)(lm * lat.eps_gc[k])));
                     }
                 } else {
                     for (int k = s_eoff[t + 1] - 1; k >= s_eoff[t]; --k) {
-                        const int u = lat.eps_src[k];
-                        val[u] = pk2::log_add(val[u], val[lat.eps_dst[k]] - (double)(lm * lat.eps_gc[k]));
+                        const int u = lat.eps_src[k], d = lat.eps_dst[k];
+                        put(u, t, pk2::log_add(get(u, t), get(d, t) - (double)(lm * lat.eps_gc[k])));
                     }
                 }
             }
@@ -387,140 +433,158 @@ __device__ void lat_chain(const pk2_lat_batch& lat, int b, const int32_t* __rest
                 if (FWD) {
                     for (int k = s_eoff[t]; k < s_eoff[t + 1]; ++k) {
                         const int u = lat.eps_src[k], d = lat.eps_dst[k];
-                        val_s[d] += exp(val[u] - (double)(lm * lat.eps_gc[k]) - val[d]) * val_s[u];
+                        put_s(d, t, get_s(d, t) + exp(get(u, t) - (double)(lm * lat.eps_gc[k]) - get(d, t)) * get_s(u, t));
                     }
                 } else {
                     for (int k = s_eoff[t + 1] - 1; k >= s_eoff[t]; --k) {
                         const int u = lat.eps_src[k], d = lat.eps_dst[k];
-                        val_s[u] += exp(val[d] - (double)(lm * lat.eps_gc[k]) - val[u]) * val_s[d];
+                        put_s(u, t, get_s(u, t) + exp(get(d, t) - (double)(lm * lat.eps_gc[k]) - get(u, t)) * get_s(d, t));
                     }
                 }
             }
             __syncthreads();
         }
     };
-    // a state without register-resident arcs (levels wider than the CTA): everything from memory
-    auto slow_state = [&](int s) {
+    const int step = FWD ? 1 : -1;
+    // a state whose arcs are not staged (levels wider than the CTA): arcs straight from memory.  pass 0: value,
+    // pass 1 (MPE): accuracy recursion with the weights normalised by their own sum (see below)
+    auto slow_state = [&](int s, int t) {
         const int k0 = arc_off[s], k1 = arc_off[s + 1];
         double m = -INFINITY;
-        for (int k = k0; k < k1; ++k) m = fmax(m, val[arc_peer[k]] + arc_like[k]);
+        for (int k = k0; k < k1; ++k) m = fmax(m, get(arc_rec[k].peer, t - step) + arc_rec[k].like);
         float sum = 0.f;
-        if (m > -INFINITY) for (int k = k0; k < k1; ++k) sum += expf((float)(val[arc_peer[k]] + arc_like[k] - m));
-        val[s] = (m > -INFINITY) ? m + (double)logf(sum) : -INFINITY;
+        if (m > -INFINITY) for (int k = k0; k < k1; ++k) sum += expf((float)(get(arc_rec[k].peer, t - step) + arc_rec[k].like - m));
+        put(s, t, (m > -INFINITY) ? m + (double)logf(sum) : -INFINITY);
     };
-    auto slow_state_s = [&](int s) {
+    auto slow_state_s = [&](int s, int t) {
         const int k0 = arc_off[s], k1 = arc_off[s + 1];
-        const double v = val[s];
-        double sc = 0.0;
-        if (v > -INFINITY)
+        double m = -INFINITY;
+        for (int k = k0; k < k1; ++k) m = fmax(m, get(arc_rec[k].peer, t - step) + arc_rec[k].like);
+        double num = 0.0, den = 0.0;
+        if (m > -INFINITY)
             for (int k = k0; k < k1; ++k) {
-                const int u = arc_peer[k];
-                sc += (double)expf((float)(val[u] + arc_like[k] - v)) * (val_s[u] + (double)arc_acc[k]);
+                const int u = arc_rec[k].peer;
+                const double w = (double)expf((float)(get(u, t - step) + arc_rec[k].like - m));
+                den += w;
+                num += w * (get_s(u, t - step) + (double)arc_rec[k].acc);
             }
-        val_s[s] = sc;
+        double sc = 0.0;
+        if (den > 0.0) {
+            sc = num / den;
+            const double a_reg = m + log(den), v = get(s, t);      // v > a_reg when epsilon arcs enter the state
+            if (v != a_reg) sc *= exp(a_reg - v);
+        }
+        put_s(s, t, sc);
     };
 
     // ---- first level
     const int t_first = FWD ? 0 : T;
     if (FWD) {
         const int s_begin = lat.seq_state_off[b];
-        for (int s = s_lvl[0] + tid; s < s_lvl[1]; s += kChain) { val[s] = (s == s_begin) ? 0.0 : -INFINITY; if (MPE) val_s[s] = 0.0; }
+        for (int s = s_lvl[0] + tid; s < s_lvl[1]; s += kChain) { put(s, 0, (s == s_begin) ? 0.0 : -INFINITY); if (MPE) put_s(s, 0, 0.0); }
     } else {
         for (int s = s_lvl[T] + tid; s < s_lvl[T + 1]; s += kChain) {
             const float fc = lat.final_cost[s];
-            val[s] = (fc < INFINITY) ? -(double)(lm * fc) : -INFINITY;
-            if (MPE) val_s[s] = 0.0;
+            put(s, T, (fc < INFINITY) ? -(double)(lm * fc) : -INFINITY);
+            if (MPE) put_s(s, T, 0.0);
         }
     }
     __syncthreads();
     eps(t_first);
     eps_s(t_first);
 
-    // ---- software pipeline: offsets two levels ahead, arcs one level ahead
-    const int step = FWD ? 1 : -1;
-    auto in_range = [&](int t) { return FWD ? (t <= T) : (t >= 0); };
-    auto load_off = [&](int t, int& k0, int& k1) {
-        k0 = k1 = 0;
-        if (in_range(t)) {
+    // ---- asynchronous staging.  Level index n = 1, 2, ... <-> level t = t_first + n * step, n <= T.
+    auto level_of = [&](int n) { return t_first + n * step; };
+    auto issue_off = [&](int n) {             // CSR range of this thread's state of level index n
+        int2* dst = &sm.off[(n % (2 * kDepth)) * kChain + tid];
+        bool ok = false;
+        if (n <= T) {
+            const int t = level_of(n);
             const int s = s_lvl[t] + tid;
-            if (s < s_lvl[t + 1]) { k0 = arc_off[s]; k1 = arc_off[s + 1]; }
+            if (s < s_lvl[t + 1]) { cp_async4(&dst->x, arc_off + s); cp_async4(&dst->y, arc_off + s + 1); ok = true; }
         }
+        if (!ok) *dst = make_int2(0, 0);
     };
-    int c_k0, c_n, c_peer[kPF];
-    double c_like[kPF];
-    uint8_t c_acc[kPF];
-    int n_k0, n_k1;
-    {
-        int k1;
-        load_off(t_first + step, c_k0, k1);
-        c_n = k1 - c_k0;
+    auto issue_arcs = [&](int n, int2 o) {    // first kPF arcs of that state
+        ArcRec* dst = sm.rec + (size_t)(n % (kDepth + 1)) * kPF * kChain + tid;
+        const int cnt = o.y - o.x;
 #pragma unroll
-        for (int i = 0; i < kPF; ++i) {
-            c_peer[i] = 0; c_like[i] = 0.0; c_acc[i] = 0;
-            if (i < c_n) { c_peer[i] = arc_peer[c_k0 + i]; c_like[i] = arc_like[c_k0 + i]; if (MPE) c_acc[i] = arc_acc[c_k0 + i]; }
-        }
-        load_off(t_first + 2 * step, n_k0, n_k1);
-    }
-    for (int t = t_first + step; in_range(t); t += step) {
-        // prefetch: arcs of the next level, offsets of the one after (independent of the values computed below)
-        int p_peer[kPF];
-        double p_like[kPF];
-        uint8_t p_acc[kPF];
-        const int p_n = n_k1 - n_k0;
-#pragma unroll
-        for (int i = 0; i < kPF; ++i) {
-            p_peer[i] = 0; p_like[i] = 0.0; p_acc[i] = 0;
-            if (i < p_n) { p_peer[i] = arc_peer[n_k0 + i]; p_like[i] = arc_like[n_k0 + i]; if (MPE) p_acc[i] = arc_acc[n_k0 + i]; }
-        }
-        int f_k0, f_k1;
-        load_off(t + 2 * step, f_k0, f_k1);
+        for (int i = 0; i < kPF; ++i) if (i < cnt) cp_async16(dst + i * kChain, arc_rec + o.x + i);
+    };
+    for (int n = 1; n <= 2 * kDepth; ++n) issue_off(n);
+    cp_async_commit();
+    cp_async_wait<0>();
+    for (int n = 1; n <= kDepth; ++n) issue_arcs(n, sm.off[(n % (2 * kDepth)) * kChain + tid]);
+    cp_async_commit();
+    cp_async_wait<0>();
+
+    for (int n = 1; n <= T; ++n) {
+        const int t = level_of(n);
+        cp_async_wait<kDepth - 1>();                      // the copies issued kDepth iterations ago have landed
+        const int2 oc = sm.off[(n % (2 * kDepth)) * kChain + tid];                       // this level
+        const int2 ob = sm.off[((n + kDepth) % (2 * kDepth)) * kChain + tid];            // kDepth levels ahead
+        issue_arcs(n + kDepth, ob);
+        issue_off(n + 2 * kDepth);
+        cp_async_commit();
 
         const int lv0 = s_lvl[t], lv1 = s_lvl[t + 1];
         const int s = lv0 + tid;
-        double x[kPF];
+        const int c_k0 = oc.x, c_n = oc.y - oc.x;
+        const ArcRec* mine = sm.rec + (size_t)(n % (kDepth + 1)) * kPF * kChain + tid;
+        double x[kPF], m = -INFINITY;
+        int peer[kPF], acc[kPF];
+        float sum = 0.f;
         if (s < lv1) {
-            double m = -INFINITY;
 #pragma unroll
             for (int i = 0; i < kPF; ++i) {
-                x[i] = -INFINITY;
-                if (i < c_n) { x[i] = val[c_peer[i]] + c_like[i]; m = fmax(m, x[i]); }
+                x[i] = -INFINITY; peer[i] = 0; acc[i] = 0;
+                if (i < c_n) {
+                    const ArcRec r = mine[i * kChain];
+                    peer[i] = r.peer; acc[i] = r.acc;
+                    x[i] = get(r.peer, t - step) + r.like;
+                    m = fmax(m, x[i]);
+                }
             }
-            for (int k = c_k0 + kPF; k < c_k0 + c_n; ++k) m = fmax(m, val[arc_peer[k]] + arc_like[k]);
-            float sum = 0.f;
+            for (int k = c_k0 + kPF; k < c_k0 + c_n; ++k) m = fmax(m, get(arc_rec[k].peer, t - step) + arc_rec[k].like);
             if (m > -INFINITY) {
 #pragma unroll
                 for (int i = 0; i < kPF; ++i) if (i < c_n) sum += expf((float)(x[i] - m));
-                for (int k = c_k0 + kPF; k < c_k0 + c_n; ++k) sum += expf((float)(val[arc_peer[k]] + arc_like[k] - m));
+                for (int k = c_k0 + kPF; k < c_k0 + c_n; ++k) sum += expf((float)(get(arc_rec[k].peer, t - step) + arc_rec[k].like - m));
             }
-            val[s] = (m > -INFINITY) ? m + (double)logf(sum) : -INFINITY;
+            put(s, t, (m > -INFINITY) ? m + (double)logf(sum) : -INFINITY);
         }
-        for (int s2 = s + kChain; s2 < lv1; s2 += kChain) slow_state(s2);
+        for (int s2 = s + kChain; s2 < lv1; s2 += kChain) slow_state(s2, t);
         __syncthreads();
         eps(t);
         if (MPE) {
+            // accuracy recursion: sum_k w_k (val_s[peer_k] + acc_k) with w_k = exp(x_k - value).  The weights are
+            // formed as exp(x_k - m) / sum: exactly normalised, so the fp32 error of logf(sum) does not bias a
+            // recursion that runs over thousands of levels (values ~ T, differences of them matter downstream)
             if (s < lv1) {
-                const double v = val[s];
-                double sc = 0.0;
-                if (v > -INFINITY) {
+                double num = 0.0;
+                if (m > -INFINITY) {
 #pragma unroll
                     for (int i = 0; i < kPF; ++i)
-                        if (i < c_n) sc += (double)expf((float)(val[c_peer[i]] + c_like[i] - v)) * (val_s[c_peer[i]] + (double)c_acc[i]);
+                        if (i < c_n) num += (double)expf((float)(x[i] - m)) * (get_s(peer[i], t - step) + (double)acc[i]);
                     for (int k = c_k0 + kPF; k < c_k0 + c_n; ++k) {
-                        const int u = arc_peer[k];
-                        sc += (double)expf((float)(val[u] + arc_like[k] - v)) * (val_s[u] + (double)arc_acc[k]);
+                        const int u = arc_rec[k].peer;
+                        num += (double)expf((float)(get(u, t - step) + arc_rec[k].like - m)) * (get_s(u, t - step) + (double)arc_rec[k].acc);
                     }
                 }
-                val_s[s] = sc;
+                double sc = 0.0;
+                if (m > -INFINITY) {
+                    sc = num / (double)sum;
+                    const double a_reg = m + (double)logf(sum), v = get(s, t);
+                    if (v != a_reg) sc *= exp(a_reg - v);          // epsilon arcs entered this state
+                }
+                put_s(s, t, sc);
             }
-            for (int s2 = s + kChain; s2 < lv1; s2 += kChain) slow_state_s(s2);
+            for (int s2 = s + kChain; s2 < lv1; s2 += kChain) slow_state_s(s2, t);
             __syncthreads();
             eps_s(t);
         }
-        c_k0 = n_k0; c_n = p_n;
-#pragma unroll
-        for (int i = 0; i < kPF; ++i) { c_peer[i] = p_peer[i]; c_like[i] = p_like[i]; c_acc[i] = p_acc[i]; }
-        n_k0 = f_k0; n_k1 = f_k1;
     }
+    cp_async_wait<0>();
 
     if (FWD) {
         // ---- total log-likelihood (and expected accuracy) from the final states
@@ -560,27 +624,44 @@ __device__ void lat_chain(const pk2_lat_batch& lat, int b, const int32_t* __rest
 }
 
 struct LatWs {
-    double *alpha, *beta, *alpha_s, *beta_s, *like_in, *like_out;
+    double *alpha, *beta, *alpha_s, *beta_s;
+    ArcRec *rec_in, *rec_out;
     int32_t* pdf_out;
 };
 
+size_t chain_smem_bytes(int max_frames, bool mpe) {
+    size_t b = 2 * (size_t)(max_frames + 2) * sizeof(int);
+    b = (b + 15) & ~(size_t)15;
+    b += (size_t)(mpe ? 4 : 2) * kValW * sizeof(double);
+    b += (size_t)2 * kDepth * kChain * sizeof(int2);
+    b += (size_t)(kDepth + 1) * kPF * kChain * sizeof(ArcRec);
+    return b;
+}
+
 template <bool MPE>
 __global__ void __launch_bounds__(kChain)
-lat_chain_kernel(pk2_lat_batch lat, LatWs w, const uint8_t* __restrict__ acc_in, const uint8_t* __restrict__ acc_out,
-                 float lm, double* __restrict__ tot_out, double* __restrict__ score_out, int max_frames) {
-    extern __shared__ int s_dyn[];
-    int* s_lvl = s_dyn;
-    int* s_eoff = s_dyn + (max_frames + 2);
+lat_chain_kernel(pk2_lat_batch lat, LatWs w, float lm, double* __restrict__ tot_out, double* __restrict__ score_out,
+                 int max_frames) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    ChainSmem sm;
+    size_t o = 0;
+    sm.lvl = reinterpret_cast<int*>(s_dyn);
+    sm.eoff = sm.lvl + (max_frames + 2);
+    o = (2 * (size_t)(max_frames + 2) * sizeof(int) + 15) & ~(size_t)15;
+    sm.sv = reinterpret_cast<double*>(s_dyn + o); o += 2 * kValW * sizeof(double);
+    sm.sv_s = reinterpret_cast<double*>(s_dyn + o); if (MPE) o += 2 * kValW * sizeof(double);
+    sm.off = reinterpret_cast<int2*>(s_dyn + o); o += (size_t)2 * kDepth * kChain * sizeof(int2);
+    sm.rec = reinterpret_cast<ArcRec*>(s_dyn + o);
     const int b = blockIdx.x >> 1;
     if ((blockIdx.x & 1) == 0)
-        lat_chain<true, MPE>(lat, b, lat.in_off, lat.in_src, w.like_in, acc_in, lm, w.alpha, w.alpha_s, tot_out, score_out, s_lvl, s_eoff);
+        lat_chain<true, MPE>(lat, b, lat.in_off, w.rec_in, lm, w.alpha, w.alpha_s, tot_out, score_out, sm);
     else
-        lat_chain<false, MPE>(lat, b, lat.out_off, lat.out_dst, w.like_out, acc_out, lm, w.beta, w.beta_s, tot_out, score_out, s_lvl, s_eoff);
+        lat_chain<false, MPE>(lat, b, lat.out_off, w.rec_out, lm, w.beta, w.beta_s, tot_out, score_out, sm);
 }
 
 template <bool MPE>
 __global__ void __launch_bounds__(256)
-lat_post_kernel(pk2_lat_batch lat, LatWs w, const uint8_t* __restrict__ acc_out, int N, int64_t row_stride_b,
+lat_post_kernel(pk2_lat_batch lat, LatWs w, int N, int64_t row_stride_b,
                 float deriv_scale, const double* __restrict__ tot_in, const double* __restrict__ score_in,
                 float* __restrict__ grad, int total_states, int total_frames) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -593,10 +674,10 @@ lat_post_kernel(pk2_lat_batch lat, LatWs w, const uint8_t* __restrict__ acc_out,
             if (a > -INFINITY) {
                 const double as = MPE ? (w.alpha_s[s] - score_in[b]) : 0.0;
                 for (int k = lat.out_off[s]; k < lat.out_off[s + 1]; ++k) {
-                    const int d = lat.out_dst[k];
-                    const float post = expf((float)(a + w.like_out[k] + w.beta[d]));
+                    const ArcRec r = w.rec_out[k];
+                    const float post = expf((float)(a + r.like + w.beta[r.peer]));
                     if (MPE) {
-                        const float v = post * (float)(as + (double)acc_out[k] + w.beta_s[d]);
+                        const float v = post * (float)(as + (double)r.acc + w.beta_s[r.peer]);
                         if (v != 0.f) atomicAdd(&grow[w.pdf_out[k]], deriv_scale * v);
                     } else if (post > 0.f) {
                         atomicAdd(&grow[w.pdf_out[k]], post);
@@ -620,34 +701,37 @@ lat_post_kernel(pk2_lat_batch lat, LatWs w, const uint8_t* __restrict__ acc_out,
 }
 
 size_t lat_ws_layout(int64_t S, int64_t A, bool mpe, void* base, LatWs* w) {
-    const size_t nd = (size_t)(mpe ? 4 : 2) * S + 2 * (size_t)A;
+    const size_t nd = (size_t)(mpe ? 4 : 2) * S;
+    const size_t vals = (nd * sizeof(double) + 15) & ~(size_t)15;
     if (w) {
         double* d = static_cast<double*>(base);
         w->alpha = d; w->beta = d + S;
         w->alpha_s = mpe ? d + 2 * S : nullptr; w->beta_s = mpe ? d + 3 * S : nullptr;
-        double* arcs = d + (size_t)(mpe ? 4 : 2) * S;
-        w->like_in = arcs; w->like_out = arcs + A;
+        ArcRec* arcs = reinterpret_cast<ArcRec*>(static_cast<char*>(base) + vals);
+        w->rec_in = arcs; w->rec_out = arcs + A;
         w->pdf_out = reinterpret_cast<int32_t*>(arcs + 2 * A);
     }
-    return nd * sizeof(double) + (size_t)A * sizeof(int32_t) + 16;
+    return vals + 2 * (size_t)A * sizeof(ArcRec) + (size_t)A * sizeof(int32_t) + 16;
 }
 
 template <bool MPE>
 int launch_lat_v1(const pk2_lat_batch* lat, const uint8_t* acc_in, const uint8_t* acc_out, const float* loglikes,
                   int num_pdfs, int max_frames, int64_t row_stride_b, float lm, float ac, void* ws, int64_t S, int64_t A,
                   float deriv_scale, float* grad, double* tot, double* score, int total_frames, cudaStream_t st) {
+    PK2_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "pk2_latfb: workspace must be 16-byte aligned");
     LatWs w;
     lat_ws_layout(S, A, MPE, ws, &w);
     const int nb = (int)((S + 255) / 256);
-    lat_arc_like_kernel<<<nb, 256, 0, st>>>(*lat, loglikes, num_pdfs, row_stride_b, lm, ac, w.like_in, w.like_out, w.pdf_out, (int)S);
+    lat_arc_like_kernel<<<nb, 256, 0, st>>>(*lat, acc_in, acc_out, loglikes, num_pdfs, row_stride_b, lm, ac, w.rec_in, w.rec_out,
+                                           w.pdf_out, (int)S);
     PK2_POST_LAUNCH();
-    const size_t smem = 2 * (size_t)(max_frames + 2) * sizeof(int);
-    PK2_REQUIRE(smem <= 200 * 1024, "pk2_latfb: utterances of more than %d frames are not supported", (int)(200 * 1024 / 8 - 2));
+    const size_t smem = chain_smem_bytes(max_frames, MPE);
+    PK2_REQUIRE(smem <= 227 * 1024, "pk2_latfb: utterances of %d frames exceed the chain kernel's shared memory", max_frames);
     PK2_CHECK(cudaFuncSetAttribute(lat_chain_kernel<MPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lat_chain_kernel<MPE><<<2 * lat->n_seq, kChain, smem, st>>>(*lat, w, acc_in, acc_out, lm, tot, score, max_frames);
+    lat_chain_kernel<MPE><<<2 * lat->n_seq, kChain, smem, st>>>(*lat, w, lm, tot, score, max_frames);
     PK2_POST_LAUNCH();
     const int64_t np = S > total_frames ? S : total_frames;
-    lat_post_kernel<MPE><<<(int)((np + 255) / 256), 256, 0, st>>>(*lat, w, acc_out, num_pdfs, row_stride_b, deriv_scale, tot, score,
+    lat_post_kernel<MPE><<<(int)((np + 255) / 256), 256, 0, st>>>(*lat, w, num_pdfs, row_stride_b, deriv_scale, tot, score,
                                                                 grad, (int)S, total_frames);
     PK2_POST_LAUNCH();
     return 0;

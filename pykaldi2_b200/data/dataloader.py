@@ -13,7 +13,7 @@ label-file formats: data/speech_dataset.py); items are raw waveforms because the
 """
 import numpy as np
 import torch
-from torch.utils.data import DataLoader, Dataset
+from torch.utils.data import DataLoader, Dataset, Sampler
 from torch.utils.data.distributed import DistributedSampler
 
 from .. import dist as pkdist
@@ -54,7 +54,49 @@ def _sampler(dataset, distributed):
     return None
 
 
-class ChunkDataloader(DataLoader):
+class _EpochMixin(object):
+    def set_epoch(self, epoch):
+        """Reseed the shuffle of the distributed / balanced sampler (the reference never calls
+        DistributedSampler.set_epoch, so every epoch sees the same order: data/dataloader.py:45-53)."""
+        for s in (getattr(self, "sampler", None), getattr(self, "batch_sampler", None)):
+            if s is not None and hasattr(s, "set_epoch"):
+                s.set_epoch(epoch)
+
+
+class BalancedBatchSampler(Sampler):
+    """Batch sampler of the variable-length trainers under data parallelism: an epoch is a seeded permutation of the
+    utterances cut into GLOBAL minibatches of batch_size * world utterances; each global minibatch is split across
+    the ranks by ``dist.balanced_shards`` (cost = tmax_weight * longest + sum of frames), and a rank yields its own
+    share.  All ranks draw the same permutation (seed + epoch), so no communication is needed.  The tail is padded
+    by wrap-around like DistributedSampler (drop_last=False)."""
+
+    def __init__(self, lengths, batch_size, world=None, rank=None, seed=0, shuffle=True, tmax_weight=50.0):
+        self.lengths = np.asarray(lengths, np.float64)
+        self.batch_size = int(batch_size)
+        self.world = pkdist.size() if world is None else int(world)
+        self.rank = pkdist.rank() if rank is None else int(rank)
+        self.seed, self.shuffle, self.tmax_weight, self.epoch = int(seed), bool(shuffle), float(tmax_weight), 0
+        self.global_batch = self.batch_size * self.world
+
+    def set_epoch(self, epoch):
+        self.epoch = int(epoch)
+
+    def __len__(self):
+        return (len(self.lengths) + self.global_batch - 1) // self.global_batch
+
+    def __iter__(self):
+        n = len(self.lengths)
+        perm = np.random.default_rng(self.seed + self.epoch).permutation(n) if self.shuffle else np.arange(n)
+        total = len(self) * self.global_batch
+        if total > n:
+            perm = np.concatenate([perm, np.resize(perm, total - n)])
+        for g in range(len(self)):
+            idx = perm[g * self.global_batch:(g + 1) * self.global_batch]
+            shards = pkdist.balanced_shards(self.lengths[idx], self.world, self.batch_size, self.tmax_weight)
+            yield [int(idx[j]) for j in shards[self.rank]]
+
+
+class ChunkDataloader(_EpochMixin, DataLoader):
     def __init__(self, dataset, batch_size, distributed=False, num_workers=0, timeout=1000):
         sampler = _sampler(dataset, distributed)
         super().__init__(dataset, batch_size=batch_size, shuffle=(sampler is None), sampler=sampler,
@@ -62,7 +104,7 @@ class ChunkDataloader(DataLoader):
                          timeout=timeout if num_workers > 0 else 0)
 
 
-class SeqDataloader(DataLoader):
+class SeqDataloader(_EpochMixin, DataLoader):
     def __init__(self, dataset, batch_size, num_workers=0, distributed=False, test_only=False, timeout=1000):
         self.test_only = test_only
         sampler = _sampler(dataset, distributed)
@@ -88,6 +130,10 @@ class SyntheticWaveDataset(Dataset):
     def __len__(self):
         return self.n
 
+    def utt_lengths(self):
+        """Frames per utterance (for length-balanced sharding), without touching the audio."""
+        return np.array([fb.num_frames(int(round(d * 16000))) for d in self.durs])
+
     def __getitem__(self, i):
         rng = np.random.default_rng(self.seed * 100003 + i)
         wav = synth.make_waveforms([self.durs[i]], rng)[0]
@@ -97,9 +143,16 @@ class SyntheticWaveDataset(Dataset):
         return wav, ["synth-%06d" % i], pdf, [tid]
 
 
-class WaveDataloader(DataLoader):
-    def __init__(self, dataset, batch_size, num_workers=0, distributed=False, timeout=1000):
+class WaveDataloader(_EpochMixin, DataLoader):
+    """``balanced=True`` (the sequence trainers): under data parallelism the global minibatch is split across ranks
+    by modelled step time (BalancedBatchSampler) instead of at random; needs ``dataset.utt_lengths()``."""
+
+    def __init__(self, dataset, batch_size, num_workers=0, distributed=False, timeout=1000, balanced=False, seed=0):
+        to = timeout if num_workers > 0 else 0
+        if balanced and distributed and pkdist.size() > 1 and hasattr(dataset, "utt_lengths"):
+            bs = BalancedBatchSampler(dataset.utt_lengths(), batch_size, seed=seed)
+            super().__init__(dataset, batch_sampler=bs, num_workers=num_workers, collate_fn=wave_collate, timeout=to)
+            return
         sampler = _sampler(dataset, distributed)
         super().__init__(dataset, batch_size=batch_size, shuffle=(sampler is None), sampler=sampler,
-                         num_workers=num_workers, collate_fn=wave_collate, drop_last=False,
-                         timeout=timeout if num_workers > 0 else 0)
+                         num_workers=num_workers, collate_fn=wave_collate, drop_last=False, timeout=to)

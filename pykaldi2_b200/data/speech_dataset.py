@@ -4,9 +4,12 @@ waveforms + labels, because feature extraction runs on the GPU here (pipeline.Fe
 
 Items have the layout of ``SyntheticWaveDataset``: ``(wav float32 [n], [utt_id], pdf labels int64 [T, 1],
 [transition ids int64 [1, T]])`` and are collated by ``WaveDataloader``.  Differences from the reference's
-``data/sr_dataset.py`` (documented, deliberate): one epoch visits every labelled utterance once in shuffled order
-instead of drawing ``sweep_size`` hours by random sampling (``sweep_size`` caps the epoch length when given), and
-the on-the-fly acoustic simulation (noise / RIR mixing, simulation/*.py) is not applied (SURVEY marks it optional).
+``data/sr_dataset.py`` (documented, deliberate): the on-the-fly acoustic simulation (noise / RIR mixing,
+simulation/*.py) is not applied (SURVEY marks it optional).  Epoch semantics follow the reference:
+  * sequence mode (``data_config.sequence_mode``: train_se / train_chain, data/sr_dataset.py:104-107,192-194): an
+    epoch visits EVERY utterance; ``sweep_size`` plays no role;
+  * chunk mode (train_ce, :55-84,128): an epoch is ``sweep_size`` hours of randomly drawn material: a fresh random
+    subset of utterances per epoch (``set_epoch``), not a fixed prefix of the sorted list.
 """
 import numpy as np
 from torch.utils.data import Dataset
@@ -19,6 +22,7 @@ class SpeechDataset(Dataset):
         self.config = config
         dc = config.get("data_config", {})
         self.load_label = dc.get("load_label", True)
+        self.sequence_mode = bool(dc.get("sequence_mode", False))
         self.fs = 16000
         self.reader = zip_io.ZipWaveIO("float32", self.fs)
         self.transform = None                     # kept for the reference's attribute protocol (bin/train_se.py:103-106)
@@ -50,13 +54,35 @@ class SpeechDataset(Dataset):
             raise ValueError("SpeechDataset: no utterance has both a waveform and labels")
         sweep = config.get("sweep_size")
         self.max_items = None
-        if sweep:                                  # hours per sweep -> utterance cap at LibriSpeech's mean 12.3 s
+        if sweep and not self.sequence_mode:       # hours per sweep -> utterances per epoch at LibriSpeech's mean 12.3 s
             self.max_items = max(1, int(float(sweep) * 3600.0 / 12.3))
+        self.seed = int(config.get("seed", 0))
+        self._subset = None
+        self.set_epoch(0)
+        # the handles opened while listing the archives must not be inherited by forked DataLoader workers (shared
+        # file offset): every process reopens its own on first use
+        self.reader.close()
+
+    def set_epoch(self, epoch):
+        """Chunk mode with a sweep cap: draw this epoch's random subset of utterances."""
+        if self.max_items is not None and self.max_items < len(self.items):
+            rng = np.random.default_rng(self.seed * 7919 + int(epoch))
+            self._subset = np.sort(rng.choice(len(self.items), self.max_items, replace=False))
+        else:
+            self._subset = None
 
     def __len__(self):
-        return len(self.items) if self.max_items is None else min(len(self.items), self.max_items)
+        return len(self.items) if self._subset is None else len(self._subset)
+
+    def utt_lengths(self):
+        """Frames per utterance for length-balanced sharding: the label length where labels exist (label and feature
+        lengths agree up to the trim of data/sr_dataset.py:358-363), else unknown (equal weights)."""
+        idx = range(len(self.items)) if self._subset is None else self._subset
+        return np.array([len(self.labels[self.items[i][1]]) if self.items[i][1] in self.labels else 1 for i in idx])
 
     def __getitem__(self, i):
+        if self._subset is not None:
+            i = int(self._subset[i])
         name, utt = self.items[i]
         _, wav = self.reader.read_wav(name)
         if wav.ndim > 1:

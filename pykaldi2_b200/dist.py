@@ -65,21 +65,25 @@ def broadcast_optimizer_state(optimizer, root_rank=0):
 
 
 class GradAverager(object):
-    """Flat-bucket gradient all-reduce (mean) for a fixed parameter list."""
+    """Flat-bucket gradient all-reduce (mean) for a fixed parameter list.
+
+    The gradients are packed into one flat buffer (one pass), averaged by a single NCCL all-reduce (ReduceOp.AVG on
+    NCCL, SUM + scale on gloo) and handed back as VIEWS of that buffer: ``p.grad`` points into the bucket afterwards,
+    so clipping and the optimizer read the averaged values without a copy back.  ``timers``: set to a list to collect
+    (start, end) CUDA events around pack + all-reduce (bench.py reports the mean as ``allreduce_ms``)."""
 
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
         self._flat = None
+        self.timers = None
 
     def average(self):
         if size() == 1:
             return
+        for p in self.params:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
         grads = [p.grad for p in self.params]
-        if any(g is None for g in grads):
-            for p in self.params:
-                if p.grad is None:
-                    p.grad = torch.zeros_like(p)
-            grads = [p.grad for p in self.params]
         n = sum(g.numel() for g in grads)
         if self._flat is None or self._flat.numel() != n or self._flat.device != grads[0].device:
             self._flat = torch.empty(n, dtype=grads[0].dtype, device=grads[0].device)
@@ -89,10 +93,21 @@ class GradAverager(object):
             v = self._flat[off:off + g.numel()].view_as(g)
             views.append(v)
             off += g.numel()
+        timed = self.timers is not None and self._flat.is_cuda
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         torch._foreach_copy_(views, grads)
-        dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
-        self._flat.div_(size())
-        torch._foreach_copy_(grads, views)
+        if dist.get_backend() == "nccl":
+            dist.all_reduce(self._flat, op=dist.ReduceOp.AVG)
+        else:
+            dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
+            self._flat.div_(size())
+        if timed:
+            e1.record()
+            self.timers.append((e0, e1))
+        for p, v in zip(self.params, views):
+            p.grad = v
 
 
 class DistributedOptimizer(object):
@@ -121,6 +136,42 @@ class DistributedOptimizer(object):
         self.synchronize()
         self._synced = False
         return self._opt.step(*a, **k)
+
+
+def balanced_shards(lengths, world, per_rank=None, tmax_weight=50.0):
+    """Split one global minibatch of utterances across ``world`` data-parallel ranks so that the ranks finish a step
+    together.  Step time of a rank is modelled as  tmax_weight * max(length) + sum(length)  (in frames): the BLSTM
+    recurrences and the padded GEMMs scale with the LONGEST utterance of the rank's batch (the reference pads to it,
+    data/dataloader.py:96-103), the denominator / lattice forward-backward and the output layer with the SUM of
+    frames.  tmax_weight = 50 is the measured ratio on B200 for the 3x512 BLSTM (22 us per padded output frame against
+    0.44 us per valid output frame, profiles/README_r2.md).
+
+    Longest-first greedy onto the rank with the lowest modelled cost that still has room (``per_rank`` utterances per
+    rank, default ceil(n / world)): the rank that receives the longest utterance pays the largest padding term and is
+    given fewer frames in exchange.  Deterministic (ties -> lowest rank); every rank computes the same split.
+    Returns a list of ``world`` index lists (positions into ``lengths``).  Replaces the random sharding of the
+    reference's DistributedSampler (data/dataloader.py:45-53,83-91)."""
+    n = len(lengths)
+    if per_rank is None:
+        per_rank = (n + world - 1) // world
+    if per_rank * world < n:
+        raise ValueError("balanced_shards: %d utterances do not fit %d ranks x %d" % (n, world, per_rank))
+    order = sorted(range(n), key=lambda i: (-float(lengths[i]), i))
+    shards = [[] for _ in range(world)]
+    tmax = [0.0] * world
+    tot = [0.0] * world
+    for i in order:
+        best, best_cost = -1, None
+        for r in range(world):
+            if len(shards[r]) >= per_rank:
+                continue
+            cost = tmax_weight * max(tmax[r], float(lengths[i])) + tot[r] + float(lengths[i])
+            if best_cost is None or cost < best_cost:
+                best, best_cost = r, cost
+        shards[best].append(i)
+        tmax[best] = max(tmax[best], float(lengths[i]))
+        tot[best] += float(lengths[i])
+    return shards
 
 
 def shard_indices(n, world, rank_):

@@ -44,6 +44,51 @@ class FeaturePipeline(object):
         return x, cu, cs
 
 
+class ChunkPool(object):
+    """Device-side stand-in for the reference's DataBuffer (data/sr_dataset.py:55-84: a 20 000-sample buffer that the
+    chunk generator keeps filled and from which training samples are popped AT RANDOM).  Chunks cut from whole
+    utterances on the GPU are appended; ``draw(n)`` removes and returns n chunks chosen uniformly at random (host
+    RNG, seeded), so a minibatch mixes chunks of many utterances and no chunk is ever discarded."""
+
+    def __init__(self, capacity, seg_len, feat_dim, device, seed=0):
+        self.capacity = int(capacity)
+        self.x = torch.empty(self.capacity, seg_len, feat_dim, dtype=torch.float32, device=device)
+        self.y = torch.empty(self.capacity, seg_len, dtype=torch.int64, device=device)
+        self.n = 0
+        self.rng = np.random.default_rng(seed)
+
+    def room(self):
+        return self.capacity - self.n
+
+    def add(self, x, y):
+        k = x.shape[0]
+        if k > self.room():
+            raise RuntimeError("ChunkPool overflow: %d chunks, room for %d" % (k, self.room()))
+        self.x[self.n:self.n + k] = x
+        self.y[self.n:self.n + k] = y
+        self.n += k
+
+    def draw(self, n):
+        n = min(int(n), self.n)
+        pick = self.rng.choice(self.n, size=n, replace=False)
+        dev = self.x.device
+        idx = torch.from_numpy(pick.astype(np.int64)).to(dev)
+        bx, by = self.x[idx], self.y[idx]
+        # fill the holes below the new end with the surviving entries of the tail
+        new_n = self.n - n
+        picked = np.zeros(self.n, bool)
+        picked[pick] = True
+        holes = pick[pick < new_n]
+        tail = np.nonzero(~picked[new_n:])[0] + new_n
+        if len(holes):
+            h = torch.from_numpy(np.sort(holes).astype(np.int64)).to(dev)
+            t = torch.from_numpy(tail.astype(np.int64)).to(dev)
+            self.x[h] = self.x[t]
+            self.y[h] = self.y[t]
+        self.n = new_n
+        return bx, by
+
+
 def ce_loss(logits, labels, reduction="mean"):
     """nn.CrossEntropyLoss(ignore_index=-100) on the fused kernel (bin/train_ce.py:134,189)."""
     return _CE.apply(logits, labels, reduction)

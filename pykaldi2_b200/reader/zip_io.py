@@ -74,9 +74,10 @@ class ZipWaveIO(object):
         self._zips = {}
 
     def _zip(self, path):
-        z = self._zips.get(path)
+        key = (os.getpid(), path)          # per process: a forked DataLoader worker must not share the parent's handle
+        z = self._zips.get(key)
         if z is None:
-            z = self._zips[path] = zipfile.ZipFile(path, "r")
+            z = self._zips[key] = zipfile.ZipFile(path, "r")
         return z
 
     def close(self):
