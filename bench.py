@@ -11,9 +11,13 @@ forward-backward -> BLSTM bwd -> (NCCL grad all-reduce) -> clip -> optimizer ste
   value  : hours of audio per wall-clock hour, inputs resident in HBM, all ranks (weak scaling)
   e2e    : same, through the public API with HOST (pinned) waveforms + supervision index arrays
            copied H2D and the loss read back D2H inside the timed region
-  roofline: denominator forward-backward kernels (den_forward+den_backward) vs measured HBM peak
+  roofline: denominator forward-backward kernels (den_forward+den_backward) vs measured HBM peak, plus
+           roofline_smem: the same kernels against the shared-memory gather bound they actually run into
   cpu_baseline / --impl reference: the reference's CPU path (numpy fbank restatement, torch-CPU
-           nn.LSTM+Linear = the reference model, restated Kaldi chain FB) on a bounded sample.
+           nn.LSTM+Linear = the reference model, restated Kaldi chain FB) on a bounded, representative
+           sample (every 16th utterance of the length-sorted batch), all physical host cores.
+  N > 1:   the global batch is split across ranks by modelled step time (dist.balanced_shards, the
+           sampler the trainers use); the line adds allreduce_ms and the per-rank compute-time spread.
 
 Launch: python bench.py --gpus 1 ;  torchrun --nproc-per-node N bench.py --gpus N
 """
@@ -47,14 +51,20 @@ def load_peaks():
 
 def make_workload(rank, batch, seed=1234, world=1):
     """Synthetic utterances of this rank.  The GLOBAL batch (batch * world utterances, durations seeded
-    independently of world) is sorted by length and dealt round-robin to the ranks: the length-bucketed
-    sharding that keeps the frame count -- and therefore the step time -- balanced across data-parallel
-    ranks (the reference's DistributedSampler shards at random; SURVEY.md section 7.3 "var-len DP load balance")."""
+    independently of world) is split across the ranks by dist.balanced_shards -- the product's sampler
+    (data.dataloader.BalancedBatchSampler, used by train_se / train_chain): cost = 50 * longest + sum of frames,
+    so the rank that holds the longest utterance gets fewer frames.  (The reference's DistributedSampler shards at
+    random; SURVEY.md section 7.3 "var-len DP load balance".)"""
+    from pykaldi2_b200 import dist as pkdist
     from pykaldi2_b200 import synth
     from pykaldi2_b200.data import fbank as fb
     rng = np.random.default_rng(seed)
-    all_durs = np.sort(synth.make_durations(batch * world, rng))[::-1]
-    durs = all_durs[rank::world]
+    all_durs = synth.make_durations(batch * world, rng)
+    if world > 1:
+        shards = pkdist.balanced_shards([fb.num_frames(int(round(d * 16000))) for d in all_durs], world, batch)
+        durs = np.sort(all_durs[shards[rank]])[::-1]
+    else:
+        durs = np.sort(all_durs)[::-1]
     rng = np.random.default_rng(seed + 1000 * (rank + 1))
     wavs = synth.make_waveforms(durs, rng)
     frames = [fb.num_frames(len(w)) for w in wavs]
@@ -118,13 +128,38 @@ DEN_TRAFFIC_BYTES = 5585641608      # ncu, profiles/ncu_den_full_r1_v24.md
 
 
 # ------------------------------------------------------------------------------ CPU arm ----
-def cpu_reference_sample(wavs, sup_fsts, den_fst, n_utts, threads=None):
-    """The reference's CPU path on n_utts utterances; returns (audio seconds, wall seconds)."""
+def host_cores():
+    """Physical cores of the box.  torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must not inherit
+    that (the N >= 2 reference arms ran on one core)."""
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False)
+    except Exception:
+        n = None
+    if not n:
+        n = max(1, (os.cpu_count() or 2) // 2)
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    return int(n)
+
+
+def cpu_sample(durs, wavs, sup_fsts):
+    """The bounded sample both CPU legs time: every 16th utterance of the length-sorted batch (4 of 64: a long, two
+    medium and a short one -- the padding ratio of the sample is that of the batch)."""
+    order = np.argsort(durs)[::-1][::16]
+    return [wavs[i] for i in order], [sup_fsts[i] for i in order], float(sum(len(wavs[i]) for i in order)) / 16000.0
+
+
+def cpu_reference_sample(wavs, sup_fsts, den_fst, threads):
+    """The reference's CPU path on the given utterances as ONE minibatch; returns (audio seconds, wall seconds)."""
     import torch.nn as nn
+    from concurrent.futures import ThreadPoolExecutor
     from oracle import c_port, chain_ref, fbank_ref
     from pykaldi2_b200.data import mel
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(threads)
+    n_utts = len(wavs)
     W = mel.mel80_window()
     oden = chain_ref.den_graph_from_fst(den_fst, N_PDF)          # graph construction is one-off: untimed
     torch.manual_seed(0)
@@ -134,7 +169,7 @@ def cpu_reference_sample(wavs, sup_fsts, den_fst, n_utts, threads=None):
     opt = torch.optim.Adam(params, lr=1e-4, amsgrad=True)
     t0 = time.perf_counter()
     feats = []
-    for w in wavs[:n_utts]:
+    for w in wavs:
         f = fbank_ref.cmn(fbank_ref.logfbank(w, W)).astype(np.float32)
         feats.append(f[::FACTOR])
     Tm = max(f.shape[0] for f in feats)
@@ -143,17 +178,25 @@ def cpu_reference_sample(wavs, sup_fsts, den_fst, n_utts, threads=None):
         x[i, :f.shape[0]] = f
     pred = lin(lstm(torch.from_numpy(x))[0])
     grad = torch.zeros_like(pred)
-    for i in range(n_utts):
+
+    def one(i):                                                   # C forward-backward: releases the GIL
         T = feats[i].shape[0]
         ll = pred[i, :T].detach().numpy()
         objf, g, _ = c_port.chain_objf_and_deriv(ll, oden, sup_fsts[i], leaky=1e-4)
         grad[i, :T] = torch.from_numpy(-g.astype(np.float32))
+    with ThreadPoolExecutor(max_workers=max(1, min(n_utts, threads))) as ex:
+        list(ex.map(one, range(n_utts)))
     pred.backward(grad)
     torch.nn.utils.clip_grad_norm_(params, 5.0)
     opt.step()
     dt = time.perf_counter() - t0
-    audio = sum(len(w) for w in wavs[:n_utts]) / 16000.0
+    audio = sum(len(w) for w in wavs) / 16000.0
     return audio, dt
+
+
+CPU_SAMPLE_TEXT = ("every 16th utterance of the length-sorted 64-utterance batch (4 utterances, one minibatch): numpy "
+                   "fbank+CMN, torch-CPU nn.LSTM+Linear fwd/bwd + Adam (the reference model), restated Kaldi chain den/num "
+                   "FB (C -O3, one thread per utterance)")
 
 
 def run_reference(args, rank):
@@ -163,16 +206,13 @@ def run_reference(args, rank):
     from pykaldi2_b200 import synth
     durs, wavs, frames, sub, sup_fsts = make_workload(0, BATCH)
     den_fst = synth.make_den_fst(DEN_STATES, N_PDF, DEN_EXTRA, seed=1234)
-    order = np.argsort(durs)[:4]                 # bounded sample: the 4 shortest utterances per step
-    wv = [wavs[i] for i in order]; sf = [sup_fsts[i] for i in order]
-    # torch's default intra-op thread count (= physical cores) for the BLSTM; more threads than that
-    # (os.cpu_count() counts hyper-threads) made the small-batch CPU LSTM 20x slower on the 64-core box
-    cores = torch.get_num_threads()
-    for _ in range(max(args.warmup, 0) and 1):
-        cpu_reference_sample(wv[:1], sf[:1], den_fst, 1)
+    wv, sf, audio = cpu_sample(durs, wavs, sup_fsts)
+    cores = host_cores()
+    for _ in range(1 if args.warmup > 0 else 0):
+        cpu_reference_sample(wv[-1:], sf[-1:], den_fst, cores)
     tot_a = tot_t = 0.0
     for _ in range(args.steps):
-        a, t = cpu_reference_sample(wv, sf, den_fst, len(wv))
+        a, t = cpu_reference_sample(wv, sf, den_fst, cores)
         tot_a += a; tot_t += t
     irtf = tot_a / tot_t
     line = {
@@ -181,10 +221,9 @@ def run_reference(args, rank):
         "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "BLSTM 3x512 LF-MMI chain, batch 64 var-len utts/GPU, S=8192 den FST (C4)",
-                   "sample": "4 shortest utterances of the batch per step"},
+                   "sample": "every 16th utterance of the length-sorted batch per step", "sample_audio_s": audio},
         "cpu_baseline": {"value": irtf, "unit": "hours audio per hour", "cores": cores, "kind": "port",
-                         "sample": "4 shortest utterances of the 64-utt batch: numpy fbank+CMN, torch-CPU nn.LSTM+Linear "
-                                   "fwd/bwd + Adam (the reference model), restated Kaldi chain den/num FB (C -O3, 1 thread per utterance)"},
+                         "sample": CPU_SAMPLE_TEXT, "sample_audio_s": audio},
         "e2e": {"value": irtf, "unit": "hours audio per hour", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -251,9 +290,12 @@ def main():
             ev.record(copy_stream)
         staged["next"] = (w, sb, ev)
 
+    step_events = []
+
     def step(resident):
         if resident:
-            return pipeline.chain_step(model, optimizer, averager, feat, den, opts, wav_dev, woff, foff, sup_dev, epoch=0)
+            return pipeline.chain_step(model, optimizer, averager, feat, den, opts, wav_dev, woff, foff, sup_dev, epoch=0,
+                                       events=step_events)
         if "next" not in staged:
             stage_next()
         w, sb, ev = staged.pop("next")
@@ -292,11 +334,30 @@ def main():
     if sampler:
         del sampler.rows[:]                  # keep only the samples taken during the timed regions
     ops.DEN_TIMERS = []
+    del step_events[:]
+    if averager is not None:
+        averager.timers = []
     n0 = L.pk2_launch_count()
     t_res = timed(True, args.steps)
     n1 = L.pk2_launch_count()
     den_ms = [a.elapsed_time(b) for a, b in ops.DEN_TIMERS]
     ops.DEN_TIMERS = None
+    compute_ms = float(np.mean([a.elapsed_time(b) for a, b in step_events])) if step_events else float("nan")
+    ar_ms = None
+    if averager is not None:
+        ar_ms = float(np.mean([a.elapsed_time(b) for a, b in averager.timers]))
+        averager.timers = None
+    # per-rank compute time (start of the step -> backward pass done, before the all-reduce joins the ranks)
+    spread = torch.tensor([compute_ms, float(sum(sub)), float(max(sub))], dtype=torch.float64, device=dev)
+    if world > 1:
+        allv = [torch.zeros_like(spread) for _ in range(world)]
+        torch.distributed.all_gather(allv, spread)
+        spread_rows = [[float(v) for v in t.tolist()] for t in allv]
+        ar_t = torch.tensor([ar_ms], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(ar_t, op=torch.distributed.ReduceOp.MIN)   # the last rank to arrive waits least
+        ar_ms = float(ar_t.item())
+    else:
+        spread_rows = [[float(v) for v in spread.tolist()]]
     t_e2e = timed(False, args.steps)
     clocks = sampler.stop() if sampler else None
 
@@ -320,7 +381,7 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "BLSTM 3x512 LF-MMI chain, batch 64 var-len utts/GPU, S=8192 den FST (C4)",
                        "global_batch": B * world, "audio_s_per_step": tot_audio, "parallelism": "dp%d" % world,
-                       "sharding": "global batch sorted by length, dealt round-robin to ranks",
+                       "sharding": "global batch split across ranks by modelled step time (dist.balanced_shards: 50 x longest + sum of frames)",
                        "l2": "no flush: every step streams > 5 GB of activations/workspace, far larger than the 126 MB L2",
                        "optimizer": "Adam(amsgrad) lr 1e-4, clip 5"},
             "e2e": {"value": e2e, "unit": "hours audio per hour", "ms_per_step": 1e3 * t_e2e / args.steps,
@@ -335,16 +396,28 @@ def main():
                          "traffic": DEN_TRAFFIC_BYTES if (B == BATCH and world == 1) else None,
                          "note": "binding bound is shared-memory gather bandwidth + the DSMEM row exchange inside a chain of "
                                  "dependent frames, not HBM (DESIGN.md section 4.4)"},
+            # the bound the denominator kernels actually run into: per frame and sequence every
+            # arc costs two 4-byte shared-memory gathers in each of the three passes (alpha, beta, gamma); an SM
+            # serves 32 conflict-free 4-byte lanes per clock
+            "roofline_smem": {"kernel": "pk2_denfb", "bound": "shared-memory gather",
+                              "achieved": sum(sub) * n_arcs * 6 / den_s / 1e9, "unit": "G gathers/s",
+                              "peak": 148 * 32 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e9 if clocks else 148 * 32 * 1.965,
+                              "frac": sum(sub) * n_arcs * 6 / den_s / (148 * 32 * ((clocks["sm_mhz"] if clocks and clocks["sm_mhz"] else 1965.0) * 1e6)),
+                              "note": "arcs x 2 gathers x 3 passes x frames / (SMs x 32 lanes x clock); conflict-free ideal"},
+            "compute_ms_per_rank": [round(r[0], 3) for r in spread_rows],
+            "frames_per_rank": [int(r[1]) for r in spread_rows],
+            "tmax_per_rank": [int(r[2]) for r in spread_rows],
+            "allreduce_ms": ar_ms,
             "clocks": clocks,
         }
         if not args.no_cpu_baseline:
             try:
-                order = np.argsort(durs)[:2]
-                a, t = cpu_reference_sample([wavs[i] for i in order], [sup_fsts[i] for i in order], den_fst, 2)
-                line["cpu_baseline"] = {"value": a / t, "unit": "hours audio per hour", "cores": torch.get_num_threads(),
-                                        "kind": "port",
-                                        "sample": "2 shortest utterances of the batch: numpy fbank+CMN, torch-CPU nn.LSTM+Linear "
-                                                  "fwd/bwd+Adam, restated Kaldi chain den/num FB (C -O3)"}
+                durs0, wavs0, _, _, sups0 = (durs, wavs, None, None, sup_fsts) if world == 1 else make_workload(0, BATCH)
+                wv, sf, audio = cpu_sample(durs0, wavs0, sups0)
+                cores = host_cores()
+                a, t = cpu_reference_sample(wv, sf, den_fst, cores)
+                line["cpu_baseline"] = {"value": a / t, "unit": "hours audio per hour", "cores": cores,
+                                        "kind": "port", "sample": CPU_SAMPLE_TEXT, "sample_audio_s": audio}
             except Exception as e:      # the CPU leg must never take the GPU line down
                 line["cpu_baseline"] = {"value": None, "error": repr(e)}
         print(json.dumps(line))

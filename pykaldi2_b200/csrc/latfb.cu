@@ -308,11 +308,15 @@ latfb_mpe_kernel(pk2_lat_batch lat, const uint8_t* __restrict__ acc_in, const ui
 // =================================================================== round-2 kernels ====
 constexpr int kChain = 128;      // threads of a chain CTA (one state per thread and level; wider levels loop)
 constexpr int kPF = 6;           // arcs per state staged in shared memory ahead of time
-constexpr int kDepth = 8;        // levels the asynchronous arc copies run ahead of the recursion
+constexpr int kDepth = 7;        // levels the asynchronous arc copies run ahead of the recursion (kDepth + 1 = 8 slots)
 constexpr int kValW = 1024;      // states per level whose value is exchanged through shared memory
+constexpr int kOffSlots = 16;    // >= 2 * kDepth, power of two
 
-// one arc as the chain and posterior kernels read it: score, state at the other end, frame accuracy (sMBR / MPFE)
-struct __align__(16) ArcRec { double like; int peer; int acc; };
+// one arc as the chain and posterior kernels read it: score, state at the other end (global index, and its index
+// inside its level | frame accuracy of sMBR / MPFE << 30)
+struct __align__(16) ArcRec { double like; int peer; int aux; };
+__device__ __forceinline__ int rec_local(const ArcRec& r) { return r.aux & 0x3fffffff; }
+__device__ __forceinline__ int rec_acc(const ArcRec& r) { return r.aux >> 30; }
 
 __device__ __forceinline__ int seq_of_state(const pk2_lat_batch& lat, int s) {
     int lo = 0, hi = lat.n_seq - 1;                   // largest b with seq_state_off[b] <= s
@@ -333,25 +337,28 @@ lat_arc_like_kernel(pk2_lat_batch lat, const uint8_t* __restrict__ acc_in, const
     const int b = seq_of_state(lat, s);
     const int t = lat.state_time[s];
     const float* ll = loglikes + (int64_t)b * row_stride_b * N;
+    const int32_t* lvl = lat.level_off + lat.lvl_base[b];
     if (t < lat.num_frames[b]) {
         const float* row = ll + (int64_t)t * N;
+        const int next0 = lvl[t + 1];                     // out-arcs end in level t + 1
         for (int k = lat.out_off[s]; k < lat.out_off[s + 1]; ++k) {
             const int p = __ldg(&lat.tid2pdf[lat.out_tid[k]]);
             ArcRec r;
             r.like = -(double)(lm * lat.out_gc[k]) + (double)ac * (double)__ldg(&row[p]);
             r.peer = lat.out_dst[k];
-            r.acc = acc_out ? (int)acc_out[k] : 0;
+            r.aux = (r.peer - next0) | ((acc_out ? (int)acc_out[k] : 0) << 30);
             rec_out[k] = r;
             pdf_out[k] = p;
         }
     }
     if (t >= 1) {
         const float* row = ll + (int64_t)(t - 1) * N;
+        const int prev0 = lvl[t - 1];                     // in-arcs start in level t - 1
         for (int k = lat.in_off[s]; k < lat.in_off[s + 1]; ++k) {
             ArcRec r;
             r.like = -(double)(lm * lat.in_gc[k]) + (double)ac * (double)__ldg(&row[lat.tid2pdf[lat.in_tid[k]]]);
             r.peer = lat.in_src[k];
-            r.acc = acc_in ? (int)acc_in[k] : 0;
+            r.aux = (r.peer - prev0) | ((acc_in ? (int)acc_in[k] : 0) << 30);
             rec_in[k] = r;
         }
     }
@@ -373,7 +380,7 @@ struct ChainSmem {
     int* eoff;         // [T + 2] first epsilon arc of every level
     double* sv;        // [2][kValW] value (alpha / beta) of the previous and the current level
     double* sv_s;      // [2][kValW] accuracy recursion (sMBR / MPFE)
-    int2* off;         // [2 * kDepth][kChain] CSR range of the thread's state, 2 * kDepth levels ahead
+    int2* off;         // [kOffSlots][kChain] CSR range of the thread's state, 2 * kDepth levels ahead
     ArcRec* rec;       // [kDepth + 1][kPF][kChain] the state's first kPF arcs, kDepth levels ahead
 };
 
@@ -463,15 +470,18 @@ __device__ void lat_chain(const pk2_lat_batch& lat, int b, const int32_t* __rest
         double num = 0.0, den = 0.0;
         if (m > -INFINITY)
             for (int k = k0; k < k1; ++k) {
-                const int u = arc_rec[k].peer;
-                const double w = (double)expf((float)(get(u, t - step) + arc_rec[k].like - m));
+                const ArcRec r = arc_rec[k];
+                const double w = exp(get(r.peer, t - step) + r.like - m);
                 den += w;
-                num += w * (get_s(u, t - step) + (double)arc_rec[k].acc);
+                num += w * (get_s(r.peer, t - step) + (double)rec_acc(r));
             }
         double sc = 0.0;
         if (den > 0.0) {
             sc = num / den;
-            const double a_reg = m + log(den), v = get(s, t);      // v > a_reg when epsilon arcs enter the state
+            // the value stored by slow_state is m + logf(fp32 sum); v exceeds it when epsilon arcs enter the state
+            float sumf = 0.f;
+            for (int k = k0; k < k1; ++k) sumf += expf((float)(get(arc_rec[k].peer, t - step) + arc_rec[k].like - m));
+            const double a_reg = m + (double)logf(sumf), v = get(s, t);
             if (v != a_reg) sc *= exp(a_reg - v);
         }
         put_s(s, t, sc);
@@ -494,9 +504,12 @@ __device__ void lat_chain(const pk2_lat_batch& lat, int b, const int32_t* __rest
     eps_s(t_first);
 
     // ---- asynchronous staging.  Level index n = 1, 2, ... <-> level t = t_first + n * step, n <= T.
+    // Offsets ring: kOffSlots (16) slots, filled 2 * kDepth levels ahead; arc ring: kDepth + 1 (8) slots.
+    static_assert(kOffSlots >= 2 * kDepth + 1 && (kOffSlots & (kOffSlots - 1)) == 0, "offset ring");
+    static_assert(((kDepth + 1) & kDepth) == 0, "arc ring depth must be a power of two");
     auto level_of = [&](int n) { return t_first + n * step; };
     auto issue_off = [&](int n) {             // CSR range of this thread's state of level index n
-        int2* dst = &sm.off[(n % (2 * kDepth)) * kChain + tid];
+        int2* dst = &sm.off[(n & (kOffSlots - 1)) * kChain + tid];
         bool ok = false;
         if (n <= T) {
             const int t = level_of(n);
@@ -506,7 +519,7 @@ __device__ void lat_chain(const pk2_lat_batch& lat, int b, const int32_t* __rest
         if (!ok) *dst = make_int2(0, 0);
     };
     auto issue_arcs = [&](int n, int2 o) {    // first kPF arcs of that state
-        ArcRec* dst = sm.rec + (size_t)(n % (kDepth + 1)) * kPF * kChain + tid;
+        ArcRec* dst = sm.rec + (size_t)(n & kDepth) * kPF * kChain + tid;
         const int cnt = o.y - o.x;
 #pragma unroll
         for (int i = 0; i < kPF; ++i) if (i < cnt) cp_async16(dst + i * kChain, arc_rec + o.x + i);
@@ -514,66 +527,87 @@ __device__ void lat_chain(const pk2_lat_batch& lat, int b, const int32_t* __rest
     for (int n = 1; n <= 2 * kDepth; ++n) issue_off(n);
     cp_async_commit();
     cp_async_wait<0>();
-    for (int n = 1; n <= kDepth; ++n) issue_arcs(n, sm.off[(n % (2 * kDepth)) * kChain + tid]);
+    for (int n = 1; n <= kDepth; ++n) issue_arcs(n, sm.off[(n & (kOffSlots - 1)) * kChain + tid]);
     cp_async_commit();
     cp_async_wait<0>();
 
     for (int n = 1; n <= T; ++n) {
         const int t = level_of(n);
         cp_async_wait<kDepth - 1>();                      // the copies issued kDepth iterations ago have landed
-        const int2 oc = sm.off[(n % (2 * kDepth)) * kChain + tid];                       // this level
-        const int2 ob = sm.off[((n + kDepth) % (2 * kDepth)) * kChain + tid];            // kDepth levels ahead
+        const int2 oc = sm.off[(n & (kOffSlots - 1)) * kChain + tid];                    // this level
+        const int2 ob = sm.off[((n + kDepth) & (kOffSlots - 1)) * kChain + tid];         // kDepth levels ahead
         issue_arcs(n + kDepth, ob);
         issue_off(n + 2 * kDepth);
         cp_async_commit();
 
         const int lv0 = s_lvl[t], lv1 = s_lvl[t + 1];
+        const int pw = s_lvl[t - step + 1] - s_lvl[t - step];          // width of the neighbouring level
         const int s = lv0 + tid;
         const int c_k0 = oc.x, c_n = oc.y - oc.x;
-        const ArcRec* mine = sm.rec + (size_t)(n % (kDepth + 1)) * kPF * kChain + tid;
+        const ArcRec* mine = sm.rec + (size_t)(n & kDepth) * kPF * kChain + tid;
+        // fast path (block-uniform): every state of the level has its own thread and the neighbouring level's values
+        // all live in shared memory -- plain indexed reads, no range checks
+        const bool fast = (lv1 - lv0 <= kChain) && (pw <= kValW);
+        const double* pv = sm.sv + sv_slot(t - step);
         double x[kPF], m = -INFINITY;
-        int peer[kPF], acc[kPF];
         float sum = 0.f;
         if (s < lv1) {
+            if (fast) {
 #pragma unroll
-            for (int i = 0; i < kPF; ++i) {
-                x[i] = -INFINITY; peer[i] = 0; acc[i] = 0;
-                if (i < c_n) {
-                    const ArcRec r = mine[i * kChain];
-                    peer[i] = r.peer; acc[i] = r.acc;
-                    x[i] = get(r.peer, t - step) + r.like;
-                    m = fmax(m, x[i]);
+                for (int i = 0; i < kPF; ++i) {
+                    x[i] = -INFINITY;
+                    if (i < c_n) {
+                        const ArcRec r = mine[i * kChain];
+                        x[i] = pv[rec_local(r)] + r.like;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < kPF; ++i) {
+                    x[i] = -INFINITY;
+                    if (i < c_n) { const ArcRec r = mine[i * kChain]; x[i] = get(r.peer, t - step) + r.like; }
                 }
             }
+            m = fmax(fmax(fmax(x[0], x[1]), fmax(x[2], x[3])), fmax(x[4], x[5]));
             for (int k = c_k0 + kPF; k < c_k0 + c_n; ++k) m = fmax(m, get(arc_rec[k].peer, t - step) + arc_rec[k].like);
             if (m > -INFINITY) {
+                // terms at -inf give exp(-inf) = 0; the spread inside one log-sum-exp is what fp32 sees
 #pragma unroll
-                for (int i = 0; i < kPF; ++i) if (i < c_n) sum += expf((float)(x[i] - m));
-                for (int k = c_k0 + kPF; k < c_k0 + c_n; ++k) sum += expf((float)(get(arc_rec[k].peer, t - step) + arc_rec[k].like - m));
+                for (int i = 0; i < kPF; ++i) sum += __expf((float)(x[i] - m));
+                for (int k = c_k0 + kPF; k < c_k0 + c_n; ++k) sum += __expf((float)(get(arc_rec[k].peer, t - step) + arc_rec[k].like - m));
             }
-            put(s, t, (m > -INFINITY) ? m + (double)logf(sum) : -INFINITY);
+            const double v = (m > -INFINITY) ? m + (double)logf(sum) : -INFINITY;
+            if (fast) { sm.sv[sv_slot(t) + tid] = v; val[s] = v; } else put(s, t, v);
         }
         for (int s2 = s + kChain; s2 < lv1; s2 += kChain) slow_state(s2, t);
         __syncthreads();
         eps(t);
         if (MPE) {
-            // accuracy recursion: sum_k w_k (val_s[peer_k] + acc_k) with w_k = exp(x_k - value).  The weights are
-            // formed as exp(x_k - m) / sum: exactly normalised, so the fp32 error of logf(sum) does not bias a
-            // recursion that runs over thousands of levels (values ~ T, differences of them matter downstream)
+            // accuracy recursion: sum_k w_k (val_s[peer_k] + acc_k), w_k = exp(x_k - value).  The weights are formed in
+            // DOUBLE as exp(x_k - m) / sum_k exp(x_k - m): exactly normalised and accurate to 1e-16 -- the recursion
+            // runs over thousands of levels and the posterior below multiplies DIFFERENCES of these values
+            // (fp32 weights left 1e-6 absolute errors in the sMBR derivatives at T = 800)
             if (s < lv1) {
-                double num = 0.0;
+                double num = 0.0, den = 0.0;
                 if (m > -INFINITY) {
 #pragma unroll
                     for (int i = 0; i < kPF; ++i)
-                        if (i < c_n) num += (double)expf((float)(x[i] - m)) * (get_s(peer[i], t - step) + (double)acc[i]);
+                        if (i < c_n) {
+                            const ArcRec r = mine[i * kChain];
+                            const double w = exp(x[i] - m);
+                            den += w;
+                            num += w * (get_s(r.peer, t - step) + (double)rec_acc(r));
+                        }
                     for (int k = c_k0 + kPF; k < c_k0 + c_n; ++k) {
-                        const int u = arc_rec[k].peer;
-                        num += (double)expf((float)(get(u, t - step) + arc_rec[k].like - m)) * (get_s(u, t - step) + (double)arc_rec[k].acc);
+                        const ArcRec r = arc_rec[k];
+                        const double w = exp(get(r.peer, t - step) + r.like - m);
+                        den += w;
+                        num += w * (get_s(r.peer, t - step) + (double)rec_acc(r));
                     }
                 }
                 double sc = 0.0;
-                if (m > -INFINITY) {
-                    sc = num / (double)sum;
+                if (den > 0.0) {
+                    sc = num / den;
                     const double a_reg = m + (double)logf(sum), v = get(s, t);
                     if (v != a_reg) sc *= exp(a_reg - v);          // epsilon arcs entered this state
                 }
@@ -633,7 +667,7 @@ size_t chain_smem_bytes(int max_frames, bool mpe) {
     size_t b = 2 * (size_t)(max_frames + 2) * sizeof(int);
     b = (b + 15) & ~(size_t)15;
     b += (size_t)(mpe ? 4 : 2) * kValW * sizeof(double);
-    b += (size_t)2 * kDepth * kChain * sizeof(int2);
+    b += (size_t)kOffSlots * kChain * sizeof(int2);
     b += (size_t)(kDepth + 1) * kPF * kChain * sizeof(ArcRec);
     return b;
 }
@@ -650,7 +684,7 @@ lat_chain_kernel(pk2_lat_batch lat, LatWs w, float lm, double* __restrict__ tot_
     o = (2 * (size_t)(max_frames + 2) * sizeof(int) + 15) & ~(size_t)15;
     sm.sv = reinterpret_cast<double*>(s_dyn + o); o += 2 * kValW * sizeof(double);
     sm.sv_s = reinterpret_cast<double*>(s_dyn + o); if (MPE) o += 2 * kValW * sizeof(double);
-    sm.off = reinterpret_cast<int2*>(s_dyn + o); o += (size_t)2 * kDepth * kChain * sizeof(int2);
+    sm.off = reinterpret_cast<int2*>(s_dyn + o); o += (size_t)kOffSlots * kChain * sizeof(int2);
     sm.rec = reinterpret_cast<ArcRec*>(s_dyn + o);
     const int b = blockIdx.x >> 1;
     if ((blockIdx.x & 1) == 0)
@@ -677,7 +711,7 @@ lat_post_kernel(pk2_lat_batch lat, LatWs w, int N, int64_t row_stride_b,
                     const ArcRec r = w.rec_out[k];
                     const float post = expf((float)(a + r.like + w.beta[r.peer]));
                     if (MPE) {
-                        const float v = post * (float)(as + (double)r.acc + w.beta_s[r.peer]);
+                        const float v = post * (float)(as + (double)rec_acc(r) + w.beta_s[r.peer]);
                         if (v != 0.f) atomicAdd(&grow[w.pdf_out[k]], deriv_scale * v);
                     } else if (post > 0.f) {
                         atomicAdd(&grow[w.pdf_out[k]], post);

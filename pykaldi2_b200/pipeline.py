@@ -136,9 +136,14 @@ def finish_step(model, optimizer, averager, max_grad_norm):
 
 
 def chain_step(model, optimizer, averager, feat, den_graph, chain_opts, wav, woff, foff, supervisions,
-               epoch=0, max_grad_norm=5.0, factor=3, after_backward=None):
+               epoch=0, max_grad_norm=5.0, factor=3, after_backward=None, events=None):
     """One LF-MMI step (bin/train_chain.py:244-292).  Returns (objf float, total input frames).
-    ``after_backward``: host callback run once the backward pass is enqueued (e.g. prefetch of the next batch)."""
+    ``after_backward``: host callback run once the backward pass is enqueued (e.g. prefetch of the next batch).
+    ``events``: list that receives (start, backward done) CUDA events of the step -- the rank's own compute time,
+    before it waits for the other ranks in the gradient all-reduce (bench.py: per-rank spread)."""
+    if events is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     shift = epoch % factor                                   # frame_shift = -(epoch % 3) then roll
     x, lens = feat.sequence_batch(wav, woff, foff, factor=factor, shift=shift)
     # the output layer runs on the frames the loss reads (one supervision frame per output frame), not on the padding
@@ -147,6 +152,9 @@ def chain_step(model, optimizer, averager, feat, den_graph, chain_opts, wav, wof
     prediction = model(x, valid_lengths=valid)
     loss = ops.ChainObjtiveFunction.apply_batch(prediction, den_graph, supervisions, chain_opts)
     loss.backward()
+    if events is not None:
+        ev1.record()
+        events.append((ev0, ev1))
     if after_backward is not None:
         after_backward()
     finish_step(model, optimizer, averager, max_grad_norm)

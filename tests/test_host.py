@@ -472,3 +472,103 @@ def test_ingestion_directory_source_and_resampling(tmp_path):
     assert np.abs(x[200:-200] - ref[200:-200]).max() < 2e-2
     with pytest.raises(ValueError):
         SpeechDataset({"source_paths": []})
+
+
+# ------------------------------------------------------------------ round 2: sharding, sampling, shuffle buffer ----
+def test_balanced_shards_cost_model():
+    """dist.balanced_shards: every utterance exactly once, per-rank capacity respected, deterministic, and the modelled
+    step time (50 x longest + sum) better balanced than the sorted round-robin deal it replaces."""
+    from pykaldi2_b200 import dist as pkdist
+    from pykaldi2_b200 import synth
+    rng = np.random.default_rng(7)
+    for world, per in ((2, 64), (8, 64), (4, 3)):
+        L = (synth.make_durations(world * per, rng) * 100).astype(int)
+        sh = pkdist.balanced_shards(L, world, per)
+        assert sorted(i for s in sh for i in s) == list(range(world * per))
+        assert all(len(s) == per for s in sh)
+        assert sh == pkdist.balanced_shards(L, world, per)
+        cost = [50 * L[s].max() + L[s].sum() for s in sh]
+        srt = np.sort(L)[::-1]
+        rr = [50 * srt[r::world].max() + srt[r::world].sum() for r in range(world)]
+        assert max(cost) <= max(rr)
+        if per >= 64:
+            assert max(cost) / np.mean(cost) < 1.03
+    # ragged tail: fewer utterances than world * per_rank
+    sh = pkdist.balanced_shards([5, 9, 2], 2)
+    assert sorted(i for s in sh for i in s) == [0, 1, 2] and max(len(s) for s in sh) == 2
+    with pytest.raises(ValueError):
+        pkdist.balanced_shards([1, 2, 3], 2, 1)
+
+
+def test_balanced_batch_sampler_covers_epoch_and_reseeds():
+    from pykaldi2_b200.data.dataloader import BalancedBatchSampler
+    L = np.arange(1, 41) * 10
+    seen = []
+    per_rank = []
+    for r in range(4):
+        bs = BalancedBatchSampler(L, batch_size=3, world=4, rank=r, seed=5)
+        assert len(bs) == 4                                   # ceil(40 / 12)
+        batches = list(bs)
+        assert all(len(b) == 3 for b in batches)
+        per_rank.append(batches)
+        seen += [i for b in batches for i in b]
+    assert set(seen) == set(range(40)) and len(seen) == 48    # tail padded by wrap-around
+    # the four ranks' shares of one global batch are disjoint
+    g0 = [i for r in range(4) for i in per_rank[r][0]]
+    assert len(set(g0)) == 12
+    bs = BalancedBatchSampler(L, batch_size=3, world=4, rank=0, seed=5)
+    e0 = list(bs)
+    bs.set_epoch(1)
+    assert list(bs) != e0
+    bs.set_epoch(0)
+    assert list(bs) == e0
+
+
+def test_chunk_pool_draws_every_chunk_once():
+    """pipeline.ChunkPool (the reference's DataBuffer, data/sr_dataset.py:55-84): random draws, nothing lost."""
+    from pykaldi2_b200 import pipeline
+    pool = pipeline.ChunkPool(50, 4, 3, torch.device("cpu"), seed=1)
+    ids = torch.arange(37, dtype=torch.float32)
+    pool.add(ids[:20].view(-1, 1, 1).expand(-1, 4, 3), ids[:20].long().view(-1, 1).expand(-1, 4))
+    out = []
+    x, y = pool.draw(8)
+    assert x.shape == (8, 4, 3) and y.shape == (8, 4) and pool.n == 12
+    out += x[:, 0, 0].tolist()
+    assert (x[:, 0, 0].long() == y[:, 0]).all()
+    pool.add(ids[20:].view(-1, 1, 1).expand(-1, 4, 3), ids[20:].long().view(-1, 1).expand(-1, 4))
+    while pool.n:
+        x, y = pool.draw(8)
+        assert (x[:, 0, 0].long() == y[:, 0]).all()
+        out += x[:, 0, 0].tolist()
+    assert sorted(out) == list(range(37))
+    assert out != sorted(out)                                  # shuffled
+    with pytest.raises(RuntimeError):
+        pool.add(torch.zeros(51, 4, 3), torch.zeros(51, 4, dtype=torch.long))
+
+
+def test_speech_dataset_epoch_semantics(tmp_path):
+    """Sequence mode visits every utterance whatever sweep_size says (reference data/sr_dataset.py:192-194); chunk mode
+    draws a fresh random subset per epoch instead of a fixed prefix."""
+    from pykaldi2_b200.data.speech_dataset import SpeechDataset
+    from pykaldi2_b200.reader import zip_io
+    rng = np.random.default_rng(0)
+    d = os.path.join(tmp_path, "c")
+    os.makedirs(d)
+    lab = os.path.join(tmp_path, "lab.txt")
+    with open(lab, "w") as f:
+        for i in range(12):
+            utt = "u%02d" % i
+            zip_io.write_wav(os.path.join(d, utt + ".wav"), 0.1 * rng.standard_normal(1600 + 160 * i))
+            f.write(utt + " " + " ".join("1" for _ in range(8 + i)) + "\n")
+    srcs = [{"type": "Any", "wav": d, "label": lab}]
+    seq = SpeechDataset({"source_paths": srcs, "sweep_size": 0.01, "data_config": {"sequence_mode": True}})
+    assert len(seq) == 12
+    assert seq.utt_lengths().tolist() == [8 + i for i in range(12)]
+    ch = SpeechDataset({"source_paths": srcs, "sweep_size": 0.01, "data_config": {"sequence_mode": False}})
+    assert len(ch) == 2                                        # 0.01 h at 12.3 s per utterance
+    picks = set()
+    for ep in range(8):
+        ch.set_epoch(ep)
+        picks |= {ch[i][1][0] for i in range(len(ch))}
+    assert len(picks) > 4                                      # not the same prefix every epoch
+    assert ch.reader._zips == {}                               # no handle survives the constructor (fork safety)

@@ -22,6 +22,7 @@ for step in "$@"; do
     phases)      timeout 300 python tools/step_phases.py > $OUT/phases_$TAG.json 2> $OUT/phases_$TAG.err; cat $OUT/phases_$TAG.json; tail -3 $OUT/phases_$TAG.err ;;
     ncu_lat)     timeout 600 ncu --set full --clock-control none --import-source on -k regex:lat_ -c 6 -o $OUT/lat_$TAG -f python tools/time_mpe.py 1500,1200,900,600 > $OUT/ncu_lat_$TAG.log 2>&1; echo "ncu_lat rc=$?" ;;
     ncu_fbank)   timeout 600 ncu --set full --clock-control none --import-source on -k regex:fbank -c 2 -o $OUT/fbank_$TAG -f python tools/kernel_bench.py fbank > $OUT/ncu_fbank_$TAG.log 2>&1; echo "ncu_fbank rc=$?" ;;
+    timeline)    timeout 300 python tools/timeline.py > $OUT/timeline_$TAG.csv 2> $OUT/timeline_$TAG.err; wc -l $OUT/timeline_$TAG.csv; tail -3 $OUT/timeline_$TAG.err ;;
     py:*)        timeout 900 python ${step#py:} > $OUT/py_$TAG.log 2>&1; echo "py rc=$?"; tail -30 $OUT/py_$TAG.log ;;
     *)           echo "unknown step $step" ;;
   esac
