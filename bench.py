@@ -266,7 +266,7 @@ def main():
     torch.manual_seed(0)
     model = LSTMAM(FEAT, N_PDF, HID, LAYERS, 0.0, True).to(dev)
     model.train()
-    optimizer = torch.optim.Adam(model.parameters(), lr=1e-4, amsgrad=True)
+    optimizer = torch.optim.Adam(model.parameters(), lr=1e-4, amsgrad=True, fused=True)
     pkdist.broadcast_parameters(model)
     averager = pkdist.GradAverager(list(model.parameters())) if world > 1 else None
     feat = pipeline.FeaturePipeline(use_cmn=True)
@@ -291,20 +291,33 @@ def main():
         staged["next"] = (w, sb, ev)
 
     step_events = []
+    losses = []                             # PendingValue of every step; read one step late (see drain_losses)
+
+    def drain_losses(keep):
+        """Read the losses of all but the newest ``keep`` steps: the device->host read of a step's result happens
+        after the NEXT step has been enqueued, so the host stays one step ahead of the GPU."""
+        out = []
+        while len(losses) > keep:
+            out.append(losses.pop(0).value())
+        return out
 
     def step(resident):
         if resident:
-            return pipeline.chain_step(model, optimizer, averager, feat, den, opts, wav_dev, woff, foff, sup_dev, epoch=0,
-                                       events=step_events)
+            loss, _ = pipeline.chain_step(model, optimizer, averager, feat, den, opts, wav_dev, woff, foff, sup_dev, epoch=0,
+                                          events=step_events, sync=False)
+            losses.append(loss)
+            drain_losses(1)
+            return
         if "next" not in staged:
             stage_next()
         w, sb, ev = staged.pop("next")
         torch.cuda.current_stream(dev).wait_event(ev)
         w.record_stream(torch.cuda.current_stream(dev))
         sb._keep[0].record_stream(torch.cuda.current_stream(dev))
-        out = pipeline.chain_step(model, optimizer, averager, feat, den, opts, w, woff, foff, sb, epoch=0,
-                                  after_backward=stage_next)
-        return out
+        loss, _ = pipeline.chain_step(model, optimizer, averager, feat, den, opts, w, woff, foff, sb, epoch=0,
+                                      after_backward=stage_next, sync=False)
+        losses.append(loss)
+        drain_losses(1)
 
     def barrier():
         if world > 1:
@@ -317,8 +330,10 @@ def main():
         e0.record()
         for _ in range(steps):
             step(resident)
+        last = drain_losses(0)              # every step's loss is read inside the timed region
         e1.record()
         barrier()
+        assert all(np.isfinite(v) for v in last), last
         t = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
         if world > 1:
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -330,6 +345,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step(True)
     step(False)
+    drain_losses(0)
     torch.cuda.synchronize()
     if sampler:
         del sampler.rows[:]                  # keep only the samples taken during the timed regions
@@ -385,7 +401,8 @@ def main():
                        "l2": "no flush: every step streams > 5 GB of activations/workspace, far larger than the 126 MB L2",
                        "optimizer": "Adam(amsgrad) lr 1e-4, clip 5"},
             "e2e": {"value": e2e, "unit": "hours audio per hour", "ms_per_step": 1e3 * t_e2e / args.steps,
-                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8 * B + 8},
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                    "note": "loss of step k read from pinned memory after step k+1 is enqueued (host one step ahead)"},
             "gpu_launches": int(n1 - n0),
             "roofline": {"kernel": "pk2_denfb: den_exp + den_forward_reg2 + den_backward_reg (15 clusters of 8) || den_fb1 (single CTAs)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

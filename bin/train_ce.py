@@ -91,7 +91,7 @@ def main():
 
     dropout = mc["dropout"] if args.dropout is None else args.dropout
     model = lstm.LSTMAM(mc["feat_dim"], mc["label_size"], mc["hidden_size"], mc["num_layers"], dropout, True).to(dev)
-    optimizer = th.optim.Adam(model.parameters(), lr=args.lr, amsgrad=True)
+    optimizer = th.optim.Adam(model.parameters(), lr=args.lr, amsgrad=True, fused=True)   # one launch for all parameters
     start_epoch = 0
     if args.resume_from_model:
         assert os.path.isfile(args.resume_from_model), "ERROR: model file {} does not exit!".format(args.resume_from_model)

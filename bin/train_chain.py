@@ -25,19 +25,40 @@ from _common import pkdist
 from pykaldi2_b200 import graphs, pipeline, synth
 from pykaldi2_b200.data.dataloader import SyntheticWaveDataset, WaveDataloader
 from pykaldi2_b200.data.speech_dataset import SpeechDataset
+from pykaldi2_b200 import chain_supervision
 from pykaldi2_b200.models import lstm
+from pykaldi2_b200.reader import kaldi_io
 from pykaldi2_b200.ops import ops
 from pykaldi2_b200.utils import utils
 
 
-class SupervisionOptions(object):
-    """kaldi_chain.SupervisionOptions stand-in (bin/train_chain.py:184-188)."""
+def SupervisionOptions():
+    """kaldi_chain.SupervisionOptions as the reference sets it (bin/train_chain.py:184-188)."""
+    return chain_supervision.SupervisionOptions(left_tolerance=5, right_tolerance=5, frame_subsampling_factor=3,
+                                                convert_to_pdfs=True)
 
-    def __init__(self):
-        self.convert_to_pdfs = True
-        self.frame_subsampling_factor = 3
-        self.left_tolerance = 5
-        self.right_tolerance = 5
+
+def _first_existing(*paths):
+    for p in paths:
+        if p and os.path.isfile(p):
+            return p
+    return None
+
+
+def load_kaldi_assets(args):
+    """The reference's Kaldi inputs (bin/train_chain.py:162-181) in TEXT form: the alignment model's transition
+    model (<ali_dir>/final.mdl[.txt]), the chain transition model (<chain_dir>/0.trans_mdl[.txt]) and tree
+    (<chain_dir>/tree[.txt]).  Returns None when -ali_dir / -chain_dir are not given."""
+    if not (args.ali_dir and args.chain_dir):
+        return None
+    ali = _first_existing(args.ali_dir + "/final.mdl.txt", args.ali_dir + "/final.mdl")
+    ctm = _first_existing(args.chain_dir + "/0.trans_mdl.txt", args.chain_dir + "/0.trans_mdl")
+    tree = _first_existing(args.chain_dir + "/tree.txt", args.chain_dir + "/tree")
+    if not (ali and ctm and tree):
+        raise SystemExit("train_chain.py: -ali_dir / -chain_dir must hold final.mdl, 0.trans_mdl and tree (text form: "
+                         "copy-transition-model --binary=false, copy-tree --binary=false)")
+    return {"ali_tm": kaldi_io.read_transition_model_text(ali), "chain_tm": kaldi_io.read_transition_model_text(ctm),
+            "tree": kaldi_io.read_tree_text(tree)}
 
 
 def main():
@@ -102,7 +123,7 @@ def main():
     print("Number of minibatches: {}".format(len(loader)))
 
     model = lstm.LSTMAM(mc["feat_dim"], mc["label_size"], mc["hidden_size"], mc["num_layers"], mc["dropout"], True).to(dev)
-    optimizer = th.optim.Adam(model.parameters(), lr=args.lr, amsgrad=True)
+    optimizer = th.optim.Adam(model.parameters(), lr=args.lr, amsgrad=True, fused=True)   # one launch for all parameters
     if args.seed_model:
         _common.load_model_state(model, args.seed_model)
         print("=> loaded checkpoint '{}' ".format(args.seed_model))
@@ -113,6 +134,9 @@ def main():
 
     supervision_opts = SupervisionOptions()
     chain_opts = graphs.ChainTrainingOptions(leaky_hmm_coefficient=1e-4, xent_regularize=args.xent_regularize)
+    kaldi = load_kaldi_assets(args)
+    if kaldi is not None and not args.den_fst and os.path.isfile(args.chain_dir + "/den.fst"):
+        args.den_fst = args.chain_dir + "/den.fst"                                   # bin/train_chain.py:167
     if args.den_fst:                      # a real denominator graph: OpenFst binary (Kaldi's den.fst) or fstprint text
         den = graphs.DenominatorGraph.from_file(args.den_fst, mc["label_size"])
     else:
@@ -120,12 +144,29 @@ def main():
 
     model.train()
     for epoch in range(args.num_epochs):
-        run_train_epoch(model, optimizer, averager, feat, loader, epoch, supervision_opts, den, chain_opts, args, rank)
+        loader.set_epoch(epoch)
+        run_train_epoch(model, optimizer, averager, feat, loader, epoch, supervision_opts, den, chain_opts, args, rank, kaldi)
         if rank == 0:
             _common.save_checkpoint(args.exp_dir + '/chain.model.' + str(epoch) + '.tar', model, optimizer)
 
 
-def run_train_epoch(model, optimizer, averager, feat, loader, epoch, supervision_opts, den, chain_opts, args, rank):
+def kaldi_supervision(kaldi, supervision_opts, trans_ids):
+    """bin/train_chain.py:262-272: alignment -> phones / durations -> proto-supervision -> supervision.  When the
+    constraints leave no path (Kaldi: "Supervision FST is empty") the tolerances are doubled until one exists."""
+    opts = chain_supervision.SupervisionOptions(supervision_opts.left_tolerance, supervision_opts.right_tolerance,
+                                                supervision_opts.frame_subsampling_factor, True)
+    while True:
+        fst, t_sub = chain_supervision.supervision_from_alignment(opts, kaldi["ali_tm"], kaldi["chain_tm"], kaldi["tree"],
+                                                                  trans_ids)
+        if fst is not None:
+            return fst, t_sub
+        if opts.left_tolerance > 4 * len(trans_ids):
+            raise RuntimeError("no numerator path: more phone states than output frames (%d frames)" % t_sub)
+        print("WARNING: empty supervision at tolerance %d, retrying with %d" % (opts.left_tolerance, 2 * opts.left_tolerance + 1))
+        opts.left_tolerance = opts.right_tolerance = 2 * opts.left_tolerance + 1
+
+
+def run_train_epoch(model, optimizer, averager, feat, loader, epoch, supervision_opts, den, chain_opts, args, rank, kaldi=None):
     batch_time = utils.AverageMeter('Time', ':6.3f')
     losses = utils.AverageMeter('Loss', ':.4e')
     grad_norm = utils.AverageMeter('grad_norm', ':.4e')
@@ -149,6 +190,11 @@ def run_train_epoch(model, optimizer, averager, feat, loader, epoch, supervision
             if args.synthetic > 0:
                 rng = np.random.default_rng(zlib.crc32(ids[0].encode()))
                 sup_fst = synth.make_supervision_fst(t_sub, den.num_pdfs(), rng)
+            elif kaldi is not None:
+                # the label file holds the alignment model's transition ids, as in the reference (y = trans_ids);
+                # the frame shift of the epoch moves the features, not the supervision (bin/train_chain.py:251-272)
+                sup_fst, t_k = kaldi_supervision(kaldi, supervision_opts, batch["label"][j][:int(num_frs[j]), 0])
+                assert t_k == t_sub, (t_k, t_sub)
             else:
                 sup_fst = synth.alignment_to_supervision_fst(batch["label"][j][:, 0], factor, shift,
                                                              slack=args.tolerance, n_out=t_sub)

@@ -110,6 +110,7 @@ def main():
 
     model.train()
     for epoch in range(args.num_epochs):
+        loader.set_epoch(epoch)
         run_train_epoch(model, optimizer, averager, feat, log_prior, loader, epoch, asr_decoder, trans_model, args, rank)
         if rank == 0:
             _common.save_checkpoint(args.exp_dir + '/model.se.' + str(epoch) + '.tar', model, optimizer, epoch)

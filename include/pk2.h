@@ -248,6 +248,17 @@ int pk2_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
 int pk2_transpose_bf16(const void* src, int src_bf16, void* dst, int R, int C, int lds, int ldd, void* stream);
 /* hprevT[dir][j][b*T+t] = y[b][t -/+ 1][dir*H + j] (0 at the sequence boundary): the h_{t-1} operand of dW_hh */
 int pk2_lstm_hprev_t(const void* y, void* hprev_t, int B, int T, int H, int ldd, void* stream);
+/* bf16 operand copies of one BLSTM layer's weights, one launch.  params: host array of 8 device pointers in nn.LSTM's
+ * order (weight_ih, weight_hh, bias_ih, bias_hh of the forward, then of the reverse direction; fp32, reference
+ * models/lstm.py:46-52).  Outputs:
+ *   wih_cat [8H, I]      rows = [W_ih fwd; W_ih rev]                          (input projection, B operand)
+ *   bias_cat[8H] fp32    b_ih + b_hh of both directions
+ *   whh_p   [2*4H, H]    recurrent weights in per-CTA order: row (dir*H/32 + cta)*128 + gate*32 + ul
+ *   whh_t   [2H, 4H]     W_hh^T per direction                                 (backward recurrence)
+ *   whh_tp  [2H, 4H]     W_hh^T with the 4H index in per-CTA order            (cluster backward kernel)
+ *   wih_t   [I, ldk]     [W_ih fwd; W_ih rev]^T, may be NULL (bottom layer)   (input gradient GEMM) */
+int pk2_lstm_pack_layer(const float* const* params, int H, int I, void* wih_cat, float* bias_cat, void* whh_p,
+                        void* whh_t, void* whh_tp, void* wih_t, int ldk, void* stream);
 /* hprev[b*T+t][dir*H + j] = y[b][t -/+ 1][dir*H + j] (0 at the sequence boundary), bf16 [B*T, 2H]: the h_{t-1} operand
  * of dW_hh in the layout the TN GEMM consumes in place */
 int pk2_lstm_hprev(const void* y, void* hprev, int B, int T, int H, void* stream);

@@ -76,6 +76,7 @@ _SIGS = {
     "pk2_lstm_hprev_t": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "pk2_colsum_bf16": (C.c_int, [vp, vp, C.c_int64, C.c_int, vp]),
     "pk2_lstm_hprev": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "pk2_lstm_pack_layer": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, vp]),
     "pk2_gather_rows_bf16": (C.c_int, [vp, C.c_int, vp, vp, C.c_int64, C.c_int, vp]),
     "pk2_zero_pad_rows": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int64, vp]),
     "pk2_lstm_input_proj": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),

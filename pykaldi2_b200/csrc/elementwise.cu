@@ -118,6 +118,45 @@ __global__ void zero_pad_rows_kernel(uint4* __restrict__ p, const int32_t* __res
     }
 }
 
+// All bf16 operand copies of one BLSTM layer's weights in ONE launch (they were ~15 torch ops per layer on the
+// critical path of every step): see pk2_lstm_pack_layer in pk2.h for the layouts.
+struct PackArgs {
+    const float *wih[2], *whh[2], *bih[2], *bhh[2];
+    __nv_bfloat16 *wih_cat, *whh_p, *whh_t, *whh_tp, *wih_t;
+    float* bias_cat;
+    int H, I, ldk;
+};
+__global__ void __launch_bounds__(256) lstm_pack_kernel(PackArgs a) {
+    const int H = a.H, I = a.I, H4 = 4 * a.H;
+    const int64_t n_ih = (int64_t)2 * H4 * I, n_hh = (int64_t)2 * H4 * H, n_b = 2 * H4;
+    const int64_t total = n_ih + n_hh + n_b;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < n_ih) {
+            const int r = (int)(i / I), c = (int)(i - (int64_t)r * I);          // r = dir*4H + gate row
+            const int d = r / H4;
+            const __nv_bfloat16 v = __float2bfloat16(a.wih[d][(int64_t)(r - d * H4) * I + c]);
+            a.wih_cat[i] = v;
+            if (a.wih_t) a.wih_t[(int64_t)c * a.ldk + r] = v;
+        } else if (i < n_ih + n_hh) {
+            const int64_t j = i - n_ih;
+            const int d = (int)(j / ((int64_t)H4 * H));
+            const int64_t jj = j - (int64_t)d * H4 * H;
+            const int row = (int)(jj / H), k = (int)(jj - (int64_t)row * H);   // row = gate*H + unit
+            const int g = row / H, u = row - g * H;
+            const int cta = u >> 5, ul = u & 31;
+            const int prow = cta * 128 + g * 32 + ul;                          // index inside the direction, per-CTA order
+            const __nv_bfloat16 v = __float2bfloat16(a.whh[d][jj]);
+            a.whh_p[((int64_t)d * H4 + prow) * H + k] = v;
+            a.whh_t[((int64_t)d * H + k) * H4 + row] = v;
+            a.whh_tp[((int64_t)d * H + k) * H4 + prow] = v;
+        } else {
+            const int r = (int)(i - n_ih - n_hh);
+            const int d = r / H4, rr = r - d * H4;
+            a.bias_cat[r] = a.bih[d][rr] + a.bhh[d][rr];
+        }
+    }
+}
+
 __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ partial, int64_t R, int C,
                                    int rows_per_block) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -175,6 +214,25 @@ extern "C" int pk2_lstm_hprev_t(const void* y, void* hprev_t, int B, int T, int 
     PK2_REQUIRE(grid.y <= 65535, "pk2_lstm_hprev_t: too many rows (%d)", M);
     hprev_t_kernel<<<grid, block, 0, pk2::as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(y),
                                                             static_cast<__nv_bfloat16*>(hprev_t), B, T, H, ldd);
+    PK2_POST_LAUNCH();
+    return 0;
+}
+
+extern "C" int pk2_lstm_pack_layer(const float* const* params, int H, int I, void* wih_cat, float* bias_cat, void* whh_p,
+                                   void* whh_t, void* whh_tp, void* wih_t, int ldk, void* stream) {
+    PK2_REQUIRE(params && wih_cat && bias_cat && whh_p && whh_t && whh_tp, "pk2_lstm_pack_layer: null argument");
+    PK2_REQUIRE(H > 0 && H % 32 == 0 && I > 0, "pk2_lstm_pack_layer: H must be a positive multiple of 32");
+    PK2_REQUIRE(!wih_t || ldk >= 8 * H, "pk2_lstm_pack_layer: ldk < 8H");
+    PackArgs a;
+    for (int d = 0; d < 2; ++d) {
+        a.wih[d] = params[4 * d + 0]; a.whh[d] = params[4 * d + 1]; a.bih[d] = params[4 * d + 2]; a.bhh[d] = params[4 * d + 3];
+        PK2_REQUIRE(a.wih[d] && a.whh[d] && a.bih[d] && a.bhh[d], "pk2_lstm_pack_layer: null parameter");
+    }
+    a.wih_cat = static_cast<__nv_bfloat16*>(wih_cat); a.whh_p = static_cast<__nv_bfloat16*>(whh_p);
+    a.whh_t = static_cast<__nv_bfloat16*>(whh_t); a.whh_tp = static_cast<__nv_bfloat16*>(whh_tp);
+    a.wih_t = static_cast<__nv_bfloat16*>(wih_t); a.bias_cat = bias_cat;
+    a.H = H; a.I = I; a.ldk = ldk;
+    lstm_pack_kernel<<<148 * 8, 256, 0, pk2::as_stream(stream)>>>(a);
     PK2_POST_LAUNCH();
     return 0;
 }

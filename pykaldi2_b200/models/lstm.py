@@ -86,21 +86,25 @@ class _Packed(object):
 
     def __init__(self, w_out, b_out, lstm_params, L, H):
         self.layers = []
+        dev = w_out.device
+        lib = _lib.lib()
+        bf = dict(dtype=th.bfloat16, device=dev)
         for l in range(L):
-            wih_f, whh_f, bih_f, bhh_f, wih_b, whh_b, bih_b, bhh_b = lstm_params[8 * l:8 * l + 8]
-            I = wih_f.shape[1]
-            d = {"I": I}
-            wih_cat32 = th.cat([wih_f, wih_b], 0).contiguous()                      # [8H, I]
-            d["wih_cat"] = _cast(wih_cat32)
-            d["bias_cat"] = th.cat([bih_f + bhh_f, bih_b + bhh_b], 0).contiguous()  # [8H] fp32
-            # recurrent weights packed per CTA: [dir][cta][gate][32][H]
-            whh = th.stack([whh_f, whh_b], 0).view(2, 4, H // 32, 32, H).permute(0, 2, 1, 3, 4).contiguous()
-            d["whh_p"] = _cast(whh.view(2 * 4 * H, H))
-            d["whh_t"] = _cast(th.cat([whh_f.t(), whh_b.t()], 0).contiguous())      # [2H, 4H]
-            # same matrix with the 4H index permuted to cta*128 + gate*32 + unit (cluster/DSMEM backward kernel)
-            d["whh_tp"] = _cast(whh.reshape(2, 4 * H, H).transpose(1, 2).reshape(2 * H, 4 * H).contiguous())
+            ps = [p.contiguous() for p in lstm_params[8 * l:8 * l + 8]]
+            if any(p.dtype != th.float32 for p in ps):
+                raise RuntimeError("LSTMAM parameters must be float32 (master weights)")
+            I = ps[0].shape[1]
+            d = {"I": I, "ldk": _pad8(8 * H),
+                 "wih_cat": th.empty(8 * H, I, **bf), "bias_cat": th.empty(8 * H, dtype=th.float32, device=dev),
+                 "whh_p": th.empty(2 * 4 * H, H, **bf), "whh_t": th.empty(2 * H, 4 * H, **bf),
+                 "whh_tp": th.empty(2 * H, 4 * H, **bf)}
             if l > 0:
-                d["wih_t"], d["ldk"] = _transpose(wih_cat32, 8 * H, I, I)           # [I, 8H]
+                d["wih_t"] = th.empty(I, d["ldk"], **bf)
+            ptrs = (C.c_void_p * 8)(*[p.data_ptr() for p in ps])
+            _lib.check(lib.pk2_lstm_pack_layer(ptrs, H, I, _lib.ptr(d["wih_cat"]), _lib.ptr(d["bias_cat"]),
+                                               _lib.ptr(d["whh_p"]), _lib.ptr(d["whh_t"]), _lib.ptr(d["whh_tp"]),
+                                               _lib.ptr(d.get("wih_t")), d["ldk"], _lib.stream()), "pk2_lstm_pack_layer")
+            self._keep = ps
             self.layers.append(d)
         w = w_out.contiguous()
         self.w_out = _cast(w)                                                       # [N, 2H]
@@ -126,6 +130,21 @@ class _BlstmAM(Function):
         th.cuda.current_stream(dev).wait_event(packed.ready)
         xin = _cast(x.contiguous().view(M, F))
         saved = {"xin": [], "y": [], "gates": [], "cstate": [], "mask": []}
+        N = packed.w_out.shape[0]
+        logits = th.empty(B, T, N, dtype=th.float32, device=dev)
+        pad_done = None
+        if valid is not None:
+            # padded logit rows are zero; filled on the side stream next to the recurrence kernels (which leave more
+            # than half of the SMs idle) instead of in front of the output GEMM
+            main, side = th.cuda.current_stream(dev), _side_stream(dev)
+            ev = th.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            logits.record_stream(side)
+            _lib.check(lib.pk2_zero_pad_rows(_lib.ptr(logits), _lib.ptr(valid[1]), B, T, 4 * N,
+                                             _lib.vp(side.cuda_stream)), "pk2_zero_pad_rows")
+            pad_done = th.cuda.Event()
+            pad_done.record(side)
         for l in range(L):
             pk = packed.layers[l]
             I = pk["I"]
@@ -150,15 +169,13 @@ class _BlstmAM(Function):
                 xin = y.view(M, 2 * H)
             saved["mask"].append(mask)
             del gx
-        N = packed.w_out.shape[0]
-        logits = th.empty(B, T, N, dtype=th.float32, device=dev)
         if valid is None:
             top, Mv, rows = xin, M, None
         else:
             rows, lens_dev, Mv = valid
             top = _gather_rows(xin, rows, Mv, 2 * H)                    # valid frames only, compact
-            _lib.check(lib.pk2_zero_pad_rows(_lib.ptr(logits), _lib.ptr(lens_dev), B, T, 4 * N, _lib.stream()),
-                       "pk2_zero_pad_rows")
+        if pad_done is not None:
+            th.cuda.current_stream(dev).wait_event(pad_done)
         _gemm(top, packed.w_out, logits, packed.b_out, Mv, N, 2 * H, 2 * H, 2 * H, N, row_map=rows)
         ctx.saved = saved
         ctx.top = top

@@ -135,9 +135,27 @@ def finish_step(model, optimizer, averager, max_grad_norm):
     return norm
 
 
+class PendingValue(object):
+    """A scalar on its way from the device to pinned host memory.  ``value()`` waits for THAT copy only, so a training
+    loop can read the loss of step k after it has enqueued step k+1: the host then runs one step ahead of the GPU and
+    its launch work (index maps, ~150 launches) never leaves the GPU idle at the start of a step."""
+
+    def __init__(self, t):
+        self._host = torch.empty((), dtype=t.dtype, pin_memory=True)
+        self._host.copy_(t.detach(), non_blocking=True)
+        self._ev = torch.cuda.Event()
+        self._ev.record()
+        self.d2h_bytes = self._host.element_size()
+
+    def value(self):
+        self._ev.synchronize()
+        return float(self._host)
+
+
 def chain_step(model, optimizer, averager, feat, den_graph, chain_opts, wav, woff, foff, supervisions,
-               epoch=0, max_grad_norm=5.0, factor=3, after_backward=None, events=None):
-    """One LF-MMI step (bin/train_chain.py:244-292).  Returns (objf float, total input frames).
+               epoch=0, max_grad_norm=5.0, factor=3, after_backward=None, events=None, sync=True):
+    """One LF-MMI step (bin/train_chain.py:244-292).  Returns (objf, total input frames); objf is a float, or with
+    ``sync=False`` a PendingValue (read it with .value() after the NEXT step has been enqueued).
     ``after_backward``: host callback run once the backward pass is enqueued (e.g. prefetch of the next batch).
     ``events``: list that receives (start, backward done) CUDA events of the step -- the rank's own compute time,
     before it waits for the other ranks in the gradient all-reduce (bench.py: per-rank spread)."""
@@ -151,6 +169,7 @@ def chain_step(model, optimizer, averager, feat, den_graph, chain_opts, wav, wof
         [s.frames_per_sequence for s in supervisions]
     prediction = model(x, valid_lengths=valid)
     loss = ops.ChainObjtiveFunction.apply_batch(prediction, den_graph, supervisions, chain_opts)
+    pending = None if sync else PendingValue(loss)
     loss.backward()
     if events is not None:
         ev1.record()
@@ -158,4 +177,4 @@ def chain_step(model, optimizer, averager, feat, den_graph, chain_opts, wav, wof
     if after_backward is not None:
         after_backward()
     finish_step(model, optimizer, averager, max_grad_norm)
-    return float(loss.item()), int(np.sum(lens))
+    return (float(loss.item()) if sync else pending), int(np.sum(lens))
