@@ -67,6 +67,22 @@ def bench_den():
         print(json.dumps({"kernel": "denfb uniform T=200 B=16", "cluster": K, "ms": ms, "us_per_frame": 1e3 * ms / Tu}))
 
 
+def bench_den1():
+    """The bench.py batch through the automatic denominator schedule, twice: the target of `ncu --set full -k regex:den_`
+    (profiles/ncu_den_full_r2_*.md) -- the capture then holds exactly the kernels of one pk2_denfb call."""
+    import bench
+    from pykaldi2_b200 import graphs, synth
+    from pykaldi2_b200.ops import ops
+    dev = torch.device("cuda", 0)
+    durs, wavs, frames, sub, sup_fsts = bench.make_workload(0, bench.BATCH)
+    den = graphs.DenominatorGraph(synth.make_den_fst(bench.DEN_STATES, bench.N_PDF, bench.DEN_EXTRA, seed=1234), bench.N_PDF)
+    opts = graphs.ChainTrainingOptions(leaky_hmm_coefficient=1e-4)
+    sb = graphs.SupervisionBatch([graphs.Supervision(f, t, bench.N_PDF) for f, t in zip(sup_fsts, sub)], device=dev)
+    pred = torch.randn(bench.BATCH, max(sub), bench.N_PDF, device=dev) * 2
+    ms = timeit(lambda: ops.chain_objf_and_deriv(pred, den, sb, opts, cluster=0), iters=1, warm=1)
+    print(json.dumps({"kernel": "pk2_denfb auto schedule, bench batch", "ms": ms, "frames": sum(sub)}))
+
+
 def bench_lstm():
     from pykaldi2_b200.models.lstm import LSTMAM
     dev = torch.device("cuda", 0)
@@ -190,4 +206,4 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["den", "lstm", "gemm", "fbank"]
     for w in which:
         {"den": bench_den, "lstm": bench_lstm, "gemm": bench_gemm, "fbank": bench_fbank, "ce": bench_ce,
-         "cudnn": bench_cudnn}[w]()
+         "cudnn": bench_cudnn, "den1": bench_den1}[w]()
