@@ -230,6 +230,14 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------ GPU arm ----
+def arm_watchdog(seconds):
+    """A hung collective must not burn the box: after `seconds` every thread's Python stack goes to stderr and the
+    process exits with status 3 (the launcher then tears the other ranks down)."""
+    import faulthandler
+    faulthandler.enable()
+    faulthandler.dump_traceback_later(seconds, exit=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -238,7 +246,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--watchdog", type=int, default=int(os.environ.get("PK2_BENCH_WATCHDOG", "420")),
+                    help="seconds after which a stuck run dumps its stacks and exits (0 = off)")
     args = ap.parse_args()
+    if args.watchdog > 0:
+        arm_watchdog(args.watchdog)
 
     from pykaldi2_b200 import dist as pkdist
     if args.impl == "reference":
@@ -254,11 +266,18 @@ def main():
     from pykaldi2_b200.models.lstm import LSTMAM
     from pykaldi2_b200.ops import ops
 
+    t_start = time.perf_counter()
+
+    def log(msg):                           # progress on stderr (stdout carries the one JSON line)
+        print("[bench rank %d +%.1fs] %s" % (rank, time.perf_counter() - t_start, msg), file=sys.stderr, flush=True)
+
     L = _lib.lib()
     B = args.batch
     durs, wavs, frames, sub, sup_fsts = make_workload(rank, B, world=world)
+    log("workload: %d utterances, %d output frames, longest %d" % (len(wavs), sum(sub), max(sub)))
     den_fst = synth.make_den_fst(DEN_STATES, N_PDF, DEN_EXTRA, seed=1234)
     den = graphs.DenominatorGraph(den_fst, N_PDF)
+    log("denominator graph on the device")
     n_arcs = len(den_fst["src"])
     opts = graphs.ChainTrainingOptions(leaky_hmm_coefficient=1e-4, xent_regularize=0.0)
     sups = [graphs.Supervision(f, t, N_PDF) for f, t in zip(sup_fsts, sub)]
@@ -342,11 +361,15 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()                      # NVML initialisation happens during the warm-up, not in the timed region
-    for _ in range(max(args.warmup, 3)):
+    for i in range(max(args.warmup, 3)):
         step(True)
+        if i == 0:
+            torch.cuda.synchronize()
+            log("first step done (graph tables built, kernels loaded)")
     step(False)
     drain_losses(0)
     torch.cuda.synchronize()
+    log("warm-up done")
     if sampler:
         del sampler.rows[:]                  # keep only the samples taken during the timed regions
     ops.DEN_TIMERS = []
@@ -374,7 +397,9 @@ def main():
         ar_ms = float(ar_t.item())
     else:
         spread_rows = [[float(v) for v in spread.tolist()]]
+    log("resident region done: %.2f ms/step" % (1e3 * t_res / args.steps))
     t_e2e = timed(False, args.steps)
+    log("e2e region done: %.2f ms/step" % (1e3 * t_e2e / args.steps))
     clocks = sampler.stop() if sampler else None
 
     tot_audio = torch.tensor([audio_s], dtype=torch.float64, device=dev)
@@ -437,7 +462,10 @@ def main():
                                         "kind": "port", "sample": CPU_SAMPLE_TEXT, "sample_audio_s": audio}
             except Exception as e:      # the CPU leg must never take the GPU line down
                 line["cpu_baseline"] = {"value": None, "error": repr(e)}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    if args.watchdog > 0:
+        import faulthandler
+        faulthandler.cancel_dump_traceback_later()
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()

@@ -691,180 +691,6 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_constan
     if (warp == 5) tmem_dealloc(tmem_base, NG * 32 < 32 ? 32 : NG * 32);
 }
 
-// ----------------------------------------------------------- backward, cluster + DSMEM ----
-// The H/32 CTAs of one (direction, group of 16 batch rows) form a cluster.  Each step every CTA
-// produces dgates for its 32 units x 4 gates (128 columns) and must read ALL 4H columns of the step
-// to form dh_{t-1} = dgates_t W_hh: an all-gather.  Instead of global memory + flags + TMA, each CTA
-// bulk-copies its [16 x 128] bf16 slice (4 KB, SWIZZLE_NONE K-major piece) into the A-operand buffer of
-// every CTA of the cluster; completion bytes land on the receiver's mbarrier.  The contraction index is
-// permuted to k' = cta*128 + gate*32 + unit so that a sender's slice is contiguous; W_hh^T is packed
-// with the same permutation on the host.  The A buffer is single (64 KB): receivers release it to the
-// senders with remote mbarrier arrives once their MMAs have retired.
-constexpr int NBB = 16;
-
-__global__ void __launch_bounds__(kThreads, 1)
-lstm_bwd_cluster_kernel(const __grid_constant__ CUtensorMap map_wt, BwdDev p) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
-    const int H = p.H, T = p.T, B = p.B;
-    const int KB = 4 * H / 64;
-    constexpr int kChunk = NBB / 8 * 128;                    // 256 B: one 16-byte K-chunk over 16 rows
-    constexpr int kSlice = NBB * 128 * 2;                    // 4 KB: what one CTA contributes per step
-    const int a_bytes = 4 * H * NBB * 2;                     // 64 KB for H = 512
-    uint8_t* Wt = smem;                                      // KB x [32 x 64] bf16, SWIZZLE_128B (k' order)
-    uint8_t* Ab = Wt + KB * 4096;                            // [4H/8 chunks][2 row groups][8][16 B] + slack
-    uint8_t* stg = Ab + a_bytes + 2048;                      // 2 x kSlice
-    float* dhs = reinterpret_cast<float*>(stg + 2 * kSlice); // [NBB][33]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(dhs) + ((NBB * 33 * 4 + 7) & ~7));
-    uint64_t* wbar = bars + 0;
-    uint64_t* mbar = bars + 1;           // MMAs of the step retired
-    uint64_t* afull = bars + 2;          // all slices of the step landed in Ab
-    uint64_t* afree = bars + 3;          // every receiver has released its A buffer (count = cluster size)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-
-    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // shfl: warp-uniform for ptxas
-    const int CS = gridDim.x;
-    const int cta = (int)cluster_ctarank();
-    const int dir = blockIdx.y, grp = blockIdx.z;
-    const int u0 = cta * 32, b0 = grp * NBB;
-    const int nbv = min(NBB, B - b0);
-    const uint32_t step_bytes = (uint32_t)CS * kSlice;
-
-    if (threadIdx.x == 0) {
-        mbar_init(wbar, 1); mbar_init(mbar, 1); mbar_init(afull, 1); mbar_init(afree, (uint32_t)CS);
-        fence_barrier_init();
-        if (T >= 2) mbar_expect_tx(afull, step_bytes);        // dgates of step 0
-    }
-    for (int i = threadIdx.x; i < (a_bytes + 2048) / 16; i += kThreads)
-        reinterpret_cast<uint4*>(Ab)[i] = make_uint4(0u, 0u, 0u, 0u);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    if (warp == 5) tmem_alloc(tmem_slot, 32);
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // uniform register: no R2UR waterfall per tcgen05 op
-
-    if (warp == 4) {
-        if (lane == 0) {
-            mbar_expect_tx(wbar, (uint32_t)KB * 4096u);
-            for (int kb = 0; kb < KB; ++kb)
-                tma_load_2d(&map_wt, wbar, Wt + kb * 4096, kb * 64, dir * H + u0);
-        }
-    } else if (warp == 5) {
-        {   // whole warp in the loop, one elected lane issues (see lstm_fwd_cluster_kernel)
-            const uint32_t idesc = make_idesc(64, 32);       // M = 64: only rows 0..15 are live
-            mbar_wait(wbar, 0);
-            const uint64_t ad0 = make_nosw_desc(smem_u32(Ab), kChunk, 128);
-            const uint64_t bd0 = make_sw128_desc(smem_u32(Wt));
-            for (int s = 1; s < T; ++s) {
-                mbar_wait(afull, (uint32_t)((s - 1) & 1));                    // dgates of step s-1 from all CTAs
-                tc_fence_after();
-                if (elect_one()) {
-                    if (s <= T - 2) mbar_expect_tx(afull, step_bytes);        // re-arm for the dgates of step s
-#pragma unroll 8
-                    for (int kk = 0; kk < 4 * H / 16; ++kk)
-                        tc_mma_bf16(tmem_base, ad0 + (uint64_t)(kk * (2 * kChunk / 16)),
-                                    bd0 + (uint64_t)((kk >> 2) * (4096 / 16) + (kk & 3) * 2), idesc, (uint32_t)(kk != 0));
-                    tc_commit(mbar);
-                }
-                __syncwarp();
-            }
-        }
-    } else {
-        float dcn[NBB / 4];
-#pragma unroll
-        for (int k = 0; k < NBB / 4; ++k) dcn[k] = 0.f;
-        uint32_t ph_m = 0;
-        for (int s = 0; s < T; ++s) {
-            const int tt = dir ? s : (T - 1 - s);
-            const int tfp = dir ? tt + 1 : tt - 1;
-            float cO[NBB / 4], a1[NBB / 4], cI[NBB / 4], cF[NBB / 4], cG[NBB / 4], fgv[NBB / 4], dyv[NBB / 4];
-#pragma unroll
-            for (int k = 0; k < NBB / 4; ++k) {
-                const int b = warp + 4 * k;
-                cO[k] = a1[k] = cI[k] = cF[k] = cG[k] = fgv[k] = dyv[k] = 0.f;
-                if (b < nbv) {
-                    const int64_t bb = b0 + b;
-                    const __nv_bfloat16* gp = p.gates + ((((int64_t)dir * T + tt) * B + bb) * 4) * H + u0 + lane;
-                    const float ig = __bfloat162float(gp[0]), fg = __bfloat162float(gp[H]);
-                    const float gg = __bfloat162float(gp[2 * H]), og = __bfloat162float(gp[3 * H]);
-                    const float c = p.cstate[(((int64_t)dir * T + tt) * B + bb) * H + u0 + lane];
-                    const float cp = (tfp >= 0 && tfp < T)
-                                         ? p.cstate[(((int64_t)dir * T + tfp) * B + bb) * H + u0 + lane] : 0.f;
-                    dyv[k] = p.dy[(bb * T + tt) * 2 * H + dir * H + u0 + lane];
-                    const float tc_ = tanhf_fast(c);
-                    cO[k] = tc_ * og * (1.0f - og);
-                    a1[k] = og * (1.0f - tc_ * tc_);
-                    cI[k] = gg * ig * (1.0f - ig);
-                    cF[k] = cp * fg * (1.0f - fg);
-                    cG[k] = ig * (1.0f - gg * gg);
-                    fgv[k] = fg;
-                }
-            }
-            if (s > 0) {
-                mbar_wait(mbar, ph_m); ph_m ^= 1;
-                tc_fence_after();
-                // the A buffer is free again: tell every sender of the cluster
-                if (warp == 1 && lane < CS) mbar_arrive_remote(mapa_u32(smem_u32(afree), (uint32_t)lane));
-                if (warp == 0) {
-                    uint32_t v[32];
-                    tc_ld_32x32b_x32(tmem_base, v);
-                    if (lane < NBB) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) dhs[lane * 33 + j] = __uint_as_float(v[j]);
-                    }
-                }
-                tc_fence_before();
-            } else {
-                for (int i = threadIdx.x; i < NBB * 33; i += kEpiThreads) dhs[i] = 0.f;
-            }
-            named_bar_sync(1, kEpiThreads);
-            uint8_t* st = stg + (s & 1) * kSlice;
-            __nv_bfloat16 dg[NBB / 4][4];
-#pragma unroll
-            for (int k = 0; k < NBB / 4; ++k) {
-                const int b = warp + 4 * k;
-                const float dh = dhs[b * 33 + lane] + dyv[k];
-                const float dc = fmaf(dh, a1[k], dcn[k]);
-                dcn[k] = dc * fgv[k];
-                dg[k][0] = __float2bfloat16(dc * cI[k]);
-                dg[k][1] = __float2bfloat16(dc * cF[k]);
-                dg[k][2] = __float2bfloat16(dc * cG[k]);
-                dg[k][3] = __float2bfloat16(dh * cO[k]);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int col = q * 32 + lane;            // k' within my slice = gate*32 + unit
-                    *reinterpret_cast<__nv_bfloat16*>(st + (col >> 3) * kChunk + (b >> 3) * 128 + (b & 7) * 16 + (col & 7) * 2) = dg[k][q];
-                }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            named_bar_sync(1, kEpiThreads);
-            if (s < T - 1 && warp == 0) {
-                if (s > 0) mbar_wait_cluster(afree, (uint32_t)((s - 1) & 1));  // all receivers released their A buffer
-                if (lane < CS) {
-                    const uint32_t dst = mapa_u32(smem_u32(Ab + cta * kSlice), (uint32_t)lane);
-                    const uint32_t bar = mapa_u32(smem_u32(afull), (uint32_t)lane);
-                    dsmem_bulk_copy(dst, smem_u32(st), (uint32_t)kSlice, bar);
-                }
-            }
-            // off the critical path: dgates in the natural layout for the weight-gradient GEMMs
-#pragma unroll
-            for (int k = 0; k < NBB / 4; ++k) {
-                const int b = warp + 4 * k;
-                if (b < nbv) {
-                    __nv_bfloat16* dp = p.dgates + (((int64_t)(b0 + b) * T + tt) * 2 + dir) * 4 * H + u0 + lane;
-                    dp[0] = dg[k][0]; dp[H] = dg[k][1]; dp[2 * H] = dg[k][2]; dp[3 * H] = dg[k][3];
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();
-    if (warp == 5) tmem_dealloc(tmem_base, 32);
-}
-
 // ------------------------------------------- backward, cluster + DSMEM, K-split / reduce-scatter ----
 // dh_{t-1}[b, j] = sum_n dgates_t[b, n] W_hh[n, j].  Instead of all-gathering dgates (4H columns), each CTA
 // contracts ONLY over the 128 gate columns it has just produced itself, for ALL H output units:
@@ -1334,56 +1160,6 @@ int launch_bwd(const pk2_lstm_bwd_args* a, cudaStream_t st) {
     return 0;
 }
 
-// Cluster/DSMEM backward; a->whh_t_perm is W_hh^T with the contraction index permuted to cta*128+gate*32+unit.
-int launch_bwd_cluster(const pk2_lstm_bwd_args* a, cudaStream_t st) {
-    const int H = a->H, T = a->T, B = a->B, KB = 4 * H / 64, CS = H / 32;
-    const int G = (B + NBB - 1) / NBB;
-    if (CS > 16 || (CS & (CS - 1)) != 0 || a->whh_t_perm == nullptr) return -1;
-    CUtensorMap mwt;
-    {
-        cuuint64_t dims[2] = {(cuuint64_t)(4 * H), (cuuint64_t)(2 * H)};
-        cuuint64_t str[1] = {(cuuint64_t)(4 * H) * 2};
-        cuuint32_t box[2] = {64, 32};
-        if (make_map(&mwt, a->whh_t_perm, 2, dims, str, box)) return 2;
-    }
-    const size_t smem = (size_t)KB * 4096 + (size_t)4 * H * NBB * 2 + 2048 + 2 * NBB * 256 + (size_t)((NBB * 33 * 4 + 7) & ~7) + 128 + 1024;
-    static bool attr_done = false, usable = true;
-    if (!attr_done) {
-        attr_done = true;
-        if (cudaFuncSetAttribute(lstm_bwd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) != cudaSuccess ||
-            cudaFuncSetAttribute(lstm_bwd_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
-            cudaGetLastError();
-            usable = false;
-        }
-    }
-    if (!usable) return -1;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(CS, 2, G);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    int max_clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, lstm_bwd_cluster_kernel, &cfg) != cudaSuccess) {
-        cudaGetLastError();
-        return -1;
-    }
-    if (getenv("PK2_LSTM_DEBUG")) fprintf(stderr, "[pk2] lstm_bwd_cluster: %d clusters of %d wanted, %d co-resident\n", 2 * G, CS, max_clusters);
-    if (max_clusters < 1) return -1;
-    BwdDev d;
-    d.B = B; d.T = T; d.H = H; d.dy = a->dy;
-    d.gates = static_cast<const __nv_bfloat16*>(a->gates);
-    d.cstate = a->cstate;
-    d.dgates = static_cast<__nv_bfloat16*>(a->dgates);
-    d.counters = a->sync; d.prof = nullptr; d.dbg = 0;
-    PK2_CHECK(cudaLaunchKernelEx(&cfg, lstm_bwd_cluster_kernel, mwt, d));
-    PK2_LAUNCHED();
-    return 0;
-}
-
 // K-split / reduce-scatter backward on clusters; needs the permuted W_hh^T (a->whh_t_perm).
 template <int EW>
 int launch_bwd_rs_t(const pk2_lstm_bwd_args* a, cudaStream_t st) {
@@ -1473,14 +1249,6 @@ extern "C" int pk2_lstm_layer_bwd(const pk2_lstm_bwd_args* a, void* stream) {
     PK2_REQUIRE(a && a->dy && a->whh_t && a->gates && a->cstate && a->dgates && a->sync, "pk2_lstm_layer_bwd: null argument");
     const int ng = a->B > 4 * NB ? 2 : 1;
     if (check_dims("pk2_lstm_layer_bwd", a->B, a->T, a->H, ng, num_sms())) return 2;
-    // The all-gather cluster kernel is correct but measured slower than the global-memory kernel (128
-    // A-read-bound MMAs per step and only 7 co-resident 16-CTA clusters on B200: profiles/README_r1.md);
-    // it stays selectable for experiments.
-    static const bool use_cluster = getenv("PK2_LSTM_BWD_CLUSTER") != nullptr;
-    if (use_cluster) {
-        const int rc = launch_bwd_cluster(a, pk2::as_stream(stream));
-        if (rc >= 0) return rc;
-    }
     static const bool no_cluster = getenv("PK2_LSTM_NO_CLUSTER") != nullptr;
     // Default: K-split / reduce-scatter kernel on clusters (9.5 k cycles per step, profiles/lstm_bwd_rs_trace_r1_v11.txt);
     // PK2_LSTM_NO_RS=1 or an unschedulable cluster falls back to the global-memory kernel (8.9 us per step).

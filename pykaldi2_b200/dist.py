@@ -67,8 +67,8 @@ def broadcast_optimizer_state(optimizer, root_rank=0):
 class GradAverager(object):
     """Flat-bucket gradient all-reduce (mean) for a fixed parameter list.
 
-    The gradients are packed into one flat buffer (one pass), averaged by a single NCCL all-reduce (ReduceOp.AVG on
-    NCCL, SUM + scale on gloo) and handed back as VIEWS of that buffer: ``p.grad`` points into the bucket afterwards,
+    The gradients are packed into one flat buffer (one pass), summed by a single all-reduce, scaled, and handed back
+    as VIEWS of that buffer: ``p.grad`` points into the bucket afterwards,
     so clipping and the optimizer read the averaged values without a copy back.  ``timers``: set to a list to collect
     (start, end) CUDA events around pack + all-reduce (bench.py reports the mean as ``allreduce_ms``)."""
 
@@ -98,11 +98,8 @@ class GradAverager(object):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         torch._foreach_copy_(views, grads)
-        if dist.get_backend() == "nccl":
-            dist.all_reduce(self._flat, op=dist.ReduceOp.AVG)
-        else:
-            dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
-            self._flat.div_(size())
+        dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
+        self._flat.div_(size())
         if timed:
             e1.record()
             self.timers.append((e0, e1))

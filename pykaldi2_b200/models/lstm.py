@@ -264,9 +264,17 @@ class _BlstmAM(Function):
                 _gemm(dg2, pk["wih_t"], dy_next, None, M, I, 8 * H, 8 * H, pk["ldk"], I)
             xin_l, y_l = saved["xin"][l], saved["y"][l]
 
-            def layer_grads(l=l, dg2=dg2, xin_l=xin_l, y_l=y_l, I=I):
-                dg2.record_stream(side); xin_l.record_stream(side); y_l.record_stream(side)
+            def grads_a(l=l, dg2=dg2, xin_l=xin_l, I=I):
+                """input weights and biases of layer l"""
+                dg2.record_stream(side); xin_l.record_stream(side)
                 d_wih = wgrad(dg2, 8 * H, xin_l, I, M, 8 * H, I)
+                d_b = th.empty(8 * H, dtype=th.float32, device=dev)
+                _lib.check(lib.pk2_colsum_bf16(_lib.ptr(dg2), _lib.ptr(d_b), M, 8 * H, _lib.stream()), "pk2_colsum_bf16")
+                results[(l, "a")] = (d_wih, d_b)
+
+            def grads_b(l=l, dg2=dg2, y_l=y_l):
+                """recurrent weights of layer l"""
+                dg2.record_stream(side); y_l.record_stream(side)
                 d_whh = []
                 if TN_GEMM:
                     hp = th.empty(M, 2 * H, dtype=th.bfloat16, device=dev)
@@ -284,22 +292,25 @@ class _BlstmAM(Function):
                         dW = th.empty(4 * H, H, dtype=th.float32, device=dev)
                         _gemm(dg_t[d * 4 * H:(d + 1) * 4 * H], hp_t[d * H:(d + 1) * H], dW, None, 4 * H, H, M, ldm, ldm, H)
                         d_whh.append(dW)
-                d_b = th.empty(8 * H, dtype=th.float32, device=dev)
-                _lib.check(lib.pk2_colsum_bf16(_lib.ptr(dg2), _lib.ptr(d_b), M, 8 * H, _lib.stream()), "pk2_colsum_bf16")
-                results[l] = (d_wih, d_whh, d_b)
+                results[(l, "b")] = d_whh
+
+            def layer_grads(a=grads_a, b=grads_b):
+                a(); b()
 
             if l > 0:
                 pending = (mark_ready(), layer_grads)
                 dy = dy_next
             else:
-                layer_grads()                     # bottom layer: nothing left to overlap with; stay on the main stream
+                # bottom layer: no recurrence left to hide behind; the two independent groups run side by side
+                on_side(mark_ready(), grads_a)
+                grads_b()
         done = th.cuda.Event()
         done.record(side)
         main.wait_event(done)
         d_w_out, d_b_out = results["out"]
         d_w_out.record_stream(main); d_b_out.record_stream(main)
         for l in range(L):
-            d_wih, d_whh, d_b = results[l]
+            (d_wih, d_b), d_whh = results[(l, "a")], results[(l, "b")]
             for t in [d_wih, d_b] + d_whh:
                 t.record_stream(main)
             grads[8 * l + 0] = d_wih[:4 * H]; grads[8 * l + 4] = d_wih[4 * H:]
