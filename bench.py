@@ -142,6 +142,23 @@ def host_cores():
         n = min(n, len(os.sched_getaffinity(0)))
     except Exception:
         pass
+    # container CPU quota (cgroup v2 cpu.max / v1 cfs quota): more spinning OpenMP threads than the quota allows are
+    # throttled together (seen on a 2-GPU box: 24 threads, iRTF 1.2 instead of 25)
+    try:
+        quota = None
+        if os.path.exists("/sys/fs/cgroup/cpu.max"):
+            q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+            if q != "max":
+                quota = float(q) / float(per)
+        elif os.path.exists("/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        if quota:
+            n = max(1, min(n, int(quota)))
+    except Exception:
+        pass
     return int(n)
 
 
@@ -246,6 +263,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--emulate-shard", default="", help="R/W: single process, no collectives, the utterances rank R of a "
+                    "W-rank run would get (shape check of the larger shards of a multi-GPU run)")
     ap.add_argument("--watchdog", type=int, default=int(os.environ.get("PK2_BENCH_WATCHDOG", "420")),
                     help="seconds after which a stuck run dumps its stacks and exits (0 = off)")
     args = ap.parse_args()
@@ -273,7 +292,11 @@ def main():
 
     L = _lib.lib()
     B = args.batch
-    durs, wavs, frames, sub, sup_fsts = make_workload(rank, B, world=world)
+    if args.emulate_shard:
+        er, ew = (int(v) for v in args.emulate_shard.split("/"))
+        durs, wavs, frames, sub, sup_fsts = make_workload(er, B, world=ew)
+    else:
+        durs, wavs, frames, sub, sup_fsts = make_workload(rank, B, world=world)
     log("workload: %d utterances, %d output frames, longest %d" % (len(wavs), sum(sub), max(sub)))
     den_fst = synth.make_den_fst(DEN_STATES, N_PDF, DEN_EXTRA, seed=1234)
     den = graphs.DenominatorGraph(den_fst, N_PDF)
@@ -452,10 +475,10 @@ def main():
             "allreduce_ms": ar_ms,
             "clocks": clocks,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1 and not args.emulate_shard:
+            # rank 0 at N = 1 only: at N > 1 the other ranks spin in the closing barrier on the same host cores
             try:
-                durs0, wavs0, _, _, sups0 = (durs, wavs, None, None, sup_fsts) if world == 1 else make_workload(0, BATCH)
-                wv, sf, audio = cpu_sample(durs0, wavs0, sups0)
+                wv, sf, audio = cpu_sample(durs, wavs, sup_fsts)
                 cores = host_cores()
                 a, t = cpu_reference_sample(wv, sf, den_fst, cores)
                 line["cpu_baseline"] = {"value": a / t, "unit": "hours audio per hour", "cores": cores,

@@ -24,7 +24,8 @@ for step in "$@"; do
     ncu_fbank)   timeout 600 ncu --set full --clock-control none --import-source on -k regex:fbank -c 2 -o $OUT/fbank_$TAG -f python tools/kernel_bench.py fbank > $OUT/ncu_fbank_$TAG.log 2>&1; echo "ncu_fbank rc=$?" ;;
     timeline)    timeout 300 python tools/timeline.py > $OUT/timeline_$TAG.csv 2> $OUT/timeline_$TAG.err; wc -l $OUT/timeline_$TAG.csv; tail -3 $OUT/timeline_$TAG.err ;;
     c3)          timeout 600 python tools/bench_c3.py > $OUT/bench_c3_$TAG.json 2> $OUT/bench_c3_$TAG.err; timeout 600 python tools/bench_c3.py --criterion smbr >> $OUT/bench_c3_$TAG.json 2>> $OUT/bench_c3_$TAG.err; cat $OUT/bench_c3_$TAG.json; tail -3 $OUT/bench_c3_$TAG.err ;;
-    ncu_den)     timeout 900 ncu --set full --clock-control none --import-source on -k regex:den_ -c 10 -o $OUT/den_$TAG -f python tools/kernel_bench.py den1 > $OUT/ncu_den_$TAG.log 2>&1; echo "ncu_den rc=$?" ;;
+    emul)        timeout 200 python bench.py --emulate-shard 0/8 --steps 3 --no-cpu-baseline --watchdog 150 > $OUT/bench_${TAG}_shard0of8.json 2> $OUT/bench_${TAG}_shard0of8.err; cut -c1-300 $OUT/bench_${TAG}_shard0of8.json; tail -4 $OUT/bench_${TAG}_shard0of8.err ;;
+    ncu_den)     timeout 900 ncu --set full --clock-control none --import-source on -k regex:den_ -s 5 -c 5 -o $OUT/den_$TAG -f python tools/kernel_bench.py den1 > $OUT/ncu_den_$TAG.log 2>&1; echo "ncu_den rc=$?" ;;
     py:*)        timeout 900 python ${step#py:} > $OUT/py_$TAG.log 2>&1; echo "py rc=$?"; tail -30 $OUT/py_$TAG.log ;;
     *)           echo "unknown step $step" ;;
   esac
