@@ -124,7 +124,7 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-DEN_TRAFFIC_BYTES = 5585641608      # ncu, profiles/ncu_den_full_r1_v24.md
+DEN_TRAFFIC_BYTES = 5588676024      # ncu --set full, profiles/ncu_den_full_r2_v10.md (den kernels unchanged since r1 v24: 5585641608)
 
 
 # ------------------------------------------------------------------------------ CPU arm ----

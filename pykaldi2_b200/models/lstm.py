@@ -326,6 +326,23 @@ class _BlstmAM(Function):
 _SIDE = {}
 _SMS = {}
 
+# Every optimizer step invalidates the packed operand copies.  In-place updates normally bump Tensor._version, but the
+# fused optimizers (torch.optim.Adam(fused=True): one multi-tensor kernel) do NOT -- found in profiles/launches_r2_v10.csv
+# (three pack launches in eight steps) -- so the cache key also carries a generation counter advanced by a global
+# optimizer post-step hook.
+_GENERATION = [0]
+
+
+def _bump_generation(*_args, **_kwargs):
+    _GENERATION[0] += 1
+
+
+try:
+    from torch.optim.optimizer import register_optimizer_step_post_hook
+    register_optimizer_step_post_hook(_bump_generation)
+except ImportError:                                  # very old torch: repack on every call
+    _GENERATION = None
+
 
 def _side_stream(dev):
     key = (dev.type, dev.index)
@@ -374,10 +391,12 @@ class LSTMAM(nn.Module):
         return out
 
     def _packed(self, flat):
-        """Operand copies of the weights, rebuilt only when a parameter changed (in-place updates bump _version,
-        .to() / load_state_dict change the storage or the version)."""
+        """Operand copies of the weights, rebuilt only when a parameter may have changed: an optimizer step anywhere in
+        the process (generation counter, see _bump_generation), an in-place update (_version), .to() / load_state_dict
+        (storage or version)."""
         ps = [self.output_layer.weight, self.output_layer.bias] + flat
-        key = tuple((p.data_ptr(), p._version) for p in ps)
+        gen = _GENERATION[0] if _GENERATION is not None else object()
+        key = (gen,) + tuple((p.data_ptr(), p._version) for p in ps)
         if key != self._pack_key:
             with th.no_grad():
                 self._pack = _Packed(ps[0].detach(), ps[1].detach(), [p.detach() for p in flat], self.num_layers,

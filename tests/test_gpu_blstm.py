@@ -303,3 +303,14 @@ def test_lstmam_weight_cache_follows_updates(dev):
     model.output_layer.load_state_dict(lin.state_dict())
     ref = lin(lstm(x.cpu())[0]).detach()
     assert rel_err(model(x).detach().cpu(), ref) < 2e-2
+    # optimizer steps: the fused multi-tensor Adam does not bump Tensor._version; the cache must follow it anyway
+    for opt in (torch.optim.Adam(model.parameters(), lr=0.05, amsgrad=True, fused=True),
+                torch.optim.SGD(model.parameters(), lr=0.5)):
+        before = model(x).detach().clone()
+        model(x).sum().backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        after = model(x).detach()
+        assert float((after - before).abs().max()) > 1e-3, type(opt).__name__
+        w = model.output_layer.weight.detach().to(torch.bfloat16)
+        torch.testing.assert_close(model._pack.w_out, w)
