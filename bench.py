@@ -52,7 +52,7 @@ def load_peaks():
 def make_workload(rank, batch, seed=1234, world=1):
     """Synthetic utterances of this rank.  The GLOBAL batch (batch * world utterances, durations seeded
     independently of world) is split across the ranks by dist.balanced_shards -- the product's sampler
-    (data.dataloader.BalancedBatchSampler, used by train_se / train_chain): cost = 50 * longest + sum of frames,
+    (data.dataloader.BalancedBatchSampler, used by train_se / train_chain): cost = 56 * longest + sum of frames,
     so the rank that holds the longest utterance gets fewer frames.  (The reference's DistributedSampler shards at
     random; SURVEY.md section 7.3 "var-len DP load balance".)"""
     from pykaldi2_b200 import dist as pkdist
@@ -445,7 +445,7 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "BLSTM 3x512 LF-MMI chain, batch 64 var-len utts/GPU, S=8192 den FST (C4)",
                        "global_batch": B * world, "audio_s_per_step": tot_audio, "parallelism": "dp%d" % world,
-                       "sharding": "global batch split across ranks by modelled step time (dist.balanced_shards: 50 x longest + sum of frames)",
+                       "sharding": "global batch split across ranks by modelled step time (dist.balanced_shards: 56 x longest + sum of frames)",
                        "l2": "no flush: every step streams > 5 GB of activations/workspace, far larger than the 126 MB L2",
                        "optimizer": "Adam(amsgrad) lr 1e-4, clip 5"},
             "e2e": {"value": e2e, "unit": "hours audio per hour", "ms_per_step": 1e3 * t_e2e / args.steps,

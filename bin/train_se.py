@@ -107,6 +107,11 @@ def main():
             raise SystemExit("%s: %d priors for %d network outputs" % (args.prior_path, len(lp), N))
         log_prior = th.from_numpy(lp).to(dev)
     asr_decoder = graphs.SyntheticLatticeProvider()
+    if args.synthetic <= 0 and rank == 0:
+        print("WARNING: this build has no decoder (SURVEY 8a row a12: HCLG decoding is outside the hot path): the "
+              "denominator lattices are SYNTHETIC (random arcs around the alignment, seeded per utterance).  The loss "
+              "kernels are exercised on the corpus' audio and alignments, but the model is not trained against real "
+              "competing hypotheses.", flush=True)
 
     model.train()
     for epoch in range(args.num_epochs):
@@ -134,13 +139,14 @@ def run_train_epoch(model, optimizer, averager, feat, log_prior, loader, epoch, 
             y[j, :num_frs[j]] = lab[:num_frs[j], 0]
         y = th.from_numpy(y).cuda(non_blocking=True)
         prediction = model(x, valid_lengths=num_frs)          # padded frames: zero logits, ignored by both losses
-        ce_loss = pipeline.ce_loss(prediction.view(-1, N), y.view(-1), reduction="sum")
+        ce_loss = pipeline.ce_loss(prediction.view(-1, prediction.shape[-1]), y.view(-1), reduction="sum")
         # synthetic decoding lattices around the alignment, seeded per utterance
         lats, alis = [], []
         for j, ids in enumerate(batch["utt_ids"]):
             rng = np.random.default_rng(zlib.crc32(ids[0].encode()))
             trans_id = batch["aux"][j][0][0][:num_frs[j]].astype(np.int32)
-            lat, _, _ = synth.make_lattice(int(num_frs[j]), N, rng, num_ali=trans_id)
+            lat, _, _ = synth.make_lattice(int(num_frs[j]), N, rng, num_ali=trans_id,
+                                               num_tids=trans_model.num_transition_ids())
             lats.append(graphs.Lattice(lat)); alis.append(trans_id)
         loglikes = prediction - log_prior                       # bin/train_se.py:241
         mmi = args.criterion == "mmi"

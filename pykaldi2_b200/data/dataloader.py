@@ -70,7 +70,7 @@ class BalancedBatchSampler(Sampler):
     share.  All ranks draw the same permutation (seed + epoch), so no communication is needed.  The tail is padded
     by wrap-around like DistributedSampler (drop_last=False)."""
 
-    def __init__(self, lengths, batch_size, world=None, rank=None, seed=0, shuffle=True, tmax_weight=50.0):
+    def __init__(self, lengths, batch_size, world=None, rank=None, seed=0, shuffle=True, tmax_weight=56.0):
         self.lengths = np.asarray(lengths, np.float64)
         self.batch_size = int(batch_size)
         self.world = pkdist.size() if world is None else int(world)

@@ -135,13 +135,13 @@ class DistributedOptimizer(object):
         return self._opt.step(*a, **k)
 
 
-def balanced_shards(lengths, world, per_rank=None, tmax_weight=50.0):
+def balanced_shards(lengths, world, per_rank=None, tmax_weight=56.0):
     """Split one global minibatch of utterances across ``world`` data-parallel ranks so that the ranks finish a step
     together.  Step time of a rank is modelled as  tmax_weight * max(length) + sum(length)  (in frames): the BLSTM
     recurrences and the padded GEMMs scale with the LONGEST utterance of the rank's batch (the reference pads to it,
     data/dataloader.py:96-103), the denominator / lattice forward-backward and the output layer with the SUM of
-    frames.  tmax_weight = 50 is the measured ratio on B200 for the 3x512 BLSTM (22 us per padded output frame against
-    0.44 us per valid output frame, profiles/README_r2.md).
+    frames.  tmax_weight = 56 is the least-squares fit of the per-rank compute times of the 1/2/4/8-GPU runs on B200 for
+    the 3x512 BLSTM: 22.9 us per padded output frame against 0.41 us per valid output frame (profiles/README_r2.md).
 
     Longest-first greedy onto the rank with the lowest modelled cost that still has room (``per_rank`` utterances per
     rank, default ceil(n / world)): the rank that receives the longest utterance pays the largest padding term and is

@@ -173,7 +173,7 @@ def _trim(fst):
 
 
 def make_lattice(T, num_pdfs, rng, num_ali=None, kmin=32, kmax=96, dmin=2, dmax=6,
-                 ali_drop=0.05, eps_frac=0.0):
+                 ali_drop=0.05, eps_frac=0.0, num_tids=None):
     """Frame-layered decoding lattice.
 
     K_t ~ U{kmin..kmax} states at each time 1..T (one start state at t=0), each
@@ -183,13 +183,16 @@ def make_lattice(T, num_pdfs, rng, num_ali=None, kmin=32, kmax=96, dmin=2, dmax=
     frame t on (1-ali_drop) of the frames; the others deliberately lack it
     (exercises drop_frames).  eps_frac>0 adds epsilon (tid 0) arcs between
     same-time states (lower index -> higher index).
+    ``num_tids``: draw the arcs' transition ids from 1..num_tids (a real transition model's id range) instead of
+    1..2N; the returned tid2pdf is the synthetic two-ids-per-pdf map either way.
     Returns (lattice dict, tid2pdf int32 [2N+1], num_ali int32 [T]).
     """
     T = int(T)
     N = int(num_pdfs)
+    n_tid = 2 * N if num_tids is None else int(num_tids)
     tid2pdf = np.concatenate([[-1], np.repeat(np.arange(N), 2)]).astype(np.int32)
     if num_ali is None:
-        num_ali = rng.integers(1, 2 * N + 1, size=T).astype(np.int32)
+        num_ali = rng.integers(1, n_tid + 1, size=T).astype(np.int32)
     src_l, dst_l, tid_l, gc_l = [], [], [], []
     base, ns = 0, 1                      # first state id and number of states of the current level
     for t in range(T):
@@ -204,8 +207,8 @@ def make_lattice(T, num_pdfs, rng, num_ali=None, kmin=32, kmax=96, dmin=2, dmax=
         newid = np.cumsum(hit) - 1
         nxt = int(hit.sum())
         d = newid[d] + base + ns
-        tid = rng.integers(1, 2 * N + 1, size=a)
-        tid[tid == num_ali[t]] = (num_ali[t] % (2 * N)) + 1   # never hit the alignment by accident
+        tid = rng.integers(1, n_tid + 1, size=a)
+        tid[tid == num_ali[t]] = (num_ali[t] % n_tid) + 1     # never hit the alignment by accident
         if rng.random() >= ali_drop:
             tid[rng.integers(0, a)] = num_ali[t]
         gc = rng.uniform(0.0, 8.0, size=a)
