@@ -314,3 +314,42 @@ def test_lstmam_weight_cache_follows_updates(dev):
         assert float((after - before).abs().max()) > 1e-3, type(opt).__name__
         w = model.output_layer.weight.detach().to(torch.bfloat16)
         torch.testing.assert_close(model._pack.w_out, w)
+
+
+def test_data_parallel_split_equals_single_process(dev):
+    """the gradients of N data-parallel ranks, summed, equal the single-process gradients on the
+    concatenated batch.  One GPU plays both ranks in turn: the two halves of a zero-padded variable-length batch
+    (padded to the SAME length, as the reference's collate of the full batch would) through the whole LF-MMI step
+    (BLSTM -> chain loss -> backward); the sum of the halves' parameter gradients must match the full batch's up to
+    the order of summation, and so must the objective.  (The NCCL all-reduce itself is covered by the 2/4/8-GPU bench
+    runs and by the gloo test of GradAverager.)"""
+    from pykaldi2_b200 import graphs, synth
+    from pykaldi2_b200.models.lstm import LSTMAM
+    from pykaldi2_b200.ops import ops
+    B, T, F, N, H, L, S = 6, 40, 80, 96, 64, 2, 128
+    torch.manual_seed(4)
+    model = LSTMAM(F, N, H, L, 0.0, True).to(dev)
+    rng = np.random.default_rng(8)
+    den = graphs.DenominatorGraph(synth.make_den_fst(S, N, 5, seed=3), N)
+    opts = graphs.ChainTrainingOptions(leaky_hmm_coefficient=1e-4, xent_regularize=0.1)
+    lens = [40, 31, 22, 37, 9, 15]
+    x = torch.randn(B, T, F)
+    for b, n in enumerate(lens):
+        x[b, n:] = 0.0
+    sups = [graphs.Supervision(synth.make_supervision_fst(n, N, rng), n, N) for n in lens]
+
+    def grads(idx):
+        for p in model.parameters():
+            p.grad = None
+        xb = x[idx].to(dev)
+        pred = model(xb, valid_lengths=[lens[i] for i in idx])
+        loss = ops.ChainObjtiveFunction.apply_batch(pred, den, [sups[i] for i in idx], opts)
+        loss.backward()
+        return float(loss.item()), [p.grad.detach().clone() for p in model.parameters()]
+
+    full_loss, full = grads(list(range(B)))
+    l0, g0 = grads([0, 2, 4])
+    l1, g1 = grads([1, 3, 5])
+    np.testing.assert_allclose(l0 + l1, full_loss, rtol=1e-5)
+    for a, b, c, (name, _) in zip(g0, g1, full, model.named_parameters()):
+        assert rel_err(a + b, c) < 2e-3, name

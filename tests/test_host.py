@@ -164,6 +164,38 @@ ws = [torch.zeros_like(w) for _ in range(world)]
 torch.distributed.all_gather(ws, w)
 assert all(torch.equal(ws[0], t) for t in ws)
 assert pkdist.shard_indices(5, world, rank) == [(rank + i * world) %% 5 for i in range(3)]
+# GradAverager hands the averaged gradients back as views of its flat bucket (no copy back): distinct storage
+# offsets per parameter, values = mean over ranks, clipping + a second step still work
+m3 = torch.nn.Sequential(torch.nn.Linear(8, 4), torch.nn.Linear(4, 3))
+pkdist.broadcast_parameters(m3)
+avg = pkdist.GradAverager(list(m3.parameters()))
+for it in range(2):
+    m3(x).pow(2).sum().backward()
+    local = [p.grad.clone() for p in m3.parameters()]
+    avg.average()
+    for p, g in zip(m3.parameters(), local):
+        both = [torch.zeros_like(g) for _ in range(world)]
+        torch.distributed.all_gather(both, g)
+        assert torch.allclose(p.grad, sum(both) / world, rtol=1e-6, atol=1e-6)
+        assert p.grad.untyped_storage().data_ptr() == avg._flat.untyped_storage().data_ptr()
+    assert len({p.grad.data_ptr() for p in m3.parameters()}) == 4
+    torch.nn.utils.clip_grad_norm_(m3.parameters(), 0.1)
+    for p in m3.parameters():
+        p.grad = None
+# length-balanced sampler: the two ranks' shares of every global minibatch are disjoint and cover it
+import numpy as np
+from pykaldi2_b200.data.dataloader import BalancedBatchSampler
+L = (np.arange(20) * 37 %% 23 + 5) * 10
+bs = BalancedBatchSampler(L, batch_size=3, seed=3)
+assert (bs.world, bs.rank) == (world, rank)
+mine = [sorted(b) for b in bs]
+theirs = [None] * world
+torch.distributed.all_gather_object(theirs, mine)
+for g in range(len(bs)):
+    union = theirs[0][g] + theirs[1][g]
+    assert len(union) == 6 and len(set(union)) >= 5          # the padded tail may repeat one utterance
+    cost = [56 * max(L[i] for i in t[g]) + sum(L[i] for i in t[g]) for t in theirs]
+    assert max(cost) / min(cost) < 1.35
 print("rank", rank, "ok")
 """
 
