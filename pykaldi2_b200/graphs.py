@@ -237,14 +237,14 @@ class SupervisionBatch(object):
         host = {
             "seq_state_off": sbase.astype(np.int32),
             "lvl_base": lvl_base.astype(np.int32),
-            "level_off": np.concatenate([s.level_off + sbase[i] for i, s in enumerate(sups)]).astype(np.int32),
+            "level_off": np.concatenate([s.level_off + np.int32(sbase[i]) for i, s in enumerate(sups)]).astype(np.int32),
             "num_frames": np.array(self.num_frames_host, np.int32),
             "out_off": _cat_off([s.out_off for s in sups]),
-            "out_dst": np.concatenate([s.out_dst + sbase[i] for i, s in enumerate(sups)]).astype(np.int32),
+            "out_dst": np.concatenate([s.out_dst + np.int32(sbase[i]) for i, s in enumerate(sups)]).astype(np.int32),
             "out_pdf": np.concatenate([s.out_pdf for s in sups]),
             "out_w": np.concatenate([s.out_w for s in sups]),
             "in_off": _cat_off([s.in_off for s in sups]),
-            "in_src": np.concatenate([s.in_src + sbase[i] for i, s in enumerate(sups)]).astype(np.int32),
+            "in_src": np.concatenate([s.in_src + np.int32(sbase[i]) for i, s in enumerate(sups)]).astype(np.int32),
             "in_pdf": np.concatenate([s.in_pdf for s in sups]),
             "in_w": np.concatenate([s.in_w for s in sups]),
             "final_cost": np.concatenate([s.final_cost for s in sups]),
@@ -350,6 +350,11 @@ class Lattice(object):
         self.out_tid = t1[o].astype(np.int32)
         self.out_gc = g1[o]
         i = np.argsort(d1, kind="stable")
+        # in-arc k is out-arc _in_from_out[k]; frame of every out-arc (host index work reused by frame_acc)
+        rank_out = np.empty(len(o), np.int64)
+        rank_out[o] = np.arange(len(o))
+        self._in_from_out = rank_out[i].astype(np.int32)
+        self._out_frame = times[s1[o]].astype(np.int32)
         self.in_off = _csr(d1, S)
         self.in_src = s1[i].astype(np.int32)
         self.in_tid = t1[i].astype(np.int32)
@@ -374,23 +379,24 @@ class Lattice(object):
         num_ali = np.asarray(num_ali, np.int64)
         if len(num_ali) != self.num_frames:
             raise ValueError("alignment length %d != lattice frames %d" % (len(num_ali), self.num_frames))
-        tid2pdf = np.asarray(tid2pdf, np.int64)
+        # per-transition-id tables (class to compare, silence flag), then ONE pass over the arcs in out-arc order;
+        # the in-arc order is a stored permutation of it
         tid2phone = np.asarray(tid2phone, np.int64)
-        sil = np.asarray(sorted(set(int(p) for p in silence_phones)), np.int64)
-        S = self.num_states
-        t_out = np.repeat(self.state_time[:S].astype(np.int64), np.diff(self.out_off))          # frame of each out-arc
-        t_in = np.repeat(self.state_time[:S].astype(np.int64), np.diff(self.in_off)) - 1        # in-arc: time of its source
-
-        def acc(tid, t):
-            tid = tid.astype(np.int64)
-            ref = num_ali[t]
-            ph, rph = tid2phone[tid], tid2phone[ref]
-            ph_sil = np.isin(ph, sil)
-            both = ph_sil & np.isin(rph, sil)
-            same = (ph == rph) if criterion == "mpfe" else (tid2pdf[tid] == tid2pdf[ref])
-            return ((same | both) if one_silence_class else (same & ~ph_sil)).astype(np.uint8)
-
-        return acc(self.in_tid, t_in), acc(self.out_tid, t_out)
+        cls = (tid2phone if criterion == "mpfe" else np.asarray(tid2pdf, np.int64)).astype(np.int32)
+        sil_phone = np.zeros(int(tid2phone.max()) + 2, bool)
+        for p in silence_phones:
+            if 0 <= int(p) < len(sil_phone):
+                sil_phone[int(p)] = True
+        tid_sil = sil_phone[np.clip(tid2phone, 0, len(sil_phone) - 1)]
+        ref = num_ali[self._out_frame]                         # reference transition id at every arc's frame
+        tid = self.out_tid
+        same = cls[tid] == cls[ref]
+        if one_silence_class:
+            out = same | (tid_sil[tid] & tid_sil[ref])
+        else:
+            out = same & ~tid_sil[tid]
+        out = out.astype(np.uint8)
+        return out[self._in_from_out], out
 
     def keep_mask(self, num_ali):
         """1 where the alignment's tid occurs among the lattice's tids of that frame
@@ -453,14 +459,14 @@ class LatticeBatch(object):
         self.total_frames = int(sum(self.num_frames_host))
         # every index the kernels dereference is validated here, once, on the host: transition ids
         # within the tid -> pdf map, pdfs within the prediction's columns (checked against N at call time)
-        t2p = np.asarray(tid2pdf, np.int64)
+        t2p = np.asarray(tid2pdf, np.int32)
         self.max_pdf = -1
         for l, a in zip(lats, num_alis):
-            for name, tids in (("lattice arc", l.out_tid), ("alignment", np.asarray(a, np.int64))):
+            for name, tids in (("lattice arc", l.out_tid), ("alignment", np.asarray(a))):
                 if len(tids) and (tids.min() < 1 or tids.max() >= len(t2p)):
                     raise ValueError("%s transition id outside 1..%d" % (name, len(t2p) - 1))
                 if len(tids):
-                    pd = t2p[np.asarray(tids, np.int64)]
+                    pd = t2p[tids]
                     if pd.min() < 0:
                         raise ValueError("%s transition id maps to no pdf" % name)
                     self.max_pdf = max(self.max_pdf, int(pd.max()))
@@ -473,14 +479,14 @@ class LatticeBatch(object):
         host = {
             "seq_state_off": sbase.astype(np.int32),
             "lvl_base": lvl_base.astype(np.int32),
-            "level_off": np.concatenate([l.level_off + sbase[i] for i, l in enumerate(lats)]).astype(np.int32),
+            "level_off": np.concatenate([l.level_off + np.int32(sbase[i]) for i, l in enumerate(lats)]).astype(np.int32),
             "num_frames": np.array(self.num_frames_host, np.int32),
             "out_off": _cat_off([l.out_off for l in lats]),
-            "out_dst": np.concatenate([l.out_dst + sbase[i] for i, l in enumerate(lats)]).astype(np.int32),
+            "out_dst": np.concatenate([l.out_dst + np.int32(sbase[i]) for i, l in enumerate(lats)]),
             "out_tid": np.concatenate([l.out_tid for l in lats]),
             "out_gc": np.concatenate([l.out_gc for l in lats]),
             "in_off": _cat_off([l.in_off for l in lats]),
-            "in_src": np.concatenate([l.in_src + sbase[i] for i, l in enumerate(lats)]).astype(np.int32),
+            "in_src": np.concatenate([l.in_src + np.int32(sbase[i]) for i, l in enumerate(lats)]),
             "in_tid": np.concatenate([l.in_tid for l in lats]),
             "in_gc": np.concatenate([l.in_gc for l in lats]),
             # eps_off is indexed with lvl_base[b] + t like level_off (T+2 entries per lattice)

@@ -604,3 +604,28 @@ def test_speech_dataset_epoch_semantics(tmp_path):
         picks |= {ch[i][1][0] for i in range(len(ch))}
     assert len(picks) > 4                                      # not the same prefix every epoch
     assert ch.reader._zips == {}                               # no handle survives the constructor (fork safety)
+
+
+def test_lattice_frame_acc_matches_oracle_per_arc():
+    """graphs.Lattice.frame_acc (per-transition-id tables, one pass over the out-arcs, stored in<-out permutation)
+    against the oracle's per-arc definition, both criteria, both silence conventions; in-arc and out-arc order."""
+    from oracle import lattice_ref
+    from pykaldi2_b200 import graphs, synth
+    rng = np.random.default_rng(19)
+    N, T = 40, 17
+    lat, tid2pdf, ali = synth.make_lattice(T, N, rng, kmin=5, kmax=11, eps_frac=0.1)
+    tid2phone = np.where(np.asarray(tid2pdf) >= 0, np.asarray(tid2pdf) // 3 + 1, 0)
+    L = graphs.Lattice(lat)
+    t_out = np.repeat(L.state_time[:L.num_states], np.diff(L.out_off))
+    t_in = np.repeat(L.state_time[:L.num_states], np.diff(L.in_off)) - 1
+    for criterion in ("smbr", "mpfe"):
+        for sil in ([1, 2], [], [3]):
+            a_in, a_out = L.frame_acc(ali, tid2pdf, tid2phone, criterion, sil)
+            ref_out = [lattice_ref.mpe_frame_acc(int(t), int(ali[tt]), tid2pdf, tid2phone, criterion, set(sil))
+                       for t, tt in zip(L.out_tid, t_out)]
+            ref_in = [lattice_ref.mpe_frame_acc(int(t), int(ali[tt]), tid2pdf, tid2phone, criterion, set(sil))
+                      for t, tt in zip(L.in_tid, t_in)]
+            assert a_out.dtype == np.uint8 and (a_out == np.asarray(ref_out, np.uint8)).all()
+            assert (a_in == np.asarray(ref_in, np.uint8)).all()
+    with pytest.raises(ValueError):
+        L.frame_acc(ali[:-1], tid2pdf, tid2phone, "smbr", [1])
