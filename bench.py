@@ -299,7 +299,9 @@ def main():
         durs, wavs, frames, sub, sup_fsts = make_workload(rank, B, world=world)
     log("workload: %d utterances, %d output frames, longest %d" % (len(wavs), sum(sub), max(sub)))
     den_fst = synth.make_den_fst(DEN_STATES, N_PDF, DEN_EXTRA, seed=1234)
+    t_den0 = time.perf_counter()
     den = graphs.DenominatorGraph(den_fst, N_PDF)
+    t_den_create = time.perf_counter() - t_den0
     log("denominator graph on the device")
     n_arcs = len(den_fst["src"])
     opts = graphs.ChainTrainingOptions(leaky_hmm_coefficient=1e-4, xent_regularize=0.0)
@@ -384,10 +386,13 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()                      # NVML initialisation happens during the warm-up, not in the timed region
+    t_first = None
     for i in range(max(args.warmup, 3)):
+        t_s0 = time.perf_counter()
         step(True)
         if i == 0:
             torch.cuda.synchronize()
+            t_first = time.perf_counter() - t_s0
             log("first step done (graph tables built, kernels loaded)")
     step(False)
     drain_losses(0)
@@ -395,6 +400,7 @@ def main():
     log("warm-up done")
     if sampler:
         del sampler.rows[:]                  # keep only the samples taken during the timed regions
+    t_setup = time.perf_counter() - t_start
     ops.DEN_TIMERS = []
     del step_events[:]
     if averager is not None:
@@ -473,6 +479,11 @@ def main():
             "frames_per_rank": [int(r[1]) for r in spread_rows],
             "tmax_per_rank": [int(r[2]) for r in spread_rows],
             "allreduce_ms": ar_ms,
+            # one-off costs outside the timed region: pk2_den_graph_create (CSR -> per-row arc lists, upload) and the first
+            # step, which builds the SELL tables of the cluster sizes it uses (incl. the bank-conflict hill-climb of the
+            # arc order), loads the kernels and creates the TMA descriptors
+            "startup_s": {"den_graph_create": round(t_den_create, 3), "first_step": round(t_first, 3),
+                          "to_timed_region": round(t_setup, 3)},
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1 and not args.emulate_shard:
