@@ -254,7 +254,24 @@ class _BlstmAM(Function):
                                  saved["cstate"][l].data_ptr(), dgates.data_ptr(), sync.data_ptr(), pk["whh_tp"].data_ptr())
             if l == L - 1:
                 _hook("bwd_recurrence_next")
-            _lib.check(lib.pk2_lstm_layer_bwd(C.byref(a), _lib.stream()), "pk2_lstm_layer_bwd")
+            if REC_PRIORITY:
+                # The recurrence runs on a HIGH-PRIORITY stream.  It and the side stream's weight-gradient GEMM of the layer
+                # above become runnable at the same moment (both wait for the input-gradient GEMM); when the GEMM's persistent
+                # CTAs are placed first they sit in every GPC and the 16-CTA LSTM clusters wait ~0.27 ms for whole GPCs
+                # (profiles/timeline_r2_v15_runahead.csv, layers 2 and 1).  With the priority the block scheduler places the
+                # clusters first and the GEMM fills the SMs that are left.
+                rec = _rec_stream(dev)
+                ev_in = th.cuda.Event()
+                ev_in.record(main)
+                rec.wait_event(ev_in)
+                for t_ in (dy, dgates, sync):
+                    t_.record_stream(rec)
+                _lib.check(lib.pk2_lstm_layer_bwd(C.byref(a), _lib.vp(rec.cuda_stream)), "pk2_lstm_layer_bwd")
+                ev_out = th.cuda.Event()
+                ev_out.record(rec)
+                main.wait_event(ev_out)
+            else:
+                _lib.check(lib.pk2_lstm_layer_bwd(C.byref(a), _lib.stream()), "pk2_lstm_layer_bwd")
             if pending is not None:               # gradients of the layer above: overlap with this recurrence
                 on_side(*pending)
                 pending = None
@@ -324,13 +341,16 @@ class _BlstmAM(Function):
 
 
 _SIDE = {}
+_REC = {}
 _SMS = {}
+REC_PRIORITY = not bool(int(__import__("os").environ.get("PK2_LSTM_NO_PRIORITY", "0")))
 
 # Every optimizer step invalidates the packed operand copies.  In-place updates normally bump Tensor._version, but the
 # fused optimizers (torch.optim.Adam(fused=True): one multi-tensor kernel) do NOT -- found in profiles/launches_r2_v10.csv
 # (three pack launches in eight steps) -- so the cache key also carries a generation counter advanced by a global
 # optimizer post-step hook.
 _GENERATION = [0]
+_FREEZE = bool(int(__import__("os").environ.get("PK2_PACK_FREEZE", "0")))
 _STEP_EVENT = {}                 # device index -> CUDA event recorded right after the latest optimizer step
 
 
@@ -354,6 +374,14 @@ def _side_stream(dev):
     if key not in _SIDE:
         _SIDE[key] = th.cuda.Stream(device=dev)
     return _SIDE[key]
+
+
+def _rec_stream(dev):
+    """High-priority stream for the backward recurrence kernels (see _BlstmAM.backward)."""
+    key = (dev.type, dev.index)
+    if key not in _REC:
+        _REC[key] = th.cuda.Stream(device=dev, priority=-1)
+    return _REC[key]
 
 
 def _num_sms(dev):
@@ -401,6 +429,8 @@ class LSTMAM(nn.Module):
         (storage or version)."""
         ps = [self.output_layer.weight, self.output_layer.bias] + flat
         gen = _GENERATION[0] if _GENERATION is not None else object()
+        if _FREEZE and self._pack_key is not None:
+            return self._pack                        # A/B timing only (PK2_PACK_FREEZE=1): stale operand copies
         key = (gen,) + tuple((p.data_ptr(), p._version) for p in ps)
         if key != self._pack_key:
             dev = ps[0].device

@@ -19,23 +19,31 @@ sups = [graphs.Supervision(f, t, bench.N_PDF) for f, t in zip(sup_fsts, sub)]
 torch.manual_seed(0)
 model = LSTMAM(bench.FEAT, bench.N_PDF, bench.HID, bench.LAYERS, 0.0, True).to(dev)
 model.train()
-opt = torch.optim.Adam(model.parameters(), lr=1e-4, amsgrad=True)
+opt = torch.optim.Adam(model.parameters(), lr=1e-4, amsgrad=True, fused=True)
 feat = pipeline.FeaturePipeline(use_cmn=True)
 wav_pinned, woff, foff = feat.ex.pack(wavs)
 wav = wav_pinned.to(dev)
 sb = graphs.SupervisionBatch(sups, device=dev)
 
 
+pending = []
+
+
 def step():
-    return pipeline.chain_step(model, opt, None, feat, den, opts, wav, woff, foff, sb, epoch=0)
+    """the bench's loop body: loss read one step late, host one step ahead of the GPU"""
+    loss, _ = pipeline.chain_step(model, opt, None, feat, den, opts, wav, woff, foff, sb, epoch=0, sync=False)
+    pending.append(loss)
+    while len(pending) > 1:
+        pending.pop(0).value()
 
 
 for _ in range(4):
     step()
 torch.cuda.synchronize()
 from torch.profiler import profile, ProfilerActivity
-with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-    step()
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(3):                       # three steps back to back: the middle one shows the steady state
+        step()
     torch.cuda.synchronize()
 evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 evs.sort(key=lambda e: e.time_range.start)
