@@ -255,11 +255,11 @@ class _BlstmAM(Function):
             if l == L - 1:
                 _hook("bwd_recurrence_next")
             if REC_PRIORITY:
-                # The recurrence runs on a HIGH-PRIORITY stream.  It and the side stream's weight-gradient GEMM of the layer
-                # above become runnable at the same moment (both wait for the input-gradient GEMM); when the GEMM's persistent
-                # CTAs are placed first they sit in every GPC and the 16-CTA LSTM clusters wait ~0.27 ms for whole GPCs
-                # (profiles/timeline_r2_v15_runahead.csv, layers 2 and 1).  With the priority the block scheduler places the
-                # clusters first and the GEMM fills the SMs that are left.
+                # EXPERIMENT (PK2_LSTM_PRIORITY=1): the recurrence on a high-priority stream.  It and the side stream's
+                # weight-gradient GEMM of the layer above become runnable at the same moment (both wait for the
+                # input-gradient GEMM); when the GEMM's persistent CTAs are placed first they sit in every GPC and the 16-CTA
+                # LSTM clusters wait ~0.27 ms for whole GPCs (profiles/timeline_r2_v15_runahead.csv, layers 2 and 1).  The
+                # priority did not change the step time measurably (27.45 against 27.51 ms): not the default.
                 rec = _rec_stream(dev)
                 ev_in = th.cuda.Event()
                 ev_in.record(main)
@@ -343,7 +343,8 @@ class _BlstmAM(Function):
 _SIDE = {}
 _REC = {}
 _SMS = {}
-REC_PRIORITY = not bool(int(__import__("os").environ.get("PK2_LSTM_NO_PRIORITY", "0")))
+# experiment switch, off by default: measured on one box 27.45 ms per step with it, 27.51 without (profiles/README_r2.md)
+REC_PRIORITY = bool(int(__import__("os").environ.get("PK2_LSTM_PRIORITY", "0")))
 
 # Every optimizer step invalidates the packed operand copies.  In-place updates normally bump Tensor._version, but the
 # fused optimizers (torch.optim.Adam(fused=True): one multi-tensor kernel) do NOT -- found in profiles/launches_r2_v10.csv
