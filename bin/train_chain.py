@@ -26,6 +26,7 @@ from pykaldi2_b200 import graphs, pipeline, synth
 from pykaldi2_b200.data.dataloader import SyntheticWaveDataset, WaveDataloader
 from pykaldi2_b200.data.speech_dataset import SpeechDataset
 from pykaldi2_b200 import chain_supervision
+from pykaldi2_b200.data import fbank as fb
 from pykaldi2_b200.models import lstm
 from pykaldi2_b200.reader import kaldi_io
 from pykaldi2_b200.ops import ops
@@ -119,8 +120,21 @@ def main():
         dataset = SpeechDataset(config)
         if not args.den_fst:
             print("WARNING: no -den_fst given: training against a synthetic denominator graph")
+    kaldi = load_kaldi_assets(args)
+    supervision_opts = SupervisionOptions()
+    batch_transform = None
+    if kaldi is not None and args.synthetic <= 0:
+        def batch_transform(batch):
+            """Numerator graphs from the alignments (bin/train_chain.py:262-272), built where the batch is collated:
+            in the DataLoader workers when -data_loader_threads > 0.  batch["sup"][j] = (fst dict, output frames)."""
+            sup = []
+            for wav, lab in zip(batch["wav"], batch["label"]):
+                n = min(fb.num_frames(len(wav)), len(lab))                    # label trim, data/sr_dataset.py:358-363
+                sup.append(kaldi_supervision(kaldi, supervision_opts, lab[:n, 0]))
+            batch["sup"] = sup
+            return batch
     loader = WaveDataloader(dataset, args.batch_size, num_workers=args.data_loader_threads, distributed=world > 1,
-                            balanced=True, seed=args.seed)
+                            balanced=True, seed=args.seed, batch_transform=batch_transform)
     feat = pipeline.FeaturePipeline(use_cmn=dc.get("use_cmn", True))
     print("Data loader set up successfully!")
     print("Number of minibatches: {}".format(len(loader)))
@@ -135,9 +149,7 @@ def main():
         pkdist.broadcast_optimizer_state(optimizer)
     averager = pkdist.GradAverager(list(model.parameters())) if world > 1 else None
 
-    supervision_opts = SupervisionOptions()
     chain_opts = graphs.ChainTrainingOptions(leaky_hmm_coefficient=1e-4, xent_regularize=args.xent_regularize)
-    kaldi = load_kaldi_assets(args)
     if kaldi is not None and not args.den_fst and os.path.isfile(args.chain_dir + "/den.fst"):
         args.den_fst = args.chain_dir + "/den.fst"                                   # bin/train_chain.py:167
     if args.den_fst:                      # a real denominator graph: OpenFst binary (Kaldi's den.fst) or fstprint text
@@ -197,7 +209,7 @@ def run_train_epoch(model, optimizer, averager, feat, loader, epoch, supervision
             elif kaldi is not None:
                 # the label file holds the alignment model's transition ids, as in the reference (y = trans_ids);
                 # the frame shift of the epoch moves the features, not the supervision (bin/train_chain.py:251-272)
-                sup_fst, t_k = kaldi_supervision(kaldi, supervision_opts, batch["label"][j][:int(num_frs[j]), 0])
+                sup_fst, t_k = batch["sup"][j]                 # built by the loader's batch_transform
                 assert t_k == t_sub, (t_k, t_sub)
             else:
                 sup_fst = synth.alignment_to_supervision_fst(batch["label"][j][:, 0], factor, shift,

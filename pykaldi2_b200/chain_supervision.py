@@ -149,72 +149,72 @@ def proto_supervision_to_supervision(tree, tm, proto, convert_to_pdfs=True):
     bin/train_chain.py:185).  ``tree``: reader.kaldi_io.ContextDependency; ``tm``: the CHAIN transition model (dict of
     read_transition_model_text).  Returns the FST dict graphs.Supervision takes:
     num_states, start, src, dst, ilabel (= pdf + 1), weight (zeros), final (0 at final states, inf elsewhere),
-    state_times -- or None when the constraints leave no path (Kaldi: "Supervision FST is empty")."""
+    state_times -- or None when the constraints leave no path (Kaldi: "Supervision FST is empty").
+
+    The transition-id acceptor after AddSelfLoops(reorder=true) + RmEpsilon is, at pdf level, the chain
+    q_k --fpdf_k--> q_{k+1}, q_{k+1} --spdf_k--> q_{k+1} over the K HMM-state slots; intersected with the per-frame
+    phone constraints its nodes are (q, t).  Every arc goes from frame t to t + 1, so reachability is a T-step
+    recursion over boolean vectors of length K + 1 (numpy; a 26 s utterance takes a few milliseconds), and the
+    breadth-first numbering of fst::SortBreadthFirstSearch visits the frames in order and, inside a frame, the
+    nodes by DECREASING q (parents in decreasing q each emit their forward arc, to q + 1, before their self-loop)."""
     if not convert_to_pdfs:
         raise NotImplementedError("only convert_to_pdfs=True (what the reference trainer sets) is built")
     slots = _hmm_slots(tree, tm, proto.phones)
     K, T = len(slots), len(proto.allowed_phones)
-    allowed = [set(a) for a in proto.allowed_phones]
-    # transition-id acceptor after AddSelfLoops(reorder=true) + RmEpsilon, at pdf level: q_k --fpdf_k--> q_{k+1},
-    # q_{k+1} --spdf_k--> q_{k+1}.  Intersected with time: node (q, t).
-    ok = np.zeros((K, T), bool)                       # slot k may emit at frame t
-    for k, (ph, _, _, _) in enumerate(slots):
-        for t in range(T):
-            ok[k, t] = ph in allowed[t]
-    # forward reachability of (q, t)
+    slot_phone = np.array([sl[0] for sl in slots], np.int64)
+    fpdf = np.array([sl[1] for sl in slots], np.int64)
+    spdf = np.array([sl[2] for sl in slots], np.int64)
+    has_loop = np.array([sl[3] for sl in slots], bool)
+    # ok[k, t]: slot k may emit at frame t (its phone is allowed there)
+    n_ph = int(max(slot_phone.max(), max((max(a) for a in proto.allowed_phones if a), default=0))) + 1
+    allowed = np.zeros((n_ph, T), bool)
+    for t, a in enumerate(proto.allowed_phones):
+        if a:
+            allowed[np.asarray(a, np.int64), t] = True
+    ok = allowed[slot_phone]                                   # [K, T]
+    fwd_ok = ok                                                # (q, t) -> (q + 1, t + 1) for q < K
+    loop_ok = np.zeros((K + 1, T), bool)                       # (q, t) -> (q, t + 1) for q >= 1: self-loop of slot q - 1
+    loop_ok[1:] = ok & has_loop[:, None]
     reach = np.zeros((K + 1, T + 1), bool)
     reach[0, 0] = True
     for t in range(T):
-        for q in range(K + 1):
-            if not reach[q, t]:
-                continue
-            if q < K and ok[q, t]:
-                reach[q + 1, t + 1] = True            # forward transition of slot q
-            if q > 0 and slots[q - 1][3] and ok[q - 1, t]:
-                reach[q, t + 1] = True                # self-loop of slot q-1
+        r = reach[:, t]
+        nxt = r & loop_ok[:, t]
+        nxt[1:] |= r[:-1] & fwd_ok[:, t]
+        reach[:, t + 1] = nxt
     if not reach[K, T]:
         return None
-    # backward co-reachability
     co = np.zeros((K + 1, T + 1), bool)
     co[K, T] = True
     for t in range(T - 1, -1, -1):
-        for q in range(K + 1):
-            if q < K and ok[q, t] and co[q + 1, t + 1]:
-                co[q, t] = True
-            if q > 0 and slots[q - 1][3] and ok[q - 1, t] and co[q, t + 1]:
-                co[q, t] = True
+        c = co[:, t + 1]
+        cur = c & loop_ok[:, t]
+        cur[:-1] |= c[1:] & fwd_ok[:, t]
+        co[:, t] = cur
     live = reach & co
-    # breadth-first numbering from (0, 0); arcs of a node in the order forward transition, self-loop
+    # breadth-first ids: frames in order, decreasing q inside a frame
     ids = -np.ones((K + 1, T + 1), np.int64)
-    order = [(0, 0)]
-    ids[0, 0] = 0
-    src, dst, lab = [], [], []
-    head = 0
-    while head < len(order):
-        q, t = order[head]
-        s = ids[q, t]
-        head += 1
-        if t == T:
-            continue
-        nxt = []
-        if q < K and ok[q, t] and live[q + 1, t + 1]:
-            nxt.append((q + 1, t + 1, slots[q][1] + 1))
-        if q > 0 and slots[q - 1][3] and ok[q - 1, t] and live[q, t + 1]:
-            nxt.append((q, t + 1, slots[q - 1][2] + 1))
-        for q2, t2, l in nxt:
-            if ids[q2, t2] < 0:
-                ids[q2, t2] = len(order)
-                order.append((q2, t2))
-            src.append(s); dst.append(ids[q2, t2]); lab.append(l)
-    n = len(order)
+    tt, qq = np.nonzero(live.T[:, ::-1])                       # row-major over (t, reversed q)
+    qq = K - qq
+    ids[qq, tt] = np.arange(len(tt))
+    n = len(tt)
+    # arcs of node (q, t), t < T: forward (needs slot q allowed at t and (q+1, t+1) live), then self-loop
+    src_f = live[:-1, :-1] & fwd_ok & live[1:, 1:]             # [K, T]   q = 0..K-1
+    src_l = live[:, :-1] & loop_ok & live[:, 1:]               # [K+1, T]
+    qf, tf = np.nonzero(src_f)
+    ql, tl = np.nonzero(src_l)
+    src = np.concatenate([ids[qf, tf], ids[ql, tl]])
+    dst = np.concatenate([ids[qf + 1, tf + 1], ids[ql, tl + 1]])
+    lab = np.concatenate([fpdf[qf] + 1, spdf[ql - 1] + 1])
+    kind = np.concatenate([np.zeros(len(qf), np.int64), np.ones(len(ql), np.int64)])
+    o = np.lexsort((kind, src))                                # by source id, forward arc before self-loop
     final = np.full(n, np.inf, np.float32)
     final[ids[K, T]] = 0.0
-    o = np.argsort(np.asarray(src, np.int64), kind="stable")
     return {
-        "num_states": n, "start": 0,
-        "src": np.asarray(src, np.int32)[o], "dst": np.asarray(dst, np.int32)[o],
-        "ilabel": np.asarray(lab, np.int32)[o], "weight": np.zeros(len(src), np.float32),
-        "final": final, "state_times": np.asarray([t for _, t in order], np.int32),
+        "num_states": int(n), "start": 0,
+        "src": src[o].astype(np.int32), "dst": dst[o].astype(np.int32),
+        "ilabel": lab[o].astype(np.int32), "weight": np.zeros(len(src), np.float32),
+        "final": final, "state_times": tt.astype(np.int32),
     }
 
 

@@ -145,14 +145,19 @@ class SyntheticWaveDataset(Dataset):
 
 class WaveDataloader(_EpochMixin, DataLoader):
     """``balanced=True`` (the sequence trainers): under data parallelism the global minibatch is split across ranks
-    by modelled step time (BalancedBatchSampler) instead of at random; needs ``dataset.utt_lengths()``."""
+    by modelled step time (BalancedBatchSampler) instead of at random; needs ``dataset.utt_lengths()``.
+    ``batch_transform``: callable applied to the collated batch dict INSIDE the loader (i.e. in the worker processes
+    when num_workers > 0): host-side per-utterance index work such as building the numerator graphs of LF-MMI from
+    the alignments belongs there, next to the reference's own CPU data path, not in the training loop."""
 
-    def __init__(self, dataset, batch_size, num_workers=0, distributed=False, timeout=1000, balanced=False, seed=0):
+    def __init__(self, dataset, batch_size, num_workers=0, distributed=False, timeout=1000, balanced=False, seed=0,
+                 batch_transform=None):
         to = timeout if num_workers > 0 else 0
+        collate = wave_collate if batch_transform is None else (lambda b: batch_transform(wave_collate(b)))
         if balanced and distributed and pkdist.size() > 1 and hasattr(dataset, "utt_lengths"):
             bs = BalancedBatchSampler(dataset.utt_lengths(), batch_size, seed=seed)
-            super().__init__(dataset, batch_sampler=bs, num_workers=num_workers, collate_fn=wave_collate, timeout=to)
+            super().__init__(dataset, batch_sampler=bs, num_workers=num_workers, collate_fn=collate, timeout=to)
             return
         sampler = _sampler(dataset, distributed)
         super().__init__(dataset, batch_size=batch_size, shuffle=(sampler is None), sampler=sampler,
-                         num_workers=num_workers, collate_fn=wave_collate, drop_last=False, timeout=to)
+                         num_workers=num_workers, collate_fn=collate, drop_last=False, timeout=to)

@@ -125,59 +125,9 @@ def test_train_chain_with_kaldi_text_assets(tmp_path):
     holds the alignment model's transition ids, as in the reference (bin/train_chain.py:162-181, 262-272)."""
     import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from test_host import _make_corpus
-    from pykaldi2_b200 import synth
-    from pykaldi2_b200.data import fbank as fb
-    from pykaldi2_b200.reader import fst_io
-    P = 10                                                   # phones 1..P
+    from test_host import _make_corpus, _make_kaldi_chain_assets
     data_yaml, wavs, _ = _make_corpus(str(tmp_path), n=5, seed=5)
-    rng = np.random.default_rng(1)
-    # alignment model: phone p, state j -> triple 3(p-1)+j, ids 2r+1 (self-loop) / 2r+2 (forward); plain order
-    lab_path = os.path.join(tmp_path, "ali-tids.txt")
-    with open(lab_path, "w") as f:
-        for utt, x in wavs.items():
-            T = fb.num_frames(len(x)) - 1
-            tids, left = [], T
-            while left > 0:
-                p = int(rng.integers(1, P + 1))
-                durs = [int(d) for d in rng.integers(1, 6, size=3)]
-                if sum(durs) > left or left - sum(durs) < 3:
-                    durs = [1, 1, max(1, left - 2)] if left >= 3 else None
-                if durs is None:
-                    tids[-1:] = tids[-1:] * (1 + left)      # stretch the last self-loop-free frame: keep it simple
-                    break
-                for j, d in enumerate(durs):
-                    r = 3 * (p - 1) + j
-                    tids += [2 * r + 1] * (d - 1) + [2 * r + 2]
-                left -= sum(durs)
-            f.write(utt + " " + " ".join(map(str, tids[:T])) + "\n")
-    with open(data_yaml) as f:
-        y = f.read()
-    y = y.replace(os.path.join(str(tmp_path), "pdf-ids.txt"), lab_path)
-    with open(data_yaml, "w") as f:
-        f.write(y)
-    ali_dir, chain_dir = os.path.join(tmp_path, "ali"), os.path.join(tmp_path, "chain")
-    os.makedirs(ali_dir); os.makedirs(chain_dir)
-    phones = " ".join(str(p) for p in range(1, P + 1))
-    with open(os.path.join(ali_dir, "final.mdl.txt"), "w") as f:
-        f.write("<TransitionModel>\n<Topology>\n<TopologyEntry>\n<ForPhones> %s </ForPhones>\n" % phones +
-                "<State> 0 <PdfClass> 0 <Transition> 0 0.75 <Transition> 1 0.25 </State>\n"
-                "<State> 1 <PdfClass> 1 <Transition> 1 0.75 <Transition> 2 0.25 </State>\n"
-                "<State> 2 <PdfClass> 2 <Transition> 2 0.75 <Transition> 3 0.25 </State>\n<State> 3 </State>\n"
-                "</TopologyEntry>\n</Topology>\n<Triples> %d\n" % (3 * P) +
-                "".join("%d %d %d\n" % (p, j, 3 * (p - 1) + j) for p in range(1, P + 1) for j in range(3)) +
-                "</Triples>\n<LogProbs> [ 0 ] </LogProbs>\n</TransitionModel>\n")
-    with open(os.path.join(chain_dir, "0.trans_mdl.txt"), "w") as f:
-        f.write("<TransitionModel>\n<Topology>\n<TopologyEntry>\n<ForPhones> %s </ForPhones>\n" % phones +
-                "<State> 0 <ForwardPdfClass> 0 <SelfLoopPdfClass> 1 <Transition> 0 0.5 <Transition> 1 0.5 </State>\n"
-                "<State> 1 </State>\n</TopologyEntry>\n</Topology>\n<Tuples> %d\n" % P +
-                "".join("%d 0 %d %d\n" % (p, 2 * (p - 1), 2 * (p - 1) + 1) for p in range(1, P + 1)) +
-                "</Tuples>\n<LogProbs> [ 0 ] </LogProbs>\n</TransitionModel>\n")
-    with open(os.path.join(chain_dir, "tree.txt"), "w") as f:
-        f.write("ContextDependency 1 0 ToPdf TE 0 %d ( NULL " % (P + 1) +
-                " ".join("TE -1 2 ( CE %d CE %d )" % (2 * (p - 1), 2 * (p - 1) + 1) for p in range(1, P + 1)) +
-                " ) EndContextDependency\n")
-    fst_io.write_fst_binary(synth.make_den_fst(256, 104, 7, seed=1234), os.path.join(chain_dir, "den.fst"))
+    ali_dir, chain_dir = _make_kaldi_chain_assets(str(tmp_path), data_yaml, wavs)
     out = run("train_chain.py", ["-exp_dir", str(tmp_path), "-config", "configs/ce_test.yaml", "-data", data_yaml,
                                  "-ali_dir", ali_dir, "-chain_dir", chain_dir, "-batch_size", "2", "-print_freq", "1",
                                  "-max_steps", "2"], tmp_path)

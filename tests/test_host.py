@@ -276,6 +276,64 @@ def io_bytes():
     return io.BytesIO()
 
 
+def _make_kaldi_chain_assets(tmp_path, data_yaml, wavs, P=10, seed=1):
+    """Text-form Kaldi inputs of train_chain.py for the corpus of _make_corpus: an alignment model with 3-state
+    phones 1..P (phone p, state j -> triple 3(p-1)+j, transition ids 2r+1 = self-loop, 2r+2 = forward), a chain
+    model with the 1-state chain topology (pdfs 2(p-1), 2(p-1)+1), a monophone tree, den.fst; the corpus' label
+    file is REPLACED by transition-id alignments of the alignment model (plain order).  Returns (ali_dir, chain_dir)."""
+    from pykaldi2_b200 import synth
+    from pykaldi2_b200.data import fbank as fb
+    from pykaldi2_b200.reader import fst_io
+    rng = np.random.default_rng(seed)
+    lab_path = os.path.join(tmp_path, "ali-tids.txt")
+    with open(lab_path, "w") as f:
+        for utt, x in wavs.items():
+            T = fb.num_frames(len(x)) - 1
+            tids, left = [], T
+            while left > 0:
+                p = int(rng.integers(1, P + 1))
+                durs = [int(d) for d in rng.integers(1, 6, size=3)]
+                if sum(durs) > left or left - sum(durs) < 3:
+                    durs = [1, 1, left - 2] if left >= 3 else None
+                if durs is None:                             # fewer than 3 frames left: stretch the last state
+                    tids += [tids[-1] - 1] * left            # its self-loop id (plain order ends on the forward id)
+                    tids[-left - 1], tids[-1] = tids[-1] - 1, tids[-left - 1]
+                    break
+                for j, d in enumerate(durs):
+                    r = 3 * (p - 1) + j
+                    tids += [2 * r + 1] * (d - 1) + [2 * r + 2]
+                left -= sum(durs)
+            assert len(tids) == T
+            f.write(utt + " " + " ".join(map(str, tids)) + "\n")
+    with open(data_yaml) as f:
+        y = f.read()
+    with open(data_yaml, "w") as f:
+        f.write(y.replace(os.path.join(tmp_path, "pdf-ids.txt"), lab_path))
+    ali_dir, chain_dir = os.path.join(tmp_path, "ali"), os.path.join(tmp_path, "chain")
+    os.makedirs(ali_dir); os.makedirs(chain_dir)
+    phones = " ".join(str(p) for p in range(1, P + 1))
+    with open(os.path.join(ali_dir, "final.mdl.txt"), "w") as f:
+        f.write("<TransitionModel>\n<Topology>\n<TopologyEntry>\n<ForPhones> %s </ForPhones>\n" % phones +
+                "<State> 0 <PdfClass> 0 <Transition> 0 0.75 <Transition> 1 0.25 </State>\n"
+                "<State> 1 <PdfClass> 1 <Transition> 1 0.75 <Transition> 2 0.25 </State>\n"
+                "<State> 2 <PdfClass> 2 <Transition> 2 0.75 <Transition> 3 0.25 </State>\n<State> 3 </State>\n"
+                "</TopologyEntry>\n</Topology>\n<Triples> %d\n" % (3 * P) +
+                "".join("%d %d %d\n" % (p, j, 3 * (p - 1) + j) for p in range(1, P + 1) for j in range(3)) +
+                "</Triples>\n<LogProbs> [ 0 ] </LogProbs>\n</TransitionModel>\n")
+    with open(os.path.join(chain_dir, "0.trans_mdl.txt"), "w") as f:
+        f.write("<TransitionModel>\n<Topology>\n<TopologyEntry>\n<ForPhones> %s </ForPhones>\n" % phones +
+                "<State> 0 <ForwardPdfClass> 0 <SelfLoopPdfClass> 1 <Transition> 0 0.5 <Transition> 1 0.5 </State>\n"
+                "<State> 1 </State>\n</TopologyEntry>\n</Topology>\n<Tuples> %d\n" % P +
+                "".join("%d 0 %d %d\n" % (p, 2 * (p - 1), 2 * (p - 1) + 1) for p in range(1, P + 1)) +
+                "</Tuples>\n<LogProbs> [ 0 ] </LogProbs>\n</TransitionModel>\n")
+    with open(os.path.join(chain_dir, "tree.txt"), "w") as f:
+        f.write("ContextDependency 1 0 ToPdf TE 0 %d ( NULL " % (P + 1) +
+                " ".join("TE -1 2 ( CE %d CE %d )" % (2 * (p - 1), 2 * (p - 1) + 1) for p in range(1, P + 1)) +
+                " ) EndContextDependency\n")
+    fst_io.write_fst_binary(synth.make_den_fst(256, 104, 7, seed=1234), os.path.join(chain_dir, "den.fst"))
+    return ali_dir, chain_dir
+
+
 def test_zip_wav_label_ingestion(tmp_path):
     """the reference's corpus formats (zip of wavs, `utt-id int int ...` label files, data yaml)."""
     import struct
@@ -629,3 +687,45 @@ def test_lattice_frame_acc_matches_oracle_per_arc():
             assert (a_in == np.asarray(ref_in, np.uint8)).all()
     with pytest.raises(ValueError):
         L.frame_acc(ali[:-1], tid2pdf, tid2phone, "smbr", [1])
+
+
+def test_train_chain_data_side_with_kaldi_assets(tmp_path):
+    """The host half of train_chain.py -ali_dir -chain_dir without a GPU: asset loading, the loader's batch_transform
+    (numerator graphs built where the batch is collated, also in worker processes), graphs.Supervision objects."""
+    import importlib.util
+    from types import SimpleNamespace
+    import yaml
+    from pykaldi2_b200 import graphs
+    from pykaldi2_b200.data import fbank as fb
+    from pykaldi2_b200.data.dataloader import WaveDataloader
+    from pykaldi2_b200.data.speech_dataset import SpeechDataset
+    sys.path.insert(0, os.path.join(ROOT, "bin"))
+    spec = importlib.util.spec_from_file_location("train_chain_mod", os.path.join(ROOT, "bin", "train_chain.py"))
+    tc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tc)
+    data_yaml, wavs, _ = _make_corpus(str(tmp_path), n=5, seed=5)
+    ali_dir, chain_dir = _make_kaldi_chain_assets(str(tmp_path), data_yaml, wavs)
+    kaldi = tc.load_kaldi_assets(SimpleNamespace(ali_dir=ali_dir, chain_dir=chain_dir))
+    assert kaldi["tree"].context_width() == 1 and kaldi["chain_tm"]["num_pdfs"] == 20
+    opts = tc.SupervisionOptions()
+    assert (opts.left_tolerance, opts.right_tolerance, opts.frame_subsampling_factor) == (5, 5, 3)
+
+    def transform(batch):
+        batch["sup"] = [tc.kaldi_supervision(kaldi, opts, lab[:min(fb.num_frames(len(w)), len(lab)), 0])
+                        for w, lab in zip(batch["wav"], batch["label"])]
+        return batch
+    with open(data_yaml) as f:
+        data = yaml.safe_load(f)
+    cfg = {"source_paths": [v for v in data["clean_source"].values()], "data_config": {"sequence_mode": True}}
+    ds = SpeechDataset(cfg)
+    for workers in (0, 2):
+        seen = 0
+        for batch in WaveDataloader(ds, 2, num_workers=workers, batch_transform=transform):
+            for w, lab, (fst, t_sub) in zip(batch["wav"], batch["label"], batch["sup"]):
+                n = min(fb.num_frames(len(w)), len(lab))
+                assert t_sub == (n - 1) // 3 + 1
+                sup = graphs.Supervision(fst, t_sub, 104)
+                assert sup.frames_per_sequence == t_sub
+                assert int(fst["ilabel"].max()) <= 20 and int(fst["ilabel"].min()) >= 1
+                seen += 1
+        assert seen == 4                                    # the utterance without aux labels is dropped by the dataset
