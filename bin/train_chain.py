@@ -114,13 +114,16 @@ def main():
     if args.synthetic > 0:
         dataset = SyntheticWaveDataset(args.synthetic, mc["label_size"])
     else:
-        # corpus in the reference's formats (zip of wavs + pdf-id label file, -data); the numerator graph of an utterance
-        # is built from its pdf alignment with a boundary tolerance (synth.alignment_to_supervision_fst) -- the
-        # reference's phone-level proto-supervision needs Kaldi's tree / topology
+        # corpus in the reference's formats (zip of wavs + label file, -data).  With -ali_dir / -chain_dir the labels are
+        # the alignment model's transition ids and the numerator graphs are built the reference's way
+        # (chain_supervision.py: phones / durations -> proto-supervision -> tree-expanded, time-constrained FST); without
+        # them the labels are pdf ids and synth.alignment_to_supervision_fst builds a pdf-level graph with a tolerance
         dataset = SpeechDataset(config)
-        if not args.den_fst:
-            print("WARNING: no -den_fst given: training against a synthetic denominator graph")
     kaldi = load_kaldi_assets(args)
+    if kaldi is not None and not args.den_fst and os.path.isfile(args.chain_dir + "/den.fst"):
+        args.den_fst = args.chain_dir + "/den.fst"                                   # bin/train_chain.py:167
+    if args.synthetic <= 0 and not args.den_fst:
+        print("WARNING: no -den_fst / <chain_dir>/den.fst: training against a synthetic denominator graph")
     supervision_opts = SupervisionOptions()
     batch_transform = None
     if kaldi is not None and args.synthetic <= 0:
@@ -150,8 +153,6 @@ def main():
     averager = pkdist.GradAverager(list(model.parameters())) if world > 1 else None
 
     chain_opts = graphs.ChainTrainingOptions(leaky_hmm_coefficient=1e-4, xent_regularize=args.xent_regularize)
-    if kaldi is not None and not args.den_fst and os.path.isfile(args.chain_dir + "/den.fst"):
-        args.den_fst = args.chain_dir + "/den.fst"                                   # bin/train_chain.py:167
     if args.den_fst:                      # a real denominator graph: OpenFst binary (Kaldi's den.fst) or fstprint text
         den = graphs.DenominatorGraph.from_file(args.den_fst, mc["label_size"])
     else:
