@@ -20,9 +20,11 @@ from . import _lib
 
 
 def _csr(keys, n):
-    off = np.zeros(n + 1, np.int32)
-    np.add.at(off, np.asarray(keys, np.int64) + 1, 1)
-    return np.cumsum(off).astype(np.int32)
+    """CSR offsets [n + 1] of `keys` (row of every entry); bincount, not np.add.at (10x faster)."""
+    cnt = np.bincount(np.asarray(keys, np.int64), minlength=n) if len(keys) else np.zeros(n, np.int64)
+    off = np.zeros(n + 1, np.int64)
+    np.cumsum(cnt, out=off[1:])
+    return off.astype(np.int32)
 
 
 class ChainTrainingOptions(object):
@@ -367,7 +369,7 @@ class Lattice(object):
         self.eps_dst = ed.astype(np.int32)
         self.eps_gc = eg.astype(np.float32)
         # tids present on each frame (for the drop_frames test), as sorted unique (t, tid) keys
-        self._frame_tid_keys = np.unique(times[s1].astype(np.int64) * (1 << 32) + t1)
+        self._frame_tid_keys = _sorted_unique(times[s1].astype(np.int64) * (1 << 32) + t1)
 
     def frame_acc(self, num_ali, tid2pdf, tid2phone, criterion, silence_phones, one_silence_class=True):
         """Per-arc frame accuracy (uint8 0/1) of Kaldi's LatticeForwardBackwardMpeVariants for the non-epsilon
@@ -408,33 +410,55 @@ class Lattice(object):
         return (self._frame_tid_keys[pos] == keys).astype(np.uint8)
 
 
+def _sorted_unique(a):
+    """np.unique for small integer arrays without its per-call overhead (called once per lattice level)."""
+    if len(a) < 2:
+        return a
+    a = np.sort(a)
+    return a[np.concatenate(([True], a[1:] != a[:-1]))]
+
+
+def _expand(off, nodes):
+    """Indices of the CSR rows `nodes` laid end to end."""
+    cnt = off[nodes + 1] - off[nodes]
+    tot = int(cnt.sum())
+    if tot == 0:
+        return np.zeros(0, np.int64)
+    return np.repeat(off[nodes], cnt) + (np.arange(tot) - np.repeat(np.cumsum(cnt) - cnt, cnt))
+
+
 def _level_sort_lattice(S, src, dst, adv):
-    """Vectorised LatticeStateTimes for topologically sorted lattices (arcs sorted by src)."""
+    """Vectorised LatticeStateTimes for topologically sorted lattices (arcs sorted by src): a frontier walk, one
+    numpy step per frame.  Label-consuming arcs lead to the next frame; epsilon arcs (adv == 0) stay inside the
+    frame and are followed to closure before the frame advances."""
     times = np.full(S, -1, np.int64)
     times[0] = 0
-    if adv.all():
-        # layered: time[dst] = time[src]+1; propagate level by level in vector form
-        off = _csr(src, S)
-        frontier = np.array([0], np.int64)
-        t = 0
-        while len(frontier):
-            cnt = off[frontier + 1] - off[frontier]
-            idx = np.repeat(off[frontier], cnt) + (np.arange(cnt.sum()) - np.repeat(np.cumsum(cnt) - cnt, cnt))
-            d = np.unique(dst[idx])
-            if len(d) and (times[d] >= 0).any():
-                raise ValueError("paths of different length reach one lattice state")
-            t += 1
-            times[d] = t
-            frontier = d
-    else:
-        for s, d, a in zip(src, dst, adv):
-            nt = times[s] + a
-            if times[s] < 0:
-                raise ValueError("lattice not connected")
-            if times[d] < 0:
-                times[d] = nt
-            elif times[d] != nt:
-                raise ValueError("paths of different length reach one lattice state")
+    is_adv = adv.astype(bool)
+    all_adv = bool(is_adv.all())
+    off_a = _csr(src[is_adv], S).astype(np.int64)
+    dst_a = dst[is_adv]
+    if not all_adv:
+        off_e = _csr(src[~is_adv], S).astype(np.int64)
+        dst_e = dst[~is_adv]
+    frontier = np.array([0], np.int64)
+    t = 0
+    while len(frontier):
+        if not all_adv:                       # epsilon closure of the frame
+            new = frontier
+            while len(new):
+                d = _sorted_unique(dst_e[_expand(off_e, new)])
+                if len(d) and ((times[d] >= 0) & (times[d] != t)).any():
+                    raise ValueError("paths of different length reach one lattice state")
+                new = d[times[d] < 0]
+                times[new] = t
+                if len(new):
+                    frontier = np.concatenate([frontier, new])
+        d = _sorted_unique(dst_a[_expand(off_a, frontier)])
+        if len(d) and (times[d] >= 0).any():
+            raise ValueError("paths of different length reach one lattice state")
+        t += 1
+        times[d] = t
+        frontier = d
     if (times < 0).any():
         raise ValueError("lattice has unreachable states")
     perm = np.argsort(times * (S + 1) + np.arange(S), kind="stable")
