@@ -729,3 +729,40 @@ def test_train_chain_data_side_with_kaldi_assets(tmp_path):
                 assert int(fst["ilabel"].max()) <= 20 and int(fst["ilabel"].min()) >= 1
                 seen += 1
         assert seen == 4                                    # the utterance without aux labels is dropped by the dataset
+
+
+def test_lattice_and_supervision_batches_on_cpu(monkeypatch):
+    """The host half of LatticeBatch / SupervisionBatch without a GPU (the upload is replaced by plain tensors): state
+    times and drop masks against the oracle with and without epsilon arcs, index validation, int32 batch arrays."""
+    from oracle import lattice_ref
+    from pykaldi2_b200 import graphs, synth
+    monkeypatch.setattr(graphs, "_upload",
+                        lambda host, device: ({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in host.items()}, None))
+    rng = np.random.default_rng(11)
+    for eps in (0.0, 0.1):
+        N, Ts = 60, [17, 9, 12]
+        lats, alis, olat = [], [], []
+        for T in Ts:
+            lat, tid2pdf, ali = synth.make_lattice(T, N, rng, kmin=4, kmax=9, ali_drop=0.2, eps_frac=eps)
+            olat.append(lat); alis.append(ali); lats.append(graphs.Lattice(lat))
+        lb = graphs.LatticeBatch(lats, tid2pdf, alis, device="cpu")
+        pred = rng.normal(0, 3.0, (len(Ts), max(Ts), N)).astype(np.float32)
+        for b, T in enumerate(Ts):
+            _, _, drop, times = lattice_ref.lattice_fb_mmi(pred[b, :T], olat[b], tid2pdf, alis[b])
+            assert (lats[b].state_times_orig == times).all()
+            assert (lb.keep_host[b] == (~drop).astype(np.uint8)).all()
+        assert lb.total_frames == sum(Ts) and lb.total_arcs == sum(len(l.in_src) for l in lats)
+        assert lb.max_pdf < N and lb._dev["out_dst"].dtype == torch.int32 and lb._dev["in_src"].dtype == torch.int32
+        # concatenated state indices point into the right lattice
+        off = np.concatenate([[0], np.cumsum([l.num_states for l in lats])])
+        od = lb._dev["out_dst"].numpy()
+        k = 0
+        for b, l in enumerate(lats):
+            seg = od[k:k + len(l.out_dst)]
+            assert seg.min() >= off[b] and seg.max() < off[b + 1]
+            k += len(l.out_dst)
+    with pytest.raises(ValueError):
+        graphs.LatticeBatch(lats, tid2pdf[:10], alis, device="cpu")
+    sups = [graphs.Supervision(synth.make_supervision_fst(T, 50, rng), T, 50) for T in (5, 9, 1)]
+    sb = graphs.SupervisionBatch(sups, device="cpu")
+    assert sb.n_seq == 3 and sb.num_frames_host == [5, 9, 1] and sb._dev["out_dst"].dtype == torch.int32
