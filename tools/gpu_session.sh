@@ -18,7 +18,7 @@ for step in "$@"; do
     bench)       timeout 600 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; cat $OUT/bench_$TAG.json; tail -3 $OUT/bench_$TAG.err ;;
     bench_ref)   timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_${TAG}_reference.json 2> $OUT/bench_${TAG}_reference.err; cat $OUT/bench_${TAG}_reference.json ;;
     launches)    timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $OUT/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/launches_$TAG.log 2>&1; echo "launches rc=$?" ;;
-    lat)         timeout 300 python tools/time_mpe.py > $OUT/lat_$TAG.jsonl 2> $OUT/lat_$TAG.err; PK2_LATFB_V0=1 timeout 300 python tools/time_mpe.py >> $OUT/lat_$TAG.jsonl 2>> $OUT/lat_$TAG.err; cat $OUT/lat_$TAG.jsonl; tail -3 $OUT/lat_$TAG.err ;;
+    lat)         timeout 300 python tools/time_mpe.py > $OUT/lat_$TAG.jsonl 2> $OUT/lat_$TAG.err; cat $OUT/lat_$TAG.jsonl; tail -3 $OUT/lat_$TAG.err ;;
     phases)      timeout 300 python tools/step_phases.py > $OUT/phases_$TAG.json 2> $OUT/phases_$TAG.err; cat $OUT/phases_$TAG.json; tail -3 $OUT/phases_$TAG.err ;;
     ncu_lat)     timeout 600 ncu --set full --clock-control none --import-source on -k regex:lat_ -c 6 -o $OUT/lat_$TAG -f python tools/time_mpe.py 1500,1200,900,600 > $OUT/ncu_lat_$TAG.log 2>&1; echo "ncu_lat rc=$?" ;;
     ncu_fbank)   timeout 600 ncu --set full --clock-control none --import-source on -k regex:fbank -c 2 -o $OUT/fbank_$TAG -f python tools/kernel_bench.py fbank > $OUT/ncu_fbank_$TAG.log 2>&1; echo "ncu_fbank rc=$?" ;;

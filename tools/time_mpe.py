@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Timing of the lattice-MMI and sMBR kernels on a C3-shaped batch (BASELINE config 3: 4 utterances per GPU,
-K_t ~ U{32..96} states per frame, ~250 arcs per frame, N = 5768).  CUDA events, warm.  PK2_LATFB_V0=1 selects the
-round-1 kernels (one CTA per utterance) for the A/B line.  Algorithmic bytes: SURVEY 8(d)
+K_t ~ U{32..96} states per frame, ~250 arcs per frame, N = 5768).  CUDA events, warm.  (The round-1 kernels,
+one CTA per utterance, were A/B-timed with this script before their removal: profiles/lattice_kernels_r2_v5.jsonl.)  Algorithmic bytes: SURVEY 8(d)
 sum_utt (4 T N + 48 A_lat + 16 S_lat)."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -36,7 +36,7 @@ for name, fn in (("lattice MMI", lambda: ops.lattice_mmi(pred, lb)), ("lattice s
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
-    print(json.dumps({"kernel": name, "impl": "v0 (round 1)" if os.environ.get("PK2_LATFB_V0") else "v1", "frames": Ts,
+    print(json.dumps({"kernel": name, "impl": "v1", "frames": Ts,
                       "arcs": lb.total_arcs, "states": lb.total_states, "ms_per_call": round(ms, 4),
                       "algorithmic_bytes": alg, "alg_GBps": round(alg / ms / 1e6, 1),
                       "frac_hbm": round(alg / ms / 1e6 / peak, 4)}), flush=True)
