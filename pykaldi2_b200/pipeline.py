@@ -10,7 +10,6 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import dist as pkdist
 from .data import fbank as fb
 from .ops import ops
 

@@ -4,7 +4,7 @@ start (us, relative to the first kernel of the step) and duration of every kerne
 time.  Shows what overlaps what across the streams -- which `ncu` (serialising) cannot.
   python tools/timeline.py > profiles/timeline.csv"""
 import os, sys
-import numpy as np, torch
+import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench
