@@ -47,19 +47,19 @@ def _first_existing(*paths):
 
 
 def load_kaldi_assets(args):
-    """The reference's Kaldi inputs (bin/train_chain.py:162-181) in TEXT form: the alignment model's transition
-    model (<ali_dir>/final.mdl[.txt]), the chain transition model (<chain_dir>/0.trans_mdl[.txt]) and tree
-    (<chain_dir>/tree[.txt]).  Returns None when -ali_dir / -chain_dir are not given."""
+    """The reference's Kaldi inputs (bin/train_chain.py:162-181), binary as Kaldi writes them or in text form: the
+    alignment model's transition model (<ali_dir>/final.mdl[.txt]), the chain transition model
+    (<chain_dir>/0.trans_mdl[.txt]) and tree (<chain_dir>/tree[.txt]).  Returns None when -ali_dir / -chain_dir are
+    not given."""
     if not (args.ali_dir and args.chain_dir):
         return None
     ali = _first_existing(args.ali_dir + "/final.mdl.txt", args.ali_dir + "/final.mdl")
     ctm = _first_existing(args.chain_dir + "/0.trans_mdl.txt", args.chain_dir + "/0.trans_mdl")
     tree = _first_existing(args.chain_dir + "/tree.txt", args.chain_dir + "/tree")
     if not (ali and ctm and tree):
-        raise SystemExit("train_chain.py: -ali_dir / -chain_dir must hold final.mdl, 0.trans_mdl and tree (text form: "
-                         "copy-transition-model --binary=false, copy-tree --binary=false)")
-    return {"ali_tm": kaldi_io.read_transition_model_text(ali), "chain_tm": kaldi_io.read_transition_model_text(ctm),
-            "tree": kaldi_io.read_tree_text(tree)}
+        raise SystemExit("train_chain.py: -ali_dir / -chain_dir must hold final.mdl, 0.trans_mdl and tree")
+    return {"ali_tm": kaldi_io.read_transition_model(ali), "chain_tm": kaldi_io.read_transition_model(ctm),
+            "tree": kaldi_io.read_tree(tree)}
 
 
 def main():

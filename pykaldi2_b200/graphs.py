@@ -292,10 +292,11 @@ class TidPdfMap(object):
 
     @classmethod
     def from_kaldi_text(cls, path):
-        """From a text-form Kaldi transition model (``copy-transition-model --binary=false final.mdl -``);
-        the reference reads the binary model through PyKaldi (bin/train_se.py:164-170)."""
+        """From a Kaldi transition model file: text form (``copy-transition-model --binary=false final.mdl -``) or the
+        binary ``final.mdl`` itself (its transition-model head; reader/kaldi_io.py).  The reference reads it through
+        PyKaldi (bin/train_se.py:164-170)."""
         from .reader import kaldi_io
-        tm = kaldi_io.read_transition_model_text(path)
+        tm = kaldi_io.read_transition_model(path)
         return cls(tm["tid2pdf"], tm["tid2phone"])
 
     def transition_id_to_pdf(self, tid):

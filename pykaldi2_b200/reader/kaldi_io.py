@@ -1,6 +1,8 @@
-"""Text-form Kaldi objects the sequence trainers take from a Kaldi setup (reference bin/train_se.py:164-184 reads
-them through PyKaldi): the transition model (``copy-transition-model --binary=false final.mdl -``) and the pdf
-occupancy vector behind the log-prior (``final.occs`` in text form).
+"""Kaldi objects the sequence trainers take from a Kaldi setup (reference bin/train_se.py:164-184 and
+bin/train_chain.py:162-181 read them through PyKaldi): the transition model (the head of ``final.mdl`` /
+``0.trans_mdl``), the context-dependency tree and the pdf occupancy vector behind the log-prior (``final.occs``), in
+text form (``copy-transition-model / copy-tree / copy-vector --binary=false``) or in Kaldi's binary form
+(``read_transition_model``, ``read_tree``, ``read_vector`` detect the "\\0B" header).
 
 Only what the hot path needs is extracted from the transition model: transition-id -> pdf and transition-id ->
 phone (``TidPdfMap``), plus -- for the chain supervision builder (chain_supervision.py) -- the transition state,
@@ -83,11 +85,17 @@ def read_transition_model_text(path_or_text):
     vals = [int(v) for v in tok[t0 + 2:t0 + 2 + n * width]]
     if tok[t0 + 2 + n * width] != endtag:
         raise ValueError("malformed %s section" % endtag)
+    tuples = [(vals[r * width], vals[r * width + 1], vals[r * width + 2],
+               vals[r * width + 3] if width == 4 else vals[r * width + 2]) for r in range(n)]
+    return _derive(topo, pdf_class, tuples)
+
+
+def _derive(topo, pdf_class, tuples):
+    """TransitionModel::ComputeDerived: per-transition-id tables from the topology and the (phone, hmm-state,
+    forward-pdf, self-loop-pdf) tuples."""
     tid2pdf, tid2phone = [-1], [0]              # transition ids start at 1
     tid2state, tid_self, tid_final = [0], [False], [False]
-    for r in range(n):
-        phone, hs, fpdf = vals[r * width], vals[r * width + 1], vals[r * width + 2]
-        spdf = vals[r * width + 3] if width == 4 else fpdf
+    for r, (phone, hs, fpdf, spdf) in enumerate(tuples):
         for dest, _ in topo[phone][hs]:
             tid2pdf.append(spdf if dest == hs else fpdf)
             tid2phone.append(phone)
@@ -98,7 +106,7 @@ def read_transition_model_text(path_or_text):
     return {"tid2pdf": np.asarray(tid2pdf, np.int32), "tid2phone": np.asarray(tid2phone, np.int32),
             "tid2state": np.asarray(tid2state, np.int32), "tid_is_self_loop": np.asarray(tid_self, bool),
             "tid_is_final": np.asarray(tid_final, bool), "topology": topo, "pdf_class": pdf_class,
-            "num_pdfs": int(max(tid2pdf)) + 1, "phones": sorted(topo)}
+            "tuples": list(tuples), "num_pdfs": int(max(tid2pdf)) + 1, "phones": sorted(topo)}
 
 
 class EventMap(object):
@@ -233,7 +241,259 @@ def read_vector_text(path_or_text):
     return np.asarray(m.group(1).split(), dtype=np.float64)
 
 
+def read_vector(path):
+    """Kaldi vector file, text (`` [ 1 2 3 ]``) or binary ("\\0B", token FV / DV, int32 size, raw values)."""
+    with open(path, "rb") as f:
+        raw = f.read()
+    if raw[:2] != b"\0B":
+        return read_vector_text(raw.decode("latin-1"))
+    r = _BinReader(raw, 2)
+    kind = r.token()
+    if kind not in ("FV", "DV"):
+        raise ValueError("expected a Kaldi vector (FV / DV), found %r" % kind)
+    n = r.int32()
+    width, code = (4, "f") if kind == "FV" else (8, "d")
+    return np.asarray(struct.unpack_from("<%d%s" % (n, code), raw, r.i), np.float64)
+
+
 def log_prior_from_occs(path_or_text):
-    """log(occs / sum(occs)) (reference bin/train_se.py:183-184)."""
-    occ = read_vector_text(path_or_text)
+    """log(occs / sum(occs)) (reference bin/train_se.py:183-184); text form, or a binary ``final.occs`` file."""
+    import os
+    if "[" not in path_or_text and os.path.isfile(path_or_text):
+        occ = read_vector(path_or_text)
+    else:
+        occ = read_vector_text(path_or_text)
     return np.log(occ / occ.sum()).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------- binary forms ----
+# Kaldi's binary I/O (base/io-funcs-inl.h): a file starts with "\0B"; tokens are written as text followed by one
+# space; a basic type is one length byte (+sizeof for signed, -sizeof for unsigned types) followed by the raw
+# little-endian value; an integer vector is one byte sizeof(T), an int32 count and the raw values; a float vector is
+# the token "FV", an int32 count (basic type) and raw floats.  The object layouts below follow
+# HmmTopology::Write / TransitionModel::Write (hmm/hmm-topology.cc, hmm/transition-model.cc) and
+# ContextDependency::Write / EventMap::Write (tree/context-dep.cc, tree/event-map.cc).  Restated from the published
+# sources; no Kaldi-written file is available in this sandbox: the readers are pinned to the writers next to them
+# (tests/test_chain_supervision.py round trips), not to Kaldi output -- parity unpinned.
+import struct
+
+
+class _BinReader(object):
+    def __init__(self, raw, pos=0):
+        self.b, self.i = raw, pos
+
+    def token(self):
+        while self.b[self.i:self.i + 1].isspace():
+            self.i += 1
+        j = self.i
+        while j < len(self.b) and not self.b[j:j + 1].isspace():
+            j += 1
+        t = self.b[self.i:j].decode("latin-1")
+        self.i = j + 1                                  # the single space after a token
+        return t
+
+    def expect(self, tok):
+        t = self.token()
+        if t != tok:
+            raise ValueError("expected %r, found %r at byte %d" % (tok, t, self.i))
+
+    def int32(self):
+        n = struct.unpack_from("b", self.b, self.i)[0]
+        if abs(n) != 4:
+            raise ValueError("expected a 4-byte integer at byte %d (length byte %d)" % (self.i, n))
+        v = struct.unpack_from("<i" if n > 0 else "<I", self.b, self.i + 1)[0]
+        self.i += 5
+        return int(v)
+
+    def float32(self):
+        n = struct.unpack_from("b", self.b, self.i)[0]
+        if n == 4:
+            v = struct.unpack_from("<f", self.b, self.i + 1)[0]
+        elif n == 8:
+            v = struct.unpack_from("<d", self.b, self.i + 1)[0]
+        else:
+            raise ValueError("expected a float at byte %d (length byte %d)" % (self.i, n))
+        self.i += 1 + n
+        return float(v)
+
+    def int_vector(self):
+        sz = struct.unpack_from("b", self.b, self.i)[0]
+        if sz != 4:
+            raise ValueError("expected an int32 vector at byte %d" % self.i)
+        n = struct.unpack_from("<i", self.b, self.i + 1)[0]
+        v = list(struct.unpack_from("<%di" % n, self.b, self.i + 5)) if n else []
+        self.i += 5 + 4 * n
+        return v
+
+
+def _w_token(out, t):
+    out.append(t.encode("latin-1") + b" ")
+
+
+def _w_int32(out, v, unsigned=False):
+    out.append(struct.pack("<bI", -4, v) if unsigned else struct.pack("<bi", 4, v))
+
+
+def _w_float(out, v):
+    out.append(struct.pack("<bf", 4, v))
+
+
+def _w_int_vector(out, v):
+    out.append(struct.pack("<bi", 4, len(v)) + struct.pack("<%di" % len(v), *v))
+
+
+def read_transition_model(path):
+    """Text or binary Kaldi transition model (the head of a ``final.mdl`` / ``0.trans_mdl``) -> the dict of
+    read_transition_model_text."""
+    with open(path, "rb") as f:
+        raw = f.read()
+    if raw[:2] != b"\0B":
+        return read_transition_model_text(raw.decode("latin-1"))
+    r = _BinReader(raw, 2)
+    r.expect("<TransitionModel>")
+    r.expect("<Topology>")
+    phones = r.int_vector()
+    phone2idx = r.int_vector()
+    n_entries = r.int32()
+    is_hmm = True
+    if n_entries == -1:                                 # extended format: self-loop pdf classes follow
+        is_hmm = False
+        n_entries = r.int32()
+    entries, classes = [], []
+    for _ in range(n_entries):
+        states, cls = [], []
+        for _ in range(r.int32()):
+            fwd = r.int32()
+            slf = fwd if is_hmm else r.int32()
+            trans = [(r.int32(), r.float32()) for _ in range(r.int32())]
+            states.append(trans)
+            cls.append(None if fwd < 0 else (fwd, slf))      # kNoPdf = -1 on non-emitting states
+        entries.append(states)
+        classes.append(cls)
+    r.expect("</Topology>")
+    topo = {p: entries[phone2idx[p]] for p in phones}
+    pdf_class = {p: classes[phone2idx[p]] for p in phones}
+    tag = r.token()
+    if tag not in ("<Triples>", "<Tuples>"):
+        raise ValueError("expected <Triples> or <Tuples>, found %r" % tag)
+    tuples = []
+    for _ in range(r.int32()):
+        ph, hs, fpdf = r.int32(), r.int32(), r.int32()
+        tuples.append((ph, hs, fpdf, r.int32() if tag == "<Tuples>" else fpdf))
+    r.expect("</Triples>" if tag == "<Triples>" else "</Tuples>")
+    return _derive(topo, pdf_class, tuples)
+
+
+def write_transition_model_binary(tm, path, log_probs=None):
+    """The transition-model head of a Kaldi model file in binary form, from the dict the readers return."""
+    phones = sorted(tm["topology"])
+    uniq, phone2idx = [], [-1] * (max(phones) + 1)
+    for p in phones:
+        key = (tm["topology"][p], tm["pdf_class"][p])
+        for i, (k, _) in enumerate(uniq):
+            if k == key:
+                phone2idx[p] = i
+                break
+        else:
+            phone2idx[p] = len(uniq)
+            uniq.append((key, p))
+    is_hmm = all(c is None or c[0] == c[1] for p in phones for c in tm["pdf_class"][p]) and \
+        all(f == s_ for _, _, f, s_ in tm["tuples"])
+    out = [b"\0B"]
+    _w_token(out, "<TransitionModel>")
+    _w_token(out, "<Topology>")
+    _w_int_vector(out, phones)
+    _w_int_vector(out, phone2idx)
+    if not is_hmm:
+        _w_int32(out, -1)
+    _w_int32(out, len(uniq))
+    for (states, classes), _ in uniq:
+        _w_int32(out, len(states))
+        for trans, c in zip(states, classes):
+            _w_int32(out, -1 if c is None else c[0])
+            if not is_hmm:
+                _w_int32(out, -1 if c is None else c[1])
+            _w_int32(out, len(trans))
+            for d, pr in trans:
+                _w_int32(out, d)
+                _w_float(out, pr)
+    _w_token(out, "</Topology>")
+    _w_token(out, "<Triples>" if is_hmm else "<Tuples>")
+    _w_int32(out, len(tm["tuples"]))
+    for ph, hs, f, s_ in tm["tuples"]:
+        _w_int32(out, ph); _w_int32(out, hs); _w_int32(out, f)
+        if not is_hmm:
+            _w_int32(out, s_)
+    _w_token(out, "</Triples>" if is_hmm else "</Tuples>")
+    _w_token(out, "<LogProbs>")
+    lp = [0.0] * len(tm["tid2pdf"]) if log_probs is None else list(log_probs)
+    _w_token(out, "FV")
+    _w_int32(out, len(lp))
+    out.append(struct.pack("<%df" % len(lp), *lp))
+    _w_token(out, "</LogProbs>")
+    _w_token(out, "</TransitionModel>")
+    with open(path, "wb") as f:
+        f.write(b"".join(out))
+
+
+def read_tree(path):
+    """Text or binary Kaldi context-dependency tree -> ContextDependency."""
+    with open(path, "rb") as f:
+        raw = f.read()
+    if raw[:2] != b"\0B":
+        return read_tree_text(raw.decode("latin-1"))
+    r = _BinReader(raw, 2)
+    r.expect("ContextDependency")
+    N, P = r.int32(), r.int32()
+    r.expect("ToPdf")
+
+    def parse():
+        t = r.token()
+        if t == "NULL":
+            return None
+        if t == "CE":
+            return EventMap("CE", answer=r.int32())
+        if t == "TE":
+            key, size = r.int32(), r.int32()
+            r.expect("(")
+            table = [parse() for _ in range(size)]
+            r.expect(")")
+            return EventMap("TE", key=key, table=table)
+        if t == "SE":
+            key = r.int32()
+            ys = set(r.int_vector())
+            r.expect("{")
+            yes, no = parse(), parse()
+            r.expect("}")
+            return EventMap("SE", key=key, yes_set=ys, yes=yes, no=no)
+        raise ValueError("unknown EventMap node %r at byte %d" % (t, r.i))
+
+    root = parse()
+    r.expect("EndContextDependency")
+    return ContextDependency(N, P, root)
+
+
+def write_tree_binary(tree, path):
+    out = [b"\0B"]
+    _w_token(out, "ContextDependency")
+    _w_int32(out, tree.N); _w_int32(out, tree.P)
+    _w_token(out, "ToPdf")
+
+    def emit(node):
+        if node is None:
+            _w_token(out, "NULL")
+        elif node.kind == "CE":
+            _w_token(out, "CE"); _w_int32(out, node.answer)
+        elif node.kind == "TE":
+            _w_token(out, "TE"); _w_int32(out, node.key); _w_int32(out, len(node.table), unsigned=True)
+            _w_token(out, "(")
+            for c in node.table:
+                emit(c)
+            _w_token(out, ")")
+        else:
+            _w_token(out, "SE"); _w_int32(out, node.key); _w_int_vector(out, sorted(node.yes_set))
+            _w_token(out, "{"); emit(node.yes); emit(node.no); _w_token(out, "}")
+    emit(tree.to_pdf)
+    _w_token(out, "EndContextDependency")
+    with open(path, "wb") as f:
+        f.write(b"".join(out))

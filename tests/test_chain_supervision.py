@@ -196,3 +196,60 @@ def test_whole_chain_feeds_supervision_object():
     assert T == 4
     sup = graphs.Supervision(fst, T, 6)
     assert sup.frames_per_sequence == 4 and sup.label_dim == 6 and sup.weight == 1.0
+
+
+def test_binary_transition_model_and_tree_round_trip(tmp_path):
+    """reader.kaldi_io binary forms (Kaldi's io-funcs layout: "\\0B", tokens + space, length-prefixed basic types,
+    int32 vectors): what the writers produce the readers parse back to the text-form result; the auto-detecting
+    readers take both forms; a GMM-style model file with trailing bytes after </TransitionModel> is accepted."""
+    import os
+    for name, text in (("ali", ALI_TM), ("chain", CHAIN_TM)):
+        tm = kaldi_io.read_transition_model_text(text)
+        p = os.path.join(tmp_path, name + ".mdl")
+        kaldi_io.write_transition_model_binary(tm, p)
+        with open(p, "ab") as f:
+            f.write(b"<DIMENSION> \x04\x27\x00\x00\x00")       # whatever follows the transition model is ignored
+        assert open(p, "rb").read(2) == b"\0B"
+        tb = kaldi_io.read_transition_model(p)
+        for k in ("tid2pdf", "tid2phone", "tid2state", "tid_is_self_loop", "tid_is_final"):
+            assert np.array_equal(tm[k], tb[k]), (name, k)
+        assert tm["tuples"] == tb["tuples"] and tm["pdf_class"] == tb["pdf_class"]
+        pt = os.path.join(tmp_path, name + ".txt")
+        with open(pt, "w") as f:
+            f.write(text)
+        assert np.array_equal(kaldi_io.read_transition_model(pt)["tid2pdf"], tm["tid2pdf"])
+    # the extended (<Tuples>) format is chosen exactly when forward and self-loop pdfs differ
+    raw = open(os.path.join(tmp_path, "chain.mdl"), "rb").read()
+    assert b"<Tuples>" in raw and b"<Triples>" in open(os.path.join(tmp_path, "ali.mdl"), "rb").read()
+    tree = kaldi_io.read_tree_text(BIPHONE_TREE)
+    pt = os.path.join(tmp_path, "tree")
+    kaldi_io.write_tree_binary(tree, pt)
+    tb = kaldi_io.read_tree(pt)
+    assert (tb.context_width(), tb.central_position()) == (2, 1)
+    for w in ([0, 1], [1, 1], [2, 1], [3, 1], [1, 2], [0, 3], [2, 3]):
+        for c in (0, 1):
+            assert tree.compute(w, c) == tb.compute(w, c)
+    with pytest.raises(ValueError):
+        kaldi_io.read_tree_text(pt)                              # the text-only reader names the conversion command
+    # the supervision built from binary assets equals the one from text assets
+    opts = cs.SupervisionOptions(5, 5, 3)
+    ali = [1, 1, 2, 3, 4, 5, 5, 6, 8, 10, 11, 12]
+    a, _ = cs.supervision_from_alignment(opts, kaldi_io.read_transition_model_text(ALI_TM),
+                                         kaldi_io.read_transition_model_text(CHAIN_TM), mono_tree(), ali)
+    kaldi_io.write_tree_binary(mono_tree(), pt)
+    b, _ = cs.supervision_from_alignment(opts, kaldi_io.read_transition_model(os.path.join(tmp_path, "ali.mdl")),
+                                         kaldi_io.read_transition_model(os.path.join(tmp_path, "chain.mdl")),
+                                         kaldi_io.read_tree(pt), ali)
+    assert all(np.array_equal(a[k], b[k]) for k in ("src", "dst", "ilabel", "state_times"))
+
+
+def test_binary_occupancy_vector(tmp_path):
+    import os
+    import struct
+    p = os.path.join(tmp_path, "final.occs")
+    with open(p, "wb") as f:
+        f.write(b"\0BFV " + struct.pack("<bi", 4, 3) + struct.pack("<3f", 10.0, 11.5, 3.25))
+    assert kaldi_io.read_vector(p).tolist() == [10.0, 11.5, 3.25]
+    want = np.log(np.array([10.0, 11.5, 3.25]) / 24.75).astype(np.float32)
+    np.testing.assert_allclose(kaldi_io.log_prior_from_occs(p), want, rtol=1e-6)
+    np.testing.assert_allclose(kaldi_io.log_prior_from_occs(" [ 10 11.5 3.25 ]"), want, rtol=1e-6)
